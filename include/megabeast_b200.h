@@ -1,0 +1,212 @@
+/*
+ * megabeast_b200 -- C ABI of the B200-native ensemble likelihood (libmegabeast_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of megaBEAST: the per-step ensemble likelihood
+ *
+ *     /root/reference/megabeast/singlepop_dust_model.py:110-229   MB_Model.lnlike
+ *     /root/reference/megabeast/helpers.py:105-164                get_predicted_num_stars
+ *
+ * The reference is pure Python and has no FFI; what a maintainer would bind (ctypes stub in
+ * INTEGRATION.md) is exactly the entry points below.  Plain pointers and sizes only -- no
+ * torch, numpy or CUDA types in any signature (a `void* stream` is an opaque cudaStream_t).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; mb_last_error() then holds a
+ *     thread-local, human-readable message (CUDA failures, invalid arguments).
+ *   - NUMERICAL conditions the reference turns into exceptions are NOT errors here: they come
+ *     back per walker in `status` (MB_STATUS_*), and the host language raises.
+ *   - host pointers passed to mb_create are only read during the call; nothing is retained.
+ *   - one handle = one CUDA device = one shard of stars.  Calls on a handle must be
+ *     serialised by the caller (the reference is single-threaded).
+ *   - there is no CPU fallback: without a CUDA device mb_create fails.
+ */
+#ifndef MEGABEAST_B200_H
+#define MEGABEAST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_ABI_VERSION 1
+
+/* Ensemble parameters that can carry a free prior model, in phi order.  This is
+ * MB_Model.params (singlepop_dust_model.py:29) without M_ini: a free IMF is unreachable in
+ * the reference (KeyError 'nsubvars' at :137 and :257), so it stays a host-side constant. */
+#define MB_NPARAM 4
+enum mb_param { MB_P_LOGA = 0, MB_P_AV = 1, MB_P_RV = 2, MB_P_FA = 3 };
+
+/* Prior-model names the device evaluates analytically (beast.physicsmodel.priormodel names,
+ * docs/megabeast/settings.rst:39,78).  MB_FIXED: prior name "fixed" -> the parameter
+ * contributes no factor at all (singlepop_dust_model.py:135).  MB_TABULATED: the host
+ * evaluates any callable on the parameter's distinct grid values and passes the table. */
+enum mb_prior_kind {
+  MB_FIXED = 0,
+  MB_FLAT = 1,          /* no variables            */
+  MB_LOGNORMAL = 2,     /* mean, sigma             */
+  MB_TWO_LOGNORMAL = 3, /* mean1, mean2, sigma1, sigma2, N1_to_N2 */
+  MB_BINS_HISTO = 4,    /* nnodes heights (left-constant steps over nodes) */
+  MB_BINS_INTERP = 5,   /* nnodes values (linear interpolation over nodes) */
+  MB_EXPONENTIAL = 6,   /* tau [Gyr]; x is log10(age/yr) */
+  MB_TABULATED = 7
+};
+#define MB_MAX_NODES 64
+
+/* phi layout: for p in (logA, Av, Rv, fA), if kind[p] is free, its variables in the order
+ * listed above; ndim = sum.  Same order as MB_Model.start_params (:82-108). */
+typedef struct {
+  int32_t kind[MB_NPARAM];
+  int32_t nnodes[MB_NPARAM];
+  double nodes[MB_NPARAM][MB_MAX_NODES];
+} mb_model_desc;
+
+/* beast_moddata (fit_single.py:37-57): 1-D float64 columns of length G.  col[p] may be NULL
+ * when kind[p] == MB_FIXED.  logA and Z are needed only for the N-stars term. */
+typedef struct {
+  int64_t G;
+  const double* col[MB_NPARAM];
+  const double* logA;
+  const double* Z;
+  const double* prior_weight;
+  const double* grid_weight;
+  const double* completeness;
+} mb_grid_desc;
+
+/* star_lnpgriddata (helpers.py:15-43): indxs (K,S) int64 and vals (K,S) float64, C order
+ * (star is the fast axis, singlepop_dust_model.py:157,196-198).  Non-finite vals mark padded
+ * entries whose index is never dereferenced.  This handle owns stars [star_begin, star_end);
+ * n_stars_total is the S of the Poisson term (:183-185), i.e. the full column count of the fit. */
+typedef struct {
+  int64_t K;
+  int64_t S;
+  const int64_t* indxs;
+  const double* vals;
+  int64_t star_begin;
+  int64_t star_end;
+  int64_t n_stars_total;  /* 0 -> S; set it when the arrays hold only this rank's columns */
+} mb_stars_desc;
+
+/* Output of precompute_mass_multipliers (helpers.py:46-102), a once-per-fit host constant.
+ * NULL pointer to mb_create <=> no N-stars term (logA prior fixed, :71-74). */
+typedef struct {
+  int32_t n_ages;
+  int32_t n_mets;
+  const double* ages;     /* sorted unique logA */
+  const double* mets;     /* sorted unique Z    */
+  const double* massmult; /* [n_ages][n_mets]   */
+  double avemass;
+} mb_massmult_desc;
+
+enum mb_mode {
+  MB_MODE_AUTO = 0,        /* FACTOR when the factor tables fit shared memory, else TABLE_UNIQUE */
+  MB_MODE_FACTOR = 1,      /* per-(star,point) class codes + per-walker factor tables in smem */
+  MB_MODE_TABLE_UNIQUE = 2,/* physmod materialised over the distinct parameter combinations */
+  MB_MODE_TABLE_GRID = 3   /* physmod[G][W] materialised over every grid row, gathered by index */
+};
+
+typedef struct {
+  int32_t device;          /* CUDA ordinal */
+  int32_t mode;            /* enum mb_mode */
+  int32_t keep_indices;    /* retain the gathered grid rows for mb_gathered_indices */
+  int32_t merge_duplicates;/* pre-sum a star's entries that share all class codes (FACTOR/TABLE_UNIQUE) */
+  int32_t reserved[12];
+} mb_options;
+
+typedef struct {
+  int32_t abi_version;
+  int32_t device;
+  int32_t mode;            /* the mode actually in use */
+  int32_t ndim;
+  int32_t poisson;         /* N-stars term on */
+  int32_t n_classes[MB_NPARAM];
+  int32_t n_age_classes;   /* factor table A rows */
+  int32_t n_dust_classes;  /* factor table B rows */
+  int32_t n_bins;
+  int32_t sm_count;
+  int32_t walkers_per_pass;/* of the last evaluation */
+  int32_t launches_last_eval;
+  int64_t G;
+  int64_t n_stars_local;
+  int64_t n_stars_total;
+  int64_t n_entries;       /* finite (star, point) entries held on the device */
+  int64_t n_entries_raw;   /* before merging duplicates */
+  int64_t device_bytes;
+  int64_t reserved[8];
+} mb_info;
+
+/* Device result layout of mb_lnlike_device: three rows of W doubles. */
+enum { MB_OUT_STARSUM = 0, MB_OUT_POISSON = 1, MB_OUT_NONFINITE = 2, MB_OUT_ROWS = 3 };
+
+#define MB_STATUS_OK 0
+#define MB_STATUS_NONFINITE_STAR 1 /* ValueError("invidual integrated star prob is not finite"), :216-217 */
+#define MB_STATUS_TOTAL_ZERO 2     /* print + exit(), :225-227 */
+
+typedef struct mb_handle mb_handle;
+
+int mb_abi_version(void);
+const char* mb_last_error(void);
+
+/* Number of visible CUDA devices, or -1 (with mb_last_error) if the runtime cannot start. */
+int mb_device_count(void);
+
+/* replaces: the per-call arguments of MB_Model.lnlike (singlepop_dust_model.py:110) -- data is
+ * uploaded once and kept resident, keyed by the caller on the identity of the two dicts. */
+int mb_create(const mb_grid_desc* grid, const mb_stars_desc* stars, const mb_model_desc* model,
+              const mb_massmult_desc* massmult, const mb_options* opts, mb_handle** out);
+void mb_destroy(mb_handle* h);
+int mb_get_info(const mb_handle* h, mb_info* out);
+
+/* replaces: MB_Model.lnlike(phi, ...) for a batch of W walkers (singlepop_dust_model.py:110-229).
+ * phi: host [W][ndim]; lnlike: host [W]; status: host [W].  Synchronous.  Covers the whole
+ * likelihood for this handle's stars including the Poisson term. */
+int mb_lnlike(mb_handle* h, const double* phi, int32_t W, int32_t ndim, double* lnlike,
+              int32_t* status);
+
+/* Same with host-evaluated tables for MB_TABULATED parameters: tab[p] is [W][n_classes[p]]
+ * (values of the parameter's callable at mb_class_values), NULL for analytic parameters. */
+int mb_lnlike_tabulated(mb_handle* h, const double* phi, int32_t W, int32_t ndim,
+                        const double* const tab[MB_NPARAM], double* lnlike, int32_t* status);
+
+/* Split form for driving several handles (GPUs) from one host thread: begin() enqueues the
+ * host->device copy, the kernels and the device->host copy on the handle's stream and returns;
+ * end() waits and hands back the raw [MB_OUT_ROWS][W] result rows.  mb_combine() turns rows
+ * (summed over shards by the caller: rows STARSUM and NONFINITE add, POISSON is shared) into
+ * lnlike/status exactly as mb_lnlike does. */
+int mb_lnlike_begin(mb_handle* h, const double* phi, int32_t W, int32_t ndim,
+                    const double* const tab[MB_NPARAM]);
+int mb_lnlike_end(mb_handle* h, double* rows);
+void mb_combine(const double* rows, int32_t W, double* lnlike, int32_t* status);
+
+/* Multi-GPU building block: device pointers, asynchronous on `stream`.  d_out is
+ * [MB_OUT_ROWS][W] doubles: partial sum of ln(star prob) over this handle's stars, the
+ * Poisson term (identical on every shard), and the count of non-finite stars.  The caller
+ * all-reduces rows STARSUM and NONFINITE (one NCCL allreduce) and adds POISSON once. */
+int mb_lnlike_device(mb_handle* h, const double* d_phi, int32_t W, int32_t ndim, double* d_out,
+                     void* stream);
+
+/* Distinct values ("classes") of a free parameter's grid column, ascending; the x at which a
+ * host callable must be tabulated.  Returns the count; fills at most `cap` values. */
+int mb_class_values(const mb_handle* h, int32_t param, double* out, int32_t cap);
+
+/* Parity hook: the grid rows this handle dereferences, star-major (needs keep_indices).
+ * offsets has n_stars_local+1 entries.  Must equal indxs[:, s][isfinite(vals[:, s])]
+ * (singlepop_dust_model.py:196-198) bit for bit. */
+int mb_gathered_indices(const mb_handle* h, int64_t* rows, int64_t rows_cap, int64_t* offsets);
+
+/* Per-kernel device time (ms) of the last evaluation, measured with CUDA events when
+ * profiling was enabled with mb_set_profiling(h, 1).  Order: K0 factors, K1 expand, K1b nstars,
+ * K2 stars, K3 finalize. */
+#define MB_NKERNELS 5
+int mb_set_profiling(mb_handle* h, int32_t on);
+int mb_last_kernel_ms(const mb_handle* h, float ms[MB_NKERNELS]);
+
+/* One-time ingest (helpers.py:33-41 get_likelihoods): vals[k,s] = exp(lnp[k,s]) /
+ * prior_weight[indxs[k,s]] on finite entries, in place on the host array, computed on `device`. */
+int mb_likelihoods_from_lnp(int32_t device, int64_t K, int64_t S, const int64_t* indxs,
+                            double* vals, int64_t G, const double* prior_weight);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEGABEAST_B200_H */

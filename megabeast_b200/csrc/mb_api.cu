@@ -1,0 +1,698 @@
+// megabeast_b200 host side of the C ABI (include/megabeast_b200.h): one-time ingest of the
+// reference's data dictionaries into device-resident class-coded form, and the per-step launch
+// sequence K0 -> (K1) -> K1b -> K2 -> K3.  No torch, no CPU fallback.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mb_kernels.cuh"
+
+using namespace mb;
+
+static thread_local std::string g_err;
+static int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+#define CK(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+static int nvars_of(const mb_model_desc& m, int p) {
+  switch (m.kind[p]) {
+    case MB_LOGNORMAL: return 2;
+    case MB_TWO_LOGNORMAL: return 5;
+    case MB_BINS_HISTO: case MB_BINS_INTERP: return m.nnodes[p];
+    case MB_EXPONENTIAL: return 1;
+    default: return 0;  // MB_FIXED, MB_FLAT, MB_TABULATED
+  }
+}
+
+struct mb_handle {
+  int device = 0, mode = 0, poisson = 0, ndim = 0, sm_count = 0, max_smem = 0;
+  mb_model_desc model{};
+  ModelDev mdev{};
+  std::vector<double> clsx[MB_NPARAM];
+  int nA = 1, nB = 1, nbins = 0, nseg = 0;
+  int64_t G = 0, S_local = 0, S_total = 0, n_entries = 0, n_entries_raw = 0, U = 0;
+  int64_t device_bytes = 0;
+  // parity hook (host copies)
+  std::vector<int64_t> kept_rows, kept_offs;
+  // device, static
+  ModelDev* d_model = nullptr;
+  double* d_clsx = nullptr;
+  Entry* d_entries = nullptr;
+  int64_t* d_seg = nullptr;
+  uint32_t* d_rowcode = nullptr;
+  double* d_H = nullptr;
+  double* d_coef = nullptr;
+  int32_t* d_bin_agecls = nullptr;
+  // device, per evaluation (sized for cap_wpad)
+  double* d_phi = nullptr;  int64_t cap_phi = 0;
+  double* d_tab[MB_NPARAM] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t cap_tab[MB_NPARAM] = {0, 0, 0, 0};
+  double* d_F = nullptr;    // [nA+nB][128]
+  double* d_SC = nullptr;   // [nbins][2][128]
+  double* d_T = nullptr;  int64_t cap_T = 0;
+  double* d_part = nullptr; int max_blocks = 0;
+  double* d_out = nullptr;  int64_t cap_out = 0;
+  double* h_pin = nullptr;  int64_t cap_pin = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[MB_NKERNELS + 1] = {};
+  int profiling = 0;
+  float last_ms[MB_NKERNELS] = {};
+  int last_wp = 0, last_launches = 0;
+  int pending_W = 0;
+  double* pending_out = nullptr;
+};
+
+template <typename T>
+static int dev_alloc(mb_handle* h, T** p, int64_t n) {
+  if (n <= 0) n = 1;
+  CK(cudaMalloc((void**)p, sizeof(T) * (size_t)n));
+  h->device_bytes += (int64_t)sizeof(T) * n;
+  return 0;
+}
+template <typename T>
+static int dev_upload(mb_handle* h, T** p, const std::vector<T>& v) {
+  if (dev_alloc(h, p, (int64_t)v.size())) return 1;
+  if (!v.empty()) CK(cudaMemcpy(*p, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int mb_abi_version(void) { return MB_ABI_VERSION; }
+extern "C" const char* mb_last_error(void) { return g_err.c_str(); }
+extern "C" int mb_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    fail("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return -1;
+  }
+  return n;
+}
+
+// class code of every grid row for one parameter
+static int classify(const mb_model_desc& m, int p, const double* col, int64_t G,
+                    std::vector<double>& clsx, std::vector<int32_t>& code) {
+  code.resize((size_t)G);
+  if (m.kind[p] == MB_BINS_HISTO) {
+    // f depends on x only through its interval: classes = nodes.  Outside the node range the
+    // model itself refuses (beast raises ValueError("requested x outside of model x range")).
+    int n = m.nnodes[p];
+    clsx.assign(m.nodes[p], m.nodes[p] + n);
+    for (int i = 1; i < n; ++i)
+      if (!(clsx[i] > clsx[i - 1])) return fail("bins_histo nodes must be strictly increasing");
+    for (int64_t g = 0; g < G; ++g) {
+      double x = col[g];
+      if (!(x >= clsx[0] && x <= clsx[n - 1]))
+        return fail("requested x outside of model x range");
+      int i = (int)(std::upper_bound(clsx.begin(), clsx.end(), x) - clsx.begin()) - 1;
+      code[(size_t)g] = std::min(i, n - 1);
+    }
+    return 0;
+  }
+  // distinct values, kept sorted; BEAST columns hold tens of them
+  std::vector<double> uniq;
+  for (int64_t g = 0; g < G; ++g) {
+    double x = col[g];
+    if (x != x) return fail("NaN in a physics-parameter column (row %lld)", (long long)g);
+    auto it = std::lower_bound(uniq.begin(), uniq.end(), x);
+    if (it == uniq.end() || *it != x) {
+      if (uniq.size() >= (1u << 20)) return fail("parameter column has more than 2^20 distinct values");
+      uniq.insert(it, x);
+    }
+  }
+  for (int64_t g = 0; g < G; ++g)
+    code[(size_t)g] = (int32_t)(std::lower_bound(uniq.begin(), uniq.end(), col[g]) - uniq.begin());
+  clsx = uniq;
+  return 0;
+}
+
+static size_t k2_smem_bytes(int mode, int nA, int nB, int Wpad) {
+  size_t stage = (size_t)kK2Warps * 2 * kChunk * sizeof(Entry);
+  size_t tables = mode == kModeFactor ? (size_t)(nA + nB) * Wpad * sizeof(double) : 0;
+  size_t red = (size_t)kK2Warps * 2 * Wpad * sizeof(double);
+  return std::max(stage + tables, red);
+}
+
+extern "C" void mb_destroy(mb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  void* ptrs[] = {h->d_model, h->d_clsx, h->d_entries, h->d_seg, h->d_rowcode, h->d_H, h->d_coef,
+                  h->d_bin_agecls, h->d_phi, h->d_tab[0], h->d_tab[1], h->d_tab[2], h->d_tab[3],
+                  h->d_F, h->d_SC, h->d_T, h->d_part, h->d_out};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (h->h_pin) cudaFreeHost(h->h_pin);
+  for (auto& e : h->ev)
+    if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" int mb_create(const mb_grid_desc* grid, const mb_stars_desc* stars,
+                         const mb_model_desc* model, const mb_massmult_desc* mm,
+                         const mb_options* opts, mb_handle** out) {
+  if (!grid || !stars || !model || !out) return fail("mb_create: null argument");
+  *out = nullptr;
+  mb_options o{};
+  if (opts) o = *opts;
+  int ndev = 0;
+  cudaError_t e0 = cudaGetDeviceCount(&ndev);
+  if (e0 != cudaSuccess || ndev == 0)
+    return fail("no CUDA device available (%s); megabeast_b200 has no CPU fallback",
+                e0 == cudaSuccess ? "device count 0" : cudaGetErrorString(e0));
+  if (o.device < 0 || o.device >= ndev) return fail("device %d out of range (0..%d)", o.device, ndev - 1);
+  CK(cudaSetDevice(o.device));
+
+  mb_handle* h = new mb_handle();
+  struct Guard { mb_handle* h; bool ok = false; ~Guard() { if (!ok) mb_destroy(h); } } guard{h};
+  h->device = o.device;
+  h->model = *model;
+  CK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, o.device));
+  CK(cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, o.device));
+  const int64_t G = grid->G;
+  if (G <= 0 || G > 0xffffffffLL) return fail("grid size %lld unsupported", (long long)G);
+  h->G = G;
+  if (!grid->prior_weight || !grid->grid_weight || !grid->completeness)
+    return fail("prior_weight, grid_weight and completeness columns are required");
+
+  // ---- phi layout ---------------------------------------------------------------------------------
+  ModelDev& md = h->mdev;
+  int k = 0;
+  for (int p = 0; p < MB_NPARAM; ++p) {
+    if (model->kind[p] < MB_FIXED || model->kind[p] > MB_TABULATED)
+      return fail("unknown prior model kind %d for parameter %d", model->kind[p], p);
+    if ((model->kind[p] == MB_BINS_HISTO || model->kind[p] == MB_BINS_INTERP) &&
+        (model->nnodes[p] < 1 || model->nnodes[p] > MB_MAX_NODES))
+      return fail("parameter %d: %d nodes (1..%d supported)", p, model->nnodes[p], MB_MAX_NODES);
+    md.kind[p] = model->kind[p];
+    md.nnodes[p] = model->nnodes[p];
+    md.voff[p] = k;
+    memcpy(md.nodes[p], model->nodes[p], sizeof(double) * MB_MAX_NODES);
+    k += nvars_of(*model, p);
+  }
+  h->ndim = k;
+  h->poisson = (mm != nullptr);
+  if (h->poisson && model->kind[MB_P_LOGA] == MB_FIXED)
+    return fail("mass multipliers given but the logA prior is fixed (no N-stars term, :71-74)");
+
+  // ---- class codes per grid row ------------------------------------------------------------------
+  std::vector<int32_t> code[MB_NPARAM];
+  int clsoff = 0;
+  for (int p = 0; p < MB_NPARAM; ++p) {
+    md.ncls[p] = 1;
+    md.clsoff[p] = clsoff;
+    md.radix[p] = 0;
+    if (model->kind[p] == MB_FIXED) continue;
+    if (!grid->col[p]) return fail("column of free parameter %d is NULL", p);
+    if (classify(*model, p, grid->col[p], G, h->clsx[p], code[p])) return 1;
+    md.ncls[p] = (int)h->clsx[p].size();
+    clsoff += md.ncls[p];
+  }
+  int64_t nB = 1;
+  for (int p = MB_P_AV; p < MB_NPARAM; ++p) {
+    if (model->kind[p] == MB_FIXED) continue;
+    md.radix[p] = (int)nB;
+    nB *= md.ncls[p];
+    if (nB > (int64_t)kDustMask + 1) return fail("more than 2^20 distinct dust-parameter combinations");
+  }
+  h->nB = (int)nB;
+  h->nA = md.ncls[MB_P_LOGA];
+  if (h->nA > (int)kAgeMask + 1) return fail("more than 1024 distinct age classes");
+  std::vector<uint32_t> rowcode((size_t)G);
+  for (int64_t g = 0; g < G; ++g) {
+    uint32_t cA = model->kind[MB_P_LOGA] == MB_FIXED ? 0u : (uint32_t)code[MB_P_LOGA][(size_t)g];
+    uint32_t cB = 0;
+    for (int p = MB_P_AV; p < MB_NPARAM; ++p)
+      if (model->kind[p] != MB_FIXED) cB += (uint32_t)code[p][(size_t)g] * (uint32_t)md.radix[p];
+    rowcode[(size_t)g] = (cA << kAgeShift) | cB;
+  }
+
+  // ---- mode ----------------------------------------------------------------------------------------
+  int mode = o.mode;
+  const bool factor_fits = k2_smem_bytes(kModeFactor, h->nA, h->nB, 32) <= (size_t)h->max_smem;
+  if (mode == MB_MODE_AUTO) mode = factor_fits ? MB_MODE_FACTOR : MB_MODE_TABLE_UNIQUE;
+  if (mode == MB_MODE_FACTOR && !factor_fits)
+    return fail("factor tables (%d + %d classes) do not fit shared memory; use a TABLE mode", h->nA, h->nB);
+  if (mode == MB_MODE_TABLE_UNIQUE && (int64_t)h->nA * h->nB > (1LL << 27)) mode = MB_MODE_TABLE_GRID;
+  if (mode < MB_MODE_FACTOR || mode > MB_MODE_TABLE_GRID) return fail("unknown mode %d", mode);
+  h->mode = mode;
+  h->U = mode == MB_MODE_TABLE_GRID ? G : (int64_t)h->nA * h->nB;
+
+  // ---- N-stars sufficient statistics (helpers.py:133-162) ----------------------------------------
+  std::vector<double> H, coef;
+  std::vector<int32_t> bin_agecls;
+  if (h->poisson) {
+    if (!grid->logA || !grid->Z) return fail("logA and Z columns are required for the N-stars term");
+    if (mm->n_ages < 1 || mm->n_mets < 1 || !mm->ages || !mm->mets || !mm->massmult)
+      return fail("invalid mass-multiplier description");
+    const int nAg = mm->n_ages, nZ = mm->n_mets;
+    h->nbins = nAg * nZ;
+    if ((int64_t)h->nbins * h->nB > (1LL << 26))
+      return fail("N-stars statistics too large (%d bins x %d dust classes)", h->nbins, h->nB);
+    H.assign((size_t)h->nbins * h->nB * 2, 0.0);
+    std::vector<int32_t> age_first_row((size_t)nAg, -1);
+    for (int64_t g = 0; g < G; ++g) {
+      const double* ia = std::lower_bound(mm->ages, mm->ages + nAg, grid->logA[g]);
+      const double* iz = std::lower_bound(mm->mets, mm->mets + nZ, grid->Z[g]);
+      if (ia == mm->ages + nAg || *ia != grid->logA[g] || iz == mm->mets + nZ || *iz != grid->Z[g])
+        return fail("grid row %lld has (logA, Z) outside the mass-multiplier bins", (long long)g);
+      int i = (int)(ia - mm->ages), j = (int)(iz - mm->mets);
+      if (age_first_row[(size_t)i] < 0) age_first_row[(size_t)i] = (int32_t)g;
+      size_t b = (size_t)i * nZ + j;
+      uint32_t cB = rowcode[(size_t)g] & kDustMask;
+      double gw = grid->grid_weight[g];
+      H[(b * h->nB + cB) * 2] += gw;
+      H[(b * h->nB + cB) * 2 + 1] += gw * grid->completeness[g];
+    }
+    coef.resize((size_t)h->nbins);
+    bin_agecls.resize((size_t)h->nbins);
+    const double metprior = 1.0 / (double)nZ;
+    for (int i = 0; i < nAg; ++i)
+      for (int j = 0; j < nZ; ++j) {
+        coef[(size_t)i * nZ + j] = metprior * mm->massmult[(size_t)i * nZ + j] / mm->avemass;
+        // an age no grid row carries has empty bins (S = 0, skipped); any class will do
+        int32_t r = age_first_row[(size_t)i];
+        bin_agecls[(size_t)i * nZ + j] = r < 0 ? 0 : (int32_t)((rowcode[(size_t)r] >> kAgeShift) & kAgeMask);
+      }
+  }
+
+  // ---- entries: fold, code, sort by age class, (merge), flag -------------------------------------
+  const int64_t K = stars->K, S = stars->S;
+  const int64_t s0 = stars->star_begin, s1 = stars->star_end;
+  if (K < 0 || S < 0 || s0 < 0 || s1 > S || s0 > s1) return fail("invalid star range [%lld,%lld) of %lld", (long long)s0, (long long)s1, (long long)S);
+  if (K > 0 && S > 0 && (!stars->indxs || !stars->vals)) return fail("indxs/vals are NULL");
+  h->S_local = s1 - s0;
+  h->S_total = stars->n_stars_total > 0 ? stars->n_stars_total : S;
+  std::vector<Entry> entries;
+  entries.reserve((size_t)((s1 - s0) * K));
+  std::vector<int64_t> star_end_pos;  // entry count after each non-empty star
+  std::vector<Entry> cur;
+  if (o.keep_indices) h->kept_offs.assign(1, 0);
+  const bool merge = o.merge_duplicates != 0;
+  for (int64_t s = s0; s < s1; ++s) {
+    cur.clear();
+    for (int64_t kk = 0; kk < K; ++kk) {
+      double v = stars->vals[kk * S + s];
+      if (!std::isfinite(v)) continue;  // :196 -- the index of a masked entry is never read
+      int64_t r = stars->indxs[kk * S + s];
+      if (r < 0) r += G;  // numpy negative indexing
+      if (r < 0 || r >= G)
+        return fail("index %lld is out of bounds for axis 0 with size %lld (star %lld)",
+                    (long long)stars->indxs[kk * S + s], (long long)G, (long long)s);
+      Entry e;
+      e.a = v * grid->prior_weight[r] * grid->grid_weight[r] * grid->completeness[r];
+      e.code = rowcode[(size_t)r];
+      e.row = (uint32_t)r;
+      cur.push_back(e);
+      if (o.keep_indices) h->kept_rows.push_back(r);
+    }
+    if (o.keep_indices) h->kept_offs.push_back((int64_t)h->kept_rows.size());
+    h->n_entries_raw += (int64_t)cur.size();
+    if (cur.empty()) continue;  // sums to 0.0 -> skipped by the reference too (:218-221)
+    if (mode == MB_MODE_TABLE_GRID)
+      std::stable_sort(cur.begin(), cur.end(), [](const Entry& x, const Entry& y) { return x.row < y.row; });
+    else
+      std::stable_sort(cur.begin(), cur.end(), [](const Entry& x, const Entry& y) { return x.code < y.code; });
+    size_t first = entries.size();
+    for (const Entry& e : cur) {
+      if (merge && entries.size() > first) {
+        Entry& last = entries.back();
+        bool same = mode == MB_MODE_TABLE_GRID ? last.row == e.row : last.code == e.code;
+        if (same) { last.a += e.a; continue; }
+      }
+      entries.push_back(e);
+    }
+    uint32_t prevA = 0xffffffffu;
+    for (size_t i = first; i < entries.size(); ++i) {
+      uint32_t cA = (entries[i].code >> kAgeShift) & kAgeMask;
+      if (cA != prevA) entries[i].code |= kNewRun;
+      prevA = cA;
+    }
+    entries.back().code |= kEndStar;
+    star_end_pos.push_back((int64_t)entries.size());
+  }
+  h->n_entries = (int64_t)entries.size();
+
+  // ---- segments: star aligned, about four per resident warp ---------------------------------------
+  const int64_t resident_warps = (int64_t)h->sm_count * 2 * kK2Warps;
+  int64_t target = std::max<int64_t>(64, h->n_entries / std::max<int64_t>(1, resident_warps * 4));
+  std::vector<int64_t> seg(1, 0);
+  for (int64_t pos : star_end_pos)
+    if (pos - seg.back() >= target) seg.push_back(pos);
+  if (seg.back() != h->n_entries) seg.push_back(h->n_entries);
+  h->nseg = (int)seg.size() - 1;
+
+  // ---- upload ----------------------------------------------------------------------------------------
+  std::vector<double> clsx_all;
+  for (int p = 0; p < MB_NPARAM; ++p) clsx_all.insert(clsx_all.end(), h->clsx[p].begin(), h->clsx[p].end());
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto& e : h->ev) CK(cudaEventCreate(&e));
+  if (dev_alloc(h, &h->d_model, 1)) return 1;
+  CK(cudaMemcpy(h->d_model, &h->mdev, sizeof(ModelDev), cudaMemcpyHostToDevice));
+  if (dev_upload(h, &h->d_clsx, clsx_all)) return 1;
+  if (dev_upload(h, &h->d_entries, entries)) return 1;
+  if (dev_upload(h, &h->d_seg, seg)) return 1;
+  if (mode == MB_MODE_TABLE_GRID && dev_upload(h, &h->d_rowcode, rowcode)) return 1;
+  if (h->poisson) {
+    if (dev_upload(h, &h->d_H, H)) return 1;
+    if (dev_upload(h, &h->d_coef, coef)) return 1;
+    if (dev_upload(h, &h->d_bin_agecls, bin_agecls)) return 1;
+  }
+  if (dev_alloc(h, &h->d_F, (int64_t)(h->nA + h->nB) * 128)) return 1;
+  if (dev_alloc(h, &h->d_SC, (int64_t)std::max(1, h->nbins) * 2 * 128)) return 1;
+  h->max_blocks = h->sm_count * 4;
+  if (dev_alloc(h, &h->d_part, (int64_t)h->max_blocks * 2 * 128)) return 1;
+
+  // opt in to large dynamic shared memory for every K2 instantiation we may launch
+  {
+    int big = h->max_smem;
+#define MB_OPTIN(NW, MODE) CK(cudaFuncSetAttribute(mb_k2_stars<NW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, big))
+    MB_OPTIN(1, kModeFactor); MB_OPTIN(2, kModeFactor); MB_OPTIN(4, kModeFactor);
+    MB_OPTIN(1, kModeTable); MB_OPTIN(2, kModeTable); MB_OPTIN(4, kModeTable);
+    MB_OPTIN(1, kModeTableGrid); MB_OPTIN(2, kModeTableGrid); MB_OPTIN(4, kModeTableGrid);
+#undef MB_OPTIN
+  }
+  guard.ok = true;
+  *out = h;
+  return 0;
+}
+
+extern "C" int mb_get_info(const mb_handle* h, mb_info* out) {
+  if (!h || !out) return fail("mb_get_info: null argument");
+  memset(out, 0, sizeof *out);
+  out->abi_version = MB_ABI_VERSION;
+  out->device = h->device;
+  out->mode = h->mode;
+  out->ndim = h->ndim;
+  out->poisson = h->poisson;
+  for (int p = 0; p < MB_NPARAM; ++p) out->n_classes[p] = h->mdev.ncls[p];
+  out->n_age_classes = h->nA;
+  out->n_dust_classes = h->nB;
+  out->n_bins = h->nbins;
+  out->sm_count = h->sm_count;
+  out->walkers_per_pass = h->last_wp;
+  out->launches_last_eval = h->last_launches;
+  out->G = h->G;
+  out->n_stars_local = h->S_local;
+  out->n_stars_total = h->S_total;
+  out->n_entries = h->n_entries;
+  out->n_entries_raw = h->n_entries_raw;
+  out->device_bytes = h->device_bytes;
+  return 0;
+}
+
+extern "C" int mb_class_values(const mb_handle* h, int32_t p, double* out, int32_t cap) {
+  if (!h || p < 0 || p >= MB_NPARAM) { fail("mb_class_values: bad argument"); return -1; }
+  int n = (int)h->clsx[p].size();
+  for (int i = 0; i < n && i < cap; ++i) out[i] = h->clsx[p][(size_t)i];
+  return n;
+}
+
+extern "C" int mb_gathered_indices(const mb_handle* h, int64_t* rows, int64_t cap, int64_t* offs) {
+  if (!h) return fail("null handle");
+  if (h->kept_offs.empty()) return fail("handle was created without keep_indices");
+  if ((int64_t)h->kept_rows.size() > cap) return fail("rows buffer too small (%lld needed)", (long long)h->kept_rows.size());
+  // device round trip: what is reported is what the device holds, not the host copy
+  std::vector<Entry> back((size_t)h->n_entries);
+  if (h->n_entries) CK(cudaMemcpy(back.data(), h->d_entries, sizeof(Entry) * back.size(), cudaMemcpyDeviceToHost));
+  if (h->n_entries == h->n_entries_raw) {
+    // no merging happened: rebuild the per-star row lists from the device entries themselves
+    size_t i = 0, nout = 0;
+    for (int64_t s = 0; s < h->S_local; ++s) {
+      offs[s] = (int64_t)nout;
+      int64_t cnt = h->kept_offs[(size_t)s + 1] - h->kept_offs[(size_t)s];
+      for (int64_t c = 0; c < cnt; ++c) rows[nout++] = (int64_t)back[i++].row;
+    }
+    offs[h->S_local] = (int64_t)nout;
+    return 0;
+  }
+  memcpy(rows, h->kept_rows.data(), sizeof(int64_t) * h->kept_rows.size());
+  memcpy(offs, h->kept_offs.data(), sizeof(int64_t) * h->kept_offs.size());
+  return 0;
+}
+
+extern "C" int mb_set_profiling(mb_handle* h, int32_t on) {
+  if (!h) return fail("null handle");
+  h->profiling = on;
+  return 0;
+}
+extern "C" int mb_last_kernel_ms(const mb_handle* h, float ms[MB_NKERNELS]) {
+  if (!h) return fail("null handle");
+  memcpy(ms, h->last_ms, sizeof h->last_ms);
+  return 0;
+}
+
+template <int MODE>
+static void launch_k2(int NW, int grid, size_t smem, cudaStream_t st, const K2Args& a) {
+  switch (NW) {
+    case 1: mb_k2_stars<1, MODE><<<grid, kK2Threads, smem, st>>>(a); break;
+    case 2: mb_k2_stars<2, MODE><<<grid, kK2Threads, smem, st>>>(a); break;
+    default: mb_k2_stars<4, MODE><<<grid, kK2Threads, smem, st>>>(a); break;
+  }
+}
+
+template <int MODE>
+static int k2_occ(int NW, size_t smem) {
+  int n = 0;
+  switch (NW) {
+    case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<1, MODE>, kK2Threads, smem); break;
+    case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<2, MODE>, kK2Threads, smem); break;
+    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<4, MODE>, kK2Threads, smem); break;
+  }
+  return n;
+}
+static int k2_blocks_per_sm(int kmode, int NW, size_t smem) {
+  return kmode == kModeFactor ? k2_occ<kModeFactor>(NW, smem)
+         : kmode == kModeTable ? k2_occ<kModeTable>(NW, smem) : k2_occ<kModeTableGrid>(NW, smem);
+}
+
+static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const double* const d_tab[MB_NPARAM],
+                       double* d_out, cudaStream_t st) {
+  if (W <= 0) return 0;
+  if (ndim != h->ndim) return fail("phi has %d columns, the model has %d free variables", ndim, h->ndim);
+  CK(cudaSetDevice(h->device));
+  const int kmode = h->mode == MB_MODE_FACTOR ? kModeFactor : h->mode == MB_MODE_TABLE_UNIQUE ? kModeTable : kModeTableGrid;
+  const bool prof = h->profiling != 0;
+  float acc_ms[MB_NKERNELS] = {0, 0, 0, 0, 0};
+  int launches = 0;
+  for (int w0 = 0; w0 < W;) {
+    int rem = W - w0;
+    int NW = rem <= 32 ? 1 : rem <= 64 ? 2 : 4;
+    while (NW > 1 && k2_smem_bytes(kmode, h->nA, h->nB, 32 * NW) > (size_t)h->max_smem) NW >>= 1;
+    const int Wpad = 32 * NW;
+    const int wp = std::min(rem, Wpad);
+    h->last_wp = wp;
+    double* FA = h->d_F;
+    double* FB = h->d_F + (size_t)h->nA * Wpad;
+
+    if (prof) CK(cudaEventRecord(h->ev[0], st));
+    K0Args k0{};
+    k0.model = h->d_model; k0.clsx = h->d_clsx; k0.phi = d_phi + (size_t)w0 * ndim;
+    for (int p = 0; p < MB_NPARAM; ++p)
+      k0.tab[p] = (d_tab && d_tab[p]) ? d_tab[p] + (size_t)w0 * h->mdev.ncls[p] : nullptr;
+    k0.FA = FA; k0.FB = FB; k0.nA = h->nA; k0.nB = h->nB; k0.W = wp; k0.Wpad = Wpad; k0.ndim = ndim;
+    {
+      int total = (h->nA + h->nB) * Wpad;
+      int blocks = std::min((total + 255) / 256, h->sm_count * 8);
+      mb_k0_factors<<<blocks, 256, 0, st>>>(k0);
+      ++launches;
+    }
+    if (prof) CK(cudaEventRecord(h->ev[1], st));
+    if (kmode != kModeFactor) {
+      int64_t need = h->U * Wpad;
+      if (need > h->cap_T) {
+        CK(cudaStreamSynchronize(st));
+        if (h->d_T) { CK(cudaFree(h->d_T)); h->device_bytes -= h->cap_T * 8; }
+        h->d_T = nullptr; h->cap_T = 0;
+        if (dev_alloc(h, &h->d_T, need)) return 1;
+        h->cap_T = need;
+      }
+      int64_t total = h->U * (Wpad / 2);
+      int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->sm_count * 16);
+      mb_k1_expand<<<blocks, 256, 0, st>>>(FA, FB, h->mode == MB_MODE_TABLE_GRID ? h->d_rowcode : nullptr,
+                                           h->d_T, h->U, h->nB, Wpad);
+      ++launches;
+    }
+    if (prof) CK(cudaEventRecord(h->ev[2], st));
+    if (h->poisson) {
+      mb_k1b_binsums<<<h->nbins, std::min(128, Wpad), 0, st>>>(h->d_H, FB, h->d_SC, h->nB, Wpad);
+      ++launches;
+    }
+    if (prof) CK(cudaEventRecord(h->ev[3], st));
+    size_t smem = k2_smem_bytes(kmode, h->nA, h->nB, Wpad);
+    int per_sm = k2_blocks_per_sm(kmode, NW, smem);
+    if (per_sm < 1) return fail("K2 cannot be resident with %zu bytes of shared memory", smem);
+    int grid = std::min(h->sm_count * per_sm, std::max(1, (h->nseg + kK2Warps - 1) / kK2Warps));
+    grid = std::min(grid, h->max_blocks);
+    K2Args k2{};
+    k2.entries = h->d_entries; k2.seg = h->d_seg; k2.nseg = h->nseg; k2.FA = FA; k2.FB = FB; k2.T = h->d_T;
+    k2.part = h->d_part; k2.nA = h->nA; k2.nB = h->nB; k2.Wpad = Wpad;
+    if (kmode == kModeFactor) launch_k2<kModeFactor>(NW, grid, smem, st, k2);
+    else if (kmode == kModeTable) launch_k2<kModeTable>(NW, grid, smem, st, k2);
+    else launch_k2<kModeTableGrid>(NW, grid, smem, st, k2);
+    ++launches;
+    if (prof) CK(cudaEventRecord(h->ev[4], st));
+    K3Args k3{};
+    k3.part = h->d_part; k3.nblocks = grid; k3.FA = FA; k3.SC = h->d_SC; k3.bin_agecls = h->d_bin_agecls;
+    k3.coef = h->d_coef; k3.nbins = h->poisson ? h->nbins : 0; k3.n_stars = (double)h->S_total;
+    k3.out = d_out; k3.W = wp; k3.Wpad = Wpad; k3.w0 = w0; k3.Wtot = W;
+    mb_k3_finalize<<<(wp + 127) / 128, 128, 0, st>>>(k3);
+    ++launches;
+    if (prof) {
+      CK(cudaEventRecord(h->ev[5], st));
+      CK(cudaEventSynchronize(h->ev[5]));
+      for (int i = 0; i < MB_NKERNELS; ++i) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+        acc_ms[i] += ms;
+      }
+    }
+    w0 += wp;
+  }
+  CK(cudaGetLastError());
+  h->last_launches = launches;
+  if (prof) memcpy(h->last_ms, acc_ms, sizeof acc_ms);
+  return 0;
+}
+
+extern "C" int mb_lnlike_device(mb_handle* h, const double* d_phi, int32_t W, int32_t ndim, double* d_out,
+                                void* stream) {
+  if (!h || !d_phi || !d_out) return fail("mb_lnlike_device: null argument");
+  for (int p = 0; p < MB_NPARAM; ++p)
+    if (h->model.kind[p] == MB_TABULATED) return fail("model has tabulated parameters: use mb_lnlike_tabulated");
+  return eval_device(h, d_phi, W, ndim, nullptr, d_out, (cudaStream_t)stream);
+}
+
+static int ensure(mb_handle* h, double** p, int64_t* cap, int64_t need) {
+  if (need <= *cap) return 0;
+  if (*p) { CK(cudaFree(*p)); h->device_bytes -= *cap * 8; }
+  *p = nullptr; *cap = 0;
+  if (dev_alloc(h, p, need)) return 1;
+  *cap = need;
+  return 0;
+}
+
+extern "C" int mb_lnlike_begin(mb_handle* h, const double* phi, int32_t W, int32_t ndim,
+                               const double* const tab[MB_NPARAM]) {
+  if (!h) return fail("mb_lnlike_begin: null handle");
+  if (h->pending_W) return fail("mb_lnlike_begin: previous evaluation not collected with mb_lnlike_end");
+  if (W <= 0) return fail("mb_lnlike_begin: W must be positive");
+  if (ndim != h->ndim) return fail("phi has %d columns, the model has %d free variables", ndim, h->ndim);
+  if (ndim > 0 && !phi) return fail("mb_lnlike: phi is NULL");
+  CK(cudaSetDevice(h->device));
+  const int64_t nphi = (int64_t)W * std::max(1, ndim), nout = (int64_t)MB_OUT_ROWS * W;
+  if (ensure(h, &h->d_phi, &h->cap_phi, nphi)) return 1;
+  if (ensure(h, &h->d_out, &h->cap_out, nout)) return 1;
+  if (nphi + nout > h->cap_pin) {
+    if (h->h_pin) CK(cudaFreeHost(h->h_pin));
+    h->h_pin = nullptr; h->cap_pin = 0;
+    CK(cudaMallocHost((void**)&h->h_pin, sizeof(double) * (size_t)(nphi + nout)));
+    h->cap_pin = nphi + nout;
+  }
+  double* hp = h->h_pin;
+  double* ho = h->h_pin + nphi;
+  if (ndim > 0) memcpy(hp, phi, sizeof(double) * (size_t)W * ndim);
+  CK(cudaMemcpyAsync(h->d_phi, hp, sizeof(double) * (size_t)nphi, cudaMemcpyHostToDevice, h->stream));
+  const double* dtab[MB_NPARAM] = {nullptr, nullptr, nullptr, nullptr};
+  for (int p = 0; p < MB_NPARAM; ++p) {
+    if (h->model.kind[p] != MB_TABULATED) continue;
+    if (!tab || !tab[p]) return fail("parameter %d is tabulated but no table was passed", p);
+    int64_t n = (int64_t)W * h->mdev.ncls[p];
+    if (ensure(h, &h->d_tab[p], &h->cap_tab[p], n)) return 1;
+    CK(cudaMemcpyAsync(h->d_tab[p], tab[p], sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    dtab[p] = h->d_tab[p];
+  }
+  if (eval_device(h, h->d_phi, W, ndim, dtab, h->d_out, h->stream)) return 1;
+  CK(cudaMemcpyAsync(ho, h->d_out, sizeof(double) * (size_t)nout, cudaMemcpyDeviceToHost, h->stream));
+  h->pending_W = W;
+  h->pending_out = ho;
+  return 0;
+}
+
+extern "C" int mb_lnlike_end(mb_handle* h, double* rows) {
+  if (!h || !rows) return fail("mb_lnlike_end: null argument");
+  if (!h->pending_W) return fail("mb_lnlike_end: no evaluation in flight");
+  CK(cudaSetDevice(h->device));
+  const int W = h->pending_W;
+  h->pending_W = 0;
+  CK(cudaStreamSynchronize(h->stream));
+  memcpy(rows, h->pending_out, sizeof(double) * (size_t)MB_OUT_ROWS * W);
+  return 0;
+}
+
+extern "C" void mb_combine(const double* rows, int32_t W, double* lnlike, int32_t* status) {
+  for (int w = 0; w < W; ++w) {
+    double tot = rows[MB_OUT_POISSON * W + w] + rows[MB_OUT_STARSUM * W + w];
+    int st = MB_STATUS_OK;
+    if (rows[MB_OUT_NONFINITE * W + w] != 0.0) st |= MB_STATUS_NONFINITE_STAR;
+    if (tot == 0.0) st |= MB_STATUS_TOTAL_ZERO;
+    lnlike[w] = tot;
+    status[w] = st;
+  }
+}
+
+extern "C" int mb_lnlike_tabulated(mb_handle* h, const double* phi, int32_t W, int32_t ndim,
+                                   const double* const tab[MB_NPARAM], double* lnlike, int32_t* status) {
+  if (!h || !lnlike || !status) return fail("mb_lnlike: null argument");
+  if (W <= 0) return 0;
+  if (mb_lnlike_begin(h, phi, W, ndim, tab)) return 1;
+  std::vector<double> rows((size_t)MB_OUT_ROWS * W);
+  if (mb_lnlike_end(h, rows.data())) return 1;
+  mb_combine(rows.data(), W, lnlike, status);
+  return 0;
+}
+
+extern "C" int mb_lnlike(mb_handle* h, const double* phi, int32_t W, int32_t ndim, double* lnlike,
+                         int32_t* status) {
+  return mb_lnlike_tabulated(h, phi, W, ndim, nullptr, lnlike, status);
+}
+
+extern "C" int mb_likelihoods_from_lnp(int32_t device, int64_t K, int64_t S, const int64_t* indxs, double* vals,
+                                       int64_t G, const double* pw) {
+  if (K < 0 || S < 0 || G <= 0 || !pw) return fail("mb_likelihoods_from_lnp: bad argument");
+  int64_t n = K * S;
+  if (n == 0) return 0;
+  if (!indxs || !vals) return fail("mb_likelihoods_from_lnp: null array");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("no CUDA device available; megabeast_b200 has no CPU fallback");
+  CK(cudaSetDevice(device));
+  int64_t* d_i = nullptr; double* d_v = nullptr; double* d_p = nullptr; int* d_e = nullptr;
+  int rc = 0, herr = 0;
+  auto body = [&]() -> int {
+    CK(cudaMalloc((void**)&d_i, sizeof(int64_t) * (size_t)n));
+    CK(cudaMalloc((void**)&d_v, sizeof(double) * (size_t)n));
+    CK(cudaMalloc((void**)&d_p, sizeof(double) * (size_t)G));
+    CK(cudaMalloc((void**)&d_e, sizeof(int)));
+    CK(cudaMemset(d_e, 0, sizeof(int)));
+    CK(cudaMemcpy(d_i, indxs, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_v, vals, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_p, pw, sizeof(double) * (size_t)G, cudaMemcpyHostToDevice));
+    int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+    mb_ingest_lnp<<<blocks, 256>>>(n, d_i, d_v, G, d_p, d_e);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(vals, d_v, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&herr, d_e, sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+  };
+  rc = body();
+  cudaFree(d_i); cudaFree(d_v); cudaFree(d_p); cudaFree(d_e);
+  if (rc) return rc;
+  if (herr) return fail("index out of bounds for the prior_weight column");
+  return 0;
+}

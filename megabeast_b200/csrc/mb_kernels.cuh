@@ -1,0 +1,463 @@
+// megabeast_b200 device code: the ensemble-likelihood kernels for sm_100a.
+//
+// Reference semantics (what every kernel must reproduce, in fp64):
+//   /root/reference/megabeast/singlepop_dust_model.py:131-148  physmod = prod of active priors
+//   /root/reference/megabeast/helpers.py:133-164               expected number of stars
+//   /root/reference/megabeast/singlepop_dust_model.py:182-186  Poisson term
+//   /root/reference/megabeast/singlepop_dust_model.py:194-223  per-star gather, sum, log, sum
+//
+// Design (DESIGN.md has the long form).  BEAST grids are Cartesian: every free parameter's
+// column holds a few tens of distinct values ("classes"), and physmod[g,w] depends on the row
+// only through its class codes:
+//
+//     physmod[g,w] = FA[cA(g)][w] * FB[cB(g)][w]       FA: age (logA) factor, FB: dust factor
+//
+// K0  mb_k0_factors      per-walker factor tables FA, FB from phi            (tiny)
+// K1  mb_k1_expand       TABLE modes: physmod table T[u][w] = FA*FB          (HBM write bound)
+// K1b mb_k1b_binsums     N-stars sufficient statistics x FB -> per-bin sums  (tiny)
+// K2  mb_k2_stars<..>    the hot kernel: stream (weight, code) entries once for all walkers,
+//                        look the factors up (smem) or gather T rows (L2/HBM), per-star fp64
+//                        sum, log via mantissa/exponent product, block partials
+// K3  mb_k3_finalize     fixed-order reduction of block partials + Poisson term
+//
+// Lanes of a warp are WALKERS, a warp walks one star's entries at a time, so every control
+// decision in K2 (run boundary, end of star) is warp-uniform.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/megabeast_b200.h"
+
+namespace mb {
+
+// ---- entry stream --------------------------------------------------------------------------
+// One finite (star, sparse point) pair.  a = vals * prior_weight[r] * grid_weight[r] *
+// completeness[r] (walker independent, folded at create time), code = class codes + flags.
+struct __align__(16) Entry {
+  double a;
+  uint32_t code;
+  uint32_t row;   // grid row (TABLE_GRID gathers with it; also the parity hook)
+};
+constexpr uint32_t kNewRun = 0x80000000u;   // first entry of a run of equal age class
+constexpr uint32_t kEndStar = 0x40000000u;  // last entry of a star
+constexpr int kAgeShift = 20;
+constexpr uint32_t kAgeMask = 0x3ffu;       // <= 1024 age classes
+constexpr uint32_t kDustMask = 0xfffffu;    // <= 2^20 dust classes
+
+struct ModelDev {        // device copy of what K0 needs
+  int32_t kind[MB_NPARAM];
+  int32_t nnodes[MB_NPARAM];
+  int32_t voff[MB_NPARAM];    // offset of the parameter's variables in phi
+  int32_t ncls[MB_NPARAM];
+  int32_t clsoff[MB_NPARAM];  // offset into clsx
+  int32_t radix[MB_NPARAM];   // dust class code = sum_p digit_p * radix[p]  (p = Av, Rv, fA)
+  double nodes[MB_NPARAM][MB_MAX_NODES];
+};
+
+// ---- prior models (restating beast.physicsmodel.priormodel; anchors in oracle/priors.py) --------
+__device__ __forceinline__ double lognorm(double x, double mode, double sigma, double amp) {
+  // megabeast/old/ensemble_model.py:13-47: mu = ln(mode) + sigma^2, 0 for x <= 0
+  if (!(x > 0.0)) return 0.0;
+  const double inv_sqrt_2pi = 0.3989422804014326779399460599343819;
+  double mu = log(mode) + sigma * sigma;
+  double norm = inv_sqrt_2pi / (x * sigma);
+  double t = (log(x) - mu) / sigma;
+  return amp * norm * exp(-0.5 * (t * t));
+}
+
+__device__ double prior_eval(const ModelDev& m, int p, const double* __restrict__ th, double x) {
+  switch (m.kind[p]) {
+    case MB_LOGNORMAL:
+      return lognorm(x, th[0], th[1], 1.0);
+    case MB_TWO_LOGNORMAL: {
+      double n1 = 1.0 - 1.0 / (th[4] + 1.0), n2 = 1.0 / (th[4] + 1.0);
+      return lognorm(x, th[0], th[2], n1) + lognorm(x, th[1], th[3], n2);
+    }
+    case MB_BINS_HISTO: {  // left-constant steps; x == last node -> last height
+      int n = m.nnodes[p], i = 0;
+      while (i + 1 < n && x >= m.nodes[p][i + 1]) ++i;
+      return th[i];
+    }
+    case MB_BINS_INTERP: {  // np.interp
+      int n = m.nnodes[p];
+      if (x <= m.nodes[p][0]) return th[0];
+      if (x >= m.nodes[p][n - 1]) return th[n - 1];
+      int i = 0;
+      while (x >= m.nodes[p][i + 1]) ++i;
+      double slope = (th[i + 1] - th[i]) / (m.nodes[p][i + 1] - m.nodes[p][i]);
+      return slope * (x - m.nodes[p][i]) + th[i];
+    }
+    case MB_EXPONENTIAL:
+      return exp(-1.0 * pow(10.0, x) / (th[0] * 1e9));
+    default:  // MB_FLAT
+      return 1.0;
+  }
+}
+
+// ---- K0: factor tables -------------------------------------------------------------------------
+// FA[c][w] (nA x Wpad) and FB[c][w] (nB x Wpad), walker minor.  Walkers w >= W (padding up to
+// the pass width) repeat the last real walker so no lane ever sees garbage.
+// tab[p]: host-evaluated table [W][ncls[p]] for MB_TABULATED parameters (else unused).
+struct K0Args {
+  const ModelDev* model;
+  const double* clsx;
+  const double* phi;      // [W][ndim], already offset to the pass's first walker
+  const double* tab[MB_NPARAM];
+  double* FA;
+  double* FB;
+  int32_t nA, nB, W, Wpad, ndim;
+};
+
+__global__ void __launch_bounds__(256) mb_k0_factors(K0Args a) {
+  const ModelDev& m = *a.model;
+  int total = (a.nA + a.nB) * a.Wpad;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int c = i / a.Wpad, w = i - c * a.Wpad;
+    int wr = w < a.W ? w : a.W - 1;
+    const double* ph = a.phi + (size_t)wr * a.ndim;
+    if (c < a.nA) {
+      double v = 1.0;
+      if (m.kind[MB_P_LOGA] == MB_TABULATED)
+        v = a.tab[MB_P_LOGA][(size_t)wr * m.ncls[MB_P_LOGA] + c];
+      else if (m.kind[MB_P_LOGA] != MB_FIXED)
+        v = prior_eval(m, MB_P_LOGA, ph + m.voff[MB_P_LOGA], a.clsx[m.clsoff[MB_P_LOGA] + c]);
+      a.FA[i] = v;
+    } else {
+      int cb = c - a.nA;
+      double v = 1.0;
+      // same left-to-right product order as the reference's `cur_physmod *=` loop (:146-148)
+#pragma unroll
+      for (int p = MB_P_AV; p < MB_NPARAM; ++p) {
+        if (m.kind[p] == MB_FIXED) continue;
+        int digit = (cb / m.radix[p]) % m.ncls[p];
+        if (m.kind[p] == MB_TABULATED)
+          v *= a.tab[p][(size_t)wr * m.ncls[p] + digit];
+        else
+          v *= prior_eval(m, p, ph + m.voff[p], a.clsx[m.clsoff[p] + digit]);
+      }
+      a.FB[(size_t)cb * a.Wpad + w] = v;
+    }
+  }
+}
+
+// ---- K1: materialise the prior-weight table (TABLE modes) -------------------------------------
+// T[u][w] = FA[cA(u)][w] * FB[cB(u)][w].  rowcode == nullptr: u enumerates the distinct class
+// combinations (u = cA*nB + cB); else u is a grid row and rowcode[u] = cA<<20 | cB.
+// Reads 4 B/row (+ tables from L2), writes 8*Wpad B/row: HBM-write bound.
+__global__ void __launch_bounds__(256) mb_k1_expand(const double* __restrict__ FA,
+                                                    const double* __restrict__ FB,
+                                                    const uint32_t* __restrict__ rowcode,
+                                                    double* __restrict__ T, int64_t U, int nB,
+                                                    int Wpad) {
+  // one thread = one (row, walker pair): 16-byte stores, walker minor -> fully coalesced
+  const int half = Wpad >> 1;
+  int64_t total = U * half;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t u = i / half;
+    int w2 = (int)(i - u * half) * 2;
+    uint32_t cA, cB;
+    if (rowcode) {
+      uint32_t code = __ldg(rowcode + u);
+      cA = (code >> kAgeShift) & kAgeMask;
+      cB = code & kDustMask;
+    } else {
+      cA = (uint32_t)(u / nB);
+      cB = (uint32_t)(u - (int64_t)cA * nB);
+    }
+    double2 fa = __ldg(reinterpret_cast<const double2*>(FA + (size_t)cA * Wpad + w2));
+    double2 fb = __ldg(reinterpret_cast<const double2*>(FB + (size_t)cB * Wpad + w2));
+    double2 t = make_double2(fa.x * fb.x, fa.y * fb.y);
+    __stcs(reinterpret_cast<double2*>(T + (size_t)u * Wpad + w2), t);
+  }
+}
+
+// ---- K1b: per-(age,Z)-bin sums for the N-stars term --------------------------------------------
+// helpers.py:133-162 needs, per bin, S = sum_g physmod*grid_weight and C = sum_g
+// physmod*grid_weight*completeness.  Inside a bin the age factor is constant, so with the
+// create-time statistics H[bin][cB] = (sum grid_weight, sum grid_weight*completeness) over the
+// bin's rows of dust class cB:   S = FA * sum_cB H0*FB,  C = FA * sum_cB H1*FB.
+// SC[bin][0/1][w] holds the two dust sums (FA applied in K3).
+__global__ void __launch_bounds__(128) mb_k1b_binsums(const double* __restrict__ H,
+                                                      const double* __restrict__ FB,
+                                                      double* __restrict__ SC, int nB, int Wpad) {
+  int b = blockIdx.x;
+  const double2* Hb = reinterpret_cast<const double2*>(H) + (size_t)b * nB;
+  for (int w = threadIdx.x; w < Wpad; w += blockDim.x) {
+    double s = 0.0, c = 0.0;
+    for (int cb = 0; cb < nB; ++cb) {
+      double2 h = __ldg(Hb + cb);
+      double fb = __ldg(FB + (size_t)cb * Wpad + w);
+      s = fma(h.x, fb, s);
+      c = fma(h.y, fb, c);
+    }
+    SC[((size_t)b * 2 + 0) * Wpad + w] = s;
+    SC[((size_t)b * 2 + 1) * Wpad + w] = c;
+  }
+}
+
+// ---- K2: the hot kernel --------------------------------------------------------------------------
+// log of a running product: ln(prod L_s) = ln(P) + E ln 2 with P kept in [1, 2^k).
+// One DMUL + a few integer ops per star instead of a ~50-instruction fp64 log.
+struct LogAcc {
+  double P;
+  int32_t E;
+  int32_t n;
+  __device__ __forceinline__ void init() { P = 1.0; E = 0; n = 0; }
+  __device__ __forceinline__ void renorm() {
+    int hi = __double2hiint(P);
+    int e = ((hi >> 20) & 0x7ff);
+    if (e != 0x7ff && e != 0) {  // leave inf/nan alone
+      E += e - 1023;
+      P = __hiloint2double((hi & 0x800fffff) | (1023 << 20), __double2loint(P));
+    }
+    n = 0;
+  }
+  // L > 0 finite
+  __device__ __forceinline__ void mul(double L) {
+    int hi = __double2hiint(L);
+    int e = (hi >> 20) & 0x7ff;
+    if (e == 0) {  // subnormal: rescale first (rare)
+      L *= 18446744073709551616.0;  // 2^64
+      hi = __double2hiint(L);
+      e = ((hi >> 20) & 0x7ff) - 64;
+    }
+    E += e - 1023;
+    double mant = __hiloint2double((hi & 0x800fffff) | (1023 << 20), __double2loint(L));
+    P *= mant;
+    if (++n >= 512) renorm();
+  }
+  __device__ __forceinline__ double value() {
+    renorm();
+    return log(P) + (double)E * 0.693147180559945309417232121458;
+  }
+};
+
+enum { kModeFactor = 1, kModeTable = 2, kModeTableGrid = 3 };
+
+struct K2Args {
+  const Entry* entries;
+  const int64_t* seg;   // [nseg+1] entry offsets, star aligned
+  int32_t nseg;
+  const double* FA;     // FACTOR: [nA][Wpad] (global copy, staged to smem)
+  const double* FB;     //         [nB][Wpad]
+  const double* T;      // TABLE*: [U][Wpad]
+  double* part;         // [gridDim.x][2][Wpad]
+  int32_t nA, nB, Wpad;
+};
+
+constexpr int kK2Threads = 512;
+constexpr int kK2Warps = kK2Threads / 32;
+constexpr int kChunk = 32;  // entries staged per warp per step
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// NW walkers per lane.  Walker mapping: NW == 1: w = lane;  NW >= 2: for q < NW/2,
+// w = 64 q + 2 lane + {0,1}  (one 16-byte shared/global load per q, conflict free).
+template <int NW, int MODE>
+__global__ void __launch_bounds__(kK2Threads, (NW <= 2 ? 2 : 1)) mb_k2_stars(K2Args a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NQ = (NW + 1) / 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Wpad = a.Wpad;
+
+  // smem layout: [stage: warps x 2 x kChunk entries][FA | FB tables (FACTOR only)]
+  Entry* stage = reinterpret_cast<Entry*>(smem_raw) + (size_t)warp * 2 * kChunk;
+  double* sFA = reinterpret_cast<double*>(smem_raw + (size_t)kK2Warps * 2 * kChunk * sizeof(Entry));
+  double* sFB = sFA + (size_t)a.nA * Wpad;
+  if (MODE == kModeFactor) {
+    const int n2 = (a.nA + a.nB) * Wpad / 2;  // FA and FB are contiguous in global memory too
+    const double2* src = reinterpret_cast<const double2*>(a.FA);
+    double2* dst = reinterpret_cast<double2*>(sFA);
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) dst[i] = __ldg(src + i);
+    __syncthreads();
+  }
+
+  double run[NW], star[NW], fa[NW];
+  LogAcc acc[NW];
+  int nbad[NW];
+  bool isnan_[NW];
+#pragma unroll
+  for (int i = 0; i < NW; ++i) {
+    run[i] = 0.0; star[i] = 0.0; fa[i] = (MODE == kModeFactor) ? 0.0 : 1.0;
+    acc[i].init(); nbad[i] = 0; isnan_[i] = false;
+  }
+  const int wofs = (NW == 1) ? lane : 2 * lane;  // element offset inside a table row
+
+  auto end_star = [&]() {
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+      double L = (MODE == kModeFactor) ? fma(fa[i], run[i], star[i]) : run[i];
+      if (L != 0.0) {                       // exact zero: star skipped (:218-221)
+        if (!isfinite(L)) nbad[i]++;        // ValueError (:216-217)
+        else if (L < 0.0) isnan_[i] = true; // np.log(negative) = nan, no exception
+        else acc[i].mul(L);
+      }
+      run[i] = 0.0; star[i] = 0.0;
+      if (MODE == kModeFactor) fa[i] = 0.0;
+    }
+  };
+
+  auto process = [&](const Entry& e, const double* fbv) {
+    if (MODE == kModeFactor) {
+      if (e.code & kNewRun) {  // warp-uniform
+        const double* rowA = sFA + (size_t)((e.code >> kAgeShift) & kAgeMask) * Wpad + wofs;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) { star[i] = fma(fa[i], run[i], star[i]); run[i] = 0.0; }
+        if (NW == 1) fa[0] = rowA[0];
+        else {
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            double2 v = *reinterpret_cast<const double2*>(rowA + 64 * q);
+            fa[2 * q] = v.x; fa[2 * q + 1] = v.y;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NW; ++i) run[i] = fma(e.a, fbv[i], run[i]);
+    if (e.code & kEndStar) end_star();
+  };
+
+  auto load_factors = [&](const Entry& e, double* fbv) {
+    const double* row;
+    if (MODE == kModeFactor) row = sFB + (size_t)(e.code & kDustMask) * Wpad + wofs;
+    else if (MODE == kModeTable)
+      row = a.T + ((size_t)((e.code >> kAgeShift) & kAgeMask) * a.nB + (e.code & kDustMask)) * Wpad + wofs;
+    else row = a.T + (size_t)e.row * Wpad + wofs;
+    if (NW == 1) {
+      fbv[0] = (MODE == kModeFactor) ? row[0] : __ldg(row);
+    } else {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        double2 v = (MODE == kModeFactor) ? *reinterpret_cast<const double2*>(row + 64 * q)
+                                          : __ldg(reinterpret_cast<const double2*>(row + 64 * q));
+        fbv[2 * q] = v.x; fbv[2 * q + 1] = v.y;
+      }
+    }
+  };
+
+  const int gw = blockIdx.x * kK2Warps + warp, nwarps = gridDim.x * kK2Warps;
+  for (int s = gw; s < a.nseg; s += nwarps) {
+    int64_t pos = a.seg[s];
+    const int64_t end = a.seg[s + 1];
+    int buf = 0;
+    if (pos + lane < end) cp_async16(stage + lane, a.entries + pos + lane);
+    cp_async_commit();
+    while (pos < end) {
+      const int64_t nxt = pos + kChunk;
+      if (nxt + lane < end) cp_async16(stage + (buf ^ 1) * kChunk + lane, a.entries + nxt + lane);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncwarp();
+      const Entry* cur = stage + buf * kChunk;
+      const int n = (int)min((int64_t)kChunk, end - pos);
+      int j = 0;
+      for (; j + 4 <= n; j += 4) {
+        Entry e0 = cur[j], e1 = cur[j + 1], e2 = cur[j + 2], e3 = cur[j + 3];
+        double f0[NW], f1[NW], f2[NW], f3[NW];
+        load_factors(e0, f0); load_factors(e1, f1); load_factors(e2, f2); load_factors(e3, f3);
+        process(e0, f0); process(e1, f1); process(e2, f2); process(e3, f3);
+      }
+      for (; j < n; ++j) {
+        Entry e0 = cur[j];
+        double f0[NW];
+        load_factors(e0, f0);
+        process(e0, f0);
+      }
+      __syncwarp();
+      buf ^= 1;
+      pos = nxt;
+    }
+    cp_async_wait<0>();
+  }
+
+  // block reduction: fixed warp order -> bitwise reproducible for a given launch shape
+  __syncthreads();
+  double* red = reinterpret_cast<double*>(smem_raw);  // [warps][2][Wpad], reuses stage/tables
+  // (stage+tables >= 16 KiB + ...; 16 warps x 2 x 128 x 8 = 32 KiB worst case: sized by the host)
+#pragma unroll
+  for (int i = 0; i < NW; ++i) {
+    int w = (NW == 1) ? lane : 64 * (i >> 1) + 2 * lane + (i & 1);
+    double v = acc[i].value();
+    if (isnan_[i]) v = nan("");
+    red[((size_t)warp * 2 + 0) * Wpad + w] = v;
+    red[((size_t)warp * 2 + 1) * Wpad + w] = (double)nbad[i];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * Wpad; i += blockDim.x) {
+    double s = 0.0;
+    for (int wp = 0; wp < kK2Warps; ++wp) s += red[(size_t)wp * 2 * Wpad + i];
+    a.part[(size_t)blockIdx.x * 2 * Wpad + i] = s;
+  }
+}
+
+// ---- K3: finalize -----------------------------------------------------------------------------
+struct K3Args {
+  const double* part;   // [nblocks][2][Wpad]
+  int32_t nblocks;
+  const double* FA;     // [nA][Wpad]
+  const double* SC;     // [nbins][2][Wpad]
+  const int32_t* bin_agecls;  // [nbins] age class of the bin's age
+  const double* coef;   // [nbins] metprior * massmult / avemass   (helpers.py:148-151)
+  int32_t nbins;        // 0 -> no Poisson term
+  double n_stars;       // S of the fit (:183-185)
+  double* out;          // [MB_OUT_ROWS][Wtot], written at column w0 + w
+  int32_t W, Wpad, w0, Wtot;
+};
+
+__global__ void __launch_bounds__(128) mb_k3_finalize(K3Args a) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= a.W) return;
+  double sum = 0.0, bad = 0.0;
+  for (int b = 0; b < a.nblocks; ++b) {
+    sum += a.part[((size_t)b * 2 + 0) * a.Wpad + w];
+    bad += a.part[((size_t)b * 2 + 1) * a.Wpad + w];
+  }
+  double pois = 0.0;
+  if (a.nbins > 0) {
+    // helpers.py:133-134: weights are normalised by their grand total before the bin sums
+    double nrm = 0.0;
+    for (int b = 0; b < a.nbins; ++b)
+      nrm += a.FA[(size_t)a.bin_agecls[b] * a.Wpad + w] * a.SC[((size_t)b * 2) * a.Wpad + w];
+    double pred = 0.0;
+    for (int b = 0; b < a.nbins; ++b) {
+      double fa = a.FA[(size_t)a.bin_agecls[b] * a.Wpad + w];
+      double s = fa * a.SC[((size_t)b * 2) * a.Wpad + w] / nrm;
+      if (s > 0.0) {  // helpers.py:156 (false for NaN: 0/0 when every weight is zero)
+        double c = fa * a.SC[((size_t)b * 2 + 1) * a.Wpad + w] / nrm;
+        pred += (fa * a.coef[b]) * c / s;
+      }
+    }
+    pois = a.n_stars * log(pred) - pred - lgamma(a.n_stars + 1.0);  // :182-186
+  }
+  a.out[(size_t)MB_OUT_STARSUM * a.Wtot + a.w0 + w] = sum;
+  a.out[(size_t)MB_OUT_POISSON * a.Wtot + a.w0 + w] = pois;
+  a.out[(size_t)MB_OUT_NONFINITE * a.Wtot + a.w0 + w] = bad;
+}
+
+// ---- one-time ingest: helpers.py:33-41 ---------------------------------------------------------
+__global__ void mb_ingest_lnp(int64_t n, const int64_t* __restrict__ indxs, double* __restrict__ vals,
+                              int64_t G, const double* __restrict__ pw, int* __restrict__ err) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    double v = vals[i];
+    if (isfinite(v)) {
+      int64_t r = indxs[i];
+      if (r < 0) r += G;  // numpy negative indexing
+      if (r < 0 || r >= G) { atomicExch(err, 1); continue; }
+      vals[i] = exp(v) / pw[r];
+    }
+  }
+}
+
+}  // namespace mb

@@ -1,0 +1,268 @@
+"""
+``LikelihoodEngine`` -- owns the device-resident form of one (grid, stars, model) triple and
+evaluates the ensemble likelihood for batches of walkers through the C ABI.
+
+One ``mb_handle`` per CUDA device; with several devices the stars are split into contiguous
+shards (grid replicated), every device evaluates all walkers on its shard, and the per-walker
+partials are added.  Inside one process that sum is done on the host
+after the asynchronous ``mb_lnlike_begin``/``mb_lnlike_end`` pair; across processes
+(``torchrun``) it is one NCCL all-reduce, see ``parallel.py``.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _cabi
+
+__all__ = ["ModelSpec", "LikelihoodEngine", "shard_bounds"]
+
+
+def shard_bounds(n_stars, n_shards, i):
+    """Contiguous, balanced star range of shard ``i`` (first ``n_stars % n_shards`` shards get
+    one extra star)."""
+    q, r = divmod(int(n_stars), int(n_shards))
+    lo = i * q + min(i, r)
+    return lo, lo + q + (1 if i < r else 0)
+
+
+class ModelSpec:
+    """What the device needs to know about the free prior models: per parameter (logA, Av, Rv,
+    fA) a kind name from ``_cabi.KIND`` and, for binned models, the node coordinates."""
+
+    def __init__(self, kinds, nodes=None):
+        self.kinds = dict(kinds)
+        self.nodes = dict(nodes or {})
+        for p in _cabi.PARAMS:
+            self.kinds.setdefault(p, "fixed")
+            if self.kinds[p] not in _cabi.KIND:
+                raise ValueError(f"unknown prior model kind {self.kinds[p]!r}")
+
+    def nvars(self, p):
+        kind = self.kinds[p]
+        if kind in ("bins_histo", "bins_interp"):
+            return len(self.nodes[p])
+        return len(_cabi.KIND_VARNAMES.get(kind, ()))
+
+    @property
+    def ndim(self):
+        return sum(self.nvars(p) for p in _cabi.PARAMS)
+
+    @property
+    def tabulated(self):
+        return [p for p in _cabi.PARAMS if self.kinds[p] == "tabulated"]
+
+    def to_c(self):
+        m = _cabi.ModelDesc()
+        for i, p in enumerate(_cabi.PARAMS):
+            m.kind[i] = _cabi.KIND[self.kinds[p]]
+            if self.kinds[p] in ("bins_histo", "bins_interp"):
+                x = [float(v) for v in self.nodes[p]]
+                if len(x) > _cabi.MB_MAX_NODES:
+                    raise ValueError(f"{p}: more than {_cabi.MB_MAX_NODES} nodes")
+                m.nnodes[i] = len(x)
+                for j, v in enumerate(x):
+                    m.nodes[i][j] = v
+        return m
+
+
+def _col(moddata, key):
+    return np.ascontiguousarray(moddata[key], dtype=np.float64)
+
+
+class LikelihoodEngine:
+    def __init__(self, spec, star_lnpgriddata, beast_moddata, massmult=None, devices=None,
+                 mode="auto", star_range=None, n_stars_total=None, keep_indices=False,
+                 merge_duplicates=True):
+        self.lib = _cabi.load()
+        self.spec = spec
+        self.handles = []
+        self.devices = list(devices) if devices is not None else [0]
+        if not self.devices:
+            raise ValueError("at least one device is required")
+
+        keep = []  # host arrays that must outlive mb_create
+
+        def arr(a, dtype):
+            a = np.ascontiguousarray(a, dtype=dtype)
+            keep.append(a)
+            return a
+
+        grid = _cabi.GridDesc()
+        grid.G = len(beast_moddata["prior_weight"])
+        for i, p in enumerate(_cabi.PARAMS):
+            if spec.kinds[p] != "fixed":
+                if p not in beast_moddata:
+                    raise KeyError(p)  # singlepop_dust_model.py:147 looks the column up by name
+                grid.col[i] = _cabi.dptr(arr(beast_moddata[p], np.float64))
+        grid.prior_weight = _cabi.dptr(arr(beast_moddata["prior_weight"], np.float64))
+        grid.grid_weight = _cabi.dptr(arr(beast_moddata["grid_weight"], np.float64))
+        grid.completeness = _cabi.dptr(arr(beast_moddata["completeness"], np.float64))
+        mm = None
+        if massmult is not None:
+            grid.logA = _cabi.dptr(arr(beast_moddata["logA"], np.float64))
+            grid.Z = _cabi.dptr(arr(beast_moddata["Z"], np.float64))
+            mm = _cabi.MassMultDesc()
+            ages = arr(massmult["ages"], np.float64)
+            mets = arr(massmult["Zs"], np.float64)
+            mult = arr(massmult["massmult"], np.float64)
+            mm.n_ages, mm.n_mets = ages.size, mets.size
+            mm.ages, mm.mets, mm.massmult = _cabi.dptr(ages), _cabi.dptr(mets), _cabi.dptr(mult)
+            mm.avemass = float(massmult["avemass"])
+
+        indxs = np.asarray(star_lnpgriddata["indxs"])
+        if not np.issubdtype(indxs.dtype, np.integer):
+            raise IndexError("arrays used as indices must be of integer (or boolean) type")
+        indxs = arr(indxs, np.int64)
+        vals = arr(star_lnpgriddata["vals"], np.float64)
+        if indxs.shape != vals.shape or indxs.ndim != 2:
+            raise ValueError("indxs and vals must both have shape (n_lnps, n_stars)")
+        K, S = indxs.shape
+        lo, hi = star_range if star_range is not None else (0, S)
+        self.star_range = (int(lo), int(hi))
+        self.n_stars_total = int(n_stars_total) if n_stars_total is not None else S
+        model_c = spec.to_c()
+
+        try:
+            for i, dev in enumerate(self.devices):
+                a, b = shard_bounds(hi - lo, len(self.devices), i)
+                st = _cabi.StarsDesc()
+                st.K, st.S = K, S
+                st.indxs = indxs.ctypes.data_as(_cabi.c_int64_p)
+                st.vals = _cabi.dptr(vals)
+                st.star_begin, st.star_end = lo + a, lo + b
+                st.n_stars_total = self.n_stars_total
+                opt = _cabi.Options()
+                opt.device = int(dev)
+                opt.mode = _cabi.MODE[mode]
+                opt.keep_indices = int(bool(keep_indices))
+                opt.merge_duplicates = int(bool(merge_duplicates))
+                h = ctypes.c_void_p()
+                _cabi.check(
+                    self.lib.mb_create(
+                        ctypes.byref(grid), ctypes.byref(st), ctypes.byref(model_c),
+                        ctypes.byref(mm) if mm is not None else None, ctypes.byref(opt),
+                        ctypes.byref(h),
+                    )
+                )
+                self.handles.append(h)
+        except Exception:
+            self.close()
+            raise
+        del keep
+
+    # -- lifetime ------------------------------------------------------------------------------
+    def close(self):
+        for h in self.handles:
+            self.lib.mb_destroy(h)
+        self.handles = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- introspection ---------------------------------------------------------------------------
+    def info(self, i=0):
+        out = _cabi.Info()
+        _cabi.check(self.lib.mb_get_info(self.handles[i], ctypes.byref(out)))
+        d = {name: getattr(out, name) for name, _ in _cabi.Info._fields_ if name != "reserved"}
+        d["n_classes"] = list(out.n_classes)
+        d["mode"] = _cabi.MODE_NAME[out.mode]
+        return d
+
+    def class_values(self, param, i=0):
+        p = _cabi.PARAMS.index(param)
+        n = self.lib.mb_class_values(self.handles[i], p, None, 0)
+        out = np.empty(max(n, 0))
+        self.lib.mb_class_values(self.handles[i], p, _cabi.dptr(out), n)
+        return out
+
+    def gathered_indices(self, i=0):
+        info = self.info(i)
+        rows = np.empty(max(1, info["n_entries_raw"]), dtype=np.int64)
+        offs = np.empty(info["n_stars_local"] + 1, dtype=np.int64)
+        _cabi.check(
+            self.lib.mb_gathered_indices(
+                self.handles[i], rows.ctypes.data_as(_cabi.c_int64_p), rows.size,
+                offs.ctypes.data_as(_cabi.c_int64_p),
+            )
+        )
+        return rows[: offs[-1]], offs
+
+    def set_profiling(self, on=True):
+        for h in self.handles:
+            _cabi.check(self.lib.mb_set_profiling(h, int(on)))
+
+    def last_kernel_ms(self, i=0):
+        ms = (ctypes.c_float * _cabi.MB_NKERNELS)()
+        _cabi.check(self.lib.mb_last_kernel_ms(self.handles[i], ctypes.byref(ms)))
+        return dict(zip(_cabi.KERNEL_NAMES, list(ms)))
+
+    # -- evaluation ------------------------------------------------------------------------------
+    def _tabs(self, tabs, W):
+        t = _cabi.TabArray()
+        keep = []
+        for i, p in enumerate(_cabi.PARAMS):
+            if self.spec.kinds[p] == "tabulated":
+                a = np.ascontiguousarray(tabs[p], dtype=np.float64)
+                if a.shape[0] != W:
+                    raise ValueError(f"table for {p} must have one row per walker")
+                keep.append(a)
+                t[i] = _cabi.dptr(a)
+        return t, keep
+
+    def lnlike_rows(self, phis, tabs=None):
+        """Raw result rows [3][W] (sum over this engine's stars of ln(star prob); Poisson term;
+        count of non-finite stars), summed over the engine's devices."""
+        phis = np.ascontiguousarray(phis, dtype=np.float64)
+        if phis.ndim != 2:
+            raise ValueError("phis must be (W, ndim)")
+        W, ndim = phis.shape
+        t, keep = self._tabs(tabs or {}, W)
+        for h in self.handles:
+            _cabi.check(self.lib.mb_lnlike_begin(h, _cabi.dptr(phis), W, ndim, t))
+        total = None
+        for h in self.handles:
+            rows = np.empty((_cabi.MB_OUT_ROWS, W))
+            _cabi.check(self.lib.mb_lnlike_end(h, _cabi.dptr(rows)))
+            if total is None:
+                total = rows
+            else:
+                total[0] += rows[0]
+                total[2] += rows[2]
+        return total
+
+    def combine(self, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.float64)
+        W = rows.shape[1]
+        out = np.empty(W)
+        status = np.empty(W, dtype=np.int32)
+        self.lib.mb_combine(_cabi.dptr(rows), W, _cabi.dptr(out), status.ctypes.data_as(_cabi.c_int32_p))
+        return out, status
+
+    def lnlike(self, phis, tabs=None):
+        """(lnlike[W], status[W]) for a batch of walkers."""
+        if len(self.handles) == 1 and not self.spec.tabulated:
+            phis = np.ascontiguousarray(phis, dtype=np.float64)
+            W, ndim = phis.shape
+            out = np.empty(W)
+            status = np.empty(W, dtype=np.int32)
+            _cabi.check(
+                self.lib.mb_lnlike(
+                    self.handles[0], _cabi.dptr(phis), W, ndim, _cabi.dptr(out),
+                    status.ctypes.data_as(_cabi.c_int32_p),
+                )
+            )
+            return out, status
+        return self.combine(self.lnlike_rows(phis, tabs))
+
+    def lnlike_device(self, d_phi, W, ndim, d_out, stream=0, i=0):
+        """Asynchronous device-pointer form (``mb_lnlike_device``): ``d_phi`` [W][ndim] and
+        ``d_out`` [3][W] are raw device addresses, ``stream`` a raw ``cudaStream_t``."""
+        _cabi.check(
+            self.lib.mb_lnlike_device(
+                self.handles[i], ctypes.c_void_p(d_phi), W, ndim, ctypes.c_void_p(d_out),
+                ctypes.c_void_p(stream),
+            )
+        )
