@@ -135,8 +135,9 @@ typedef struct {
   int64_t reserved[8];
 } mb_info;
 
-/* Device result layout of mb_lnlike_device: three rows of W doubles. */
-enum { MB_OUT_STARSUM = 0, MB_OUT_POISSON = 1, MB_OUT_NONFINITE = 2, MB_OUT_ROWS = 3 };
+/* Device result layout of mb_lnlike_device: three rows of W doubles.  The two rows that add over
+ * star shards come first so that one all-reduce of 2*W doubles covers them. */
+enum { MB_OUT_STARSUM = 0, MB_OUT_NONFINITE = 1, MB_OUT_POISSON = 2, MB_OUT_ROWS = 3 };
 
 #define MB_STATUS_OK 0
 #define MB_STATUS_NONFINITE_STAR 1 /* ValueError("invidual integrated star prob is not finite"), :216-217 */
@@ -179,9 +180,9 @@ int mb_lnlike_end(mb_handle* h, double* rows);
 void mb_combine(const double* rows, int32_t W, double* lnlike, int32_t* status);
 
 /* Multi-GPU building block: device pointers, asynchronous on `stream`.  d_out is
- * [MB_OUT_ROWS][W] doubles: partial sum of ln(star prob) over this handle's stars, the
- * Poisson term (identical on every shard), and the count of non-finite stars.  The caller
- * all-reduces rows STARSUM and NONFINITE (one NCCL allreduce) and adds POISSON once. */
+ * [MB_OUT_ROWS][W] doubles: partial sum of ln(star prob) over this handle's stars, the count of
+ * non-finite stars, and the Poisson term (identical on every shard).  The caller all-reduces
+ * the first 2*W doubles (rows STARSUM, NONFINITE: one NCCL allreduce) and adds POISSON once. */
 int mb_lnlike_device(mb_handle* h, const double* d_phi, int32_t W, int32_t ndim, double* d_out,
                      void* stream);
 

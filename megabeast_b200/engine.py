@@ -213,8 +213,8 @@ class LikelihoodEngine:
         return t, keep
 
     def lnlike_rows(self, phis, tabs=None):
-        """Raw result rows [3][W] (sum over this engine's stars of ln(star prob); Poisson term;
-        count of non-finite stars), summed over the engine's devices."""
+        """Raw result rows [3][W] (sum over this engine's stars of ln(star prob); count of
+        non-finite stars; Poisson term), summed over the engine's devices."""
         phis = np.ascontiguousarray(phis, dtype=np.float64)
         if phis.ndim != 2:
             raise ValueError("phis must be (W, ndim)")
@@ -229,8 +229,7 @@ class LikelihoodEngine:
             if total is None:
                 total = rows
             else:
-                total[0] += rows[0]
-                total[2] += rows[2]
+                total[:2] += rows[:2]  # STARSUM and NONFINITE add over shards, POISSON is shared
         return total
 
     def combine(self, rows):

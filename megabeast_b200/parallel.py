@@ -1,0 +1,147 @@
+"""
+Star-sharded ensemble likelihood across processes: one process per GPU (``torchrun``), every
+rank owns a contiguous shard of stars plus a replicated grid, evaluates all W walkers on its
+shard, and ONE all-reduce of 2*W doubles (partial sums of ln(star prob) + non-finite counts)
+per step completes the likelihood (BASELINE.json north_star item 4).
+
+torch is used for what it is good at here -- device buffers, the current stream and
+``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests); the likelihood itself is the C ABI.
+"""
+import numpy as np
+
+from . import _cabi
+from .engine import LikelihoodEngine, shard_bounds
+
+__all__ = ["dist_info", "allreduce_rows", "combine_rows", "ShardedLikelihood"]
+
+
+def dist_info(group=None):
+    """(rank, world_size) of the default process group, (0, 1) when there is none."""
+    try:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(group), dist.get_world_size(group)
+    except ImportError:
+        pass
+    return 0, 1
+
+
+def allreduce_rows(rows, group=None):
+    """Sum the shard-additive rows (STARSUM, NONFINITE = the first 2*W values) of a [3][W]
+    tensor over all ranks, in place; the POISSON row is identical everywhere and is left alone.
+    Works for CUDA tensors (NCCL) and CPU tensors (gloo)."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        W = rows.shape[1]
+        dist.all_reduce(rows.view(-1)[: 2 * W], op=dist.ReduceOp.SUM, group=group)
+    return rows
+
+
+def combine_rows(rows):
+    """(lnlike[W], status[W]) from reduced rows -- the arithmetic of ``mb_combine``."""
+    rows = np.asarray(rows, dtype=np.float64)
+    total = rows[2] + rows[0]
+    status = np.where(rows[1] != 0.0, _cabi.STATUS_NONFINITE_STAR, 0).astype(np.int32)
+    status |= np.where(total == 0.0, _cabi.STATUS_TOTAL_ZERO, 0).astype(np.int32)
+    return total, status
+
+
+class ShardedLikelihood:
+    """
+    Per-rank evaluator.  ``model`` is an ``MB_Model``; the data dictionaries are the full ones
+    (every rank holds them, only its shard goes to its GPU).
+
+    ``lnlike_device(d_phi)``  phi already on the device -> reduced rows on the device, all
+                              asynchronous on torch's current stream (K0..K3 + one all-reduce)
+    ``lnprob(phis_host)``     the user-facing call: prior box on the host, pinned H2D of phi,
+                              kernels, all-reduce, D2H of the rows, exceptions as the reference
+    """
+
+    def __init__(self, model, star_lnpgriddata, beast_moddata, device=None, mode="auto", group=None):
+        import torch
+
+        from .helpers import precompute_mass_multipliers
+
+        self.torch = torch
+        self.model = model
+        self.group = group
+        self.rank, self.world = dist_info(group)
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.spec, self.perm, self.ndim = model._spec()
+        if self.spec.tabulated:
+            raise NotImplementedError("tabulated prior models are single-process only")
+        mm = None
+        if model.compute_N_stars:
+            model.massmultipliers = precompute_mass_multipliers(
+                beast_moddata, model.physics_model["M_ini"]["model"])
+            model.compute_massmult = False
+            mm = model.massmultipliers
+        S = np.asarray(star_lnpgriddata["indxs"]).shape[1]
+        self.star_range = shard_bounds(S, self.world, self.rank)
+        self.engine = LikelihoodEngine(self.spec, star_lnpgriddata, beast_moddata, massmult=mm,
+                                       devices=[self.device], mode=mode,
+                                       star_range=self.star_range, n_stars_total=S)
+        self._cap = 0
+        self._ensure(64)
+
+    def _ensure(self, W):
+        if W <= self._cap:
+            return
+        t = self.torch
+        dev = t.device("cuda", self.device)
+        self._cap = W
+        self.d_phi = t.empty((W, max(1, self.ndim)), dtype=t.float64, device=dev)
+        self.d_rows = t.empty((_cabi.MB_OUT_ROWS, W), dtype=t.float64, device=dev)
+        self.h_phi = t.empty((W, max(1, self.ndim)), dtype=t.float64).pin_memory()
+        self.h_rows = t.empty((_cabi.MB_OUT_ROWS, W), dtype=t.float64).pin_memory()
+
+    def lnlike_device(self, d_phi, d_rows=None):
+        t = self.torch
+        W = d_phi.shape[0]
+        if d_rows is None:
+            self._ensure(W)
+            d_rows = self.d_rows if W == self._cap else self.d_rows.view(-1)[: 3 * W].view(3, W)
+        stream = t.cuda.current_stream(self.device).cuda_stream
+        self.engine.lnlike_device(d_phi.data_ptr(), W, self.ndim, d_rows.data_ptr(), stream)
+        allreduce_rows(d_rows, self.group)
+        return d_rows
+
+    def lnlike_rows(self, phis):
+        """Host phi (W, ndim in device order) -> reduced host rows [3][W]."""
+        t = self.torch
+        phis = np.ascontiguousarray(phis, dtype=np.float64)
+        W = phis.shape[0]
+        self._ensure(W)
+        h_phi = self.h_phi[:W]
+        h_phi.numpy()[...] = phis.reshape(W, -1) if self.ndim else 0.0
+        d_phi = self.d_phi[:W]
+        d_phi.copy_(h_phi, non_blocking=True)
+        d_rows = self.d_rows.view(-1)[: 3 * W].view(3, W)
+        self.lnlike_device(d_phi, d_rows)
+        h_rows = self.h_rows.view(-1)[: 3 * W].view(3, W)
+        h_rows.copy_(d_rows, non_blocking=True)
+        t.cuda.current_stream(self.device).synchronize()
+        return h_rows.numpy()
+
+    def lnprob(self, phi):
+        phi = np.asarray(phi, dtype=np.float64)
+        single = phi.ndim == 1
+        phis = phi[None, :] if single else phi
+        lp = np.asarray(self.model.lnprior(phis), dtype=np.float64)
+        out = np.full(len(phis), -np.inf)
+        inside = np.isfinite(lp)
+        if inside.any():
+            rows = self.lnlike_rows(phis[inside][:, self.perm])
+            vals, status = combine_rows(rows)
+            if np.any(status & _cabi.STATUS_NONFINITE_STAR):
+                raise ValueError("invidual integrated star prob is not finite")
+            if np.any(status & _cabi.STATUS_TOTAL_ZERO):
+                print(0.0)
+                raise SystemExit
+            out[inside] = lp[inside] + vals
+        return out[0] if single else out
+
+    def close(self):
+        self.engine.close()
