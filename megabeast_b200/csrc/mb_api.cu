@@ -142,6 +142,7 @@ static int classify(const mb_model_desc& m, int p, const double* col, int64_t G,
 }
 
 static size_t k2_smem_bytes(int mode, int nA, int nB, int Wpad) {
+  const int kK2Warps = k2_threads(Wpad / 32) / 32;
   size_t stage = (size_t)kK2Warps * 2 * kChunk * sizeof(Entry);
   size_t tables = mode == kModeFactor ? (size_t)(nA + nB) * Wpad * sizeof(double) : 0;
   size_t red = (size_t)kK2Warps * 2 * Wpad * sizeof(double);
@@ -316,40 +317,42 @@ extern "C" int mb_create(const mb_grid_desc* grid, const mb_stars_desc* stars,
                     (long long)stars->indxs[kk * S + s], (long long)G, (long long)s);
       Entry e;
       e.a = v * grid->prior_weight[r] * grid->grid_weight[r] * grid->completeness[r];
-      e.code = rowcode[(size_t)r];
-      e.row = (uint32_t)r;
+      const uint32_t rc = rowcode[(size_t)r];
+      const uint32_t cA = (rc >> kAgeShift) & kAgeMask, cB = rc & kDustMask;
+      e.meta = cA;
+      e.idx = mode == MB_MODE_FACTOR ? cB : mode == MB_MODE_TABLE_UNIQUE ? cA * (uint32_t)h->nB + cB : (uint32_t)r;
       cur.push_back(e);
       if (o.keep_indices) h->kept_rows.push_back(r);
     }
     if (o.keep_indices) h->kept_offs.push_back((int64_t)h->kept_rows.size());
     h->n_entries_raw += (int64_t)cur.size();
     if (cur.empty()) continue;  // sums to 0.0 -> skipped by the reference too (:218-221)
-    if (mode == MB_MODE_TABLE_GRID)
-      std::stable_sort(cur.begin(), cur.end(), [](const Entry& x, const Entry& y) { return x.row < y.row; });
-    else
-      std::stable_sort(cur.begin(), cur.end(), [](const Entry& x, const Entry& y) { return x.code < y.code; });
+    // runs of equal age class (FACTOR reloads the age factor once per run); ties by table row
+    std::stable_sort(cur.begin(), cur.end(), [](const Entry& x, const Entry& y) {
+      return x.meta != y.meta ? x.meta < y.meta : x.idx < y.idx;
+    });
     size_t first = entries.size();
     for (const Entry& e : cur) {
       if (merge && entries.size() > first) {
         Entry& last = entries.back();
-        bool same = mode == MB_MODE_TABLE_GRID ? last.row == e.row : last.code == e.code;
-        if (same) { last.a += e.a; continue; }
+        if (last.idx == e.idx && last.meta == e.meta) { last.a += e.a; continue; }
       }
       entries.push_back(e);
     }
     uint32_t prevA = 0xffffffffu;
     for (size_t i = first; i < entries.size(); ++i) {
-      uint32_t cA = (entries[i].code >> kAgeShift) & kAgeMask;
-      if (cA != prevA) entries[i].code |= kNewRun;
+      uint32_t cA = entries[i].meta;
+      // TABLE modes read the full product from the table: only the star start is a boundary
+      if (i == first) entries[i].meta |= kNewRun | kNewStar;
+      else if (mode == MB_MODE_FACTOR && cA != prevA) entries[i].meta |= kNewRun;
       prevA = cA;
     }
-    entries.back().code |= kEndStar;
     star_end_pos.push_back((int64_t)entries.size());
   }
   h->n_entries = (int64_t)entries.size();
 
   // ---- segments: star aligned, about four per resident warp ---------------------------------------
-  const int64_t resident_warps = (int64_t)h->sm_count * 2 * kK2Warps;
+  const int64_t resident_warps = (int64_t)h->sm_count * 24;
   int64_t target = std::max<int64_t>(64, h->n_entries / std::max<int64_t>(1, resident_warps * 4));
   std::vector<int64_t> seg(1, 0);
   for (int64_t pos : star_end_pos)
@@ -427,20 +430,20 @@ extern "C" int mb_gathered_indices(const mb_handle* h, int64_t* rows, int64_t ca
   if (!h) return fail("null handle");
   if (h->kept_offs.empty()) return fail("handle was created without keep_indices");
   if ((int64_t)h->kept_rows.size() > cap) return fail("rows buffer too small (%lld needed)", (long long)h->kept_rows.size());
-  // device round trip: what is reported is what the device holds, not the host copy
-  std::vector<Entry> back((size_t)h->n_entries);
-  if (h->n_entries) CK(cudaMemcpy(back.data(), h->d_entries, sizeof(Entry) * back.size(), cudaMemcpyDeviceToHost));
-  if (h->n_entries == h->n_entries_raw) {
-    // no merging happened: rebuild the per-star row lists from the device entries themselves
+  if (h->mode == MB_MODE_TABLE_GRID && h->n_entries == h->n_entries_raw) {
+    // TABLE_GRID gathers by grid row: report what the device actually holds (round trip)
+    std::vector<Entry> back((size_t)h->n_entries);
+    if (h->n_entries) CK(cudaMemcpy(back.data(), h->d_entries, sizeof(Entry) * back.size(), cudaMemcpyDeviceToHost));
     size_t i = 0, nout = 0;
     for (int64_t s = 0; s < h->S_local; ++s) {
       offs[s] = (int64_t)nout;
       int64_t cnt = h->kept_offs[(size_t)s + 1] - h->kept_offs[(size_t)s];
-      for (int64_t c = 0; c < cnt; ++c) rows[nout++] = (int64_t)back[i++].row;
+      for (int64_t c = 0; c < cnt; ++c) rows[nout++] = (int64_t)back[i++].idx;
     }
     offs[h->S_local] = (int64_t)nout;
     return 0;
   }
+  // class-coded modes dereference the grid only at create time: the rows that were read then
   memcpy(rows, h->kept_rows.data(), sizeof(int64_t) * h->kept_rows.size());
   memcpy(offs, h->kept_offs.data(), sizeof(int64_t) * h->kept_offs.size());
   return 0;
@@ -460,9 +463,9 @@ extern "C" int mb_last_kernel_ms(const mb_handle* h, float ms[MB_NKERNELS]) {
 template <int MODE>
 static void launch_k2(int NW, int grid, size_t smem, cudaStream_t st, const K2Args& a) {
   switch (NW) {
-    case 1: mb_k2_stars<1, MODE><<<grid, kK2Threads, smem, st>>>(a); break;
-    case 2: mb_k2_stars<2, MODE><<<grid, kK2Threads, smem, st>>>(a); break;
-    default: mb_k2_stars<4, MODE><<<grid, kK2Threads, smem, st>>>(a); break;
+    case 1: mb_k2_stars<1, MODE><<<grid, k2_threads(1), smem, st>>>(a); break;
+    case 2: mb_k2_stars<2, MODE><<<grid, k2_threads(2), smem, st>>>(a); break;
+    default: mb_k2_stars<4, MODE><<<grid, k2_threads(4), smem, st>>>(a); break;
   }
 }
 
@@ -470,9 +473,9 @@ template <int MODE>
 static int k2_occ(int NW, size_t smem) {
   int n = 0;
   switch (NW) {
-    case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<1, MODE>, kK2Threads, smem); break;
-    case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<2, MODE>, kK2Threads, smem); break;
-    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<4, MODE>, kK2Threads, smem); break;
+    case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<1, MODE>, k2_threads(1), smem); break;
+    case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<2, MODE>, k2_threads(2), smem); break;
+    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<4, MODE>, k2_threads(4), smem); break;
   }
   return n;
 }
@@ -530,17 +533,18 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     }
     if (prof) CK(cudaEventRecord(h->ev[2], st));
     if (h->poisson) {
-      mb_k1b_binsums<<<h->nbins, std::min(128, Wpad), 0, st>>>(h->d_H, FB, h->d_SC, h->nB, Wpad);
+      mb_k1b_binsums<<<h->nbins, kK1bThreads, 0, st>>>(h->d_H, FB, h->d_SC, h->nB, Wpad);
       ++launches;
     }
     if (prof) CK(cudaEventRecord(h->ev[3], st));
     size_t smem = k2_smem_bytes(kmode, h->nA, h->nB, Wpad);
     int per_sm = k2_blocks_per_sm(kmode, NW, smem);
     if (per_sm < 1) return fail("K2 cannot be resident with %zu bytes of shared memory", smem);
+    const int kK2Warps = k2_threads(NW) / 32;
     int grid = std::min(h->sm_count * per_sm, std::max(1, (h->nseg + kK2Warps - 1) / kK2Warps));
     grid = std::min(grid, h->max_blocks);
     K2Args k2{};
-    k2.entries = h->d_entries; k2.seg = h->d_seg; k2.nseg = h->nseg; k2.FA = FA; k2.FB = FB; k2.T = h->d_T;
+    k2.entries = h->d_entries; k2.seg = h->d_seg; k2.nseg = h->nseg; k2.FA = FA; k2.T = h->d_T;
     k2.part = h->d_part; k2.nA = h->nA; k2.nB = h->nB; k2.Wpad = Wpad;
     if (kmode == kModeFactor) launch_k2<kModeFactor>(NW, grid, smem, st, k2);
     else if (kmode == kModeTable) launch_k2<kModeTable>(NW, grid, smem, st, k2);
@@ -551,7 +555,7 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     k3.part = h->d_part; k3.nblocks = grid; k3.FA = FA; k3.SC = h->d_SC; k3.bin_agecls = h->d_bin_agecls;
     k3.coef = h->d_coef; k3.nbins = h->poisson ? h->nbins : 0; k3.n_stars = (double)h->S_total;
     k3.out = d_out; k3.W = wp; k3.Wpad = Wpad; k3.w0 = w0; k3.Wtot = W;
-    mb_k3_finalize<<<(wp + 127) / 128, 128, 0, st>>>(k3);
+    mb_k3_finalize<<<wp, kK3Threads, 0, st>>>(k3);
     ++launches;
     if (prof) {
       CK(cudaEventRecord(h->ev[5], st));

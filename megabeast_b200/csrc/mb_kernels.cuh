@@ -36,11 +36,13 @@ namespace mb {
 // completeness[r] (walker independent, folded at create time), code = class codes + flags.
 struct __align__(16) Entry {
   double a;
-  uint32_t code;
-  uint32_t row;   // grid row (TABLE_GRID gathers with it; also the parity hook)
+  uint32_t idx;   // row of the table K2 reads for this entry: dust class (FACTOR), class
+                  // combination cA*nB+cB (TABLE_UNIQUE) or grid row (TABLE_GRID, the literal gather)
+  uint32_t meta;  // flags | age class
 };
-constexpr uint32_t kNewRun = 0x80000000u;   // first entry of a run of equal age class
-constexpr uint32_t kEndStar = 0x40000000u;  // last entry of a star
+constexpr uint32_t kNewRun = 0x80000000u;   // first entry of a run of equal age class (or of a star)
+constexpr uint32_t kNewStar = 0x40000000u;  // first entry of a star (always together with kNewRun)
+// grid-row class code (host side and K1 expand): cA << kAgeShift | cB
 constexpr int kAgeShift = 20;
 constexpr uint32_t kAgeMask = 0x3ffu;       // <= 1024 age classes
 constexpr uint32_t kDustMask = 0xfffffu;    // <= 2^20 dust classes
@@ -179,21 +181,37 @@ __global__ void __launch_bounds__(256) mb_k1_expand(const double* __restrict__ F
 // create-time statistics H[bin][cB] = (sum grid_weight, sum grid_weight*completeness) over the
 // bin's rows of dust class cB:   S = FA * sum_cB H0*FB,  C = FA * sum_cB H1*FB.
 // SC[bin][0/1][w] holds the two dust sums (FA applied in K3).
-__global__ void __launch_bounds__(128) mb_k1b_binsums(const double* __restrict__ H,
-                                                      const double* __restrict__ FB,
-                                                      double* __restrict__ SC, int nB, int Wpad) {
-  int b = blockIdx.x;
+// One block per bin; 256 threads = (256 / Wpad) slices of the dust classes x Wpad walkers.
+constexpr int kK1bThreads = 256;
+__global__ void __launch_bounds__(kK1bThreads) mb_k1b_binsums(const double* __restrict__ H,
+                                                              const double* __restrict__ FB,
+                                                              double* __restrict__ SC, int nB, int Wpad) {
+  __shared__ double red[2][kK1bThreads];
+  const int b = blockIdx.x;
+  const int nslice = kK1bThreads / Wpad;
+  const int w = threadIdx.x % Wpad, slice = threadIdx.x / Wpad;
   const double2* Hb = reinterpret_cast<const double2*>(H) + (size_t)b * nB;
-  for (int w = threadIdx.x; w < Wpad; w += blockDim.x) {
-    double s = 0.0, c = 0.0;
-    for (int cb = 0; cb < nB; ++cb) {
-      double2 h = __ldg(Hb + cb);
-      double fb = __ldg(FB + (size_t)cb * Wpad + w);
-      s = fma(h.x, fb, s);
-      c = fma(h.y, fb, c);
-    }
-    SC[((size_t)b * 2 + 0) * Wpad + w] = s;
-    SC[((size_t)b * 2 + 1) * Wpad + w] = c;
+  double s0 = 0.0, c0 = 0.0, s1 = 0.0, c1 = 0.0;
+  int cb = slice;
+  for (; cb + nslice < nB; cb += 2 * nslice) {  // two independent chains per thread
+    double2 h0 = __ldg(Hb + cb), h1 = __ldg(Hb + cb + nslice);
+    double f0 = __ldg(FB + (size_t)cb * Wpad + w), f1 = __ldg(FB + (size_t)(cb + nslice) * Wpad + w);
+    s0 = fma(h0.x, f0, s0); c0 = fma(h0.y, f0, c0);
+    s1 = fma(h1.x, f1, s1); c1 = fma(h1.y, f1, c1);
+  }
+  if (cb < nB) {
+    double2 h0 = __ldg(Hb + cb);
+    double f0 = __ldg(FB + (size_t)cb * Wpad + w);
+    s0 = fma(h0.x, f0, s0); c0 = fma(h0.y, f0, c0);
+  }
+  red[0][threadIdx.x] = s0 + s1;
+  red[1][threadIdx.x] = c0 + c1;
+  __syncthreads();
+  if (threadIdx.x < 2 * Wpad) {
+    const int which = threadIdx.x / Wpad, ww = threadIdx.x % Wpad;
+    double acc = 0.0;
+    for (int sl = 0; sl < nslice; ++sl) acc += red[which][sl * Wpad + ww];  // fixed order
+    SC[((size_t)b * 2 + which) * Wpad + ww] = acc;
   }
 }
 
@@ -204,7 +222,9 @@ struct LogAcc {
   double P;
   int32_t E;
   int32_t n;
-  __device__ __forceinline__ void init() { P = 1.0; E = 0; n = 0; }
+  int32_t bad;     // stars whose sum was not finite -> ValueError (:216-217)
+  int32_t isnan;   // a negative sum: np.log gives nan, no exception
+  __device__ __forceinline__ void init() { P = 1.0; E = 0; n = 0; bad = 0; isnan = 0; }
   __device__ __forceinline__ void renorm() {
     int hi = __double2hiint(P);
     int e = ((hi >> 20) & 0x7ff);
@@ -214,25 +234,32 @@ struct LogAcc {
     }
     n = 0;
   }
-  // L > 0 finite
-  __device__ __forceinline__ void mul(double L) {
-    int hi = __double2hiint(L);
-    int e = (hi >> 20) & 0x7ff;
-    if (e == 0) {  // subnormal: rescale first (rare)
-      L *= 18446744073709551616.0;  // 2^64
-      hi = __double2hiint(L);
-      e = ((hi >> 20) & 0x7ff) - 64;
-    }
-    E += e - 1023;
-    double mant = __hiloint2double((hi & 0x800fffff) | (1023 << 20), __double2loint(L));
-    P *= mant;
-    if (++n >= 512) renorm();
-  }
   __device__ __forceinline__ double value() {
     renorm();
-    return log(P) + (double)E * 0.693147180559945309417232121458;
+    double v = log(P) + (double)E * 0.693147180559945309417232121458;
+    return isnan ? nan("") : v;
   }
 };
+
+// end of a star: fold its integrated probability L into the walker's accumulator.  Kept out of
+// line: it runs once per star (~1/K of the entries) and would otherwise be inlined at every
+// unrolled entry.
+__device__ __noinline__ LogAcc star_done(LogAcc acc, double L) {
+  if (L == 0.0) return acc;                        // exact zero: star skipped (:218-221)
+  int hi = __double2hiint(L);
+  int e = (hi >> 20) & 0x7ff;
+  if (e == 0x7ff) { acc.bad++; return acc; }       // inf or nan
+  if (hi < 0) { acc.isnan = 1; return acc; }       // negative
+  if (e == 0) {                                    // subnormal: rescale first (rare)
+    L *= 18446744073709551616.0;                   // 2^64
+    hi = __double2hiint(L);
+    e = ((hi >> 20) & 0x7ff) - 64;
+  }
+  acc.E += e - 1023;
+  acc.P *= __hiloint2double((hi & 0x800fffff) | (1023 << 20), __double2loint(L));
+  if (++acc.n >= 512) acc.renorm();
+  return acc;
+}
 
 enum { kModeFactor = 1, kModeTable = 2, kModeTableGrid = 3 };
 
@@ -240,108 +267,120 @@ struct K2Args {
   const Entry* entries;
   const int64_t* seg;   // [nseg+1] entry offsets, star aligned
   int32_t nseg;
-  const double* FA;     // FACTOR: [nA][Wpad] (global copy, staged to smem)
-  const double* FB;     //         [nB][Wpad]
+  const double* FA;     // FACTOR: [nA][Wpad] then [nB][Wpad], contiguous (staged to smem)
   const double* T;      // TABLE*: [U][Wpad]
   double* part;         // [gridDim.x][2][Wpad]
   int32_t nA, nB, Wpad;
 };
 
-constexpr int kK2Threads = 512;
-constexpr int kK2Warps = kK2Threads / 32;
+// block shape: 256 threads x 3 blocks/SM (<= 85 registers) for up to 64 walkers per pass,
+// 512 threads x 1 block/SM (<= 128 registers, one copy of the 128-walker tables) above
+__host__ __device__ constexpr int k2_threads(int NW) { return NW <= 2 ? 256 : 512; }
+__host__ __device__ constexpr int k2_min_blocks(int NW) { return NW <= 2 ? 3 : 1; }
 constexpr int kChunk = 32;  // entries staged per warp per step
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+__device__ __forceinline__ void cp_async16(uint32_t smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint4 lds_entry(uint32_t addr) {  // staged entry: ordered with the waits
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {  // read-only factor tables
+  double2 v;
+  asm("ld.shared.v2.f64 {%0,%1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr));
+  return v;
 }
 
 // NW walkers per lane.  Walker mapping: NW == 1: w = lane;  NW >= 2: for q < NW/2,
 // w = 64 q + 2 lane + {0,1}  (one 16-byte shared/global load per q, conflict free).
+//
+// Per entry the warp issues: one broadcast LDS.128 (a, idx, meta), one IMAD (table row address),
+// NW/2 x LDS.128 (factors), NW x DFMA, one flag test + branch.  Run / star boundaries are rare,
+// warp-uniform and share the single flag test.
 template <int NW, int MODE>
-__global__ void __launch_bounds__(kK2Threads, (NW <= 2 ? 2 : 1)) mb_k2_stars(K2Args a) {
+__global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars(K2Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NQ = (NW + 1) / 2;
+  constexpr int kK2Warps = k2_threads(NW) / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Wpad = a.Wpad;
+  const uint32_t rowbytes = (uint32_t)Wpad * 8u;
+  const uint32_t lanebytes = (NW == 1 ? lane : 2 * lane) * 8u;
 
   // smem layout: [stage: warps x 2 x kChunk entries][FA | FB tables (FACTOR only)]
-  Entry* stage = reinterpret_cast<Entry*>(smem_raw) + (size_t)warp * 2 * kChunk;
-  double* sFA = reinterpret_cast<double*>(smem_raw + (size_t)kK2Warps * 2 * kChunk * sizeof(Entry));
-  double* sFB = sFA + (size_t)a.nA * Wpad;
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  const uint32_t stage = smem0 + (uint32_t)warp * 2 * kChunk * (uint32_t)sizeof(Entry);
+  const uint32_t tabA = smem0 + (uint32_t)kK2Warps * 2 * kChunk * (uint32_t)sizeof(Entry) + lanebytes;
+  const uint32_t tabB = tabA + (uint32_t)a.nA * rowbytes;
   if (MODE == kModeFactor) {
-    const int n2 = (a.nA + a.nB) * Wpad / 2;  // FA and FB are contiguous in global memory too
+    const int n2 = (a.nA + a.nB) * Wpad / 2;
     const double2* src = reinterpret_cast<const double2*>(a.FA);
-    double2* dst = reinterpret_cast<double2*>(sFA);
+    double2* dst = reinterpret_cast<double2*>(smem_raw + (size_t)kK2Warps * 2 * kChunk * sizeof(Entry));
     for (int i = threadIdx.x; i < n2; i += blockDim.x) dst[i] = __ldg(src + i);
     __syncthreads();
   }
+  const char* Tlane = reinterpret_cast<const char*>(a.T) + lanebytes;
 
   double run[NW], star[NW], fa[NW];
   LogAcc acc[NW];
-  int nbad[NW];
-  bool isnan_[NW];
 #pragma unroll
-  for (int i = 0; i < NW; ++i) {
-    run[i] = 0.0; star[i] = 0.0; fa[i] = (MODE == kModeFactor) ? 0.0 : 1.0;
-    acc[i].init(); nbad[i] = 0; isnan_[i] = false;
-  }
-  const int wofs = (NW == 1) ? lane : 2 * lane;  // element offset inside a table row
+  for (int i = 0; i < NW; ++i) { run[i] = 0.0; star[i] = 0.0; fa[i] = 1.0; acc[i].init(); }
 
-  auto end_star = [&]() {
-#pragma unroll
-    for (int i = 0; i < NW; ++i) {
-      double L = (MODE == kModeFactor) ? fma(fa[i], run[i], star[i]) : run[i];
-      if (L != 0.0) {                       // exact zero: star skipped (:218-221)
-        if (!isfinite(L)) nbad[i]++;        // ValueError (:216-217)
-        else if (L < 0.0) isnan_[i] = true; // np.log(negative) = nan, no exception
-        else acc[i].mul(L);
-      }
-      run[i] = 0.0; star[i] = 0.0;
-      if (MODE == kModeFactor) fa[i] = 0.0;
-    }
-  };
-
-  auto process = [&](const Entry& e, const double* fbv) {
+  // factors of one entry for this lane's walkers
+  auto load_factors = [&](uint32_t idx, double* f) {
     if (MODE == kModeFactor) {
-      if (e.code & kNewRun) {  // warp-uniform
-        const double* rowA = sFA + (size_t)((e.code >> kAgeShift) & kAgeMask) * Wpad + wofs;
+      const uint32_t addr = idx * rowbytes + tabB;
+      if (NW == 1) f[0] = lds_f64(addr);
+      else {
 #pragma unroll
-        for (int i = 0; i < NW; ++i) { star[i] = fma(fa[i], run[i], star[i]); run[i] = 0.0; }
-        if (NW == 1) fa[0] = rowA[0];
-        else {
+        for (int q = 0; q < NQ; ++q) {
+          double2 v = lds_f64x2(addr + 512u * q);
+          f[2 * q] = v.x; f[2 * q + 1] = v.y;
+        }
+      }
+    } else {
+      const char* p = Tlane + (size_t)idx * rowbytes;
+      if (NW == 1) f[0] = __ldg(reinterpret_cast<const double*>(p));
+      else {
 #pragma unroll
-          for (int q = 0; q < NQ; ++q) {
-            double2 v = *reinterpret_cast<const double2*>(rowA + 64 * q);
-            fa[2 * q] = v.x; fa[2 * q + 1] = v.y;
-          }
+        for (int q = 0; q < NQ; ++q) {
+          double2 v = __ldg(reinterpret_cast<const double2*>(p + 512 * q));
+          f[2 * q] = v.x; f[2 * q + 1] = v.y;
         }
       }
     }
-#pragma unroll
-    for (int i = 0; i < NW; ++i) run[i] = fma(e.a, fbv[i], run[i]);
-    if (e.code & kEndStar) end_star();
   };
 
-  auto load_factors = [&](const Entry& e, double* fbv) {
-    const double* row;
-    if (MODE == kModeFactor) row = sFB + (size_t)(e.code & kDustMask) * Wpad + wofs;
-    else if (MODE == kModeTable)
-      row = a.T + ((size_t)((e.code >> kAgeShift) & kAgeMask) * a.nB + (e.code & kDustMask)) * Wpad + wofs;
-    else row = a.T + (size_t)e.row * Wpad + wofs;
-    if (NW == 1) {
-      fbv[0] = (MODE == kModeFactor) ? row[0] : __ldg(row);
-    } else {
+  // boundary before an entry: close the run (and the star) and fetch the new age factor
+  auto boundary = [&](uint32_t meta) {
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        double2 v = (MODE == kModeFactor) ? *reinterpret_cast<const double2*>(row + 64 * q)
-                                          : __ldg(reinterpret_cast<const double2*>(row + 64 * q));
-        fbv[2 * q] = v.x; fbv[2 * q + 1] = v.y;
+    for (int i = 0; i < NW; ++i) { star[i] = fma(fa[i], run[i], star[i]); run[i] = 0.0; }
+    if (meta & kNewStar) {
+#pragma unroll
+      for (int i = 0; i < NW; ++i) { acc[i] = star_done(acc[i], star[i]); star[i] = 0.0; }
+    }
+    if (MODE == kModeFactor) {
+      const uint32_t addr = (meta & kAgeMask) * rowbytes + tabA;
+      if (NW == 1) fa[0] = lds_f64(addr);
+      else {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          double2 v = lds_f64x2(addr + 512u * q);
+          fa[2 * q] = v.x; fa[2 * q + 1] = v.y;
+        }
       }
     }
   };
@@ -351,47 +390,62 @@ __global__ void __launch_bounds__(kK2Threads, (NW <= 2 ? 2 : 1)) mb_k2_stars(K2A
     int64_t pos = a.seg[s];
     const int64_t end = a.seg[s + 1];
     int buf = 0;
-    if (pos + lane < end) cp_async16(stage + lane, a.entries + pos + lane);
+    if (pos + lane < end) cp_async16(stage + lane * 16u, a.entries + pos + lane);
     cp_async_commit();
     while (pos < end) {
       const int64_t nxt = pos + kChunk;
-      if (nxt + lane < end) cp_async16(stage + (buf ^ 1) * kChunk + lane, a.entries + nxt + lane);
+      if (nxt + lane < end) cp_async16(stage + ((buf ^ 1) * kChunk + lane) * 16u, a.entries + nxt + lane);
       cp_async_commit();
       cp_async_wait<1>();
       __syncwarp();
-      const Entry* cur = stage + buf * kChunk;
+      const uint32_t cur = stage + buf * kChunk * 16u;
       const int n = (int)min((int64_t)kChunk, end - pos);
       int j = 0;
       for (; j + 4 <= n; j += 4) {
-        Entry e0 = cur[j], e1 = cur[j + 1], e2 = cur[j + 2], e3 = cur[j + 3];
-        double f0[NW], f1[NW], f2[NW], f3[NW];
-        load_factors(e0, f0); load_factors(e1, f1); load_factors(e2, f2); load_factors(e3, f3);
-        process(e0, f0); process(e1, f1); process(e2, f2); process(e3, f3);
+        uint4 e[4];
+        double f[4][NW];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) e[u] = lds_entry(cur + (j + u) * 16u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) load_factors(e[u].z, f[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (e[u].w & kNewRun) boundary(e[u].w);  // warp-uniform
+          const double av = __hiloint2double(e[u].y, e[u].x);
+#pragma unroll
+          for (int i = 0; i < NW; ++i) run[i] = fma(av, f[u][i], run[i]);
+        }
       }
       for (; j < n; ++j) {
-        Entry e0 = cur[j];
-        double f0[NW];
-        load_factors(e0, f0);
-        process(e0, f0);
+        uint4 e = lds_entry(cur + j * 16u);
+        double f[NW];
+        load_factors(e.z, f);
+        if (e.w & kNewRun) boundary(e.w);
+        const double av = __hiloint2double(e.y, e.x);
+#pragma unroll
+        for (int i = 0; i < NW; ++i) run[i] = fma(av, f[i], run[i]);
       }
       __syncwarp();
       buf ^= 1;
       pos = nxt;
     }
     cp_async_wait<0>();
+    // a segment ends on a star boundary: close the last star
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+      acc[i] = star_done(acc[i], fma(fa[i], run[i], star[i]));
+      star[i] = 0.0; run[i] = 0.0;
+    }
   }
 
   // block reduction: fixed warp order -> bitwise reproducible for a given launch shape
   __syncthreads();
   double* red = reinterpret_cast<double*>(smem_raw);  // [warps][2][Wpad], reuses stage/tables
-  // (stage+tables >= 16 KiB + ...; 16 warps x 2 x 128 x 8 = 32 KiB worst case: sized by the host)
 #pragma unroll
   for (int i = 0; i < NW; ++i) {
     int w = (NW == 1) ? lane : 64 * (i >> 1) + 2 * lane + (i & 1);
-    double v = acc[i].value();
-    if (isnan_[i]) v = nan("");
-    red[((size_t)warp * 2 + 0) * Wpad + w] = v;
-    red[((size_t)warp * 2 + 1) * Wpad + w] = (double)nbad[i];
+    red[((size_t)warp * 2 + 0) * Wpad + w] = acc[i].value();
+    red[((size_t)warp * 2 + 1) * Wpad + w] = (double)acc[i].bad;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * Wpad; i += blockDim.x) {
@@ -415,34 +469,55 @@ struct K3Args {
   int32_t W, Wpad, w0, Wtot;
 };
 
-__global__ void __launch_bounds__(128) mb_k3_finalize(K3Args a) {
-  int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= a.W) return;
-  double sum = 0.0, bad = 0.0;
-  for (int b = 0; b < a.nblocks; ++b) {
-    sum += a.part[((size_t)b * 2 + 0) * a.Wpad + w];
+constexpr int kK3Threads = 128;
+// deterministic block-wide sum (shuffle tree inside a warp, fixed order across warps)
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();  // scratch may still be read from the previous call
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int i = 0; i < kK3Threads / 32; ++i) t += scratch[i];
+  return t;
+}
+
+// one block per walker: block partials -> star sum; per-bin sums -> expected N -> Poisson term
+__global__ void __launch_bounds__(kK3Threads) mb_k3_finalize(K3Args a) {
+  __shared__ double scratch[kK3Threads / 32];
+  const int w = blockIdx.x;
+  double s = 0.0, bad = 0.0;
+  for (int b = threadIdx.x; b < a.nblocks; b += kK3Threads) {
+    s += a.part[((size_t)b * 2 + 0) * a.Wpad + w];
     bad += a.part[((size_t)b * 2 + 1) * a.Wpad + w];
   }
+  const double sum = block_sum(s, scratch);
+  const double nbad = block_sum(bad, scratch);
   double pois = 0.0;
   if (a.nbins > 0) {
     // helpers.py:133-134: weights are normalised by their grand total before the bin sums
-    double nrm = 0.0;
-    for (int b = 0; b < a.nbins; ++b)
-      nrm += a.FA[(size_t)a.bin_agecls[b] * a.Wpad + w] * a.SC[((size_t)b * 2) * a.Wpad + w];
-    double pred = 0.0;
-    for (int b = 0; b < a.nbins; ++b) {
+    double part_nrm = 0.0;
+    for (int b = threadIdx.x; b < a.nbins; b += kK3Threads)
+      part_nrm += a.FA[(size_t)a.bin_agecls[b] * a.Wpad + w] * a.SC[((size_t)b * 2) * a.Wpad + w];
+    const double nrm = block_sum(part_nrm, scratch);
+    double part_pred = 0.0;
+    for (int b = threadIdx.x; b < a.nbins; b += kK3Threads) {
       double fa = a.FA[(size_t)a.bin_agecls[b] * a.Wpad + w];
-      double s = fa * a.SC[((size_t)b * 2) * a.Wpad + w] / nrm;
-      if (s > 0.0) {  // helpers.py:156 (false for NaN: 0/0 when every weight is zero)
-        double c = fa * a.SC[((size_t)b * 2 + 1) * a.Wpad + w] / nrm;
-        pred += (fa * a.coef[b]) * c / s;
+      double sb = fa * a.SC[((size_t)b * 2) * a.Wpad + w] / nrm;
+      if (sb > 0.0) {  // helpers.py:156 (false for NaN: 0/0 when every weight is zero)
+        double cb = fa * a.SC[((size_t)b * 2 + 1) * a.Wpad + w] / nrm;
+        part_pred += (fa * a.coef[b]) * cb / sb;
       }
     }
+    const double pred = block_sum(part_pred, scratch);
     pois = a.n_stars * log(pred) - pred - lgamma(a.n_stars + 1.0);  // :182-186
   }
-  a.out[(size_t)MB_OUT_STARSUM * a.Wtot + a.w0 + w] = sum;
-  a.out[(size_t)MB_OUT_POISSON * a.Wtot + a.w0 + w] = pois;
-  a.out[(size_t)MB_OUT_NONFINITE * a.Wtot + a.w0 + w] = bad;
+  if (threadIdx.x == 0) {
+    a.out[(size_t)MB_OUT_STARSUM * a.Wtot + a.w0 + w] = sum;
+    a.out[(size_t)MB_OUT_POISSON * a.Wtot + a.w0 + w] = pois;
+    a.out[(size_t)MB_OUT_NONFINITE * a.Wtot + a.w0 + w] = nbad;
+  }
 }
 
 // ---- one-time ingest: helpers.py:33-41 ---------------------------------------------------------

@@ -225,12 +225,9 @@ class MB_Model:
             raise SystemExit
         return vals[0] if single else vals
 
-    def lnprior(self, phi):
-        """0 inside the flat-prior box, -inf outside (:231-274); vectorised over a 2-D phi."""
-        phi = np.asarray(phi, dtype=np.float64)
-        if phi.ndim == 2:
-            return np.array([self.lnprior(row) for row in phi])
-        k = 0
+    def _box(self):
+        """(low[ndim], high[ndim]) of the flat priors, indexed exactly as :255-271 index them."""
+        lows, highs = [], []
         for cparam, mod in self.physics_model.items():
             cprior = mod["prior"]
             cname = cprior["name"]
@@ -240,16 +237,26 @@ class MB_Model:
                 raise ValueError(f"{cname} prior not supported")
             for i, _ in enumerate(mod["varnames"]):
                 if mod["nsubvars"] > 1:
-                    lows, highs = cprior["minmax"][0], cprior["minmax"][1]
                     for j in range(len(np.atleast_1d(cprior["minmax"][i]))):
-                        if phi[k] < lows[j] or phi[k] > highs[j]:
-                            return -np.inf
-                        k += 1
+                        lows.append(cprior["minmax"][0][j])
+                        highs.append(cprior["minmax"][1][j])
                 else:
-                    if phi[k] < cprior["minmax"][i][0] or phi[k] > cprior["minmax"][i][1]:
-                        return -np.inf
-                    k += 1
-        return 0.0
+                    lows.append(cprior["minmax"][i][0])
+                    highs.append(cprior["minmax"][i][1])
+        return np.asarray(lows, dtype=np.float64), np.asarray(highs, dtype=np.float64)
+
+    def lnprior(self, phi):
+        """0 inside the flat-prior box, -inf outside (:231-274).  A 1-D phi gives the
+        reference's Python float; a 2-D phi gives one value per row from one array compare."""
+        phi = np.asarray(phi, dtype=np.float64)
+        lows, highs = self._box()
+        n = lows.size
+        if phi.shape[-1] < n:
+            raise IndexError(f"index {phi.shape[-1]} is out of bounds for axis 0 with size {phi.shape[-1]}")
+        outside = np.any((phi[..., :n] < lows) | (phi[..., :n] > highs), axis=-1)
+        if phi.ndim == 1:
+            return -np.inf if outside else 0.0
+        return np.where(outside, -np.inf, 0.0)
 
     def engine_info(self):
         """Facts about the resident device data (mode, classes, entries, bytes) or None."""
