@@ -196,9 +196,9 @@ int mb_class_values(const mb_handle* h, int32_t param, double* out, int32_t cap)
 int mb_gathered_indices(const mb_handle* h, int64_t* rows, int64_t rows_cap, int64_t* offsets);
 
 /* Per-kernel device time (ms) of the last evaluation, measured with CUDA events when
- * profiling was enabled with mb_set_profiling(h, 1).  Order: K0 factors, K1 expand, K1b nstars,
- * K2 stars, K3 finalize. */
-#define MB_NKERNELS 5
+ * profiling was enabled with mb_set_profiling(h, 1).  Order: K0 factors + Poisson term, K1 expand
+ * (TABLE modes), (unused), K2 stars (its tail is the K3 reduction over stars). */
+#define MB_NKERNELS 4
 int mb_set_profiling(mb_handle* h, int32_t on);
 int mb_last_kernel_ms(const mb_handle* h, float ms[MB_NKERNELS]);
 

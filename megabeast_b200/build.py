@@ -15,7 +15,8 @@ DEPS = SRC + [
     os.path.join(PKG, "csrc", "mb_kernels.cuh"),
     os.path.join(PKG, "..", "include", "megabeast_b200.h"),
 ]
-LIB = os.path.join(PKG, "libmegabeast_b200.so")
+# MEGABEAST_B200_LIB points the loader at an alternative build (kernel-tuning variants)
+LIB = os.environ.get("MEGABEAST_B200_LIB") or os.path.join(PKG, "libmegabeast_b200.so")
 
 NVCC_FLAGS = [
     "-O3",
@@ -41,11 +42,13 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None):
     """Compile when missing or older than its sources; returns the library path."""
-    if not force and not is_stale():
+    out = out or LIB
+    if not force and out == LIB and not is_stale():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SRC
+    cmd = ([nvcc_path()] + NVCC_FLAGS + [f"-D{d}" for d in defines]
+           + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SRC)
     # the image's $CC/$CXX point at a gcc without the default search paths nvcc expects
     env = dict(os.environ)
     env.pop("CC", None)
@@ -56,7 +59,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libmegabeast_b200.so")
     if verbose:
         sys.stderr.write(res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

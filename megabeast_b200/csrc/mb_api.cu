@@ -64,7 +64,7 @@ struct mb_handle {
   double* d_tab[MB_NPARAM] = {nullptr, nullptr, nullptr, nullptr};
   int64_t cap_tab[MB_NPARAM] = {0, 0, 0, 0};
   double* d_F = nullptr;    // [nA+nB][128]
-  double* d_SC = nullptr;   // [nbins][2][128]
+  unsigned int* d_counter = nullptr;
   double* d_T = nullptr;  int64_t cap_T = 0;
   double* d_part = nullptr; int max_blocks = 0;
   double* d_out = nullptr;  int64_t cap_out = 0;
@@ -145,7 +145,7 @@ static size_t k2_smem_bytes(int mode, int nA, int nB, int Wpad) {
   const int kK2Warps = k2_threads(Wpad / 32) / 32;
   size_t stage = (size_t)kK2Warps * 2 * kChunk * sizeof(Entry);
   size_t tables = mode == kModeFactor ? (size_t)(nA + nB) * Wpad * sizeof(double) : 0;
-  size_t red = (size_t)kK2Warps * 2 * Wpad * sizeof(double);
+  size_t red = (size_t)kK2Warps * 2 * Wpad * sizeof(double);  // reduction scratch reuses the front
   return std::max(stage + tables, red);
 }
 
@@ -154,7 +154,7 @@ extern "C" void mb_destroy(mb_handle* h) {
   cudaSetDevice(h->device);
   void* ptrs[] = {h->d_model, h->d_clsx, h->d_entries, h->d_seg, h->d_rowcode, h->d_H, h->d_coef,
                   h->d_bin_agecls, h->d_phi, h->d_tab[0], h->d_tab[1], h->d_tab[2], h->d_tab[3],
-                  h->d_F, h->d_SC, h->d_T, h->d_part, h->d_out};
+                  h->d_F, h->d_counter, h->d_T, h->d_part, h->d_out};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -185,6 +185,7 @@ extern "C" int mb_create(const mb_grid_desc* grid, const mb_stars_desc* stars,
   h->model = *model;
   CK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, o.device));
   CK(cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, o.device));
+  h->max_smem -= 1024;  // room for the kernels' few bytes of static shared memory
   const int64_t G = grid->G;
   if (G <= 0 || G > 0xffffffffLL) return fail("grid size %lld unsupported", (long long)G);
   h->G = G;
@@ -263,7 +264,7 @@ extern "C" int mb_create(const mb_grid_desc* grid, const mb_stars_desc* stars,
       return fail("invalid mass-multiplier description");
     const int nAg = mm->n_ages, nZ = mm->n_mets;
     h->nbins = nAg * nZ;
-    if ((int64_t)h->nbins * h->nB > (1LL << 26))
+    if ((int64_t)h->nbins * h->nB > (1LL << 26) || h->nbins > 2048)
       return fail("N-stars statistics too large (%d bins x %d dust classes)", h->nbins, h->nB);
     H.assign((size_t)h->nbins * h->nB * 2, 0.0);
     std::vector<int32_t> age_first_row((size_t)nAg, -1);
@@ -277,8 +278,8 @@ extern "C" int mb_create(const mb_grid_desc* grid, const mb_stars_desc* stars,
       size_t b = (size_t)i * nZ + j;
       uint32_t cB = rowcode[(size_t)g] & kDustMask;
       double gw = grid->grid_weight[g];
-      H[(b * h->nB + cB) * 2] += gw;
-      H[(b * h->nB + cB) * 2 + 1] += gw * grid->completeness[g];
+      H[((size_t)cB * h->nbins + b) * 2] += gw;       // Ht[cB][bin]: bin minor, read coalesced by KP
+      H[((size_t)cB * h->nbins + b) * 2 + 1] += gw * grid->completeness[g];
     }
     coef.resize((size_t)h->nbins);
     bin_agecls.resize((size_t)h->nbins);
@@ -377,10 +378,18 @@ extern "C" int mb_create(const mb_grid_desc* grid, const mb_stars_desc* stars,
     if (dev_upload(h, &h->d_bin_agecls, bin_agecls)) return 1;
   }
   if (dev_alloc(h, &h->d_F, (int64_t)(h->nA + h->nB) * 128)) return 1;
-  if (dev_alloc(h, &h->d_SC, (int64_t)std::max(1, h->nbins) * 2 * 128)) return 1;
+  if (dev_alloc(h, &h->d_counter, 1)) return 1;
+  CK(cudaMemset(h->d_counter, 0, sizeof(unsigned int)));
   h->max_blocks = h->sm_count * 4;
   if (dev_alloc(h, &h->d_part, (int64_t)h->max_blocks * 2 * 128)) return 1;
 
+  {
+    const int nslice = std::max(1, kK0Threads / std::max(1, h->nbins));
+    size_t smem0 = sizeof(double) * ((size_t)(h->nA + h->nB) + (size_t)(nslice + 1) * h->nbins * 2);
+    if (smem0 > (size_t)h->max_smem)
+      return fail("K0 needs %zu bytes of shared memory (%d classes, %d bins)", smem0, h->nA + h->nB, h->nbins);
+    CK(cudaFuncSetAttribute(mb_k0_factors, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+  }
   // opt in to large dynamic shared memory for every K2 instantiation we may launch
   {
     int big = h->max_smem;
@@ -491,7 +500,7 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
   CK(cudaSetDevice(h->device));
   const int kmode = h->mode == MB_MODE_FACTOR ? kModeFactor : h->mode == MB_MODE_TABLE_UNIQUE ? kModeTable : kModeTableGrid;
   const bool prof = h->profiling != 0;
-  float acc_ms[MB_NKERNELS] = {0, 0, 0, 0, 0};
+  float acc_ms[MB_NKERNELS] = {0, 0, 0, 0};
   int launches = 0;
   for (int w0 = 0; w0 < W;) {
     int rem = W - w0;
@@ -508,11 +517,14 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     k0.model = h->d_model; k0.clsx = h->d_clsx; k0.phi = d_phi + (size_t)w0 * ndim;
     for (int p = 0; p < MB_NPARAM; ++p)
       k0.tab[p] = (d_tab && d_tab[p]) ? d_tab[p] + (size_t)w0 * h->mdev.ncls[p] : nullptr;
-    k0.FA = FA; k0.FB = FB; k0.nA = h->nA; k0.nB = h->nB; k0.W = wp; k0.Wpad = Wpad; k0.ndim = ndim;
+    k0.F = h->d_F; k0.Ht = h->d_H; k0.bin_agecls = h->d_bin_agecls; k0.coef = h->d_coef;
+    k0.n_stars = (double)h->S_total; k0.out = d_out;
+    k0.nA = h->nA; k0.nB = h->nB; k0.nbins = h->poisson ? h->nbins : 0; k0.W = wp; k0.Wpad = Wpad;
+    k0.ndim = ndim; k0.w0 = w0; k0.Wtot = W;
     {
-      int total = (h->nA + h->nB) * Wpad;
-      int blocks = std::min((total + 255) / 256, h->sm_count * 8);
-      mb_k0_factors<<<blocks, 256, 0, st>>>(k0);
+      const int nslice = std::max(1, kK0Threads / std::max(1, h->nbins));
+      size_t smem0 = sizeof(double) * ((size_t)(h->nA + h->nB) + (size_t)(nslice + 1) * h->nbins * 2);
+      mb_k0_factors<<<Wpad, kK0Threads, smem0, st>>>(k0);
       ++launches;
     }
     if (prof) CK(cudaEventRecord(h->ev[1], st));
@@ -532,10 +544,6 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
       ++launches;
     }
     if (prof) CK(cudaEventRecord(h->ev[2], st));
-    if (h->poisson) {
-      mb_k1b_binsums<<<h->nbins, kK1bThreads, 0, st>>>(h->d_H, FB, h->d_SC, h->nB, Wpad);
-      ++launches;
-    }
     if (prof) CK(cudaEventRecord(h->ev[3], st));
     size_t smem = k2_smem_bytes(kmode, h->nA, h->nB, Wpad);
     int per_sm = k2_blocks_per_sm(kmode, NW, smem);
@@ -545,21 +553,16 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     grid = std::min(grid, h->max_blocks);
     K2Args k2{};
     k2.entries = h->d_entries; k2.seg = h->d_seg; k2.nseg = h->nseg; k2.FA = FA; k2.T = h->d_T;
-    k2.part = h->d_part; k2.nA = h->nA; k2.nB = h->nB; k2.Wpad = Wpad;
+    k2.part = h->d_part; k2.counter = h->d_counter; k2.out = d_out;
+    k2.nA = h->nA; k2.nB = h->nB; k2.Wpad = Wpad; k2.W = wp; k2.w0 = w0; k2.Wtot = W;
+    k2.zero_poisson = h->poisson ? 0 : 1;
     if (kmode == kModeFactor) launch_k2<kModeFactor>(NW, grid, smem, st, k2);
     else if (kmode == kModeTable) launch_k2<kModeTable>(NW, grid, smem, st, k2);
     else launch_k2<kModeTableGrid>(NW, grid, smem, st, k2);
     ++launches;
-    if (prof) CK(cudaEventRecord(h->ev[4], st));
-    K3Args k3{};
-    k3.part = h->d_part; k3.nblocks = grid; k3.FA = FA; k3.SC = h->d_SC; k3.bin_agecls = h->d_bin_agecls;
-    k3.coef = h->d_coef; k3.nbins = h->poisson ? h->nbins : 0; k3.n_stars = (double)h->S_total;
-    k3.out = d_out; k3.W = wp; k3.Wpad = Wpad; k3.w0 = w0; k3.Wtot = W;
-    mb_k3_finalize<<<wp, kK3Threads, 0, st>>>(k3);
-    ++launches;
     if (prof) {
-      CK(cudaEventRecord(h->ev[5], st));
-      CK(cudaEventSynchronize(h->ev[5]));
+      CK(cudaEventRecord(h->ev[4], st));
+      CK(cudaEventSynchronize(h->ev[4]));
       for (int i = 0; i < MB_NKERNELS; ++i) {
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));

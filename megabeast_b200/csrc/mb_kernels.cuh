@@ -12,13 +12,13 @@
 //
 //     physmod[g,w] = FA[cA(g)][w] * FB[cB(g)][w]       FA: age (logA) factor, FB: dust factor
 //
-// K0  mb_k0_factors      per-walker factor tables FA, FB from phi            (tiny)
+// K0  mb_k0_factors      one block per walker: factor tables FA, FB from phi, then the N-stars
+//                        sufficient statistics x FB -> per-bin sums -> expected N -> Poisson term
 // K1  mb_k1_expand       TABLE modes: physmod table T[u][w] = FA*FB          (HBM write bound)
-// K1b mb_k1b_binsums     N-stars sufficient statistics x FB -> per-bin sums  (tiny)
-// K2  mb_k2_stars<..>    the hot kernel: stream (weight, code) entries once for all walkers,
+// K2  mb_k2_stars<..>    the hot kernel: stream (weight, table row) entries once for all walkers,
 //                        look the factors up (smem) or gather T rows (L2/HBM), per-star fp64
-//                        sum, log via mantissa/exponent product, block partials
-// K3  mb_k3_finalize     fixed-order reduction of block partials + Poisson term
+//                        sum, log via mantissa/exponent product; K3 is fused into its tail:
+//                        warp -> block -> last-block-done reduction over stars in fixed order
 //
 // Lanes of a warp are WALKERS, a warp walks one star's entries at a time, so every control
 // decision in K2 (run boundary, end of star) is warp-uniform.
@@ -97,37 +97,66 @@ __device__ double prior_eval(const ModelDev& m, int p, const double* __restrict_
   }
 }
 
-// ---- K0: factor tables -------------------------------------------------------------------------
-// FA[c][w] (nA x Wpad) and FB[c][w] (nB x Wpad), walker minor.  Walkers w >= W (padding up to
-// the pass width) repeat the last real walker so no lane ever sees garbage.
+// deterministic block-wide sum (shuffle tree inside a warp, fixed order across warps)
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();  // scratch may still be read from the previous call
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int i = 0; i < THREADS / 32; ++i) t += scratch[i];
+  return t;
+}
+
+// ---- K0: per-walker factor tables + the whole N-stars / Poisson term ---------------------------
+// One block per walker column (Wpad blocks; columns w >= W repeat the last real walker so no
+// lane of K2 ever sees garbage).
+//
+// Phase 1  FA[c][w] (nA rows) and FB[c][w] (nB rows): the prior models evaluated on the classes
+//          (singlepop_dust_model.py:146-148 restricted to the distinct column values).
+// Phase 2  helpers.py:133-162 needs, per (age, Z) bin, S = sum_g physmod*grid_weight and
+//          C = sum_g physmod*grid_weight*completeness over the bin's rows.  Inside a bin the age
+//          factor is constant, so with the create-time statistics Ht[cB][bin] = (sum grid_weight,
+//          sum grid_weight*completeness) over the bin's rows of dust class cB:
+//              S_bin = FA[age(bin)] * sum_cB Ht[cB][bin].x * FB[cB]      (C_bin with .y)
+// Phase 3  normalise by the grand total (:133-134), skip empty bins (:156), expected number of
+//          stars, Poisson term (singlepop_dust_model.py:182-186) -> out[POISSON][w].
 // tab[p]: host-evaluated table [W][ncls[p]] for MB_TABULATED parameters (else unused).
 struct K0Args {
   const ModelDev* model;
   const double* clsx;
-  const double* phi;      // [W][ndim], already offset to the pass's first walker
+  const double* phi;          // [W][ndim], already offset to the pass's first walker
   const double* tab[MB_NPARAM];
-  double* FA;
-  double* FB;
-  int32_t nA, nB, W, Wpad, ndim;
+  double* F;                  // [nA + nB][Wpad]: FA rows then FB rows
+  const double* Ht;           // [nB][nbins][2]   (nbins == 0: no N-stars term)
+  const int32_t* bin_agecls;  // [nbins] FA row of the bin's age
+  const double* coef;         // [nbins] metprior * massmult / avemass   (helpers.py:148-151)
+  double n_stars;             // S of the fit (:183-185)
+  double* out;                // [MB_OUT_ROWS][Wtot]; row POISSON written at column w0 + w
+  int32_t nA, nB, nbins, W, Wpad, ndim, w0, Wtot;
 };
+constexpr int kK0Threads = 1024;
 
-__global__ void __launch_bounds__(256) mb_k0_factors(K0Args a) {
+__global__ void __launch_bounds__(kK0Threads) mb_k0_factors(K0Args a) {
+  extern __shared__ double k0s[];  // [nA+nB] this walker's factors | [nslice+1][nbins][2] bin sums
+  __shared__ double scratch[kK0Threads / 32];
   const ModelDev& m = *a.model;
-  int total = (a.nA + a.nB) * a.Wpad;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    int c = i / a.Wpad, w = i - c * a.Wpad;
-    int wr = w < a.W ? w : a.W - 1;
-    const double* ph = a.phi + (size_t)wr * a.ndim;
+  const int w = blockIdx.x;
+  const int wr = w < a.W ? w : a.W - 1;
+  const double* ph = a.phi + (size_t)wr * a.ndim;
+  double* sF = k0s;
+  for (int c = threadIdx.x; c < a.nA + a.nB; c += kK0Threads) {
+    double v = 1.0;
     if (c < a.nA) {
-      double v = 1.0;
       if (m.kind[MB_P_LOGA] == MB_TABULATED)
         v = a.tab[MB_P_LOGA][(size_t)wr * m.ncls[MB_P_LOGA] + c];
       else if (m.kind[MB_P_LOGA] != MB_FIXED)
         v = prior_eval(m, MB_P_LOGA, ph + m.voff[MB_P_LOGA], a.clsx[m.clsoff[MB_P_LOGA] + c]);
-      a.FA[i] = v;
     } else {
-      int cb = c - a.nA;
-      double v = 1.0;
+      const int cb = c - a.nA;
       // same left-to-right product order as the reference's `cur_physmod *=` loop (:146-148)
 #pragma unroll
       for (int p = MB_P_AV; p < MB_NPARAM; ++p) {
@@ -138,9 +167,67 @@ __global__ void __launch_bounds__(256) mb_k0_factors(K0Args a) {
         else
           v *= prior_eval(m, p, ph + m.voff[p], a.clsx[m.clsoff[p] + digit]);
       }
-      a.FB[(size_t)cb * a.Wpad + w] = v;
     }
+    sF[c] = v;
+    a.F[(size_t)c * a.Wpad + w] = v;
   }
+  if (a.nbins == 0 || w >= a.W) return;
+  __syncthreads();
+
+  // phase 2: nslice slices of the dust classes per bin, combined in slice order
+  const int nbins = a.nbins;
+  const int nslice = kK0Threads / nbins > 0 ? kK0Threads / nbins : 1;
+  double* part = k0s + (a.nA + a.nB);            // [nslice][nbins][2]
+  double* sc = part + (size_t)nslice * nbins * 2;  // [nbins][2]
+  const double2* Ht = reinterpret_cast<const double2*>(a.Ht);
+  const double* sFB = sF + a.nA;
+  for (int item = threadIdx.x; item < nbins * nslice; item += kK0Threads) {
+    const int b = item % nbins, sl = item / nbins;
+    double s = 0.0, c = 0.0;
+    int cb = sl;
+    // batches of 8 independent L2 loads in flight, then the multiply-adds in class order
+    for (; cb + 7 * nslice < a.nB; cb += 8 * nslice) {
+      double2 h[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) h[u] = __ldg(Ht + (size_t)(cb + u * nslice) * nbins + b);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const double f = sFB[cb + u * nslice];
+        s = fma(h[u].x, f, s); c = fma(h[u].y, f, c);
+      }
+    }
+    for (; cb < a.nB; cb += nslice) {
+      double2 h0 = __ldg(Ht + (size_t)cb * nbins + b);
+      s = fma(h0.x, sFB[cb], s); c = fma(h0.y, sFB[cb], c);
+    }
+    part[((size_t)sl * nbins + b) * 2] = s;
+    part[((size_t)sl * nbins + b) * 2 + 1] = c;
+  }
+  __syncthreads();
+  double part_nrm = 0.0;
+  for (int b = threadIdx.x; b < nbins; b += kK0Threads) {
+    double S = 0.0, C = 0.0;
+    for (int sl = 0; sl < nslice; ++sl) {
+      S += part[((size_t)sl * nbins + b) * 2];
+      C += part[((size_t)sl * nbins + b) * 2 + 1];
+    }
+    const double fa = sF[a.bin_agecls[b]];
+    S *= fa; C *= fa;
+    sc[2 * b] = S; sc[2 * b + 1] = C;
+    part_nrm += S;
+  }
+  // phase 3.  helpers.py:133-134: weights are normalised by their grand total before the bin sums
+  const double nrm = block_sum<kK0Threads>(part_nrm, scratch);
+  double part_pred = 0.0;
+  for (int b = threadIdx.x; b < nbins; b += kK0Threads) {
+    const double sb = sc[2 * b] / nrm;
+    if (sb > 0.0)  // helpers.py:156 (false for NaN: 0/0 when every weight is zero)
+      part_pred += (sF[a.bin_agecls[b]] * a.coef[b]) * (sc[2 * b + 1] / nrm) / sb;
+  }
+  const double pred = block_sum<kK0Threads>(part_pred, scratch);
+  if (threadIdx.x == 0)
+    a.out[(size_t)MB_OUT_POISSON * a.Wtot + a.w0 + w] =
+        a.n_stars * log(pred) - pred - lgamma(a.n_stars + 1.0);  // :182-186
 }
 
 // ---- K1: materialise the prior-weight table (TABLE modes) -------------------------------------
@@ -172,46 +259,6 @@ __global__ void __launch_bounds__(256) mb_k1_expand(const double* __restrict__ F
     double2 fb = __ldg(reinterpret_cast<const double2*>(FB + (size_t)cB * Wpad + w2));
     double2 t = make_double2(fa.x * fb.x, fa.y * fb.y);
     __stcs(reinterpret_cast<double2*>(T + (size_t)u * Wpad + w2), t);
-  }
-}
-
-// ---- K1b: per-(age,Z)-bin sums for the N-stars term --------------------------------------------
-// helpers.py:133-162 needs, per bin, S = sum_g physmod*grid_weight and C = sum_g
-// physmod*grid_weight*completeness.  Inside a bin the age factor is constant, so with the
-// create-time statistics H[bin][cB] = (sum grid_weight, sum grid_weight*completeness) over the
-// bin's rows of dust class cB:   S = FA * sum_cB H0*FB,  C = FA * sum_cB H1*FB.
-// SC[bin][0/1][w] holds the two dust sums (FA applied in K3).
-// One block per bin; 256 threads = (256 / Wpad) slices of the dust classes x Wpad walkers.
-constexpr int kK1bThreads = 256;
-__global__ void __launch_bounds__(kK1bThreads) mb_k1b_binsums(const double* __restrict__ H,
-                                                              const double* __restrict__ FB,
-                                                              double* __restrict__ SC, int nB, int Wpad) {
-  __shared__ double red[2][kK1bThreads];
-  const int b = blockIdx.x;
-  const int nslice = kK1bThreads / Wpad;
-  const int w = threadIdx.x % Wpad, slice = threadIdx.x / Wpad;
-  const double2* Hb = reinterpret_cast<const double2*>(H) + (size_t)b * nB;
-  double s0 = 0.0, c0 = 0.0, s1 = 0.0, c1 = 0.0;
-  int cb = slice;
-  for (; cb + nslice < nB; cb += 2 * nslice) {  // two independent chains per thread
-    double2 h0 = __ldg(Hb + cb), h1 = __ldg(Hb + cb + nslice);
-    double f0 = __ldg(FB + (size_t)cb * Wpad + w), f1 = __ldg(FB + (size_t)(cb + nslice) * Wpad + w);
-    s0 = fma(h0.x, f0, s0); c0 = fma(h0.y, f0, c0);
-    s1 = fma(h1.x, f1, s1); c1 = fma(h1.y, f1, c1);
-  }
-  if (cb < nB) {
-    double2 h0 = __ldg(Hb + cb);
-    double f0 = __ldg(FB + (size_t)cb * Wpad + w);
-    s0 = fma(h0.x, f0, s0); c0 = fma(h0.y, f0, c0);
-  }
-  red[0][threadIdx.x] = s0 + s1;
-  red[1][threadIdx.x] = c0 + c1;
-  __syncthreads();
-  if (threadIdx.x < 2 * Wpad) {
-    const int which = threadIdx.x / Wpad, ww = threadIdx.x % Wpad;
-    double acc = 0.0;
-    for (int sl = 0; sl < nslice; ++sl) acc += red[which][sl * Wpad + ww];  // fixed order
-    SC[((size_t)b * 2 + which) * Wpad + ww] = acc;
   }
 }
 
@@ -269,14 +316,24 @@ struct K2Args {
   int32_t nseg;
   const double* FA;     // FACTOR: [nA][Wpad] then [nB][Wpad], contiguous (staged to smem)
   const double* T;      // TABLE*: [U][Wpad]
-  double* part;         // [gridDim.x][2][Wpad]
-  int32_t nA, nB, Wpad;
+  double* part;         // [gridDim.x][2][Wpad] block partials
+  unsigned int* counter;// blocks done (zero between launches)
+  double* out;          // [MB_OUT_ROWS][Wtot]; rows STARSUM, NONFINITE (and POISSON = 0 when
+                        // there is no N-stars term) written at columns w0 .. w0+W-1
+  int32_t nA, nB, Wpad, W, w0, Wtot, zero_poisson;
 };
 
-// block shape: 256 threads x 3 blocks/SM (<= 85 registers) for up to 64 walkers per pass,
-// 512 threads x 1 block/SM (<= 128 registers, one copy of the 128-walker tables) above
-__host__ __device__ constexpr int k2_threads(int NW) { return NW <= 2 ? 256 : 512; }
-__host__ __device__ constexpr int k2_min_blocks(int NW) { return NW <= 2 ? 3 : 1; }
+// block shape: ONE block per SM -- 768 threads (<= 85 registers) for up to 64 walkers per pass,
+// 512 threads (<= 128 registers) for 128; one copy of the factor tables per SM and only
+// #SM block partials for the final reduction
+#ifndef MB_K2_THREADS_LO
+#define MB_K2_THREADS_LO 768
+#endif
+#ifndef MB_K2_UNROLL
+#define MB_K2_UNROLL 4
+#endif
+__host__ __device__ constexpr int k2_threads(int NW) { return NW <= 2 ? MB_K2_THREADS_LO : 512; }
+__host__ __device__ constexpr int k2_min_blocks(int NW) { return 1; }
 constexpr int kChunk = 32;  // entries staged per warp per step
 
 __device__ __forceinline__ void cp_async16(uint32_t smem, const void* gmem) {
@@ -401,15 +458,16 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
       const uint32_t cur = stage + buf * kChunk * 16u;
       const int n = (int)min((int64_t)kChunk, end - pos);
       int j = 0;
-      for (; j + 4 <= n; j += 4) {
-        uint4 e[4];
-        double f[4][NW];
+      constexpr int UN = MB_K2_UNROLL;
+      for (; j + UN <= n; j += UN) {
+        uint4 e[UN];
+        double f[UN][NW];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) e[u] = lds_entry(cur + (j + u) * 16u);
+        for (int u = 0; u < UN; ++u) e[u] = lds_entry(cur + (j + u) * 16u);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) load_factors(e[u].z, f[u]);
+        for (int u = 0; u < UN; ++u) load_factors(e[u].z, f[u]);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < UN; ++u) {
           if (e[u].w & kNewRun) boundary(e[u].w);  // warp-uniform
           const double av = __hiloint2double(e[u].y, e[u].x);
 #pragma unroll
@@ -438,7 +496,9 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     }
   }
 
-  // block reduction: fixed warp order -> bitwise reproducible for a given launch shape
+  // ---- K3 (fused): block-then-grid reduction over stars, fixed order -> bitwise reproducible ---
+  // for a given launch shape.  Warps -> block partial -> the last block to finish adds the
+  // block partials in block order and writes the result rows.
   __syncthreads();
   double* red = reinterpret_cast<double*>(smem_raw);  // [warps][2][Wpad], reuses stage/tables
 #pragma unroll
@@ -453,71 +513,40 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     for (int wp = 0; wp < kK2Warps; ++wp) s += red[(size_t)wp * 2 * Wpad + i];
     a.part[(size_t)blockIdx.x * 2 * Wpad + i] = s;
   }
-}
-
-// ---- K3: finalize -----------------------------------------------------------------------------
-struct K3Args {
-  const double* part;   // [nblocks][2][Wpad]
-  int32_t nblocks;
-  const double* FA;     // [nA][Wpad]
-  const double* SC;     // [nbins][2][Wpad]
-  const int32_t* bin_agecls;  // [nbins] age class of the bin's age
-  const double* coef;   // [nbins] metprior * massmult / avemass   (helpers.py:148-151)
-  int32_t nbins;        // 0 -> no Poisson term
-  double n_stars;       // S of the fit (:183-185)
-  double* out;          // [MB_OUT_ROWS][Wtot], written at column w0 + w
-  int32_t W, Wpad, w0, Wtot;
-};
-
-constexpr int kK3Threads = 128;
-// deterministic block-wide sum (shuffle tree inside a warp, fixed order across warps)
-__device__ __forceinline__ double block_sum(double v, double* scratch) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();  // scratch may still be read from the previous call
-  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __shared__ unsigned int ticket;
+  __threadfence();
   __syncthreads();
-  double t = 0.0;
-#pragma unroll
-  for (int i = 0; i < kK3Threads / 32; ++i) t += scratch[i];
-  return t;
-}
-
-// one block per walker: block partials -> star sum; per-bin sums -> expected N -> Poisson term
-__global__ void __launch_bounds__(kK3Threads) mb_k3_finalize(K3Args a) {
-  __shared__ double scratch[kK3Threads / 32];
-  const int w = blockIdx.x;
-  double s = 0.0, bad = 0.0;
-  for (int b = threadIdx.x; b < a.nblocks; b += kK3Threads) {
-    s += a.part[((size_t)b * 2 + 0) * a.Wpad + w];
-    bad += a.part[((size_t)b * 2 + 1) * a.Wpad + w];
-  }
-  const double sum = block_sum(s, scratch);
-  const double nbad = block_sum(bad, scratch);
-  double pois = 0.0;
-  if (a.nbins > 0) {
-    // helpers.py:133-134: weights are normalised by their grand total before the bin sums
-    double part_nrm = 0.0;
-    for (int b = threadIdx.x; b < a.nbins; b += kK3Threads)
-      part_nrm += a.FA[(size_t)a.bin_agecls[b] * a.Wpad + w] * a.SC[((size_t)b * 2) * a.Wpad + w];
-    const double nrm = block_sum(part_nrm, scratch);
-    double part_pred = 0.0;
-    for (int b = threadIdx.x; b < a.nbins; b += kK3Threads) {
-      double fa = a.FA[(size_t)a.bin_agecls[b] * a.Wpad + w];
-      double sb = fa * a.SC[((size_t)b * 2) * a.Wpad + w] / nrm;
-      if (sb > 0.0) {  // helpers.py:156 (false for NaN: 0/0 when every weight is zero)
-        double cb = fa * a.SC[((size_t)b * 2 + 1) * a.Wpad + w] / nrm;
-        part_pred += (fa * a.coef[b]) * cb / sb;
-      }
+  if (threadIdx.x == 0) ticket = atomicAdd(a.counter, 1u);
+  __syncthreads();
+  if (ticket != gridDim.x - 1) return;
+  __threadfence();
+  // last block: thread (g, i) adds blocks g, g+G, ... for output i; groups combined in order
+  const int nout = 2 * Wpad, G = k2_threads(NW) / nout;  // >= 2 groups (768/256, 512/256, ...)
+  const int i = threadIdx.x % nout, g = threadIdx.x / nout;
+  double s = 0.0;
+  if (g < G) {
+    const int nb = (int)gridDim.x;
+    int b = g;
+    for (; b + 3 * G < nb; b += 4 * G) {  // four loads in flight, added in block order
+      double v0 = __ldcg(a.part + (size_t)b * nout + i), v1 = __ldcg(a.part + (size_t)(b + G) * nout + i);
+      double v2 = __ldcg(a.part + (size_t)(b + 2 * G) * nout + i), v3 = __ldcg(a.part + (size_t)(b + 3 * G) * nout + i);
+      s += v0; s += v1; s += v2; s += v3;
     }
-    const double pred = block_sum(part_pred, scratch);
-    pois = a.n_stars * log(pred) - pred - lgamma(a.n_stars + 1.0);  // :182-186
+    for (; b < nb; b += G) s += __ldcg(a.part + (size_t)b * nout + i);
   }
-  if (threadIdx.x == 0) {
-    a.out[(size_t)MB_OUT_STARSUM * a.Wtot + a.w0 + w] = sum;
-    a.out[(size_t)MB_OUT_POISSON * a.Wtot + a.w0 + w] = pois;
-    a.out[(size_t)MB_OUT_NONFINITE * a.Wtot + a.w0 + w] = nbad;
+  __syncthreads();
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x < nout) {
+    double t = 0.0;
+    for (int gg = 0; gg < G; ++gg) t += red[gg * nout + threadIdx.x];
+    const int row = threadIdx.x / Wpad, w = threadIdx.x % Wpad;  // row 0 = STARSUM, 1 = NONFINITE
+    if (w < a.W) {
+      a.out[(size_t)row * a.Wtot + a.w0 + w] = t;
+      if (row == 0 && a.zero_poisson) a.out[(size_t)MB_OUT_POISSON * a.Wtot + a.w0 + w] = 0.0;
+    }
   }
+  if (threadIdx.x == 0) *a.counter = 0u;
 }
 
 // ---- one-time ingest: helpers.py:33-41 ---------------------------------------------------------
