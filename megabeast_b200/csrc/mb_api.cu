@@ -65,8 +65,9 @@ struct mb_handle {
   int64_t cap_tab[MB_NPARAM] = {0, 0, 0, 0};
   double* d_F = nullptr;    // [nA+nB][128]
   unsigned int* d_counter = nullptr;
+  unsigned long long* d_gacc = nullptr;
   double* d_T = nullptr;  int64_t cap_T = 0;
-  double* d_part = nullptr; int max_blocks = 0;
+  int max_blocks = 0;
   double* d_out = nullptr;  int64_t cap_out = 0;
   double* h_pin = nullptr;  int64_t cap_pin = 0;
   cudaStream_t stream = nullptr;
@@ -145,8 +146,7 @@ static size_t k2_smem_bytes(int mode, int nA, int nB, int Wpad) {
   const int kK2Warps = k2_threads(Wpad / 32) / 32;
   size_t stage = (size_t)kK2Warps * 2 * kChunk * sizeof(Entry);
   size_t tables = mode == kModeFactor ? (size_t)(nA + nB) * Wpad * sizeof(double) : 0;
-  size_t red = (size_t)kK2Warps * 2 * Wpad * sizeof(double);  // reduction scratch reuses the front
-  return std::max(stage + tables, red);
+  return stage + tables;  // the reduction scratch (3 x Wpad words) reuses the front of the stage
 }
 
 extern "C" void mb_destroy(mb_handle* h) {
@@ -154,7 +154,7 @@ extern "C" void mb_destroy(mb_handle* h) {
   cudaSetDevice(h->device);
   void* ptrs[] = {h->d_model, h->d_clsx, h->d_entries, h->d_seg, h->d_rowcode, h->d_H, h->d_coef,
                   h->d_bin_agecls, h->d_phi, h->d_tab[0], h->d_tab[1], h->d_tab[2], h->d_tab[3],
-                  h->d_F, h->d_counter, h->d_T, h->d_part, h->d_out};
+                  h->d_F, h->d_counter, h->d_gacc, h->d_T, h->d_out};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -378,10 +378,11 @@ extern "C" int mb_create(const mb_grid_desc* grid, const mb_stars_desc* stars,
     if (dev_upload(h, &h->d_bin_agecls, bin_agecls)) return 1;
   }
   if (dev_alloc(h, &h->d_F, (int64_t)(h->nA + h->nB) * 128)) return 1;
-  if (dev_alloc(h, &h->d_counter, 1)) return 1;
-  CK(cudaMemset(h->d_counter, 0, sizeof(unsigned int)));
+  if (dev_alloc(h, &h->d_counter, kCtrWords)) return 1;
+  CK(cudaMemset(h->d_counter, 0, sizeof(unsigned int) * kCtrWords));
+  if (dev_alloc(h, &h->d_gacc, 3 * 128)) return 1;
+  CK(cudaMemset(h->d_gacc, 0, sizeof(unsigned long long) * 3 * 128));
   h->max_blocks = h->sm_count * 4;
-  if (dev_alloc(h, &h->d_part, (int64_t)h->max_blocks * 2 * 128)) return 1;
 
   {
     const int nslice = std::max(1, kK0Threads / std::max(1, h->nbins));
@@ -553,7 +554,7 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     grid = std::min(grid, h->max_blocks);
     K2Args k2{};
     k2.entries = h->d_entries; k2.seg = h->d_seg; k2.nseg = h->nseg; k2.FA = FA; k2.T = h->d_T;
-    k2.part = h->d_part; k2.counter = h->d_counter; k2.out = d_out;
+    k2.gacc = h->d_gacc; k2.counters = h->d_counter; k2.out = d_out;
     k2.nA = h->nA; k2.nB = h->nB; k2.Wpad = Wpad; k2.W = wp; k2.w0 = w0; k2.Wtot = W;
     k2.zero_poisson = h->poisson ? 0 : 1;
     if (kmode == kModeFactor) launch_k2<kModeFactor>(NW, grid, smem, st, k2);

@@ -18,7 +18,7 @@
 // K2  mb_k2_stars<..>    the hot kernel: stream (weight, table row) entries once for all walkers,
 //                        look the factors up (smem) or gather T rows (L2/HBM), per-star fp64
 //                        sum, log via mantissa/exponent product; K3 is fused into its tail:
-//                        warp -> block -> last-block-done reduction over stars in fixed order
+//                        warp -> block -> grid reduction over stars in 64-bit fixed point
 //
 // Lanes of a warp are WALKERS, a warp walks one star's entries at a time, so every control
 // decision in K2 (run boundary, end of star) is warp-uniform.
@@ -281,12 +281,20 @@ struct LogAcc {
     }
     n = 0;
   }
-  __device__ __forceinline__ double value() {
+  // ln of the product so far; the product restarts, the bad / nan flags persist
+  __device__ __forceinline__ double take_value() {
     renorm();
     double v = log(P) + (double)E * 0.693147180559945309417232121458;
-    return isnan ? nan("") : v;
+    P = 1.0; E = 0; n = 0;
+    return v;
   }
 };
+// Segment log-sums are accumulated as 64-bit fixed point (2^-32 resolution, range +-2.1e9):
+// integer addition is exact, so the total is independent of the order in which warps, blocks
+// and GPUs contribute -- bitwise reproducible under dynamic scheduling.  Rounding is 1.2e-10
+// absolute per segment, ~1e-8 over the ~1e4 segments of a 100k-star shard whose total is ~1e6.
+constexpr double kFixScale = 4294967296.0;
+enum { kCtrSegment = 0, kCtrBlocks = 1, kCtrWords = 2 };
 
 // end of a star: fold its integrated probability L into the walker's accumulator.  Kept out of
 // line: it runs once per star (~1/K of the entries) and would otherwise be inlined at every
@@ -316,8 +324,8 @@ struct K2Args {
   int32_t nseg;
   const double* FA;     // FACTOR: [nA][Wpad] then [nB][Wpad], contiguous (staged to smem)
   const double* T;      // TABLE*: [U][Wpad]
-  double* part;         // [gridDim.x][2][Wpad] block partials
-  unsigned int* counter;// blocks done (zero between launches)
+  unsigned long long* gacc;  // [3][Wpad] fixed-point log-sum, non-finite stars, nan flags (zero between launches)
+  unsigned int* counters;    // [kCtrWords] next segment, blocks done (zero between launches)
   double* out;          // [MB_OUT_ROWS][Wtot]; rows STARSUM, NONFINITE (and POISSON = 0 when
                         // there is no N-stars term) written at columns w0 .. w0+W-1
   int32_t nA, nB, Wpad, W, w0, Wtot, zero_poisson;
@@ -442,8 +450,17 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     }
   };
 
-  const int gw = blockIdx.x * kK2Warps + warp, nwarps = gridDim.x * kK2Warps;
-  for (int s = gw; s < a.nseg; s += nwarps) {
+  // Segments are claimed dynamically (one atomic per segment, issued a segment ahead): SMs that
+  // run faster take more.  The result does not depend on who processed what: each segment's
+  // value depends only on its own entries, and segment values are added as 64-bit fixed point.
+  long long fix[NW];
+#pragma unroll
+  for (int i = 0; i < NW; ++i) fix[i] = 0;
+  int s = 0, s_next = 0;
+  if (lane == 0) s = (int)atomicAdd(a.counters + kCtrSegment, 1u);
+  s = __shfl_sync(0xffffffffu, s, 0);
+  while (s < a.nseg) {
+    if (lane == 0) s_next = (int)atomicAdd(a.counters + kCtrSegment, 1u);
     int64_t pos = a.seg[s];
     const int64_t end = a.seg[s + 1];
     int buf = 0;
@@ -488,65 +505,50 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
       pos = nxt;
     }
     cp_async_wait<0>();
-    // a segment ends on a star boundary: close the last star
+    // a segment ends on a star boundary: close the last star, bank the segment's log-sum
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
       acc[i] = star_done(acc[i], fma(fa[i], run[i], star[i]));
       star[i] = 0.0; run[i] = 0.0;
+      fix[i] += __double2ll_rn(acc[i].take_value() * kFixScale);
     }
+    s = __shfl_sync(0xffffffffu, s_next, 0);
   }
 
-  // ---- K3 (fused): block-then-grid reduction over stars, fixed order -> bitwise reproducible ---
-  // for a given launch shape.  Warps -> block partial -> the last block to finish adds the
-  // block partials in block order and writes the result rows.
+  // ---- K3 (fused): warp -> block (shared atomics) -> grid (global atomics) reduction over stars,
+  // all in integers; the last block to finish converts and writes the result rows.
   __syncthreads();
-  double* red = reinterpret_cast<double*>(smem_raw);  // [warps][2][Wpad], reuses stage/tables
+  unsigned long long* sacc = reinterpret_cast<unsigned long long*>(smem_raw);  // [3][Wpad], reuses stage
+  for (int i = threadIdx.x; i < 3 * Wpad; i += blockDim.x) sacc[i] = 0ull;
+  __syncthreads();
 #pragma unroll
   for (int i = 0; i < NW; ++i) {
     int w = (NW == 1) ? lane : 64 * (i >> 1) + 2 * lane + (i & 1);
-    red[((size_t)warp * 2 + 0) * Wpad + w] = acc[i].value();
-    red[((size_t)warp * 2 + 1) * Wpad + w] = (double)acc[i].bad;
+    atomicAdd(sacc + w, (unsigned long long)fix[i]);
+    if (acc[i].bad) atomicAdd(sacc + Wpad + w, (unsigned long long)acc[i].bad);
+    if (acc[i].isnan) atomicAdd(sacc + 2 * Wpad + w, 1ull);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * Wpad; i += blockDim.x) {
-    double s = 0.0;
-    for (int wp = 0; wp < kK2Warps; ++wp) s += red[(size_t)wp * 2 * Wpad + i];
-    a.part[(size_t)blockIdx.x * 2 * Wpad + i] = s;
-  }
+  for (int i = threadIdx.x; i < 3 * Wpad; i += blockDim.x)
+    if (sacc[i] != 0ull) atomicAdd(a.gacc + i, sacc[i]);
   __shared__ unsigned int ticket;
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) ticket = atomicAdd(a.counter, 1u);
+  if (threadIdx.x == 0) ticket = atomicAdd(a.counters + kCtrBlocks, 1u);
   __syncthreads();
   if (ticket != gridDim.x - 1) return;
   __threadfence();
-  // last block: thread (g, i) adds blocks g, g+G, ... for output i; groups combined in order
-  const int nout = 2 * Wpad, G = k2_threads(NW) / nout;  // >= 2 groups (768/256, 512/256, ...)
-  const int i = threadIdx.x % nout, g = threadIdx.x / nout;
-  double s = 0.0;
-  if (g < G) {
-    const int nb = (int)gridDim.x;
-    int b = g;
-    for (; b + 3 * G < nb; b += 4 * G) {  // four loads in flight, added in block order
-      double v0 = __ldcg(a.part + (size_t)b * nout + i), v1 = __ldcg(a.part + (size_t)(b + G) * nout + i);
-      double v2 = __ldcg(a.part + (size_t)(b + 2 * G) * nout + i), v3 = __ldcg(a.part + (size_t)(b + 3 * G) * nout + i);
-      s += v0; s += v1; s += v2; s += v3;
-    }
-    for (; b < nb; b += G) s += __ldcg(a.part + (size_t)b * nout + i);
-  }
-  __syncthreads();
-  red[threadIdx.x] = s;
-  __syncthreads();
-  if (threadIdx.x < nout) {
-    double t = 0.0;
-    for (int gg = 0; gg < G; ++gg) t += red[gg * nout + threadIdx.x];
-    const int row = threadIdx.x / Wpad, w = threadIdx.x % Wpad;  // row 0 = STARSUM, 1 = NONFINITE
+  for (int w = threadIdx.x; w < Wpad; w += blockDim.x) {
+    const long long f = (long long)__ldcg(a.gacc + w);
+    const unsigned long long nbad = __ldcg(a.gacc + Wpad + w), nnan = __ldcg(a.gacc + 2 * Wpad + w);
+    a.gacc[w] = 0ull; a.gacc[Wpad + w] = 0ull; a.gacc[2 * Wpad + w] = 0ull;
     if (w < a.W) {
-      a.out[(size_t)row * a.Wtot + a.w0 + w] = t;
-      if (row == 0 && a.zero_poisson) a.out[(size_t)MB_OUT_POISSON * a.Wtot + a.w0 + w] = 0.0;
+      a.out[(size_t)MB_OUT_STARSUM * a.Wtot + a.w0 + w] = nnan ? nan("") : (double)f / kFixScale;
+      a.out[(size_t)MB_OUT_NONFINITE * a.Wtot + a.w0 + w] = (double)nbad;
+      if (a.zero_poisson) a.out[(size_t)MB_OUT_POISSON * a.Wtot + a.w0 + w] = 0.0;
     }
   }
-  if (threadIdx.x == 0) *a.counter = 0u;
+  if (threadIdx.x == 0) { a.counters[kCtrSegment] = 0u; a.counters[kCtrBlocks] = 0u; }
 }
 
 // ---- one-time ingest: helpers.py:33-41 ---------------------------------------------------------
