@@ -138,9 +138,10 @@ SIGNATURES = {
     ),
     "mb_destroy": (None, [ctypes.c_void_p]),
     "mb_get_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(Info)]),
+    # hot call: raw addresses (ints) instead of typed pointers keeps the per-call ctypes cost low
     "mb_lnlike": (
         ctypes.c_int,
-        [ctypes.c_void_p, c_double_p, ctypes.c_int32, ctypes.c_int32, c_double_p, c_int32_p],
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p],
     ),
     "mb_lnlike_tabulated": (
         ctypes.c_int,

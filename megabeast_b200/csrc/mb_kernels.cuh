@@ -456,11 +456,12 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   long long fix[NW];
 #pragma unroll
   for (int i = 0; i < NW; ++i) fix[i] = 0;
-  int s = 0, s_next = 0;
-  if (lane == 0) s = (int)atomicAdd(a.counters + kCtrSegment, 1u);
-  s = __shfl_sync(0xffffffffu, s, 0);
+  // every warp's first segment is its own index (no atomic storm at kernel start); later ones
+  // come from the shared counter, offset by the number of warps
+  const int nwarps_total = (int)gridDim.x * kK2Warps;
+  int s = (int)blockIdx.x * kK2Warps + warp, s_next = 0;
   while (s < a.nseg) {
-    if (lane == 0) s_next = (int)atomicAdd(a.counters + kCtrSegment, 1u);
+    if (lane == 0) s_next = nwarps_total + (int)atomicAdd(a.counters + kCtrSegment, 1u);
     int64_t pos = a.seg[s];
     const int64_t end = a.seg[s + 1];
     int buf = 0;

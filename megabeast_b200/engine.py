@@ -74,6 +74,8 @@ class LikelihoodEngine:
                  mode="auto", star_range=None, n_stars_total=None, keep_indices=False,
                  merge_duplicates=True):
         self.lib = _cabi.load()
+        self._mb_lnlike = self.lib.mb_lnlike
+        self._bufs = {}
         self.spec = spec
         self.handles = []
         self.devices = list(devices) if devices is not None else [0]
@@ -241,18 +243,19 @@ class LikelihoodEngine:
         return out, status
 
     def lnlike(self, phis, tabs=None):
-        """(lnlike[W], status[W]) for a batch of walkers."""
+        """(lnlike[W], status[W]) for a batch of walkers.  The returned arrays are reused by the
+        next call with the same W (copy them to keep them)."""
         if len(self.handles) == 1 and not self.spec.tabulated:
-            phis = np.ascontiguousarray(phis, dtype=np.float64)
+            if not (phis.dtype == np.float64 and phis.flags.c_contiguous):
+                phis = np.ascontiguousarray(phis, dtype=np.float64)
             W, ndim = phis.shape
-            out = np.empty(W)
-            status = np.empty(W, dtype=np.int32)
-            _cabi.check(
-                self.lib.mb_lnlike(
-                    self.handles[0], _cabi.dptr(phis), W, ndim, _cabi.dptr(out),
-                    status.ctypes.data_as(_cabi.c_int32_p),
-                )
-            )
+            buf = self._bufs.get(W)
+            if buf is None:
+                out, status = np.empty(W), np.empty(W, dtype=np.int32)
+                buf = self._bufs[W] = (out, status, out.ctypes.data, status.ctypes.data)
+            out, status, p_out, p_status = buf
+            if self._mb_lnlike(self.handles[0], phis.ctypes.data, W, ndim, p_out, p_status):
+                _cabi.check(1)
             return out, status
         return self.combine(self.lnlike_rows(phis, tabs))
 

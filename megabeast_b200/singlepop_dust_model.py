@@ -86,6 +86,9 @@ class MB_Model:
         self.devices = devices
         self.mode = mode
         self._engines = {}  # identity of the data dictionaries -> (engine, strong refs)
+        # the model structure (which priors are free, their boxes) is fixed at construction
+        self._layout_cache = None
+        self._box_cache = None
 
     # ------------------------------------------------------------------------------------------
     def start_params(self):
@@ -111,6 +114,8 @@ class MB_Model:
 
     def _layout(self):
         """[(param, varname, first column in phi, count)] in the reference's order (:133-143)."""
+        if self._layout_cache is not None:
+            return self._layout_cache
         out, k = [], 0
         for p in self._free():
             mod = self.physics_model[p]
@@ -119,6 +124,7 @@ class MB_Model:
                 # a vector variable is always written to ["values"] (:139 hard-codes the key)
                 out.append((p, "values" if n > 1 else vname, k, n))
                 k += n
+        self._layout_cache = (out, k)
         return out, k
 
     def _store_phi(self, phi):
@@ -185,6 +191,8 @@ class MB_Model:
             raise
         for old in list(self._engines.values()):  # one resident data set at a time
             old[0].close()
+        if self._identity_perm(perm, ndim):
+            perm = None  # device order == reference order (the usual case): no column shuffle
         self._engines = {key: (engine, (spec, perm, ndim), (star_lnpgriddata, beast_moddata))}
         return engine, (spec, perm, ndim)
 
@@ -217,16 +225,24 @@ class MB_Model:
             raise IndexError(f"index {phis.shape[1]} is out of bounds for axis 0 with size {phis.shape[1]}")
         tabs = self._tables(engine, spec, phis) if spec.tabulated else None
         self._store_phi(phis[-1])
-        vals, status = engine.lnlike(phis[:, perm], tabs)
-        if np.any(status & _cabi.STATUS_NONFINITE_STAR):
-            raise ValueError(_NONFINITE_MSG)
-        if np.any(status & _cabi.STATUS_TOTAL_ZERO):
+        if perm is None and phis.shape[1] != ndim:
+            phis = phis[:, :ndim]
+        vals, status = engine.lnlike(phis if perm is None else phis[:, perm], tabs)
+        if status.any():
+            if np.any(status & _cabi.STATUS_NONFINITE_STAR):
+                raise ValueError(_NONFINITE_MSG)
             print(0.0)
             raise SystemExit
-        return vals[0] if single else vals
+        return vals[0] if single else vals.copy()
+
+    @staticmethod
+    def _identity_perm(perm, ndim):
+        return perm.size == ndim and np.array_equal(perm, np.arange(ndim))
 
     def _box(self):
         """(low[ndim], high[ndim]) of the flat priors, indexed exactly as :255-271 index them."""
+        if self._box_cache is not None:
+            return self._box_cache
         lows, highs = [], []
         for cparam, mod in self.physics_model.items():
             cprior = mod["prior"]
@@ -243,7 +259,8 @@ class MB_Model:
                 else:
                     lows.append(cprior["minmax"][i][0])
                     highs.append(cprior["minmax"][i][1])
-        return np.asarray(lows, dtype=np.float64), np.asarray(highs, dtype=np.float64)
+        self._box_cache = (np.asarray(lows, dtype=np.float64), np.asarray(highs, dtype=np.float64))
+        return self._box_cache
 
     def lnprior(self, phi):
         """0 inside the flat-prior box, -inf outside (:231-274).  A 1-D phi gives the

@@ -50,6 +50,8 @@ def one(lib, workload, index_mode):
     d_phi = torch.from_numpy(np.ascontiguousarray(phis[:, sh.perm])).to(dev)
     d_rows = torch.empty((3, len(phis)), dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    if os.environ.get("MB_NO_FLUSH"):
+        flush = torch.empty(16, dtype=torch.uint8, device=dev)
     for _ in range(5):
         flush.zero_()
         sh.lnlike_device(d_phi, d_rows)

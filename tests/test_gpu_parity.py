@@ -158,3 +158,37 @@ def test_two_devices_or_two_shards_sum_to_whole():
     devs = [0, 1] if torch.cuda.device_count() > 1 else [0, 0]
     model = MB_Model(copy.deepcopy(settings), devices=devs)
     assert_close(lnprob(phis, model, stars, moddata), expect, RTOL)
+
+
+def test_config1_drivers_scipy_and_ensemble_sampler():
+    """BASELINE config 1: the reference's two drivers (scipy minimize on -lnprob, pattern at
+    singlepop_dust_model.py:348-362; the ensemble sampler of fit_ensemble :364-383) run unchanged
+    on the GPU lnprob and follow the same trajectory as on the oracle."""
+    from scipy.optimize import minimize
+
+    from megabeast_b200 import fit_ensemble
+    from megabeast_b200.sampler import StretchMoveSampler
+
+    settings, moddata, stars, _ = synth.make_problem("cfg1")
+    model = MB_Model(copy.deepcopy(settings))
+    pm = port.PortModel(copy.deepcopy(settings))
+    x0 = np.asarray(model.start_params()[1], dtype=float)
+
+    r_gpu = minimize(lambda p: -lnprob(p, model, stars, moddata), x0, method="Nelder-Mead",
+                     options={"maxfev": 50, "xatol": 1e-12, "fatol": 1e-12})
+    r_cpu = minimize(lambda p: -port.lnprob(p, pm, stars, moddata, loop=False), x0, method="Nelder-Mead",
+                     options={"maxfev": 50, "xatol": 1e-12, "fatol": 1e-12})
+    assert r_gpu.nfev == r_cpu.nfev
+    assert np.allclose(r_gpu.x, r_cpu.x, rtol=1e-9, atol=0)
+    assert abs(r_gpu.fun - r_cpu.fun) <= 1e-9 * abs(r_cpu.fun)
+
+    model2 = MB_Model(copy.deepcopy(settings))
+    best = fit_ensemble(model2, stars, moddata, nsteps=6, seed=5)
+    ndim = len(x0)
+    rng = np.random.default_rng(5)
+    pos = x0 * (1.0 + 1e-1 * rng.standard_normal((5 * ndim, ndim)))
+    ref = StretchMoveSampler(5 * ndim, ndim, lambda p: c_oracle.lnprob_batch(pm, p, stars, moddata), seed=5)
+    ref.run_mcmc(pos, 6)
+    k, t = np.unravel_index(np.nanargmax(ref.lnprobability), ref.lnprobability.shape)
+    assert np.allclose(best, ref.chain[k, t], rtol=1e-9, atol=0)
+    assert np.isfinite(lnprob(best, model2, stars, moddata))
