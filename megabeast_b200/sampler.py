@@ -16,8 +16,8 @@ __all__ = ["StretchMoveSampler"]
 
 class StretchMoveSampler:
     def __init__(self, nwalkers, ndim, log_prob_fn, args=(), kwargs=None, a=2.0, seed=None):
-        if nwalkers < 2 * ndim or nwalkers % 2:
-            raise ValueError("need an even number of walkers, at least 2 * ndim")
+        if nwalkers < 2 * ndim:
+            raise ValueError("need at least 2 * ndim walkers")  # the reference uses 5 * ndim (:364)
         self.nwalkers, self.ndim = nwalkers, ndim
         self.log_prob_fn, self.args, self.kwargs = log_prob_fn, tuple(args), dict(kwargs or {})
         self.a = float(a)
