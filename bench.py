@@ -334,10 +334,10 @@ def run_ours(args):
         sub_i, sub_v = stars["indxs"][:, lo:hi], stars["vals"][:, lo:hi]
         touched = int(np.unique(sub_i[np.isfinite(sub_v)]).size)
     alg = {
-        "k0_factors_poisson": 8 * W * ndim + 8 * (nA + nB) * Wpad + 16 * info["n_bins"] * nB + 8 * W,
+        "k0_factors": 8 * W * ndim + 8 * (nA + nB) * Wpad,
         "k1_expand": (4 * U if mode == "table_grid" else 0) + 8 * U * Wpad,
         "unused": 0,
-        "k2_stars": 16 * n_ent + (8 * (nA + nB) * Wpad if mode == "factor"
+        "k2_stars": 16 * n_ent + 16 * info["n_bins"] * nB + (8 * (nA + nB) * Wpad if mode == "factor"
                                   else 8 * Wpad * (touched if touched is not None else U)),
     }
     dur_s = kms[dom] * 1e-3

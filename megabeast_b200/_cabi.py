@@ -37,7 +37,7 @@ KIND_VARNAMES = {
 }
 MODE = {"auto": 0, "factor": 1, "table_unique": 2, "table_grid": 3}
 MODE_NAME = {v: k for k, v in MODE.items()}
-KERNEL_NAMES = ("k0_factors_poisson", "k1_expand", "unused", "k2_stars")
+KERNEL_NAMES = ("k0_factors", "k1_expand", "unused", "k2_stars")
 
 STATUS_NONFINITE_STAR = 1
 STATUS_TOTAL_ZERO = 2

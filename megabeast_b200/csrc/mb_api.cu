@@ -51,7 +51,6 @@ struct mb_handle {
   // parity hook (host copies)
   std::vector<int64_t> kept_rows, kept_offs;
   // device, static
-  ModelDev* d_model = nullptr;
   double* d_clsx = nullptr;
   Entry* d_entries = nullptr;
   int64_t* d_seg = nullptr;
@@ -142,17 +141,30 @@ static int classify(const mb_model_desc& m, int p, const double* col, int64_t G,
   return 0;
 }
 
-static size_t k2_smem_bytes(int mode, int nA, int nB, int Wpad) {
-  const int kK2Warps = k2_threads(Wpad / 32) / 32;
-  size_t stage = (size_t)kK2Warps * 2 * kChunk * sizeof(Entry);
+// slices of the dust classes per bin in the Poisson prologue: as many as the block has threads
+// for, as long as the scratch [(nslice + 1)][nbins][2] stays within 48 KB
+static int poisson_nslice(int threads, int nbins) {
+  if (nbins <= 0) return 1;
+  int ns = std::max(1, threads / nbins);
+  while (ns > 1 && (size_t)(ns + 1) * nbins * 16 > 48 * 1024) --ns;
+  return ns;
+}
+// front region of K2's dynamic shared memory: entry stage, reused as Poisson / reduction scratch
+static size_t k2_front_bytes(int nbins, int Wpad) {
+  const int threads = k2_threads(Wpad / 32);
+  size_t stage = (size_t)(threads / 32) * 2 * kChunk * sizeof(Entry);
+  size_t pois = nbins > 0 ? (size_t)(poisson_nslice(threads, nbins) + 1) * nbins * 16 : 0;
+  return (std::max(stage, pois) + 15) & ~(size_t)15;
+}
+static size_t k2_smem_bytes(int mode, int nA, int nB, int nbins, int Wpad) {
   size_t tables = mode == kModeFactor ? (size_t)(nA + nB) * Wpad * sizeof(double) : 0;
-  return stage + tables;  // the reduction scratch (3 x Wpad words) reuses the front of the stage
+  return k2_front_bytes(nbins, Wpad) + tables;
 }
 
 extern "C" void mb_destroy(mb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  void* ptrs[] = {h->d_model, h->d_clsx, h->d_entries, h->d_seg, h->d_rowcode, h->d_H, h->d_coef,
+  void* ptrs[] = {h->d_clsx, h->d_entries, h->d_seg, h->d_rowcode, h->d_H, h->d_coef,
                   h->d_bin_agecls, h->d_phi, h->d_tab[0], h->d_tab[1], h->d_tab[2], h->d_tab[3],
                   h->d_F, h->d_counter, h->d_gacc, h->d_T, h->d_out};
   for (void* p : ptrs)
@@ -246,7 +258,7 @@ extern "C" int mb_create(const mb_grid_desc* grid, const mb_stars_desc* stars,
 
   // ---- mode ----------------------------------------------------------------------------------------
   int mode = o.mode;
-  const bool factor_fits = k2_smem_bytes(kModeFactor, h->nA, h->nB, 32) <= (size_t)h->max_smem;
+  const bool factor_fits = k2_smem_bytes(kModeFactor, h->nA, h->nB, mm ? mm->n_ages * mm->n_mets : 0, 32) <= (size_t)h->max_smem;
   if (mode == MB_MODE_AUTO) mode = factor_fits ? MB_MODE_FACTOR : MB_MODE_TABLE_UNIQUE;
   if (mode == MB_MODE_FACTOR && !factor_fits)
     return fail("factor tables (%d + %d classes) do not fit shared memory; use a TABLE mode", h->nA, h->nB);
@@ -366,8 +378,6 @@ extern "C" int mb_create(const mb_grid_desc* grid, const mb_stars_desc* stars,
   for (int p = 0; p < MB_NPARAM; ++p) clsx_all.insert(clsx_all.end(), h->clsx[p].begin(), h->clsx[p].end());
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto& e : h->ev) CK(cudaEventCreate(&e));
-  if (dev_alloc(h, &h->d_model, 1)) return 1;
-  CK(cudaMemcpy(h->d_model, &h->mdev, sizeof(ModelDev), cudaMemcpyHostToDevice));
   if (dev_upload(h, &h->d_clsx, clsx_all)) return 1;
   if (dev_upload(h, &h->d_entries, entries)) return 1;
   if (dev_upload(h, &h->d_seg, seg)) return 1;
@@ -384,13 +394,6 @@ extern "C" int mb_create(const mb_grid_desc* grid, const mb_stars_desc* stars,
   CK(cudaMemset(h->d_gacc, 0, sizeof(unsigned long long) * 3 * 128));
   h->max_blocks = h->sm_count * 4;
 
-  {
-    const int nslice = std::max(1, kK0Threads / std::max(1, h->nbins));
-    size_t smem0 = sizeof(double) * ((size_t)(h->nA + h->nB) + (size_t)(nslice + 1) * h->nbins * 2);
-    if (smem0 > (size_t)h->max_smem)
-      return fail("K0 needs %zu bytes of shared memory (%d classes, %d bins)", smem0, h->nA + h->nB, h->nbins);
-    CK(cudaFuncSetAttribute(mb_k0_factors, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
-  }
   // opt in to large dynamic shared memory for every K2 instantiation we may launch
   {
     int big = h->max_smem;
@@ -506,7 +509,7 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
   for (int w0 = 0; w0 < W;) {
     int rem = W - w0;
     int NW = rem <= 32 ? 1 : rem <= 64 ? 2 : 4;
-    while (NW > 1 && k2_smem_bytes(kmode, h->nA, h->nB, 32 * NW) > (size_t)h->max_smem) NW >>= 1;
+    while (NW > 1 && k2_smem_bytes(kmode, h->nA, h->nB, h->nbins, 32 * NW) > (size_t)h->max_smem) NW >>= 1;
     const int Wpad = 32 * NW;
     const int wp = std::min(rem, Wpad);
     h->last_wp = wp;
@@ -515,19 +518,12 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
 
     if (prof) CK(cudaEventRecord(h->ev[0], st));
     K0Args k0{};
-    k0.model = h->d_model; k0.clsx = h->d_clsx; k0.phi = d_phi + (size_t)w0 * ndim;
+    k0.model = h->mdev; k0.clsx = h->d_clsx; k0.phi = d_phi + (size_t)w0 * ndim;
     for (int p = 0; p < MB_NPARAM; ++p)
       k0.tab[p] = (d_tab && d_tab[p]) ? d_tab[p] + (size_t)w0 * h->mdev.ncls[p] : nullptr;
-    k0.F = h->d_F; k0.Ht = h->d_H; k0.bin_agecls = h->d_bin_agecls; k0.coef = h->d_coef;
-    k0.n_stars = (double)h->S_total; k0.out = d_out;
-    k0.nA = h->nA; k0.nB = h->nB; k0.nbins = h->poisson ? h->nbins : 0; k0.W = wp; k0.Wpad = Wpad;
-    k0.ndim = ndim; k0.w0 = w0; k0.Wtot = W;
-    {
-      const int nslice = std::max(1, kK0Threads / std::max(1, h->nbins));
-      size_t smem0 = sizeof(double) * ((size_t)(h->nA + h->nB) + (size_t)(nslice + 1) * h->nbins * 2);
-      mb_k0_factors<<<Wpad, kK0Threads, smem0, st>>>(k0);
-      ++launches;
-    }
+    k0.F = h->d_F; k0.nA = h->nA; k0.nB = h->nB; k0.W = wp; k0.Wpad = Wpad; k0.ndim = ndim;
+    mb_k0_factors<<<((h->nA + h->nB) * Wpad + kK0Threads - 1) / kK0Threads, kK0Threads, 0, st>>>(k0);
+    ++launches;
     if (prof) CK(cudaEventRecord(h->ev[1], st));
     if (kmode != kModeFactor) {
       int64_t need = h->U * Wpad;
@@ -546,17 +542,22 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     }
     if (prof) CK(cudaEventRecord(h->ev[2], st));
     if (prof) CK(cudaEventRecord(h->ev[3], st));
-    size_t smem = k2_smem_bytes(kmode, h->nA, h->nB, Wpad);
+    size_t smem = k2_smem_bytes(kmode, h->nA, h->nB, h->nbins, Wpad);
     int per_sm = k2_blocks_per_sm(kmode, NW, smem);
     if (per_sm < 1) return fail("K2 cannot be resident with %zu bytes of shared memory", smem);
     const int kK2Warps = k2_threads(NW) / 32;
-    int grid = std::min(h->sm_count * per_sm, std::max(1, (h->nseg + kK2Warps - 1) / kK2Warps));
+    // at least one block even without entries: the Poisson prologue and the result rows live in K2
+    int grid = std::min(h->sm_count * per_sm,
+                        std::max(h->poisson ? wp : 1, (h->nseg + kK2Warps - 1) / kK2Warps));
     grid = std::min(grid, h->max_blocks);
     K2Args k2{};
     k2.entries = h->d_entries; k2.seg = h->d_seg; k2.nseg = h->nseg; k2.FA = FA; k2.T = h->d_T;
     k2.gacc = h->d_gacc; k2.counters = h->d_counter; k2.out = d_out;
     k2.nA = h->nA; k2.nB = h->nB; k2.Wpad = Wpad; k2.W = wp; k2.w0 = w0; k2.Wtot = W;
-    k2.zero_poisson = h->poisson ? 0 : 1;
+    k2.tab_off = (int32_t)k2_front_bytes(h->nbins, Wpad);
+    k2.pois.Ht = h->d_H; k2.pois.bin_agecls = h->d_bin_agecls; k2.pois.coef = h->d_coef;
+    k2.pois.n_stars = (double)h->S_total; k2.pois.nbins = h->poisson ? h->nbins : 0;
+    k2.pois.nslice = poisson_nslice(k2_threads(NW), h->nbins);
     if (kmode == kModeFactor) launch_k2<kModeFactor>(NW, grid, smem, st, k2);
     else if (kmode == kModeTable) launch_k2<kModeTable>(NW, grid, smem, st, k2);
     else launch_k2<kModeTableGrid>(NW, grid, smem, st, k2);

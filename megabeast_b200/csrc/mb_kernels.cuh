@@ -12,10 +12,11 @@
 //
 //     physmod[g,w] = FA[cA(g)][w] * FB[cB(g)][w]       FA: age (logA) factor, FB: dust factor
 //
-// K0  mb_k0_factors      one block per walker: factor tables FA, FB from phi, then the N-stars
-//                        sufficient statistics x FB -> per-bin sums -> expected N -> Poisson term
+// K0  mb_k0_factors      per-walker factor tables FA, FB from phi (tiny)
 // K1  mb_k1_expand       TABLE modes: physmod table T[u][w] = FA*FB          (HBM write bound)
-// K2  mb_k2_stars<..>    the hot kernel: stream (weight, table row) entries once for all walkers,
+// K2  mb_k2_stars<..>    prologue (first W blocks): N-stars sufficient statistics x FB -> per-bin
+//                        sums -> expected N -> Poisson term.  Then the hot loop:
+//                        stream (weight, table row) entries once for all walkers,
 //                        look the factors up (smem) or gather T rows (L2/HBM), per-star fp64
 //                        sum, log via mantissa/exponent product; K3 is fused into its tail:
 //                        warp -> block -> grid reduction over stars in 64-bit fixed point
@@ -111,123 +112,125 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
   return t;
 }
 
-// ---- K0: per-walker factor tables + the whole N-stars / Poisson term ---------------------------
-// One block per walker column (Wpad blocks; columns w >= W repeat the last real walker so no
-// lane of K2 ever sees garbage).
-//
-// Phase 1  FA[c][w] (nA rows) and FB[c][w] (nB rows): the prior models evaluated on the classes
-//          (singlepop_dust_model.py:146-148 restricted to the distinct column values).
-// Phase 2  helpers.py:133-162 needs, per (age, Z) bin, S = sum_g physmod*grid_weight and
-//          C = sum_g physmod*grid_weight*completeness over the bin's rows.  Inside a bin the age
-//          factor is constant, so with the create-time statistics Ht[cB][bin] = (sum grid_weight,
-//          sum grid_weight*completeness) over the bin's rows of dust class cB:
-//              S_bin = FA[age(bin)] * sum_cB Ht[cB][bin].x * FB[cB]      (C_bin with .y)
-// Phase 3  normalise by the grand total (:133-134), skip empty bins (:156), expected number of
-//          stars, Poisson term (singlepop_dust_model.py:182-186) -> out[POISSON][w].
+// ---- K0: per-walker factor tables ----------------------------------------------------------------
+// FA[c][w] (nA rows) and FB[c][w] (nB rows), walker minor: the prior models evaluated on the
+// classes (singlepop_dust_model.py:146-148 restricted to the distinct column values).  Columns
+// w >= W (padding up to the pass width) repeat the last real walker so no lane of K2 ever sees
+// garbage.  The model description travels in the kernel parameters (constant bank).
 // tab[p]: host-evaluated table [W][ncls[p]] for MB_TABULATED parameters (else unused).
 struct K0Args {
-  const ModelDev* model;
+  ModelDev model;
   const double* clsx;
   const double* phi;          // [W][ndim], already offset to the pass's first walker
   const double* tab[MB_NPARAM];
   double* F;                  // [nA + nB][Wpad]: FA rows then FB rows
-  const double* Ht;           // [nB][nbins][2]   (nbins == 0: no N-stars term)
+  int32_t nA, nB, W, Wpad, ndim;
+};
+constexpr int kK0Threads = 128;
+
+__global__ void __launch_bounds__(kK0Threads) mb_k0_factors(const __grid_constant__ K0Args a) {
+  const ModelDev& m = a.model;
+  const int i = blockIdx.x * kK0Threads + threadIdx.x;
+  if (i >= (a.nA + a.nB) * a.Wpad) return;
+  const int c = i / a.Wpad, w = i - c * a.Wpad;
+  const int wr = w < a.W ? w : a.W - 1;
+  const double* ph = a.phi + (size_t)wr * a.ndim;
+  double v = 1.0;
+  if (c < a.nA) {
+    if (m.kind[MB_P_LOGA] == MB_TABULATED)
+      v = a.tab[MB_P_LOGA][(size_t)wr * m.ncls[MB_P_LOGA] + c];
+    else if (m.kind[MB_P_LOGA] != MB_FIXED)
+      v = prior_eval(m, MB_P_LOGA, ph + m.voff[MB_P_LOGA], a.clsx[m.clsoff[MB_P_LOGA] + c]);
+  } else {
+    const int cb = c - a.nA;
+    // same left-to-right product order as the reference's `cur_physmod *=` loop (:146-148)
+#pragma unroll
+    for (int p = MB_P_AV; p < MB_NPARAM; ++p) {
+      if (m.kind[p] == MB_FIXED) continue;
+      int digit = (cb / m.radix[p]) % m.ncls[p];
+      if (m.kind[p] == MB_TABULATED)
+        v *= a.tab[p][(size_t)wr * m.ncls[p] + digit];
+      else
+        v *= prior_eval(m, p, ph + m.voff[p], a.clsx[m.clsoff[p] + digit]);
+    }
+  }
+  a.F[i] = v;
+}
+
+// ---- N-stars / Poisson term of one walker, computed by a whole block ------------------------------
+// helpers.py:133-162 needs, per (age, Z) bin, S = sum_g physmod*grid_weight and
+// C = sum_g physmod*grid_weight*completeness over the bin's rows.  Inside a bin the age factor is
+// constant, so with the create-time statistics Ht[cB][bin] = (sum grid_weight, sum
+// grid_weight*completeness) over the bin's rows of dust class cB:
+//     S_bin = FA[age(bin)] * sum_cB Ht[cB][bin].x * FB[cB]      (C_bin with .y)
+// then: normalise by the grand total (:133-134), skip empty bins (:156), expected number of stars,
+// Poisson term (singlepop_dust_model.py:182-186).  Runs as a prologue of K2 (block b does walker
+// b, b + gridDim, ...) on the factor tables the block already holds.
+struct PoissonArgs {
+  const double* Ht;           // [nB][nbins][2]
   const int32_t* bin_agecls;  // [nbins] FA row of the bin's age
   const double* coef;         // [nbins] metprior * massmult / avemass   (helpers.py:148-151)
   double n_stars;             // S of the fit (:183-185)
-  double* out;                // [MB_OUT_ROWS][Wtot]; row POISSON written at column w0 + w
-  int32_t nA, nB, nbins, W, Wpad, ndim, w0, Wtot;
+  int32_t nbins;              // 0: no N-stars term
+  int32_t nslice;             // slices of the dust classes per bin (host: fits the scratch)
 };
-constexpr int kK0Threads = 1024;
 
-__global__ void __launch_bounds__(kK0Threads) mb_k0_factors(K0Args a) {
-  extern __shared__ double k0s[];  // [nA+nB] this walker's factors | [nslice+1][nbins][2] bin sums
-  __shared__ double scratch[kK0Threads / 32];
-  const ModelDev& m = *a.model;
-  const int w = blockIdx.x;
-  const int wr = w < a.W ? w : a.W - 1;
-  const double* ph = a.phi + (size_t)wr * a.ndim;
-  double* sF = k0s;
-  for (int c = threadIdx.x; c < a.nA + a.nB; c += kK0Threads) {
-    double v = 1.0;
-    if (c < a.nA) {
-      if (m.kind[MB_P_LOGA] == MB_TABULATED)
-        v = a.tab[MB_P_LOGA][(size_t)wr * m.ncls[MB_P_LOGA] + c];
-      else if (m.kind[MB_P_LOGA] != MB_FIXED)
-        v = prior_eval(m, MB_P_LOGA, ph + m.voff[MB_P_LOGA], a.clsx[m.clsoff[MB_P_LOGA] + c]);
-    } else {
-      const int cb = c - a.nA;
-      // same left-to-right product order as the reference's `cur_physmod *=` loop (:146-148)
-#pragma unroll
-      for (int p = MB_P_AV; p < MB_NPARAM; ++p) {
-        if (m.kind[p] == MB_FIXED) continue;
-        int digit = (cb / m.radix[p]) % m.ncls[p];
-        if (m.kind[p] == MB_TABULATED)
-          v *= a.tab[p][(size_t)wr * m.ncls[p] + digit];
-        else
-          v *= prior_eval(m, p, ph + m.voff[p], a.clsx[m.clsoff[p] + digit]);
-      }
-    }
-    sF[c] = v;
-    a.F[(size_t)c * a.Wpad + w] = v;
-  }
-  if (a.nbins == 0 || w >= a.W) return;
-  __syncthreads();
-
-  // phase 2: nslice slices of the dust classes per bin, combined in slice order
-  const int nbins = a.nbins;
-  const int nslice = kK0Threads / nbins > 0 ? kK0Threads / nbins : 1;
-  double* part = k0s + (a.nA + a.nB);            // [nslice][nbins][2]
+// F: this pass's factor tables (shared or global), element (c, w) at F[c * Wpad + w].
+// part: scratch [(nslice + 1)][nbins][2] doubles.  All threads of the block must call.
+template <int THREADS>
+__device__ double poisson_term(const PoissonArgs& pa, const double* F, int nA, int nB, int Wpad, int w,
+                               double* part, double* scratch) {
+  const int nbins = pa.nbins, nslice = pa.nslice;
   double* sc = part + (size_t)nslice * nbins * 2;  // [nbins][2]
-  const double2* Ht = reinterpret_cast<const double2*>(a.Ht);
-  const double* sFB = sF + a.nA;
-  for (int item = threadIdx.x; item < nbins * nslice; item += kK0Threads) {
+  const double2* Ht = reinterpret_cast<const double2*>(pa.Ht);
+  const double* FB = F + (size_t)nA * Wpad + w;
+  for (int item = threadIdx.x; item < nbins * nslice; item += THREADS) {
     const int b = item % nbins, sl = item / nbins;
     double s = 0.0, c = 0.0;
     int cb = sl;
     // batches of 8 independent L2 loads in flight, then the multiply-adds in class order
-    for (; cb + 7 * nslice < a.nB; cb += 8 * nslice) {
+    for (; cb + 7 * nslice < nB; cb += 8 * nslice) {
       double2 h[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) h[u] = __ldg(Ht + (size_t)(cb + u * nslice) * nbins + b);
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const double f = sFB[cb + u * nslice];
+        const double f = FB[(size_t)(cb + u * nslice) * Wpad];
         s = fma(h[u].x, f, s); c = fma(h[u].y, f, c);
       }
     }
-    for (; cb < a.nB; cb += nslice) {
+    for (; cb < nB; cb += nslice) {
       double2 h0 = __ldg(Ht + (size_t)cb * nbins + b);
-      s = fma(h0.x, sFB[cb], s); c = fma(h0.y, sFB[cb], c);
+      const double f = FB[(size_t)cb * Wpad];
+      s = fma(h0.x, f, s); c = fma(h0.y, f, c);
     }
     part[((size_t)sl * nbins + b) * 2] = s;
     part[((size_t)sl * nbins + b) * 2 + 1] = c;
   }
   __syncthreads();
   double part_nrm = 0.0;
-  for (int b = threadIdx.x; b < nbins; b += kK0Threads) {
+  for (int b = threadIdx.x; b < nbins; b += THREADS) {
     double S = 0.0, C = 0.0;
-    for (int sl = 0; sl < nslice; ++sl) {
+    for (int sl = 0; sl < nslice; ++sl) {  // fixed slice order
       S += part[((size_t)sl * nbins + b) * 2];
       C += part[((size_t)sl * nbins + b) * 2 + 1];
     }
-    const double fa = sF[a.bin_agecls[b]];
+    const double fa = F[(size_t)pa.bin_agecls[b] * Wpad + w];
     S *= fa; C *= fa;
     sc[2 * b] = S; sc[2 * b + 1] = C;
     part_nrm += S;
   }
-  // phase 3.  helpers.py:133-134: weights are normalised by their grand total before the bin sums
-  const double nrm = block_sum<kK0Threads>(part_nrm, scratch);
+  // helpers.py:133-134: weights are normalised by their grand total before the bin sums
+  const double nrm = block_sum<THREADS>(part_nrm, scratch);
   double part_pred = 0.0;
-  for (int b = threadIdx.x; b < nbins; b += kK0Threads) {
+  for (int b = threadIdx.x; b < nbins; b += THREADS) {
     const double sb = sc[2 * b] / nrm;
     if (sb > 0.0)  // helpers.py:156 (false for NaN: 0/0 when every weight is zero)
-      part_pred += (sF[a.bin_agecls[b]] * a.coef[b]) * (sc[2 * b + 1] / nrm) / sb;
+      part_pred += (F[(size_t)pa.bin_agecls[b] * Wpad + w] * pa.coef[b]) * (sc[2 * b + 1] / nrm) / sb;
   }
-  const double pred = block_sum<kK0Threads>(part_pred, scratch);
-  if (threadIdx.x == 0)
-    a.out[(size_t)MB_OUT_POISSON * a.Wtot + a.w0 + w] =
-        a.n_stars * log(pred) - pred - lgamma(a.n_stars + 1.0);  // :182-186
+  const double pred = block_sum<THREADS>(part_pred, scratch);
+  __syncthreads();  // scratch / part are free again
+  return pa.n_stars * log(pred) - pred - lgamma(pa.n_stars + 1.0);  // :182-186
 }
 
 // ---- K1: materialise the prior-weight table (TABLE modes) -------------------------------------
@@ -328,7 +331,9 @@ struct K2Args {
   unsigned int* counters;    // [kCtrWords] next segment, blocks done (zero between launches)
   double* out;          // [MB_OUT_ROWS][Wtot]; rows STARSUM, NONFINITE (and POISSON = 0 when
                         // there is no N-stars term) written at columns w0 .. w0+W-1
-  int32_t nA, nB, Wpad, W, w0, Wtot, zero_poisson;
+  int32_t nA, nB, Wpad, W, w0, Wtot;
+  int32_t tab_off;           // byte offset of the factor tables in dynamic shared memory
+  PoissonArgs pois;          // N-stars term, computed by the first W blocks before the star loop
 };
 
 // block shape: ONE block per SM -- 768 threads (<= 85 registers) for up to 64 walkers per pass,
@@ -385,17 +390,31 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   const uint32_t rowbytes = (uint32_t)Wpad * 8u;
   const uint32_t lanebytes = (NW == 1 ? lane : 2 * lane) * 8u;
 
-  // smem layout: [stage: warps x 2 x kChunk entries][FA | FB tables (FACTOR only)]
+  // smem layout: [stage: warps x 2 x kChunk entries (also the Poisson / reduction scratch)]
+  //              [FA | FB tables at tab_off (FACTOR only)]
   const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
   const uint32_t stage = smem0 + (uint32_t)warp * 2 * kChunk * (uint32_t)sizeof(Entry);
-  const uint32_t tabA = smem0 + (uint32_t)kK2Warps * 2 * kChunk * (uint32_t)sizeof(Entry) + lanebytes;
+  const uint32_t tabA = smem0 + (uint32_t)a.tab_off + lanebytes;
   const uint32_t tabB = tabA + (uint32_t)a.nA * rowbytes;
   if (MODE == kModeFactor) {
     const int n2 = (a.nA + a.nB) * Wpad / 2;
     const double2* src = reinterpret_cast<const double2*>(a.FA);
-    double2* dst = reinterpret_cast<double2*>(smem_raw + (size_t)kK2Warps * 2 * kChunk * sizeof(Entry));
+    double2* dst = reinterpret_cast<double2*>(smem_raw + a.tab_off);
     for (int i = threadIdx.x; i < n2; i += blockDim.x) dst[i] = __ldg(src + i);
     __syncthreads();
+  }
+  // Poisson prologue: block b computes the N-stars term of walkers b, b + gridDim.x, ... from the
+  // tables it just staged; dynamic segment scheduling absorbs the few microseconds it starts late
+  {
+    __shared__ double pscratch[k2_threads(NW) / 32];
+    const double* Ftab = (MODE == kModeFactor) ? reinterpret_cast<const double*>(smem_raw + a.tab_off) : a.FA;
+    for (int w = blockIdx.x; w < a.W; w += gridDim.x) {
+      double pois = 0.0;
+      if (a.pois.nbins > 0)
+        pois = poisson_term<k2_threads(NW)>(a.pois, Ftab, a.nA, a.nB, Wpad, w,
+                                            reinterpret_cast<double*>(smem_raw), pscratch);
+      if (threadIdx.x == 0) a.out[(size_t)MB_OUT_POISSON * a.Wtot + a.w0 + w] = pois;
+    }
   }
   const char* Tlane = reinterpret_cast<const char*>(a.T) + lanebytes;
 
@@ -546,7 +565,6 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     if (w < a.W) {
       a.out[(size_t)MB_OUT_STARSUM * a.Wtot + a.w0 + w] = nnan ? nan("") : (double)f / kFixScale;
       a.out[(size_t)MB_OUT_NONFINITE * a.Wtot + a.w0 + w] = (double)nbad;
-      if (a.zero_poisson) a.out[(size_t)MB_OUT_POISSON * a.Wtot + a.w0 + w] = 0.0;
     }
   }
   if (threadIdx.x == 0) { a.counters[kCtrSegment] = 0u; a.counters[kCtrBlocks] = 0u; }
