@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=4, help="walkers the CPU baseline evaluates")
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps (not the headline)")
     ap.add_argument("--all-modes", action="store_true", help="also time the other engine modes")
+    ap.add_argument("--reduce", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N > 1: how the star-shard partials are added")
     return ap.parse_args()
 
 
@@ -242,7 +244,7 @@ def run_ours(args):
     model = MB_Model(copy.deepcopy(settings), devices=[local], mode=args.mode)
     phis = synth.make_walkers(model, W, seed=3)
     t0 = time.perf_counter()
-    sharded = ShardedLikelihood(model, stars, moddata, device=local, mode=args.mode)
+    sharded = ShardedLikelihood(model, stars, moddata, device=local, mode=args.mode, reduce=args.reduce)
     t_ingest = time.perf_counter() - t0
     info = sharded.engine.info()
     ndim = sharded.ndim
@@ -381,7 +383,9 @@ def run_ours(args):
             "workload": f"{args.workload}: {cfg['S']} stars x {cfg['K']} sparse points, {G}-row grid, "
                         f"{W} walkers, docs-example model (9 parameters)",
             "index_mode": args.index_mode, "engine_mode": mode,
-            "sharding": f"stars split over {world} rank(s), grid replicated, one all-reduce of {2 * W} doubles per step",
+            "sharding": f"stars split over {world} rank(s), grid replicated; shard reduction: "
+                        + {"none": "none (1 GPU)", "nccl": f"one NCCL all-reduce of {2 * W} doubles per step",
+                           "p2p": "fused into K2's tail over NVLink peer memory (no collective launch)"}[sharded.reduce],
             "l2": "kept warm" if args.no_flush else f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB memset, outside the timed events)",
             "entries": n_ent, "entries_raw": raw, "age_classes": nA, "dust_classes": nB,
             "bins": info["n_bins"], "ingest_s": round(t_ingest, 3),

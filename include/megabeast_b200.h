@@ -142,6 +142,7 @@ enum { MB_OUT_STARSUM = 0, MB_OUT_NONFINITE = 1, MB_OUT_POISSON = 2, MB_OUT_ROWS
 #define MB_STATUS_OK 0
 #define MB_STATUS_NONFINITE_STAR 1 /* ValueError("invidual integrated star prob is not finite"), :216-217 */
 #define MB_STATUS_TOTAL_ZERO 2     /* print + exit(), :225-227 */
+#define MB_STATUS_PEER_TIMEOUT 4   /* a peer GPU never delivered its shard (mb_peer_connect path) */
 
 typedef struct mb_handle mb_handle;
 
@@ -185,6 +186,20 @@ void mb_combine(const double* rows, int32_t W, double* lnlike, int32_t* status);
  * the first 2*W doubles (rows STARSUM, NONFINITE: one NCCL allreduce) and adds POISSON once. */
 int mb_lnlike_device(mb_handle* h, const double* d_phi, int32_t W, int32_t ndim, double* d_out,
                      void* stream);
+
+/* Star shards on several GPUs, one process per GPU: fuse the reduction over the shards into the
+ * likelihood kernel itself, over NVLink peer memory (no separate collective launch).
+ *   mb_peer_export   writes an opaque MB_PEER_HANDLE_BYTES token for this handle's exchange buffer
+ *   mb_peer_connect  takes the tokens of all `world` ranks in rank order (exchanged by the caller,
+ *                    e.g. torch.distributed.all_gather) and maps the peers' buffers (CUDA IPC)
+ * Afterwards every mb_lnlike* call on the handle returns rows STARSUM and NONFINITE already summed
+ * over all ranks, identical on every rank, provided all ranks issue the same sequence of calls.
+ * A rank that waits more than ~2 s for a peer reports MB_STATUS_PEER_TIMEOUT. */
+#define MB_MAX_PEERS 16
+#define MB_PEER_HANDLE_BYTES 64
+int mb_peer_export(mb_handle* h, void* token);
+int mb_peer_connect(mb_handle* h, int32_t rank, int32_t world, const void* tokens);
+int mb_peer_disconnect(mb_handle* h);
 
 /* Distinct values ("classes") of a free parameter's grid column, ascending; the x at which a
  * host callable must be tabulated.  Returns the count; fills at most `cap` values. */

@@ -41,6 +41,9 @@ KERNEL_NAMES = ("k0_factors", "k1_expand", "unused", "k2_stars")
 
 STATUS_NONFINITE_STAR = 1
 STATUS_TOTAL_ZERO = 2
+STATUS_PEER_TIMEOUT = 4
+MB_MAX_PEERS = 16
+MB_PEER_HANDLE_BYTES = 64
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int64_p = ctypes.POINTER(ctypes.c_int64)
@@ -158,6 +161,9 @@ SIGNATURES = {
         [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
          ctypes.c_void_p],
     ),
+    "mb_peer_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "mb_peer_connect": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]),
+    "mb_peer_disconnect": (ctypes.c_int, [ctypes.c_void_p]),
     "mb_class_values": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, c_double_p, ctypes.c_int32]),
     "mb_gathered_indices": (ctypes.c_int, [ctypes.c_void_p, c_int64_p, ctypes.c_int64, c_int64_p]),
     "mb_set_profiling": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),

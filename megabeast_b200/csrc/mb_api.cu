@@ -65,6 +65,10 @@ struct mb_handle {
   double* d_F = nullptr;    // [nA+nB][128]
   unsigned int* d_counter = nullptr;
   unsigned long long* d_gacc = nullptr;
+  unsigned long long* d_xbuf = nullptr;        // this GPU's exchange buffer (cudaMalloc: IPC-exportable)
+  unsigned long long* peer_xbuf[MB_MAX_PEERS] = {};
+  int peer_world = 1, peer_rank = 0;
+  unsigned int peer_seq = 0;
   double* d_T = nullptr;  int64_t cap_T = 0;
   int max_blocks = 0;
   double* d_out = nullptr;  int64_t cap_out = 0;
@@ -161,9 +165,61 @@ static size_t k2_smem_bytes(int mode, int nA, int nB, int nbins, int Wpad) {
   return k2_front_bytes(nbins, Wpad) + tables;
 }
 
+extern "C" int mb_peer_disconnect(mb_handle* h) {
+  if (!h) return fail("null handle");
+  CK(cudaSetDevice(h->device));
+  for (int p = 0; p < h->peer_world; ++p)
+    if (p != h->peer_rank && h->peer_xbuf[p]) cudaIpcCloseMemHandle(h->peer_xbuf[p]);
+  for (auto& x : h->peer_xbuf) x = nullptr;
+  h->peer_world = 1;
+  h->peer_rank = 0;
+  return 0;
+}
+
+extern "C" int mb_peer_export(mb_handle* h, void* token) {
+  if (!h || !token) return fail("mb_peer_export: null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) <= MB_PEER_HANDLE_BYTES, "token too small");
+  CK(cudaSetDevice(h->device));
+  cudaIpcMemHandle_t ipc;
+  CK(cudaIpcGetMemHandle(&ipc, h->d_xbuf));
+  memset(token, 0, MB_PEER_HANDLE_BYTES);
+  memcpy(token, &ipc, sizeof ipc);
+  return 0;
+}
+
+extern "C" int mb_peer_connect(mb_handle* h, int32_t rank, int32_t world, const void* tokens) {
+  if (!h || !tokens) return fail("mb_peer_connect: null argument");
+  if (world < 1 || world > MB_MAX_PEERS || rank < 0 || rank >= world)
+    return fail("mb_peer_connect: rank %d of %d (at most %d ranks)", rank, world, MB_MAX_PEERS);
+  if (h->peer_world > 1 && mb_peer_disconnect(h)) return 1;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemset(h->d_xbuf, 0, kXBufBytes));
+  for (int p = 0; p < world; ++p) {
+    if (p == rank) { h->peer_xbuf[p] = h->d_xbuf; continue; }
+    cudaIpcMemHandle_t ipc;
+    memcpy(&ipc, (const char*)tokens + (size_t)p * MB_PEER_HANDLE_BYTES, sizeof ipc);
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, ipc, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      for (int q = 0; q < p; ++q)
+        if (q != rank && h->peer_xbuf[q]) cudaIpcCloseMemHandle(h->peer_xbuf[q]);
+      for (auto& x : h->peer_xbuf) x = nullptr;
+      return fail("cudaIpcOpenMemHandle for rank %d failed: %s", p, cudaGetErrorString(e));
+    }
+    h->peer_xbuf[p] = (unsigned long long*)ptr;
+  }
+  h->peer_world = world;
+  h->peer_rank = rank;
+  h->peer_seq = 0;
+  return 0;
+}
+
 extern "C" void mb_destroy(mb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  if (h->peer_world > 1) mb_peer_disconnect(h);
+  if (h->d_xbuf) cudaFree(h->d_xbuf);
   void* ptrs[] = {h->d_clsx, h->d_entries, h->d_seg, h->d_rowcode, h->d_H, h->d_coef,
                   h->d_bin_agecls, h->d_phi, h->d_tab[0], h->d_tab[1], h->d_tab[2], h->d_tab[3],
                   h->d_F, h->d_counter, h->d_gacc, h->d_T, h->d_out};
@@ -393,6 +449,9 @@ extern "C" int mb_create(const mb_grid_desc* grid, const mb_stars_desc* stars,
   if (dev_alloc(h, &h->d_gacc, 3 * 128)) return 1;
   CK(cudaMemset(h->d_gacc, 0, sizeof(unsigned long long) * 3 * 128));
   h->max_blocks = h->sm_count * 4;
+  CK(cudaMalloc((void**)&h->d_xbuf, kXBufBytes));
+  CK(cudaMemset(h->d_xbuf, 0, kXBufBytes));
+  h->device_bytes += (int64_t)kXBufBytes;
 
   // opt in to large dynamic shared memory for every K2 instantiation we may launch
   {
@@ -558,6 +617,11 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     k2.pois.Ht = h->d_H; k2.pois.bin_agecls = h->d_bin_agecls; k2.pois.coef = h->d_coef;
     k2.pois.n_stars = (double)h->S_total; k2.pois.nbins = h->poisson ? h->nbins : 0;
     k2.pois.nslice = poisson_nslice(k2_threads(NW), h->nbins);
+    k2.peer.world = h->peer_world; k2.peer.rank = h->peer_rank;
+    if (h->peer_world > 1) {
+      k2.peer.seq = ++h->peer_seq;
+      for (int p = 0; p < h->peer_world; ++p) k2.peer.xbuf[p] = h->peer_xbuf[p];
+    }
     if (kmode == kModeFactor) launch_k2<kModeFactor>(NW, grid, smem, st, k2);
     else if (kmode == kModeTable) launch_k2<kModeTable>(NW, grid, smem, st, k2);
     else launch_k2<kModeTableGrid>(NW, grid, smem, st, k2);
@@ -648,7 +712,8 @@ extern "C" void mb_combine(const double* rows, int32_t W, double* lnlike, int32_
   for (int w = 0; w < W; ++w) {
     double tot = rows[MB_OUT_POISSON * W + w] + rows[MB_OUT_STARSUM * W + w];
     int st = MB_STATUS_OK;
-    if (rows[MB_OUT_NONFINITE * W + w] != 0.0) st |= MB_STATUS_NONFINITE_STAR;
+    if (rows[MB_OUT_NONFINITE * W + w] > 0.0) st |= MB_STATUS_NONFINITE_STAR;
+    if (rows[MB_OUT_NONFINITE * W + w] < 0.0) st |= MB_STATUS_PEER_TIMEOUT;
     if (tot == 0.0) st |= MB_STATUS_TOTAL_ZERO;
     lnlike[w] = tot;
     status[w] = st;

@@ -321,6 +321,30 @@ __device__ __noinline__ LogAcc star_done(LogAcc acc, double L) {
 
 enum { kModeFactor = 1, kModeTable = 2, kModeTableGrid = 3 };
 
+// ---- star shards on several GPUs: reduction over NVLink peer memory, fused into K2's tail --------
+// Every GPU owns an exchange buffer (cudaMalloc, opened by the other ranks through CUDA IPC):
+//   data [2 parities][MB_MAX_PEERS sources][3 * 128] u64   fixed-point log-sum, non-finite, nan
+//   flags[2 parities][MB_MAX_PEERS sources]         u32   sequence number of the data in the slot
+// The last block of rank r's K2 stores its shard totals into slot r of EVERY rank's buffer (plain
+// stores to peer addresses, NVLink), fences system-wide, publishes the launch's sequence number in
+// each flag, then waits for the flags of all sources in its own buffer and adds the slots.
+// Integer sums: the order is irrelevant, every rank gets bitwise the same totals.  Two parities:
+// a rank can be at most one launch ahead of the slowest one (it needs everyone's flag of launch n
+// to leave launch n), so launch n + 2 never overwrites data of launch n that is still being read.
+constexpr int kXWords = 3 * 128;
+__host__ __device__ constexpr size_t xbuf_data_off(int par, int src) {   // in u64 words
+  return ((size_t)par * MB_MAX_PEERS + src) * kXWords;
+}
+__host__ __device__ constexpr size_t xbuf_flag_off(int par, int src) {   // in u32 words
+  return 2 * (size_t)2 * MB_MAX_PEERS * kXWords + (size_t)par * MB_MAX_PEERS + src;
+}
+constexpr size_t kXBufBytes = 8 * (size_t)2 * MB_MAX_PEERS * kXWords + 4 * (size_t)2 * MB_MAX_PEERS + 64;
+struct PeerArgs {
+  int32_t world, rank;   // world <= 1: single shard, no exchange
+  uint32_t seq;          // sequence number of this launch, identical on all ranks
+  unsigned long long* xbuf[MB_MAX_PEERS];  // exchange buffer of every rank, as mapped on THIS GPU
+};
+
 struct K2Args {
   const Entry* entries;
   const int64_t* seg;   // [nseg+1] entry offsets, star aligned
@@ -334,6 +358,7 @@ struct K2Args {
   int32_t nA, nB, Wpad, W, w0, Wtot;
   int32_t tab_off;           // byte offset of the factor tables in dynamic shared memory
   PoissonArgs pois;          // N-stars term, computed by the first W blocks before the star loop
+  PeerArgs peer;             // cross-GPU reduction of the shard totals
 };
 
 // block shape: ONE block per SM -- 768 threads (<= 85 registers) for up to 64 walkers per pass,
@@ -558,16 +583,54 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   __syncthreads();
   if (ticket != gridDim.x - 1) return;
   __threadfence();
-  for (int w = threadIdx.x; w < Wpad; w += blockDim.x) {
-    const long long f = (long long)__ldcg(a.gacc + w);
-    const unsigned long long nbad = __ldcg(a.gacc + Wpad + w), nnan = __ldcg(a.gacc + 2 * Wpad + w);
-    a.gacc[w] = 0ull; a.gacc[Wpad + w] = 0ull; a.gacc[2 * Wpad + w] = 0ull;
-    if (w < a.W) {
-      a.out[(size_t)MB_OUT_STARSUM * a.Wtot + a.w0 + w] = nnan ? nan("") : (double)f / kFixScale;
-      a.out[(size_t)MB_OUT_NONFINITE * a.Wtot + a.w0 + w] = (double)nbad;
-    }
+  // last block of this GPU: take the shard totals, leave the accumulators zero for the next launch
+  unsigned long long* tot = sacc;  // [3][Wpad]
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * Wpad; i += blockDim.x) {
+    tot[i] = __ldcg(a.gacc + i);
+    a.gacc[i] = 0ull;
   }
   if (threadIdx.x == 0) { a.counters[kCtrSegment] = 0u; a.counters[kCtrBlocks] = 0u; }
+  __syncthreads();
+  __shared__ int timed_out;
+  if (threadIdx.x == 0) timed_out = 0;
+  if (a.peer.world > 1) {
+    const int par = (int)(a.peer.seq & 1u), me = a.peer.rank, world = a.peer.world;
+    for (int i = threadIdx.x; i < 3 * Wpad; i += blockDim.x) {
+      const unsigned long long v = tot[i];
+      for (int p = 0; p < world; ++p)  // my totals into slot `me` of every rank (peer stores)
+        *reinterpret_cast<volatile unsigned long long*>(a.peer.xbuf[p] + xbuf_data_off(par, me) + i) = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < world) {
+      volatile unsigned int* theirs =
+          reinterpret_cast<volatile unsigned int*>(a.peer.xbuf[threadIdx.x]) + xbuf_flag_off(par, me);
+      *theirs = a.peer.seq;  // publish
+      volatile unsigned int* mine =
+          reinterpret_cast<volatile unsigned int*>(a.peer.xbuf[me]) + xbuf_flag_off(par, threadIdx.x);
+      unsigned int spins = 0;
+      while (*mine != a.peer.seq) {  // bounded wait (~2 s) for source threadIdx.x
+        __nanosleep(64);
+        if (++spins > (1u << 24)) { timed_out = 1; break; }
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * Wpad; i += blockDim.x) {
+      unsigned long long t = 0ull;
+      for (int r = 0; r < world; ++r)
+        t += *reinterpret_cast<volatile unsigned long long*>(a.peer.xbuf[me] + xbuf_data_off(par, r) + i);
+      tot[i] = t;
+    }
+    __syncthreads();
+  }
+  for (int w = threadIdx.x; w < a.W; w += blockDim.x) {
+    const long long f = (long long)tot[w];
+    const unsigned long long nbad = tot[Wpad + w], nnan = tot[2 * Wpad + w];
+    a.out[(size_t)MB_OUT_STARSUM * a.Wtot + a.w0 + w] = (nnan || timed_out) ? nan("") : (double)f / kFixScale;
+    a.out[(size_t)MB_OUT_NONFINITE * a.Wtot + a.w0 + w] = timed_out ? -1.0 : (double)nbad;
+  }
 }
 
 // ---- one-time ingest: helpers.py:33-41 ---------------------------------------------------------

@@ -192,6 +192,24 @@ class LikelihoodEngine:
         )
         return rows[: offs[-1]], offs
 
+    # -- cross-GPU reduction fused into the likelihood kernel (one process per GPU) -------------
+    def peer_export(self, i=0):
+        """Opaque token of this handle's exchange buffer, to be all-gathered across ranks."""
+        token = ctypes.create_string_buffer(_cabi.MB_PEER_HANDLE_BYTES)
+        _cabi.check(self.lib.mb_peer_export(self.handles[i], token))
+        return token.raw
+
+    def peer_connect(self, rank, world, tokens, i=0):
+        """Map every rank's exchange buffer (tokens in rank order); afterwards result rows come
+        back already summed over all ranks."""
+        blob = b"".join(tokens)
+        if len(blob) != world * _cabi.MB_PEER_HANDLE_BYTES:
+            raise ValueError("need one token per rank")
+        _cabi.check(self.lib.mb_peer_connect(self.handles[i], rank, world, blob))
+
+    def peer_disconnect(self, i=0):
+        _cabi.check(self.lib.mb_peer_disconnect(self.handles[i]))
+
     def set_profiling(self, on=True):
         for h in self.handles:
             _cabi.check(self.lib.mb_set_profiling(h, int(on)))

@@ -1,8 +1,12 @@
 """
 Star-sharded ensemble likelihood across processes: one process per GPU (``torchrun``), every
 rank owns a contiguous shard of stars plus a replicated grid, evaluates all W walkers on its
-shard, and ONE all-reduce of 2*W doubles (partial sums of ln(star prob) + non-finite counts)
-per step completes the likelihood (BASELINE.json north_star item 4).
+shard, and ONE reduction of 2*W values (partial sums of ln(star prob) + non-finite counts) per
+step completes the likelihood (BASELINE.json north_star item 4).  The
+reduction runs either as one NCCL all-reduce after the kernels ("nccl") or -- the default when
+the GPUs can map each other's memory -- INSIDE the likelihood kernel: the last block of every
+rank's K2 stores its shard totals into all peers over NVLink and adds what the peers stored
+("p2p", see mb_peer_connect in include/megabeast_b200.h).
 
 torch is used for what it is good at here -- device buffers, the current stream and
 ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests); the likelihood itself is the C ABI.
@@ -43,7 +47,8 @@ def combine_rows(rows):
     """(lnlike[W], status[W]) from reduced rows -- the arithmetic of ``mb_combine``."""
     rows = np.asarray(rows, dtype=np.float64)
     total = rows[2] + rows[0]
-    status = np.where(rows[1] != 0.0, _cabi.STATUS_NONFINITE_STAR, 0).astype(np.int32)
+    status = np.where(rows[1] > 0.0, _cabi.STATUS_NONFINITE_STAR, 0).astype(np.int32)
+    status |= np.where(rows[1] < 0.0, _cabi.STATUS_PEER_TIMEOUT, 0).astype(np.int32)
     status |= np.where(total == 0.0, _cabi.STATUS_TOTAL_ZERO, 0).astype(np.int32)
     return total, status
 
@@ -59,7 +64,8 @@ class ShardedLikelihood:
                               kernels, all-reduce, D2H of the rows, exceptions as the reference
     """
 
-    def __init__(self, model, star_lnpgriddata, beast_moddata, device=None, mode="auto", group=None):
+    def __init__(self, model, star_lnpgriddata, beast_moddata, device=None, mode="auto", group=None,
+                 reduce="auto"):
         import torch
 
         from .helpers import precompute_mass_multipliers
@@ -83,8 +89,36 @@ class ShardedLikelihood:
         self.engine = LikelihoodEngine(self.spec, star_lnpgriddata, beast_moddata, massmult=mm,
                                        devices=[self.device], mode=mode,
                                        star_range=self.star_range, n_stars_total=S)
+        # how the shard partials are added: "p2p" = inside the likelihood kernel over NVLink peer
+        # memory (mb_peer_connect), "nccl" = one all-reduce after it; "auto" tries p2p first
+        self.reduce = "none" if self.world == 1 else self._setup_reduce(reduce)
         self._cap = 0
         self._ensure(64)
+
+    def _setup_reduce(self, want):
+        import torch.distributed as dist
+
+        if want not in ("auto", "p2p", "nccl"):
+            raise ValueError("reduce must be 'auto', 'p2p' or 'nccl'")
+        if want == "nccl":
+            return "nccl"
+        t = self.torch
+        ok = 1
+        try:
+            tokens = [None] * self.world
+            dist.all_gather_object(tokens, self.engine.peer_export(), group=self.group)
+            self.engine.peer_connect(self.rank, self.world, tokens)
+        except Exception as exc:  # no peer access / IPC: every rank must fall back together
+            ok, self._p2p_error = 0, repr(exc)
+        flag = t.tensor([ok], dtype=t.int32, device=t.device("cuda", self.device))
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 1:
+            return "p2p"
+        if ok:
+            self.engine.peer_disconnect()
+        if want == "p2p":
+            raise RuntimeError("peer-memory reduction unavailable: " + getattr(self, "_p2p_error", "a peer failed"))
+        return "nccl"
 
     def _ensure(self, W):
         if W <= self._cap:
@@ -105,8 +139,9 @@ class ShardedLikelihood:
             d_rows = self.d_rows if W == self._cap else self.d_rows.view(-1)[: 3 * W].view(3, W)
         stream = t.cuda.current_stream(self.device).cuda_stream
         self.engine.lnlike_device(d_phi.data_ptr(), W, self.ndim, d_rows.data_ptr(), stream)
-        allreduce_rows(d_rows, self.group)
-        return d_rows
+        if self.reduce == "nccl":
+            allreduce_rows(d_rows, self.group)
+        return d_rows  # "p2p": the kernel already summed the shards over NVLink
 
     def lnlike_rows(self, phis):
         """Host phi (W, ndim in device order) -> reduced host rows [3][W]."""
@@ -135,6 +170,8 @@ class ShardedLikelihood:
         if inside.any():
             rows = self.lnlike_rows(phis[inside][:, self.perm])
             vals, status = combine_rows(rows)
+            if np.any(status & _cabi.STATUS_PEER_TIMEOUT):
+                raise RuntimeError("a peer GPU did not deliver its star shard (timeout)")
             if np.any(status & _cabi.STATUS_NONFINITE_STAR):
                 raise ValueError("invidual integrated star prob is not finite")
             if np.any(status & _cabi.STATUS_TOTAL_ZERO):

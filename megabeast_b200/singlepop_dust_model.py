@@ -229,6 +229,8 @@ class MB_Model:
             phis = phis[:, :ndim]
         vals, status = engine.lnlike(phis if perm is None else phis[:, perm], tabs)
         if status.any():
+            if np.any(status & _cabi.STATUS_PEER_TIMEOUT):
+                raise RuntimeError("a peer GPU did not deliver its star shard (timeout)")
             if np.any(status & _cabi.STATUS_NONFINITE_STAR):
                 raise ValueError(_NONFINITE_MSG)
             print(0.0)
