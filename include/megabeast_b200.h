@@ -110,7 +110,8 @@ typedef struct {
   int32_t mode;            /* enum mb_mode */
   int32_t keep_indices;    /* retain the gathered grid rows for mb_gathered_indices */
   int32_t merge_duplicates;/* pre-sum a star's entries that share all class codes (FACTOR/TABLE_UNIQUE) */
-  int32_t reserved[12];
+  int32_t segments_per_warp;/* scheduling granularity of K2: entry-stream segments per resident warp (0 -> 1) */
+  int32_t reserved[11];
 } mb_options;
 
 typedef struct {

@@ -99,7 +99,8 @@ class Options(ctypes.Structure):
         ("mode", ctypes.c_int32),
         ("keep_indices", ctypes.c_int32),
         ("merge_duplicates", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 12),
+        ("segments_per_warp", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 11),
     ]
 
 

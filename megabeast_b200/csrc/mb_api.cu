@@ -422,7 +422,10 @@ extern "C" int mb_create(const mb_grid_desc* grid, const mb_stars_desc* stars,
 
   // ---- segments: star aligned, about four per resident warp ---------------------------------------
   const int64_t resident_warps = (int64_t)h->sm_count * 24;
-  int64_t target = std::max<int64_t>(64, h->n_entries / std::max<int64_t>(1, resident_warps * 4));
+  // measured on B200 (config 3 and its 1/2, 1/8 shards): 1 segment per warp beats 2, 4, 8 by 3-4 %
+  // -- per-segment costs (pipeline restart, one log) outweigh what dynamic balancing recovers
+  const int spw = o.segments_per_warp > 0 ? o.segments_per_warp : 1;
+  int64_t target = std::max<int64_t>(64, h->n_entries / std::max<int64_t>(1, resident_warps * spw));
   std::vector<int64_t> seg(1, 0);
   for (int64_t pos : star_end_pos)
     if (pos - seg.back() >= target) seg.push_back(pos);

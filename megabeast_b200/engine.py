@@ -9,6 +9,7 @@ after the asynchronous ``mb_lnlike_begin``/``mb_lnlike_end`` pair; across proces
 (``torchrun``) it is one NCCL all-reduce, see ``parallel.py``.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -72,7 +73,7 @@ def _col(moddata, key):
 class LikelihoodEngine:
     def __init__(self, spec, star_lnpgriddata, beast_moddata, massmult=None, devices=None,
                  mode="auto", star_range=None, n_stars_total=None, keep_indices=False,
-                 merge_duplicates=True):
+                 merge_duplicates=True, segments_per_warp=0):
         self.lib = _cabi.load()
         self._mb_lnlike = self.lib.mb_lnlike
         self._bufs = {}
@@ -138,6 +139,7 @@ class LikelihoodEngine:
                 opt.mode = _cabi.MODE[mode]
                 opt.keep_indices = int(bool(keep_indices))
                 opt.merge_duplicates = int(bool(merge_duplicates))
+                opt.segments_per_warp = int(os.environ.get("MB_SEGMENTS_PER_WARP", segments_per_warp))
                 h = ctypes.c_void_p()
                 _cabi.check(
                     self.lib.mb_create(

@@ -37,6 +37,10 @@ CONFIGS = {
     "cfg2": dict(axes=(41, 4, 61, 10, 3, 1), S=10_000, K=100, W=32),
     "cfg3": dict(axes=(41, 4, 61, 20, 5, 1), S=100_000, K=50, W=64),
     "cfg4": dict(axes=(41, 4, 61, 20, 10, 1), S=1_000_000, K=50, W=128),
+    # config 3 with 1/2, 1/4, 1/8 of the stars: what one GPU holds when it is sharded 2/4/8 ways
+    "cfg3_half": dict(axes=(41, 4, 61, 20, 5, 1), S=50_000, K=50, W=64),
+    "cfg3_quarter": dict(axes=(41, 4, 61, 20, 5, 1), S=25_000, K=50, W=64),
+    "cfg3_eighth": dict(axes=(41, 4, 61, 20, 5, 1), S=12_500, K=50, W=64),
 }
 
 _STELLAR = {
