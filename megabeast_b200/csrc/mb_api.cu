@@ -425,11 +425,19 @@ extern "C" int mb_create(const mb_grid_desc* grid, const mb_stars_desc* stars,
   // measured on B200 (config 3 and its 1/2, 1/8 shards): 1 segment per warp beats 2, 4, 8 by 3-4 %
   // -- per-segment costs (pipeline restart, one log) outweigh what dynamic balancing recovers
   const int spw = o.segments_per_warp > 0 ? o.segments_per_warp : 1;
-  int64_t target = std::max<int64_t>(64, h->n_entries / std::max<int64_t>(1, resident_warps * spw));
+  // `want` star-aligned segments of equal entry count (at least 64 entries each): boundary i is the
+  // first star end at or after i * n / want, so every resident warp gets its share
+  int64_t want = std::max<int64_t>(1, std::min<int64_t>(resident_warps * spw, h->n_entries / 64));
   std::vector<int64_t> seg(1, 0);
-  for (int64_t pos : star_end_pos)
-    if (pos - seg.back() >= target) seg.push_back(pos);
-  if (seg.back() != h->n_entries) seg.push_back(h->n_entries);
+  {
+    size_t j = 0;
+    for (int64_t i = 1; i <= want && j < star_end_pos.size(); ++i) {
+      const int64_t goal = (h->n_entries * i + want - 1) / want;
+      while (j < star_end_pos.size() && star_end_pos[j] < goal) ++j;
+      if (j < star_end_pos.size() && star_end_pos[j] > seg.back()) seg.push_back(star_end_pos[j]);
+    }
+  }
+  if (h->n_entries > 0 && seg.back() != h->n_entries) seg.push_back(h->n_entries);
   h->nseg = (int)seg.size() - 1;
 
   // ---- upload ----------------------------------------------------------------------------------------
