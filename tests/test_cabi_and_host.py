@@ -175,3 +175,42 @@ def test_stretch_move_sampler_on_a_gaussian():
     assert np.all(np.abs(tail.mean(axis=0)) < 0.25) and np.all(np.abs(tail.std(axis=0) - 1.0) < 0.25)
     assert s.n_calls == 1 + 2 * 400  # one batched call per half-ensemble proposal
     assert 0.2 < s.acceptance_fraction.mean() < 0.9
+
+
+def test_mbsettings_reads_the_docs_example(tmp_path):
+    from megabeast_b200.mbsettings import mbsettings
+
+    text = '''
+# BEAST results files
+beast_base = "beast_sim/scylla_sim/scylla_sim"   # comment after a value
+
+# stellar population model
+stellar_model = {
+    "name": "bins_histo",
+    "x": [6.0, 7.0, 8.0, 9.0, 10.0],  # units are log(years)
+    "logA": {"name": "bins_histo", "varnames": ["values"],
+             "varinit": [[1e-8, 1e-8, 1e-8, 1e-8, 1e-8]],
+             "prior": {"name": "flat",
+                       "minmax": [[0.0, 0.0, 0.0, 0.0, 0.0], [1e-3, 1e-3, 1e-3, 1e-3, 1e-3]]}},
+    "M_ini": {"name": "kroupa", "varnames": ["slope"], "varinit": [2.35],
+              "prior": {"name": "fixed", "minmax": [[2.0, 3.0]]}},
+}
+import numpy as np
+fd_model = {
+    "Av": {"name": "lognormal", "varnames": ["mean", "sigma"], "varinit": [0.5, 0.25],
+           "prior": {"name": "flat", "minmax": [[0.005, 5.0], [0.05, 1.0]]}},
+    "Rv": {"name": "lognormal", "varnames": ["mean", "sigma"], "varinit": [4.0, 0.25],
+           "prior": {"name": "flat", "minmax": [[2.0, 6.0], [0.05, 1.0]]}},
+    "fA": {"name": "lognormal", "varnames": ["mean", "sigma"], "varinit": [1.0, 0.25],
+           "prior": {"name": "fixed", "minmax": [[0.0, 1.0], [0.05, 0.5]]}},
+}
+'''
+    path = tmp_path / "settings.txt"
+    path.write_text(text)
+    s = mbsettings(str(path))
+    assert s.beast_base == "beast_sim/scylla_sim/scylla_sim"
+    assert not hasattr(s, "np")
+    m = MB_Model(s)
+    ref = MB_Model(synth.docs_example_settings())
+    assert m.start_params() == ref.start_params()
+    assert isinstance(mbsettings(), mbsettings)  # the reference's one live test (tests/basic_test.py:4-7)

@@ -192,3 +192,31 @@ def test_config1_drivers_scipy_and_ensemble_sampler():
     k, t = np.unravel_index(np.nanargmax(ref.lnprobability), ref.lnprobability.shape)
     assert np.allclose(best, ref.chain[k, t], rtol=1e-9, atol=0)
     assert np.isfinite(lnprob(best, model2, stars, moddata))
+
+
+def test_fit_single_cli_end_to_end(tmp_path, capsys):
+    """The reference's only entry point (fit_single.py:12-76) on npz inputs: settings file ->
+    MB_Model -> GPU ingest of the lnp file -> start lnprob -> short fit -> final lnprob."""
+    from megabeast_b200 import fit_single
+
+    settings, moddata, _, cfg = synth.make_problem("cfg1")
+    lnp = synth.make_lnp(moddata, cfg["axes"], 400, 30, seed=9)
+    base = str(tmp_path / "sim")
+    np.savez(base + "_moddata.npz", **{k: v for k, v in moddata.items() if k != "fA"})
+    np.savez(base + "_lnp.npz", vals=lnp["vals"], indxs=lnp["indxs"])
+    text = (f"beast_base = {base!r}\n"
+            f"stellar_model = {settings.stellar_model!r}\n"
+            f"fd_model = {settings.fd_model!r}\n")
+    sfile = tmp_path / "settings.txt"
+    sfile.write_text(text)
+    best = fit_single.main([str(sfile), "--nsteps", "4", "--seed", "1"])
+    out = capsys.readouterr().out
+    assert "starting parameters" in out and "final parameters" in out
+    # the start lnprob printed by the driver equals the oracle's on the same ingested data
+    pm = port.PortModel(copy.deepcopy(settings))
+    stars = port.likelihoods_from_lnp({"vals": lnp["vals"] - lnp["vals"].max(axis=0), "indxs": lnp["indxs"]}, moddata)
+    want = port.lnprob(np.asarray(pm.start_params()[1], float), pm, stars, moddata, loop=False)
+    line = [ln for ln in out.splitlines() if ln.startswith("[") and "]" in ln][1]
+    got = float(line.rsplit("]", 1)[1])
+    assert abs(got - want) <= 1e-9 * abs(want)
+    assert best.shape == (9,)
