@@ -216,7 +216,8 @@ def test_fit_single_cli_end_to_end(tmp_path, capsys):
     pm = port.PortModel(copy.deepcopy(settings))
     stars = port.likelihoods_from_lnp({"vals": lnp["vals"] - lnp["vals"].max(axis=0), "indxs": lnp["indxs"]}, moddata)
     want = port.lnprob(np.asarray(pm.start_params()[1], float), pm, stars, moddata, loop=False)
-    line = [ln for ln in out.splitlines() if ln.startswith("[") and "]" in ln][1]
+    lines = out.splitlines()
+    line = lines[[i for i, ln in enumerate(lines) if "logA_values1" in ln][0] + 1]
     got = float(line.rsplit("]", 1)[1])
     assert abs(got - want) <= 1e-9 * abs(want)
     assert best.shape == (9,)
