@@ -202,6 +202,22 @@ int mb_peer_export(mb_handle* h, void* token);
 int mb_peer_connect(mb_handle* h, int32_t rank, int32_t world, const void* tokens);
 int mb_peer_disconnect(mb_handle* h);
 
+/* Pixel batches (origin old/megabeast_fit.py:97-182, a serial loop of one
+ * fit per sky pixel): n_pixels independent ensembles over ONE shared grid.  Pixel p owns the stars
+ * (columns of indxs/vals) [star_offsets[p], star_offsets[p+1]); every pixel has its own W walkers
+ * and its own Poisson term (S = its star count).  phi is [n_pixels][W][ndim], lnlike/status are
+ * [n_pixels][W]; ALL pixels and walkers are evaluated by one launch.  The device form writes rows
+ * [n_pixels][MB_OUT_ROWS][W].  1 <= W <= 128; FACTOR mode only.  To use several GPUs give each
+ * rank a subset of the pixels: pixels are independent, no collective is needed. */
+int mb_create_pixels(const mb_grid_desc* grid, const mb_stars_desc* stars, const mb_model_desc* model,
+                     const mb_massmult_desc* massmult, const mb_options* opts, int64_t n_pixels,
+                     const int64_t* star_offsets, mb_handle** out);
+int mb_lnlike_pixels(mb_handle* h, const double* phi, int32_t W, int32_t ndim, double* lnlike,
+                     int32_t* status);
+int mb_lnlike_pixels_device(mb_handle* h, const double* d_phi, int32_t W, int32_t ndim, double* d_out,
+                            void* stream);
+int64_t mb_pixel_count(const mb_handle* h);
+
 /* Distinct values ("classes") of a free parameter's grid column, ascending; the x at which a
  * host callable must be tabulated.  Returns the count; fills at most `cap` values. */
 int mb_class_values(const mb_handle* h, int32_t param, double* out, int32_t cap);

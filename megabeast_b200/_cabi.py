@@ -162,6 +162,21 @@ SIGNATURES = {
         [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
          ctypes.c_void_p],
     ),
+    "mb_create_pixels": (
+        ctypes.c_int,
+        [ctypes.POINTER(GridDesc), ctypes.POINTER(StarsDesc), ctypes.POINTER(ModelDesc),
+         ctypes.POINTER(MassMultDesc), ctypes.POINTER(Options), ctypes.c_int64, c_int64_p,
+         ctypes.POINTER(ctypes.c_void_p)],
+    ),
+    "mb_lnlike_pixels": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p],
+    ),
+    "mb_lnlike_pixels_device": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p],
+    ),
+    "mb_pixel_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "mb_peer_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "mb_peer_connect": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]),
     "mb_peer_disconnect": (ctypes.c_int, [ctypes.c_void_p]),

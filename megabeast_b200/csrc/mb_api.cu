@@ -45,7 +45,7 @@ struct mb_handle {
   mb_model_desc model{};
   ModelDev mdev{};
   std::vector<double> clsx[MB_NPARAM];
-  int nA = 1, nB = 1, nbins = 0, nseg = 0;
+  int nA = 1, nB = 1, nbins = 0, nseg = 0, ncls_total = 0;
   int64_t G = 0, S_local = 0, S_total = 0, n_entries = 0, n_entries_raw = 0, U = 0;
   int64_t device_bytes = 0;
   // parity hook (host copies)
@@ -79,6 +79,11 @@ struct mb_handle {
   float last_ms[MB_NKERNELS] = {};
   int last_wp = 0, last_launches = 0;
   int pending_W = 0;
+  // pixel batches
+  int64_t P = 0;
+  int64_t* d_pix_seg = nullptr;
+  int32_t* d_pix_nstars = nullptr;
+  double* d_Fpix = nullptr; int64_t cap_Fpix = 0;
   double* pending_out = nullptr;
 };
 
@@ -222,7 +227,7 @@ extern "C" void mb_destroy(mb_handle* h) {
   if (h->d_xbuf) cudaFree(h->d_xbuf);
   void* ptrs[] = {h->d_clsx, h->d_entries, h->d_seg, h->d_rowcode, h->d_H, h->d_coef,
                   h->d_bin_agecls, h->d_phi, h->d_tab[0], h->d_tab[1], h->d_tab[2], h->d_tab[3],
-                  h->d_F, h->d_counter, h->d_gacc, h->d_T, h->d_out};
+                  h->d_F, h->d_counter, h->d_gacc, h->d_T, h->d_out, h->d_pix_seg, h->d_pix_nstars, h->d_Fpix};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -232,9 +237,9 @@ extern "C" void mb_destroy(mb_handle* h) {
   delete h;
 }
 
-extern "C" int mb_create(const mb_grid_desc* grid, const mb_stars_desc* stars,
-                         const mb_model_desc* model, const mb_massmult_desc* mm,
-                         const mb_options* opts, mb_handle** out) {
+static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
+                       const mb_model_desc* model, const mb_massmult_desc* mm,
+                       const mb_options* opts, int64_t n_pixels, const int64_t* pix_off, mb_handle** out) {
   if (!grid || !stars || !model || !out) return fail("mb_create: null argument");
   *out = nullptr;
   mb_options o{};
@@ -293,6 +298,8 @@ extern "C" int mb_create(const mb_grid_desc* grid, const mb_stars_desc* stars,
     md.ncls[p] = (int)h->clsx[p].size();
     clsoff += md.ncls[p];
   }
+  h->ncls_total = clsoff;
+  if (clsoff > 4096) return fail("more than 4096 classes in total (%d): K0 look-up table too large", clsoff);
   int64_t nB = 1;
   for (int p = MB_P_AV; p < MB_NPARAM; ++p) {
     if (model->kind[p] == MB_FIXED) continue;
@@ -363,7 +370,14 @@ extern "C" int mb_create(const mb_grid_desc* grid, const mb_stars_desc* stars,
 
   // ---- entries: fold, code, sort by age class, (merge), flag -------------------------------------
   const int64_t K = stars->K, S = stars->S;
-  const int64_t s0 = stars->star_begin, s1 = stars->star_end;
+  int64_t s0 = stars->star_begin, s1 = stars->star_end;
+  if (n_pixels > 0) {
+    if (!pix_off) return fail("pixel star offsets are NULL");
+    for (int64_t p = 0; p < n_pixels; ++p)
+      if (pix_off[p] > pix_off[p + 1]) return fail("pixel star offsets must be non-decreasing");
+    s0 = pix_off[0];
+    s1 = pix_off[n_pixels];
+  }
   if (K < 0 || S < 0 || s0 < 0 || s1 > S || s0 > s1) return fail("invalid star range [%lld,%lld) of %lld", (long long)s0, (long long)s1, (long long)S);
   if (K > 0 && S > 0 && (!stars->indxs || !stars->vals)) return fail("indxs/vals are NULL");
   h->S_local = s1 - s0;
@@ -374,7 +388,15 @@ extern "C" int mb_create(const mb_grid_desc* grid, const mb_stars_desc* stars,
   std::vector<Entry> cur;
   if (o.keep_indices) h->kept_offs.assign(1, 0);
   const bool merge = o.merge_duplicates != 0;
+  // pixel batches: entry / star-end bookkeeping per pixel
+  std::vector<int64_t> pix_ent, pix_se;
+  int64_t next_pix = 0;
   for (int64_t s = s0; s < s1; ++s) {
+    while (next_pix < n_pixels && pix_off[next_pix] == s) {
+      pix_ent.push_back((int64_t)entries.size());
+      pix_se.push_back((int64_t)star_end_pos.size());
+      ++next_pix;
+    }
     cur.clear();
     for (int64_t kk = 0; kk < K; ++kk) {
       double v = stars->vals[kk * S + s];
@@ -419,6 +441,11 @@ extern "C" int mb_create(const mb_grid_desc* grid, const mb_stars_desc* stars,
     star_end_pos.push_back((int64_t)entries.size());
   }
   h->n_entries = (int64_t)entries.size();
+  while (next_pix <= n_pixels && n_pixels > 0) {  // trailing empty pixels + the end sentinel
+    pix_ent.push_back((int64_t)entries.size());
+    pix_se.push_back((int64_t)star_end_pos.size());
+    ++next_pix;
+  }
 
   // ---- segments: star aligned, about four per resident warp ---------------------------------------
   const int64_t resident_warps = (int64_t)h->sm_count * 24;
@@ -473,10 +500,123 @@ extern "C" int mb_create(const mb_grid_desc* grid, const mb_stars_desc* stars,
     MB_OPTIN(1, kModeTableGrid); MB_OPTIN(2, kModeTableGrid); MB_OPTIN(4, kModeTableGrid);
 #undef MB_OPTIN
   }
+  if (n_pixels > 0) {
+    if (mode != MB_MODE_FACTOR) return fail("pixel batches need the factor tables in shared memory (FACTOR mode)");
+    h->P = n_pixels;
+    std::vector<int64_t> pseg((size_t)n_pixels * (kPixWarps + 1));
+    std::vector<int32_t> pns((size_t)n_pixels);
+    for (int64_t p = 0; p < n_pixels; ++p) {
+      const int64_t e0 = pix_ent[(size_t)p], e1 = pix_ent[(size_t)p + 1];
+      size_t j = (size_t)pix_se[(size_t)p];
+      const size_t j1 = (size_t)pix_se[(size_t)p + 1];
+      int64_t* row = &pseg[(size_t)p * (kPixWarps + 1)];
+      row[0] = e0;
+      for (int i = 1; i <= kPixWarps; ++i) {  // boundary i: first star end at or after the i/12 point
+        const int64_t goal = e0 + ((e1 - e0) * i + kPixWarps - 1) / kPixWarps;
+        while (j < j1 && star_end_pos[j] < goal) ++j;
+        row[i] = i == kPixWarps ? e1 : (j < j1 ? star_end_pos[j] : e1);
+      }
+      pns[(size_t)p] = (int32_t)(pix_off[p + 1] - pix_off[p]);
+    }
+    if (dev_upload(h, &h->d_pix_seg, pseg)) return 1;
+    if (dev_upload(h, &h->d_pix_nstars, pns)) return 1;
+    CK(cudaFuncSetAttribute(mb_k2_pixels<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+    CK(cudaFuncSetAttribute(mb_k2_pixels<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+    CK(cudaFuncSetAttribute(mb_k2_pixels<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+  }
   guard.ok = true;
   *out = h;
   return 0;
 }
+
+extern "C" int mb_create(const mb_grid_desc* grid, const mb_stars_desc* stars,
+                         const mb_model_desc* model, const mb_massmult_desc* mm,
+                         const mb_options* opts, mb_handle** out) {
+  return create_impl(grid, stars, model, mm, opts, 0, nullptr, out);
+}
+
+extern "C" int mb_create_pixels(const mb_grid_desc* grid, const mb_stars_desc* stars,
+                                const mb_model_desc* model, const mb_massmult_desc* mm,
+                                const mb_options* opts, int64_t n_pixels, const int64_t* star_offsets,
+                                mb_handle** out) {
+  if (n_pixels <= 0) return fail("mb_create_pixels: need at least one pixel");
+  return create_impl(grid, stars, model, mm, opts, n_pixels, star_offsets, out);
+}
+
+// ---- pixel batches: P independent ensembles in one launch -------------------------------------------
+static size_t pix_front_bytes(int nbins, int Wpad) {
+  size_t stage = (size_t)kPixWarps * 2 * kChunk * sizeof(Entry);
+  size_t red = nbins > 0 ? (size_t)(Wpad / 8) * ((nbins + 31) / 32) * 16 * sizeof(double) : 0;
+  return (std::max(stage, red) + 15) & ~(size_t)15;
+}
+static size_t pix_smem_bytes(int nA, int nB, int nbins, int Wpad) {
+  return pix_front_bytes(nbins, Wpad) + (size_t)(nA + nB) * Wpad * 8 + (size_t)Wpad * 8 + (size_t)3 * Wpad * 8;
+}
+
+static int eval_pixels_device(mb_handle* h, const double* d_phi, int W, int ndim, double* d_out, cudaStream_t st) {
+  if (h->P <= 0) return fail("handle was not created with mb_create_pixels");
+  if (ndim != h->ndim) return fail("phi has %d columns, the model has %d free variables", ndim, h->ndim);
+  if (W < 1 || W > 128) return fail("pixel batches take 1..128 walkers per pixel (got %d)", W);
+  for (int p = 0; p < MB_NPARAM; ++p)
+    if (h->model.kind[p] == MB_TABULATED) return fail("tabulated prior models are not supported for pixel batches");
+  CK(cudaSetDevice(h->device));
+  int NW = W <= 32 ? 1 : W <= 64 ? 2 : 4;
+  const int Wpad = 32 * NW;
+  const size_t smem = pix_smem_bytes(h->nA, h->nB, h->nbins, Wpad);
+  if (smem > (size_t)h->max_smem) return fail("pixel kernel needs %zu bytes of shared memory", smem);
+  const int64_t needF = h->P * (int64_t)(h->nA + h->nB) * Wpad;
+  if (needF > h->cap_Fpix) {
+    CK(cudaStreamSynchronize(st));
+    if (h->d_Fpix) { CK(cudaFree(h->d_Fpix)); h->device_bytes -= h->cap_Fpix * 8; }
+    h->d_Fpix = nullptr; h->cap_Fpix = 0;
+    if (dev_alloc(h, &h->d_Fpix, needF)) return 1;
+    h->cap_Fpix = needF;
+  }
+  const bool prof = h->profiling != 0;
+  if (prof) CK(cudaEventRecord(h->ev[0], st));
+  K0Args k0{};
+  k0.model = h->mdev; k0.clsx = h->d_clsx; k0.phi = d_phi; k0.F = h->d_Fpix;
+  k0.nA = h->nA; k0.nB = h->nB; k0.W = W; k0.Wpad = Wpad; k0.ndim = ndim; k0.ncls_total = h->ncls_total;
+  mb_k0_factors<<<(unsigned)(h->P * Wpad), kK0Threads, sizeof(double) * std::max(1, h->ncls_total), st>>>(k0);
+  if (prof) { CK(cudaEventRecord(h->ev[1], st)); CK(cudaEventRecord(h->ev[2], st)); CK(cudaEventRecord(h->ev[3], st)); }
+  KPixArgs ka{};
+  ka.entries = h->d_entries; ka.pix_seg = h->d_pix_seg; ka.F = h->d_Fpix; ka.pix_nstars = h->d_pix_nstars;
+  ka.out = d_out; ka.counters = h->d_counter;
+  ka.pois.Ht = h->d_H; ka.pois.bin_agecls = h->d_bin_agecls; ka.pois.coef = h->d_coef;
+  ka.pois.nbins = h->poisson ? h->nbins : 0; ka.pois.nslice = 1; ka.pois.n_stars = 0.0;
+  ka.P = (int)h->P; ka.nA = h->nA; ka.nB = h->nB; ka.Wpad = Wpad; ka.W = W;
+  ka.tab_off = (int32_t)pix_front_bytes(h->nbins, Wpad);
+  int per_sm = 0;
+  switch (NW) {
+    case 1: CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mb_k2_pixels<1>, kPixThreads, smem)); break;
+    case 2: CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mb_k2_pixels<2>, kPixThreads, smem)); break;
+    default: CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mb_k2_pixels<4>, kPixThreads, smem)); break;
+  }
+  if (per_sm < 1) return fail("pixel kernel cannot be resident");
+  const int grid = (int)std::min<int64_t>(h->P, (int64_t)h->sm_count * per_sm);
+  switch (NW) {
+    case 1: mb_k2_pixels<1><<<grid, kPixThreads, smem, st>>>(ka); break;
+    case 2: mb_k2_pixels<2><<<grid, kPixThreads, smem, st>>>(ka); break;
+    default: mb_k2_pixels<4><<<grid, kPixThreads, smem, st>>>(ka); break;
+  }
+  if (prof) {
+    CK(cudaEventRecord(h->ev[4], st));
+    CK(cudaEventSynchronize(h->ev[4]));
+    for (int i = 0; i < MB_NKERNELS; ++i) CK(cudaEventElapsedTime(&h->last_ms[i], h->ev[i], h->ev[i + 1]));
+  }
+  CK(cudaGetLastError());
+  h->last_wp = W;
+  h->last_launches = 2;
+  return 0;
+}
+
+extern "C" int mb_lnlike_pixels_device(mb_handle* h, const double* d_phi, int32_t W, int32_t ndim,
+                                       double* d_out, void* stream) {
+  if (!h || !d_phi || !d_out) return fail("mb_lnlike_pixels_device: null argument");
+  return eval_pixels_device(h, d_phi, W, ndim, d_out, (cudaStream_t)stream);
+}
+
+extern "C" int64_t mb_pixel_count(const mb_handle* h) { return h ? h->P : 0; }
 
 extern "C" int mb_get_info(const mb_handle* h, mb_info* out) {
   if (!h || !out) return fail("mb_get_info: null argument");
@@ -592,7 +732,8 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     for (int p = 0; p < MB_NPARAM; ++p)
       k0.tab[p] = (d_tab && d_tab[p]) ? d_tab[p] + (size_t)w0 * h->mdev.ncls[p] : nullptr;
     k0.F = h->d_F; k0.nA = h->nA; k0.nB = h->nB; k0.W = wp; k0.Wpad = Wpad; k0.ndim = ndim;
-    mb_k0_factors<<<((h->nA + h->nB) * Wpad + kK0Threads - 1) / kK0Threads, kK0Threads, 0, st>>>(k0);
+    k0.ncls_total = h->ncls_total;
+    mb_k0_factors<<<Wpad, kK0Threads, sizeof(double) * std::max(1, h->ncls_total), st>>>(k0);
     ++launches;
     if (prof) CK(cudaEventRecord(h->ev[1], st));
     if (kmode != kModeFactor) {
@@ -745,6 +886,36 @@ extern "C" int mb_lnlike_tabulated(mb_handle* h, const double* phi, int32_t W, i
 extern "C" int mb_lnlike(mb_handle* h, const double* phi, int32_t W, int32_t ndim, double* lnlike,
                          int32_t* status) {
   return mb_lnlike_tabulated(h, phi, W, ndim, nullptr, lnlike, status);
+}
+
+extern "C" int mb_lnlike_pixels(mb_handle* h, const double* phi, int32_t W, int32_t ndim, double* lnlike,
+                                int32_t* status) {
+  if (!h || !lnlike || !status) return fail("mb_lnlike_pixels: null argument");
+  if (h->P <= 0) return fail("handle was not created with mb_create_pixels");
+  if (ndim != h->ndim) return fail("phi has %d columns, the model has %d free variables", ndim, h->ndim);
+  if (ndim > 0 && !phi) return fail("mb_lnlike_pixels: phi is NULL");
+  if (W < 1) return fail("mb_lnlike_pixels: W must be positive");
+  CK(cudaSetDevice(h->device));
+  const int64_t ncol = h->P * W;
+  const int64_t nphi = ncol * std::max(1, ndim), nout = (int64_t)MB_OUT_ROWS * ncol;
+  if (ensure(h, &h->d_phi, &h->cap_phi, nphi)) return 1;
+  if (ensure(h, &h->d_out, &h->cap_out, nout)) return 1;
+  if (nphi + nout > h->cap_pin) {
+    if (h->h_pin) CK(cudaFreeHost(h->h_pin));
+    h->h_pin = nullptr; h->cap_pin = 0;
+    CK(cudaMallocHost((void**)&h->h_pin, sizeof(double) * (size_t)(nphi + nout)));
+    h->cap_pin = nphi + nout;
+  }
+  double* hp = h->h_pin;
+  double* ho = h->h_pin + nphi;
+  if (ndim > 0) memcpy(hp, phi, sizeof(double) * (size_t)ncol * ndim);
+  CK(cudaMemcpyAsync(h->d_phi, hp, sizeof(double) * (size_t)nphi, cudaMemcpyHostToDevice, h->stream));
+  if (eval_pixels_device(h, h->d_phi, W, ndim, h->d_out, h->stream)) return 1;
+  CK(cudaMemcpyAsync(ho, h->d_out, sizeof(double) * (size_t)nout, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int64_t p = 0; p < h->P; ++p)  // rows are [p][3][W]
+    mb_combine(ho + (size_t)p * MB_OUT_ROWS * W, W, lnlike + (size_t)p * W, status + (size_t)p * W);
+  return 0;
 }
 
 extern "C" int mb_likelihoods_from_lnp(int32_t device, int64_t K, int64_t S, const int64_t* indxs, double* vals,

@@ -113,48 +113,60 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
 }
 
 // ---- K0: per-walker factor tables ----------------------------------------------------------------
-// FA[c][w] (nA rows) and FB[c][w] (nB rows), walker minor: the prior models evaluated on the
-// classes (singlepop_dust_model.py:146-148 restricted to the distinct column values).  Columns
-// w >= W (padding up to the pass width) repeat the last real walker so no lane of K2 ever sees
-// garbage.  The model description travels in the kernel parameters (constant bank).
-// tab[p]: host-evaluated table [W][ncls[p]] for MB_TABULATED parameters (else unused).
+// One block per walker column.  Phase 1: every free parameter's prior model evaluated on its
+// classes (singlepop_dust_model.py:146-148 restricted to the distinct column values) into a
+// shared-memory look-up table -- a few tens of fp64 exp/log evaluations per walker.  Phase 2:
+// FA[c][w] (nA rows) and FB[c][w] (nB rows = products over the dust parameters, in the
+// reference's left-to-right order), walker minor.  Columns w >= W (padding up to the pass width)
+// repeat the last real walker so no lane of K2 ever sees garbage.  The model description travels
+// in the kernel parameters (constant bank).  Pixel batches: P independent ensembles, tables laid
+// out [p][class][Wpad], phi [p][W][ndim].
+// tab[p]: host-evaluated table [columns][ncls[p]] for MB_TABULATED parameters (else unused).
 struct K0Args {
   ModelDev model;
   const double* clsx;
-  const double* phi;          // [W][ndim], already offset to the pass's first walker
+  const double* phi;          // [P][W][ndim], already offset to the pass's first walker
   const double* tab[MB_NPARAM];
-  double* F;                  // [nA + nB][Wpad]: FA rows then FB rows
-  int32_t nA, nB, W, Wpad, ndim;
+  double* F;                  // [P][nA + nB][Wpad]: FA rows then FB rows
+  int32_t nA, nB, W, Wpad, ndim, ncls_total;
 };
 constexpr int kK0Threads = 128;
 
 __global__ void __launch_bounds__(kK0Threads) mb_k0_factors(const __grid_constant__ K0Args a) {
+  extern __shared__ double lut[];  // [sum of ncls over the parameters], offsets = model.clsoff
   const ModelDev& m = a.model;
-  const int i = blockIdx.x * kK0Threads + threadIdx.x;
-  if (i >= (a.nA + a.nB) * a.Wpad) return;
-  const int c = i / a.Wpad, w = i - c * a.Wpad;
+  const int pix = blockIdx.x / a.Wpad, w = blockIdx.x - pix * a.Wpad;
   const int wr = w < a.W ? w : a.W - 1;
-  const double* ph = a.phi + (size_t)wr * a.ndim;
-  double v = 1.0;
-  if (c < a.nA) {
-    if (m.kind[MB_P_LOGA] == MB_TABULATED)
-      v = a.tab[MB_P_LOGA][(size_t)wr * m.ncls[MB_P_LOGA] + c];
-    else if (m.kind[MB_P_LOGA] != MB_FIXED)
-      v = prior_eval(m, MB_P_LOGA, ph + m.voff[MB_P_LOGA], a.clsx[m.clsoff[MB_P_LOGA] + c]);
-  } else {
-    const int cb = c - a.nA;
-    // same left-to-right product order as the reference's `cur_physmod *=` loop (:146-148)
+  const size_t col = (size_t)pix * a.W + wr;
+  const double* ph = a.phi + col * a.ndim;
+  for (int i = threadIdx.x; i < a.ncls_total; i += kK0Threads) {
+    int p = 0;
 #pragma unroll
-    for (int p = MB_P_AV; p < MB_NPARAM; ++p) {
-      if (m.kind[p] == MB_FIXED) continue;
-      int digit = (cb / m.radix[p]) % m.ncls[p];
-      if (m.kind[p] == MB_TABULATED)
-        v *= a.tab[p][(size_t)wr * m.ncls[p] + digit];
-      else
-        v *= prior_eval(m, p, ph + m.voff[p], a.clsx[m.clsoff[p] + digit]);
-    }
+    for (int q = 1; q < MB_NPARAM; ++q)
+      if (i >= m.clsoff[q]) p = q;
+    const int c = i - m.clsoff[p];
+    double v = 1.0;
+    if (m.kind[p] == MB_TABULATED) v = a.tab[p][col * m.ncls[p] + c];
+    else if (m.kind[p] != MB_FIXED) v = prior_eval(m, p, ph + m.voff[p], a.clsx[i]);
+    lut[i] = v;
   }
-  a.F[i] = v;
+  __syncthreads();
+  double* F = a.F + (size_t)pix * (a.nA + a.nB) * a.Wpad + w;
+  for (int c = threadIdx.x; c < a.nA + a.nB; c += kK0Threads) {
+    double v = 1.0;
+    if (c < a.nA) {
+      if (m.kind[MB_P_LOGA] != MB_FIXED) v = lut[m.clsoff[MB_P_LOGA] + c];
+    } else {
+      const int cb = c - a.nA;
+      // same left-to-right product order as the reference's `cur_physmod *=` loop (:146-148)
+#pragma unroll
+      for (int p = MB_P_AV; p < MB_NPARAM; ++p) {
+        if (m.kind[p] == MB_FIXED) continue;
+        v *= lut[m.clsoff[p] + (cb / m.radix[p]) % m.ncls[p]];
+      }
+    }
+    F[(size_t)c * a.Wpad] = v;
+  }
 }
 
 // ---- N-stars / Poisson term of one walker, computed by a whole block ------------------------------
@@ -631,6 +643,233 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     a.out[(size_t)MB_OUT_STARSUM * a.Wtot + a.w0 + w] = (nnan || timed_out) ? nan("") : (double)f / kFixScale;
     a.out[(size_t)MB_OUT_NONFINITE * a.Wtot + a.w0 + w] = timed_out ? -1.0 : (double)nbad;
   }
+}
+
+// ---- pixel batches: many independent small ensembles over one shared grid -----------------------
+// SURVEY.md section 8(f) "next #3" (origin: old/megabeast_fit.py:97-182, a serial loop over sky
+// pixels with one fit each).  Every pixel has its own stars and its own W walkers; all pixels of
+// all walkers are evaluated in ONE launch.  A block owns one pixel at a time (pixels claimed
+// dynamically): it stages that pixel's factor tables, computes the N-stars / Poisson terms of
+// all W walkers at once, streams the pixel's entries (12 star-aligned pieces, one per warp) and
+// writes the pixel's result rows -- no cross-block reduction.
+constexpr int kPixThreads = 384;
+constexpr int kPixWarps = kPixThreads / 32;
+struct KPixArgs {
+  const Entry* entries;
+  const int64_t* pix_seg;     // [P][kPixWarps + 1] entry offsets of the pixel's warp pieces
+  const double* F;            // [P][nA + nB][Wpad]
+  const int32_t* pix_nstars;  // [P] S of each pixel's Poisson term
+  double* out;                // [P][MB_OUT_ROWS][W]
+  unsigned int* counters;     // [kCtrWords]: next pixel, blocks done (zero between launches)
+  PoissonArgs pois;           // shared statistics; n_stars is per pixel
+  int32_t P, nA, nB, Wpad, W, tab_off;
+};
+
+// Poisson terms of ALL walkers of one ensemble: tasks = (group of 8 walkers) x (chunk of 32 bins),
+// lanes = bins (Ht read coalesced), the 8 walkers' factors are warp-uniform broadcasts.  One
+// pass: pred = sum over bins with S > 0 of coef * FA * C / S; the grand total only decides
+// the all-zero case (helpers.py:133-134,156: 0/0 weights skip every bin -> pred = 0).
+template <int THREADS>
+__device__ void poisson_all_walkers(const PoissonArgs& pa, const double* sF, int nA, int nB, int Wpad,
+                                    double n_stars, double* red /* [tasks][16] */, double* spois /* [Wpad] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = THREADS / 32;
+  const int nbins = pa.nbins, ngroups = Wpad / 8, nchunks = (nbins + 31) / 32;
+  const double2* Ht = reinterpret_cast<const double2*>(pa.Ht);
+  const double* sFB = sF + (size_t)nA * Wpad;
+  for (int task = warp; task < ngroups * nchunks; task += nwarps) {
+    const int wg = task / nchunks, b = (task - wg * nchunks) * 32 + lane;
+    double S[8], C[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { S[k] = 0.0; C[k] = 0.0; }
+    if (b < nbins) {
+      for (int cb = 0; cb < nB; ++cb) {
+        const double2 h = __ldg(Ht + (size_t)cb * nbins + b);
+        const double2* f2 = reinterpret_cast<const double2*>(sFB + (size_t)cb * Wpad + wg * 8);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+          const double2 f = f2[k2];
+          S[2 * k2] = fma(h.x, f.x, S[2 * k2]);         C[2 * k2] = fma(h.y, f.x, C[2 * k2]);
+          S[2 * k2 + 1] = fma(h.x, f.y, S[2 * k2 + 1]); C[2 * k2 + 1] = fma(h.y, f.y, C[2 * k2 + 1]);
+        }
+      }
+    }
+    double v[16];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      double nrm = 0.0, pred = 0.0;
+      if (b < nbins) {
+        const double fa = sF[(size_t)pa.bin_agecls[b] * Wpad + wg * 8 + k];
+        const double s = fa * S[k], c = fa * C[k];
+        nrm = s;
+        if (s > 0.0) pred = (fa * pa.coef[b]) * c / s;
+      }
+      v[k] = nrm; v[8 + k] = pred;
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if (lane == 0)
+#pragma unroll
+      for (int k = 0; k < 16; ++k) red[(size_t)task * 16 + k] = v[k];
+  }
+  __syncthreads();
+  for (int w = threadIdx.x; w < Wpad; w += THREADS) {
+    const int wg = w / 8, k = w % 8;
+    double nrm = 0.0, pred = 0.0;
+    for (int ch = 0; ch < nchunks; ++ch) {  // fixed chunk order
+      nrm += red[(size_t)(wg * nchunks + ch) * 16 + k];
+      pred += red[(size_t)(wg * nchunks + ch) * 16 + 8 + k];
+    }
+    if (!(nrm > 0.0) && !(nrm != nrm)) pred = 0.0;  // all weights zero: every bin skipped
+    spois[w] = n_stars * log(pred) - pred - lgamma(n_stars + 1.0);  // :182-186
+  }
+  __syncthreads();
+}
+
+template <int NW>
+__global__ void __launch_bounds__(kPixThreads, (NW <= 2 ? 2 : 1)) mb_k2_pixels(KPixArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NQ = (NW + 1) / 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Wpad = a.Wpad;
+  const uint32_t rowbytes = (uint32_t)Wpad * 8u;
+  const uint32_t lanebytes = (NW == 1 ? lane : 2 * lane) * 8u;
+  // smem: [front: entry stage (12 x 1 KB) / Poisson task scratch][tables][spois Wpad][sacc 3 x Wpad]
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  const uint32_t stage = smem0 + (uint32_t)warp * 2 * kChunk * (uint32_t)sizeof(Entry);
+  double* sF = reinterpret_cast<double*>(smem_raw + a.tab_off);
+  double* spois = sF + (size_t)(a.nA + a.nB) * Wpad;
+  unsigned long long* sacc = reinterpret_cast<unsigned long long*>(spois + Wpad);
+  const uint32_t tabA = smem0 + (uint32_t)a.tab_off + lanebytes;
+  const uint32_t tabB = tabA + (uint32_t)a.nA * rowbytes;
+  __shared__ int cur_pixel;
+
+  auto load_factors = [&](uint32_t idx, double* f) {
+    const uint32_t addr = idx * rowbytes + tabB;
+    if (NW == 1) f[0] = lds_f64(addr);
+    else {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        double2 v = lds_f64x2(addr + 512u * q);
+        f[2 * q] = v.x; f[2 * q + 1] = v.y;
+      }
+    }
+  };
+
+  bool first = true;
+  while (true) {
+    if (threadIdx.x == 0)
+      cur_pixel = first ? (int)blockIdx.x : (int)gridDim.x + (int)atomicAdd(a.counters + kCtrSegment, 1u);
+    first = false;
+    __syncthreads();
+    const int pix = cur_pixel;
+    if (pix >= a.P) break;
+    {  // this pixel's factor tables
+      const int n2 = (a.nA + a.nB) * Wpad / 2;
+      const double2* src = reinterpret_cast<const double2*>(a.F + (size_t)pix * (a.nA + a.nB) * Wpad);
+      double2* dst = reinterpret_cast<double2*>(sF);
+      for (int i = threadIdx.x; i < n2; i += kPixThreads) dst[i] = __ldg(src + i);
+      for (int i = threadIdx.x; i < 3 * Wpad; i += kPixThreads) sacc[i] = 0ull;
+    }
+    __syncthreads();
+    const double n_stars = (double)a.pix_nstars[pix];
+    if (a.pois.nbins > 0)
+      poisson_all_walkers<kPixThreads>(a.pois, sF, a.nA, a.nB, Wpad, n_stars,
+                                       reinterpret_cast<double*>(smem_raw), spois);
+    else {
+      for (int w = threadIdx.x; w < Wpad; w += kPixThreads) spois[w] = 0.0;
+      __syncthreads();
+    }
+
+    // ---- this warp's piece of the pixel's entry stream (same inner loop as mb_k2_stars) ----------
+    double run[NW], star[NW], fa[NW];
+    LogAcc acc[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) { run[i] = 0.0; star[i] = 0.0; fa[i] = 1.0; acc[i].init(); }
+    auto boundary = [&](uint32_t meta) {
+#pragma unroll
+      for (int i = 0; i < NW; ++i) { star[i] = fma(fa[i], run[i], star[i]); run[i] = 0.0; }
+      if (meta & kNewStar) {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) { acc[i] = star_done(acc[i], star[i]); star[i] = 0.0; }
+      }
+      const uint32_t addr = (meta & kAgeMask) * rowbytes + tabA;
+      if (NW == 1) fa[0] = lds_f64(addr);
+      else {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          double2 v = lds_f64x2(addr + 512u * q);
+          fa[2 * q] = v.x; fa[2 * q + 1] = v.y;
+        }
+      }
+    };
+    int64_t pos = a.pix_seg[(size_t)pix * (kPixWarps + 1) + warp];
+    const int64_t end = a.pix_seg[(size_t)pix * (kPixWarps + 1) + warp + 1];
+    int buf = 0;
+    if (pos + lane < end) cp_async16(stage + lane * 16u, a.entries + pos + lane);
+    cp_async_commit();
+    while (pos < end) {
+      const int64_t nxt = pos + kChunk;
+      if (nxt + lane < end) cp_async16(stage + ((buf ^ 1) * kChunk + lane) * 16u, a.entries + nxt + lane);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncwarp();
+      const uint32_t cur = stage + buf * kChunk * 16u;
+      const int n = (int)min((int64_t)kChunk, end - pos);
+      int j = 0;
+      for (; j + 4 <= n; j += 4) {
+        uint4 e[4];
+        double f[4][NW];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) e[u] = lds_entry(cur + (j + u) * 16u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) load_factors(e[u].z, f[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (e[u].w & kNewRun) boundary(e[u].w);
+          const double av = __hiloint2double(e[u].y, e[u].x);
+#pragma unroll
+          for (int i = 0; i < NW; ++i) run[i] = fma(av, f[u][i], run[i]);
+        }
+      }
+      for (; j < n; ++j) {
+        uint4 e = lds_entry(cur + j * 16u);
+        double f[NW];
+        load_factors(e.z, f);
+        if (e.w & kNewRun) boundary(e.w);
+        const double av = __hiloint2double(e.y, e.x);
+#pragma unroll
+        for (int i = 0; i < NW; ++i) run[i] = fma(av, f[i], run[i]);
+      }
+      __syncwarp();
+      buf ^= 1;
+      pos = nxt;
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+      acc[i] = star_done(acc[i], fma(fa[i], run[i], star[i]));
+      const int w = (NW == 1) ? lane : 64 * (i >> 1) + 2 * lane + (i & 1);
+      const long long fixv = __double2ll_rn(acc[i].take_value() * kFixScale);
+      if (fixv) atomicAdd(sacc + w, (unsigned long long)fixv);
+      if (acc[i].bad) atomicAdd(sacc + Wpad + w, (unsigned long long)acc[i].bad);
+      if (acc[i].isnan) atomicAdd(sacc + 2 * Wpad + w, 1ull);
+    }
+    __syncthreads();
+    double* out = a.out + (size_t)pix * MB_OUT_ROWS * a.W;
+    for (int w = threadIdx.x; w < a.W; w += kPixThreads) {
+      out[(size_t)MB_OUT_STARSUM * a.W + w] = sacc[2 * Wpad + w] ? nan("") : (double)(long long)sacc[w] / kFixScale;
+      out[(size_t)MB_OUT_NONFINITE * a.W + w] = (double)sacc[Wpad + w];
+      out[(size_t)MB_OUT_POISSON * a.W + w] = spois[w];
+    }
+    __syncthreads();  // tables, sacc and the stage are reused by the next pixel
+  }
+  // the last block out re-arms the counters for the next launch
+  __shared__ unsigned int ticket;
+  if (threadIdx.x == 0) ticket = atomicAdd(a.counters + kCtrBlocks, 1u);
+  __syncthreads();
+  if (ticket == gridDim.x - 1 && threadIdx.x == 0) { a.counters[kCtrSegment] = 0u; a.counters[kCtrBlocks] = 0u; }
 }
 
 // ---- one-time ingest: helpers.py:33-41 ---------------------------------------------------------

@@ -73,7 +73,7 @@ def _col(moddata, key):
 class LikelihoodEngine:
     def __init__(self, spec, star_lnpgriddata, beast_moddata, massmult=None, devices=None,
                  mode="auto", star_range=None, n_stars_total=None, keep_indices=False,
-                 merge_duplicates=True, segments_per_warp=0):
+                 merge_duplicates=True, segments_per_warp=0, pixel_offsets=None):
         self.lib = _cabi.load()
         self._mb_lnlike = self.lib.mb_lnlike
         self._bufs = {}
@@ -124,6 +124,12 @@ class LikelihoodEngine:
         self.star_range = (int(lo), int(hi))
         self.n_stars_total = int(n_stars_total) if n_stars_total is not None else S
         model_c = spec.to_c()
+        self.n_pixels = 0
+        if pixel_offsets is not None:
+            if len(self.devices) != 1:
+                raise ValueError("a pixel batch lives on one device; give each rank its own pixels")
+            pixel_offsets = arr(pixel_offsets, np.int64)
+            self.n_pixels = pixel_offsets.size - 1
 
         try:
             for i, dev in enumerate(self.devices):
@@ -141,13 +147,22 @@ class LikelihoodEngine:
                 opt.merge_duplicates = int(bool(merge_duplicates))
                 opt.segments_per_warp = int(os.environ.get("MB_SEGMENTS_PER_WARP", segments_per_warp))
                 h = ctypes.c_void_p()
-                _cabi.check(
-                    self.lib.mb_create(
-                        ctypes.byref(grid), ctypes.byref(st), ctypes.byref(model_c),
-                        ctypes.byref(mm) if mm is not None else None, ctypes.byref(opt),
-                        ctypes.byref(h),
+                if pixel_offsets is not None:
+                    _cabi.check(
+                        self.lib.mb_create_pixels(
+                            ctypes.byref(grid), ctypes.byref(st), ctypes.byref(model_c),
+                            ctypes.byref(mm) if mm is not None else None, ctypes.byref(opt),
+                            self.n_pixels, pixel_offsets.ctypes.data_as(_cabi.c_int64_p), ctypes.byref(h),
+                        )
                     )
-                )
+                else:
+                    _cabi.check(
+                        self.lib.mb_create(
+                            ctypes.byref(grid), ctypes.byref(st), ctypes.byref(model_c),
+                            ctypes.byref(mm) if mm is not None else None, ctypes.byref(opt),
+                            ctypes.byref(h),
+                        )
+                    )
                 self.handles.append(h)
         except Exception:
             self.close()
@@ -278,6 +293,23 @@ class LikelihoodEngine:
                 _cabi.check(1)
             return out, status
         return self.combine(self.lnlike_rows(phis, tabs))
+
+    def lnlike_pixels(self, phis):
+        """Pixel batch: phis [P][W][ndim] -> (lnlike[P][W], status[P][W]), one launch."""
+        phis = np.ascontiguousarray(phis, dtype=np.float64)
+        if phis.ndim != 3 or phis.shape[0] != self.n_pixels:
+            raise ValueError(f"phis must be ({self.n_pixels}, W, ndim)")
+        P, W, ndim = phis.shape
+        out = np.empty((P, W))
+        status = np.empty((P, W), dtype=np.int32)
+        _cabi.check(self.lib.mb_lnlike_pixels(self.handles[0], phis.ctypes.data, W, ndim,
+                                              out.ctypes.data, status.ctypes.data))
+        return out, status
+
+    def lnlike_pixels_device(self, d_phi, W, ndim, d_out, stream=0):
+        """Device-pointer form: d_phi [P][W][ndim], d_out [P][3][W], asynchronous on ``stream``."""
+        _cabi.check(self.lib.mb_lnlike_pixels_device(self.handles[0], ctypes.c_void_p(d_phi), W, ndim,
+                                                     ctypes.c_void_p(d_out), ctypes.c_void_p(stream)))
 
     def lnlike_device(self, d_phi, W, ndim, d_out, stream=0, i=0):
         """Asynchronous device-pointer form (``mb_lnlike_device``): ``d_phi`` [W][ndim] and

@@ -27,6 +27,7 @@ __all__ = [
     "make_star_data",
     "make_walkers",
     "make_problem",
+    "make_pixel_problem",
 ]
 
 # axis sizes in the order (logA, Z, M_ini, Av, Rv, fA); SURVEY.md section 8(d)
@@ -223,6 +224,19 @@ def make_walkers(model, W, seed=3):
             out[n] = cand
             n += 1
     return out
+
+
+def make_pixel_problem(n_pixels=64, mean_stars=50, axes=(21, 3, 9, 8, 3, 1), K=20, mode="clustered",
+                       seeds=(1, 2, 4)):
+    """BASELINE config 5 in miniature: ``n_pixels`` sky pixels with Poisson(mean_stars) stars each
+    over ONE shared grid.  Returns (settings, beast_moddata, star_lnpgriddata, star_offsets)."""
+    rng = np.random.default_rng(seeds[2])
+    counts = rng.poisson(mean_stars, size=n_pixels)
+    offsets = np.zeros(n_pixels + 1, dtype=np.int64)
+    np.cumsum(counts, out=offsets[1:])
+    moddata = make_grid(axes, seed=seeds[0])
+    stars = make_star_data(moddata, axes, int(offsets[-1]), K, mode=mode, seed=seeds[1])
+    return docs_example_settings(), moddata, stars, offsets
 
 
 def make_problem(name="cfg1", mode="uniform", seeds=(1, 2, 3)):
