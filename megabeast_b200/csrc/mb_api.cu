@@ -13,6 +13,13 @@
 
 using namespace mb;
 
+// host-side form of an entry while a star is being sorted / merged
+struct Entry {
+  double a;
+  uint32_t idx;   // dust class (FACTOR), class combination (TABLE_UNIQUE) or grid row (TABLE_GRID)
+  uint32_t meta;  // age class
+};
+
 static thread_local std::string g_err;
 static int fail(const char* fmt, ...) {
   char buf[1024];
@@ -52,7 +59,8 @@ struct mb_handle {
   std::vector<int64_t> kept_rows, kept_offs;
   // device, static
   double* d_clsx = nullptr;
-  Entry* d_entries = nullptr;
+  double* d_ea = nullptr;       // entry weights
+  uint32_t* d_ec = nullptr;     // entry codes
   int64_t* d_seg = nullptr;
   uint32_t* d_rowcode = nullptr;
   double* d_H = nullptr;
@@ -79,6 +87,8 @@ struct mb_handle {
   float last_ms[MB_NKERNELS] = {};
   int last_wp = 0, last_launches = 0;
   int pending_W = 0;
+  int occ_cache[3] = {0, 0, 0};
+  size_t occ_smem[3] = {0, 0, 0};
   // pixel batches
   int64_t P = 0;
   int64_t* d_pix_seg = nullptr;
@@ -161,7 +171,7 @@ static int poisson_nslice(int threads, int nbins) {
 // front region of K2's dynamic shared memory: entry stage, reused as Poisson / reduction scratch
 static size_t k2_front_bytes(int nbins, int Wpad) {
   const int threads = k2_threads(Wpad / 32);
-  size_t stage = (size_t)(threads / 32) * 2 * kChunk * sizeof(Entry);
+  size_t stage = (size_t)(threads / 32) * kStageBytes;
   size_t pois = nbins > 0 ? (size_t)(poisson_nslice(threads, nbins) + 1) * nbins * 16 : 0;
   return (std::max(stage, pois) + 15) & ~(size_t)15;
 }
@@ -225,7 +235,7 @@ extern "C" void mb_destroy(mb_handle* h) {
   cudaSetDevice(h->device);
   if (h->peer_world > 1) mb_peer_disconnect(h);
   if (h->d_xbuf) cudaFree(h->d_xbuf);
-  void* ptrs[] = {h->d_clsx, h->d_entries, h->d_seg, h->d_rowcode, h->d_H, h->d_coef,
+  void* ptrs[] = {h->d_clsx, h->d_ea, h->d_ec, h->d_seg, h->d_rowcode, h->d_H, h->d_coef,
                   h->d_bin_agecls, h->d_phi, h->d_tab[0], h->d_tab[1], h->d_tab[2], h->d_tab[3],
                   h->d_F, h->d_counter, h->d_gacc, h->d_T, h->d_out, h->d_pix_seg, h->d_pix_nstars, h->d_Fpix};
   for (void* p : ptrs)
@@ -260,7 +270,7 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
   CK(cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, o.device));
   h->max_smem -= 1024;  // room for the kernels' few bytes of static shared memory
   const int64_t G = grid->G;
-  if (G <= 0 || G > 0xffffffffLL) return fail("grid size %lld unsupported", (long long)G);
+  if (G <= 0 || G > 0x7fffffffLL) return fail("grid size %lld unsupported", (long long)G);
   h->G = G;
   if (!grid->prior_weight || !grid->grid_weight || !grid->completeness)
     return fail("prior_weight, grid_weight and completeness columns are required");
@@ -383,7 +393,9 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
   h->S_local = s1 - s0;
   h->S_total = stars->n_stars_total > 0 ? stars->n_stars_total : S;
   std::vector<Entry> entries;
+  std::vector<uint32_t> codes;
   entries.reserve((size_t)((s1 - s0) * K));
+  codes.reserve((size_t)((s1 - s0) * K));
   std::vector<int64_t> star_end_pos;  // entry count after each non-empty star
   std::vector<Entry> cur;
   if (o.keep_indices) h->kept_offs.assign(1, 0);
@@ -430,12 +442,21 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
       }
       entries.push_back(e);
     }
+    // device code words: FACTOR [31] new run, [30] new star, [29:20] age class, [19:0] dust class;
+    // TABLE modes read the full product from the table: [31] new star, [30:0] table row
     uint32_t prevA = 0xffffffffu;
     for (size_t i = first; i < entries.size(); ++i) {
-      uint32_t cA = entries[i].meta;
-      // TABLE modes read the full product from the table: only the star start is a boundary
-      if (i == first) entries[i].meta |= kNewRun | kNewStar;
-      else if (mode == MB_MODE_FACTOR && cA != prevA) entries[i].meta |= kNewRun;
+      const uint32_t cA = entries[i].meta;
+      uint32_t code;
+      if (mode == MB_MODE_FACTOR) {
+        code = (cA << kAgeShift) | entries[i].idx;
+        if (i == first) code |= kNewRun | kNewStar;
+        else if (cA != prevA) code |= kNewRun;
+      } else {
+        code = entries[i].idx;
+        if (i == first) code |= kNewRun;
+      }
+      codes.push_back(code);
       prevA = cA;
     }
     star_end_pos.push_back((int64_t)entries.size());
@@ -473,7 +494,12 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto& e : h->ev) CK(cudaEventCreate(&e));
   if (dev_upload(h, &h->d_clsx, clsx_all)) return 1;
-  if (dev_upload(h, &h->d_entries, entries)) return 1;
+  {
+    std::vector<double> wts(entries.size());
+    for (size_t i = 0; i < entries.size(); ++i) wts[i] = entries[i].a;
+    if (dev_upload(h, &h->d_ea, wts)) return 1;
+    if (dev_upload(h, &h->d_ec, codes)) return 1;
+  }
   if (dev_upload(h, &h->d_seg, seg)) return 1;
   if (mode == MB_MODE_TABLE_GRID && dev_upload(h, &h->d_rowcode, rowcode)) return 1;
   if (h->poisson) {
@@ -545,7 +571,7 @@ extern "C" int mb_create_pixels(const mb_grid_desc* grid, const mb_stars_desc* s
 
 // ---- pixel batches: P independent ensembles in one launch -------------------------------------------
 static size_t pix_front_bytes(int nbins, int Wpad) {
-  size_t stage = (size_t)kPixWarps * 2 * kChunk * sizeof(Entry);
+  size_t stage = (size_t)kPixWarps * kStageBytes;
   size_t red = nbins > 0 ? (size_t)(Wpad / 8) * ((nbins + 31) / 32) * 16 * sizeof(double) : 0;
   return (std::max(stage, red) + 15) & ~(size_t)15;
 }
@@ -580,7 +606,7 @@ static int eval_pixels_device(mb_handle* h, const double* d_phi, int W, int ndim
   mb_k0_factors<<<(unsigned)(h->P * Wpad), kK0Threads, sizeof(double) * std::max(1, h->ncls_total), st>>>(k0);
   if (prof) { CK(cudaEventRecord(h->ev[1], st)); CK(cudaEventRecord(h->ev[2], st)); CK(cudaEventRecord(h->ev[3], st)); }
   KPixArgs ka{};
-  ka.entries = h->d_entries; ka.pix_seg = h->d_pix_seg; ka.F = h->d_Fpix; ka.pix_nstars = h->d_pix_nstars;
+  ka.ea = h->d_ea; ka.ec = h->d_ec; ka.pix_seg = h->d_pix_seg; ka.F = h->d_Fpix; ka.pix_nstars = h->d_pix_nstars;
   ka.out = d_out; ka.counters = h->d_counter;
   ka.pois.Ht = h->d_H; ka.pois.bin_agecls = h->d_bin_agecls; ka.pois.coef = h->d_coef;
   ka.pois.nbins = h->poisson ? h->nbins : 0; ka.pois.nslice = 1; ka.pois.n_stars = 0.0;
@@ -655,13 +681,13 @@ extern "C" int mb_gathered_indices(const mb_handle* h, int64_t* rows, int64_t ca
   if ((int64_t)h->kept_rows.size() > cap) return fail("rows buffer too small (%lld needed)", (long long)h->kept_rows.size());
   if (h->mode == MB_MODE_TABLE_GRID && h->n_entries == h->n_entries_raw) {
     // TABLE_GRID gathers by grid row: report what the device actually holds (round trip)
-    std::vector<Entry> back((size_t)h->n_entries);
-    if (h->n_entries) CK(cudaMemcpy(back.data(), h->d_entries, sizeof(Entry) * back.size(), cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> back((size_t)h->n_entries);
+    if (h->n_entries) CK(cudaMemcpy(back.data(), h->d_ec, sizeof(uint32_t) * back.size(), cudaMemcpyDeviceToHost));
     size_t i = 0, nout = 0;
     for (int64_t s = 0; s < h->S_local; ++s) {
       offs[s] = (int64_t)nout;
       int64_t cnt = h->kept_offs[(size_t)s + 1] - h->kept_offs[(size_t)s];
-      for (int64_t c = 0; c < cnt; ++c) rows[nout++] = (int64_t)back[i++].idx;
+      for (int64_t c = 0; c < cnt; ++c) rows[nout++] = (int64_t)(back[i++] & kRowMask);
     }
     offs[h->S_local] = (int64_t)nout;
     return 0;
@@ -754,7 +780,13 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     if (prof) CK(cudaEventRecord(h->ev[2], st));
     if (prof) CK(cudaEventRecord(h->ev[3], st));
     size_t smem = k2_smem_bytes(kmode, h->nA, h->nB, h->nbins, Wpad);
-    int per_sm = k2_blocks_per_sm(kmode, NW, smem);
+    // occupancy query cached per pass shape (it costs microseconds of host time per call)
+    int& cached = h->occ_cache[NW == 1 ? 0 : NW == 2 ? 1 : 2];
+    if (cached <= 0 || h->occ_smem[NW == 1 ? 0 : NW == 2 ? 1 : 2] != smem) {
+      cached = k2_blocks_per_sm(kmode, NW, smem);
+      h->occ_smem[NW == 1 ? 0 : NW == 2 ? 1 : 2] = smem;
+    }
+    int per_sm = cached;
     if (per_sm < 1) return fail("K2 cannot be resident with %zu bytes of shared memory", smem);
     const int kK2Warps = k2_threads(NW) / 32;
     // at least one block even without entries: the Poisson prologue and the result rows live in K2
@@ -762,7 +794,7 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
                         std::max(h->poisson ? wp : 1, (h->nseg + kK2Warps - 1) / kK2Warps));
     grid = std::min(grid, h->max_blocks);
     K2Args k2{};
-    k2.entries = h->d_entries; k2.seg = h->d_seg; k2.nseg = h->nseg; k2.FA = FA; k2.T = h->d_T;
+    k2.ea = h->d_ea; k2.ec = h->d_ec; k2.seg = h->d_seg; k2.nseg = h->nseg; k2.FA = FA; k2.T = h->d_T;
     k2.gacc = h->d_gacc; k2.counters = h->d_counter; k2.out = d_out;
     k2.nA = h->nA; k2.nB = h->nB; k2.Wpad = Wpad; k2.W = wp; k2.w0 = w0; k2.Wtot = W;
     k2.tab_off = (int32_t)k2_front_bytes(h->nbins, Wpad);

@@ -33,16 +33,16 @@
 namespace mb {
 
 // ---- entry stream --------------------------------------------------------------------------
-// One finite (star, sparse point) pair.  a = vals * prior_weight[r] * grid_weight[r] *
-// completeness[r] (walker independent, folded at create time), code = class codes + flags.
-struct __align__(16) Entry {
-  double a;
-  uint32_t idx;   // row of the table K2 reads for this entry: dust class (FACTOR), class
-                  // combination cA*nB+cB (TABLE_UNIQUE) or grid row (TABLE_GRID, the literal gather)
-  uint32_t meta;  // flags | age class
-};
-constexpr uint32_t kNewRun = 0x80000000u;   // first entry of a run of equal age class (or of a star)
-constexpr uint32_t kNewStar = 0x40000000u;  // first entry of a star (always together with kNewRun)
+// One finite (star, sparse point) pair = an 8-byte weight and a 4-byte code in two parallel arrays:
+//   ea[i] = vals * prior_weight[r] * grid_weight[r] * completeness[r]   (walker independent,
+//           folded at create time)
+//   ec[i] = FACTOR:  [31] first entry of a run of equal age class (or of a star),
+//                    [30] first entry of a star, [29:20] age class, [19:0] dust class
+//           TABLE*:  [31] first entry of a star, [30:0] table row: class combination cA*nB+cB
+//                    (TABLE_UNIQUE) or grid row (TABLE_GRID, the literal gather)
+constexpr uint32_t kNewRun = 0x80000000u;
+constexpr uint32_t kNewStar = 0x40000000u;
+constexpr uint32_t kRowMask = 0x7fffffffu;
 // grid-row class code (host side and K1 expand): cA << kAgeShift | cB
 constexpr int kAgeShift = 20;
 constexpr uint32_t kAgeMask = 0x3ffu;       // <= 1024 age classes
@@ -281,12 +281,13 @@ __global__ void __launch_bounds__(256) mb_k1_expand(const double* __restrict__ F
 // log of a running product: ln(prod L_s) = ln(P) + E ln 2 with P kept in [1, 2^k).
 // One DMUL + a few integer ops per star instead of a ~50-instruction fp64 log.
 struct LogAcc {
-  double P;
-  int32_t E;
-  int32_t n;
+  double P;        // running product of mantissas, in [1, 2^k)
+  int32_t E;       // running sum of BIASED exponents (bias removed in take_value)
+  int32_t n;       // stars folded in since the last renormalisation of P (<= 512) / since init
+  int32_t nb;      // stars folded in since take_value (for the bias)
   int32_t bad;     // stars whose sum was not finite -> ValueError (:216-217)
   int32_t isnan;   // a negative sum: np.log gives nan, no exception
-  __device__ __forceinline__ void init() { P = 1.0; E = 0; n = 0; bad = 0; isnan = 0; }
+  __device__ __forceinline__ void init() { P = 1.0; E = 0; n = 0; nb = 0; bad = 0; isnan = 0; }
   __device__ __forceinline__ void renorm() {
     int hi = __double2hiint(P);
     int e = ((hi >> 20) & 0x7ff);
@@ -299,8 +300,8 @@ struct LogAcc {
   // ln of the product so far; the product restarts, the bad / nan flags persist
   __device__ __forceinline__ double take_value() {
     renorm();
-    double v = log(P) + (double)E * 0.693147180559945309417232121458;
-    P = 1.0; E = 0; n = 0;
+    double v = log(P) + (double)(E - 1023 * nb) * 0.693147180559945309417232121458;
+    P = 1.0; E = 0; n = 0; nb = 0;
     return v;
   }
 };
@@ -311,24 +312,36 @@ struct LogAcc {
 constexpr double kFixScale = 4294967296.0;
 enum { kCtrSegment = 0, kCtrBlocks = 1, kCtrWords = 2 };
 
-// end of a star: fold its integrated probability L into the walker's accumulator.  Kept out of
-// line: it runs once per star (~1/K of the entries) and would otherwise be inlined at every
-// unrolled entry.
-__device__ __noinline__ LogAcc star_done(LogAcc acc, double L) {
-  if (L == 0.0) return acc;                        // exact zero: star skipped (:218-221)
+// Rare star outcomes, kept out of line: exact zero (skipped, :218-221), non-finite (counted ->
+// ValueError, :216-217), negative (np.log gives nan), subnormal (rescaled by 2^64 first).
+__device__ __noinline__ LogAcc star_done_slow(LogAcc acc, double L) {
+  if (L == 0.0) return acc;
   int hi = __double2hiint(L);
   int e = (hi >> 20) & 0x7ff;
-  if (e == 0x7ff) { acc.bad++; return acc; }       // inf or nan
-  if (hi < 0) { acc.isnan = 1; return acc; }       // negative
-  if (e == 0) {                                    // subnormal: rescale first (rare)
-    L *= 18446744073709551616.0;                   // 2^64
-    hi = __double2hiint(L);
-    e = ((hi >> 20) & 0x7ff) - 64;
-  }
-  acc.E += e - 1023;
-  acc.P *= __hiloint2double((hi & 0x800fffff) | (1023 << 20), __double2loint(L));
+  if (e == 0x7ff) { acc.bad++; return acc; }
+  if (hi < 0) { acc.isnan = 1; return acc; }
+  L *= 18446744073709551616.0;  // subnormal: 2^64
+  hi = __double2hiint(L);
+  acc.E += ((hi >> 20) & 0x7ff) - 64;
+  acc.nb++;
+  acc.P *= __hiloint2double((hi & 0x000fffff) | (1023 << 20), __double2loint(L));
   if (++acc.n >= 512) acc.renorm();
   return acc;
+}
+
+// End of a star: fold its integrated probability L into the walker's accumulator.  The common
+// case (L positive, normal) is a handful of integer ops and one DMUL.
+__device__ __forceinline__ void star_done(LogAcc& acc, double L) {
+  const int hi = __double2hiint(L);
+  const unsigned e = (unsigned)hi >> 20;         // sign + exponent field
+  if (e - 1u < 2046u) {                          // 1 <= e <= 2046: positive, normal, finite
+    acc.E += (int)e;
+    acc.nb++;
+    acc.P *= __hiloint2double((hi & 0x000fffff) | (1023 << 20), __double2loint(L));
+    if (++acc.n >= 512) acc.renorm();
+  } else {
+    acc = star_done_slow(acc, L);
+  }
 }
 
 enum { kModeFactor = 1, kModeTable = 2, kModeTableGrid = 3 };
@@ -358,15 +371,15 @@ struct PeerArgs {
 };
 
 struct K2Args {
-  const Entry* entries;
+  const double* ea;     // entry weights  [n_entries]
+  const uint32_t* ec;   // entry codes    [n_entries]
   const int64_t* seg;   // [nseg+1] entry offsets, star aligned
   int32_t nseg;
   const double* FA;     // FACTOR: [nA][Wpad] then [nB][Wpad], contiguous (staged to smem)
   const double* T;      // TABLE*: [U][Wpad]
   unsigned long long* gacc;  // [3][Wpad] fixed-point log-sum, non-finite stars, nan flags (zero between launches)
   unsigned int* counters;    // [kCtrWords] next segment, blocks done (zero between launches)
-  double* out;          // [MB_OUT_ROWS][Wtot]; rows STARSUM, NONFINITE (and POISSON = 0 when
-                        // there is no N-stars term) written at columns w0 .. w0+W-1
+  double* out;          // [MB_OUT_ROWS][Wtot], written at columns w0 .. w0+W-1
   int32_t nA, nB, Wpad, W, w0, Wtot;
   int32_t tab_off;           // byte offset of the factor tables in dynamic shared memory
   PoissonArgs pois;          // N-stars term, computed by the first W blocks before the star loop
@@ -374,30 +387,46 @@ struct K2Args {
 };
 
 // block shape: ONE block per SM -- 768 threads (<= 85 registers) for up to 64 walkers per pass,
-// 512 threads (<= 128 registers) for 128; one copy of the factor tables per SM and only
-// #SM block partials for the final reduction
+// 512 threads (<= 128 registers) for 128; one copy of the factor tables per SM
 #ifndef MB_K2_THREADS_LO
 #define MB_K2_THREADS_LO 768
 #endif
-#ifndef MB_K2_UNROLL
-#define MB_K2_UNROLL 4
-#endif
 __host__ __device__ constexpr int k2_threads(int NW) { return NW <= 2 ? MB_K2_THREADS_LO : 512; }
 __host__ __device__ constexpr int k2_min_blocks(int NW) { return 1; }
-constexpr int kChunk = 32;  // entries staged per warp per step
+constexpr int kChunk = 32;                          // entries staged per warp per step
+constexpr int kStageBytes = 2 * kChunk * (8 + 4);   // per warp: double-buffered weights + codes
 
-__device__ __forceinline__ void cp_async16(uint32_t smem, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem), "l"(gmem));
+__device__ __forceinline__ void cp_async8(uint32_t smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(uint32_t smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
-__device__ __forceinline__ uint4 lds_entry(uint32_t addr) {  // staged entry: ordered with the waits
+// staged entry data (ordered with the cp.async waits): warp-uniform addresses = broadcasts
+__device__ __forceinline__ uint4 lds_stage_u4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ double2 lds_stage_d2(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ double lds_stage_d(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_stage_u(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
 __device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {  // read-only factor tables
@@ -411,26 +440,164 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
   return v;
 }
 
-// NW walkers per lane.  Walker mapping: NW == 1: w = lane;  NW >= 2: for q < NW/2,
-// w = 64 q + 2 lane + {0,1}  (one 16-byte shared/global load per q, conflict free).
-//
-// Per entry the warp issues: one broadcast LDS.128 (a, idx, meta), one IMAD (table row address),
-// NW/2 x LDS.128 (factors), NW x DFMA, one flag test + branch.  Run / star boundaries are rare,
-// warp-uniform and share the single flag test.
+// Launder a loop-invariant address through an opaque move: without it ptxas, short of registers,
+// re-derives the shared-memory addresses from %tid / %cgaid / kernel parameters inside the hot
+// loop (~20 instructions per group of four entries in the first build of this kernel).
+__device__ __forceinline__ uint32_t keep_in_register(uint32_t x) {
+  uint32_t y;
+  asm volatile("mov.u32 %0, %1;\n" : "=r"(y) : "r"(x));
+  return y;
+}
+
+// Per-lane state of the NW walkers a lane owns while its warp walks stars.
+// Walker mapping: NW == 1: w = lane;  NW >= 2: for q < NW/2, w = 64 q + 2 lane + {0,1}
+// (one 16-byte shared/global load per q, conflict free).
+template <int NW, int MODE>
+struct Lanes {
+  static constexpr int NQ = (NW + 1) / 2;
+  static constexpr uint32_t rowbytes = 32u * NW * 8u;  // one table row: Wpad = 32 NW walkers
+  double run[NW], star[NW], fa[NW];
+  LogAcc acc[NW];
+  uint32_t tabA, tabB;            // FACTOR: shared-memory byte addresses (lane offset included)
+  const char* Tlane;              // TABLE*: global table base + lane offset
+
+  __device__ __forceinline__ void init(uint32_t tabA_, uint32_t tabB_, const char* Tlane_) {
+    tabA = keep_in_register(tabA_); tabB = keep_in_register(tabB_); Tlane = Tlane_;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) { run[i] = 0.0; star[i] = 0.0; fa[i] = 1.0; acc[i].init(); }
+  }
+  // factors of one entry for this lane's walkers
+  __device__ __forceinline__ void load_factors(uint32_t code, double* f) const {
+    if (MODE == kModeFactor) {
+      const uint32_t addr = (code & kDustMask) * rowbytes + tabB;
+      if (NW == 1) f[0] = lds_f64(addr);
+      else {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          double2 v = lds_f64x2(addr + 512u * q);
+          f[2 * q] = v.x; f[2 * q + 1] = v.y;
+        }
+      }
+    } else {
+      const char* p = Tlane + (size_t)(code & kRowMask) * rowbytes;
+      if (NW == 1) f[0] = __ldg(reinterpret_cast<const double*>(p));
+      else {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          double2 v = __ldg(reinterpret_cast<const double2*>(p + 512 * q));
+          f[2 * q] = v.x; f[2 * q + 1] = v.y;
+        }
+      }
+    }
+  }
+  // boundary before an entry (warp-uniform): close the run (and the star), fetch the new age factor
+  __device__ __forceinline__ void boundary(uint32_t code) {
+#pragma unroll
+    for (int i = 0; i < NW; ++i) { star[i] = fma(fa[i], run[i], star[i]); run[i] = 0.0; }
+    if (MODE != kModeFactor || (code & kNewStar)) {
+#pragma unroll
+      for (int i = 0; i < NW; ++i) { star_done(acc[i], star[i]); star[i] = 0.0; }
+    }
+    if (MODE == kModeFactor) {
+      const uint32_t addr = ((code >> kAgeShift) & kAgeMask) * rowbytes + tabA;
+      if (NW == 1) fa[0] = lds_f64(addr);
+      else {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          double2 v = lds_f64x2(addr + 512u * q);
+          fa[2 * q] = v.x; fa[2 * q + 1] = v.y;
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void mac(double a, const double* f) {
+#pragma unroll
+    for (int i = 0; i < NW; ++i) run[i] = fma(a, f[i], run[i]);
+  }
+  __device__ __forceinline__ void step(double a, uint32_t code, const double* f) {
+    if ((int32_t)code < 0) boundary(code);  // bit 31, warp-uniform
+    mac(a, f);
+  }
+  // a streamed range ends on a star boundary: close the last star
+  __device__ __forceinline__ void close() {
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+      star_done(acc[i], fma(fa[i], run[i], star[i]));
+      star[i] = 0.0; run[i] = 0.0;
+    }
+  }
+};
+
+// Stream entries [pos, end) through this warp's double-buffered stage (weights at st_a, codes at
+// st_c) and fold them into L.  Per group of four entries the warp issues three broadcast loads
+// (four codes; two weight pairs) = 1.5 shared-memory wavefronts per entry, then per entry one
+// IMAD (table row address), NW/2 x LDS.128 (factors), NW x DFMA and one sign test.
+template <int NW, int MODE>
+__device__ __forceinline__ void stream_range(Lanes<NW, MODE>& L, const double* __restrict__ ga,
+                                             const uint32_t* __restrict__ gc, int64_t pos, const int64_t end,
+                                             const uint32_t st_a, const uint32_t st_c, const int lane) {
+  const uint32_t sa = keep_in_register(st_a), sc = keep_in_register(st_c);
+  const uint32_t sa_lane = keep_in_register(st_a + lane * 8u), sc_lane = keep_in_register(st_c + lane * 4u);
+  uint32_t bufa = 0, bufc = 0;  // byte offsets of the current buffer (0 or one buffer)
+  if (pos + lane < end) {
+    cp_async8(sa_lane, ga + pos + lane);
+    cp_async4(sc_lane, gc + pos + lane);
+  }
+  cp_async_commit();
+  while (pos < end) {
+    const int64_t nxt = pos + kChunk;
+    if (nxt + lane < end) {
+      cp_async8(sa_lane + (bufa ^ (kChunk * 8u)), ga + nxt + lane);
+      cp_async4(sc_lane + (bufc ^ (kChunk * 4u)), gc + nxt + lane);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+    uint32_t pa = sa + bufa, pc = sc + bufc;
+    int n = (int)min((int64_t)kChunk, end - pos);
+    for (; n >= 4; n -= 4, pa += 32u, pc += 16u) {
+      const uint4 c = lds_stage_u4(pc);
+      const double2 a01 = lds_stage_d2(pa), a23 = lds_stage_d2(pa + 16u);
+      double f0[NW], f1[NW], f2[NW], f3[NW];
+      L.load_factors(c.x, f0); L.load_factors(c.y, f1); L.load_factors(c.z, f2); L.load_factors(c.w, f3);
+      if ((int32_t)(c.x | c.y | c.z | c.w) < 0) {  // a run / star boundary somewhere in the group
+        L.step(a01.x, c.x, f0); L.step(a01.y, c.y, f1); L.step(a23.x, c.z, f2); L.step(a23.y, c.w, f3);
+      } else {                                     // common case: four plain multiply-adds
+        L.mac(a01.x, f0); L.mac(a01.y, f1); L.mac(a23.x, f2); L.mac(a23.y, f3);
+      }
+    }
+    for (; n > 0; --n, pa += 8u, pc += 4u) {
+      const uint32_t c = lds_stage_u(pc);
+      const double a = lds_stage_d(pa);
+      double f[NW];
+      L.load_factors(c, f);
+      L.step(a, c, f);
+    }
+    __syncwarp();
+    bufa ^= kChunk * 8u;
+    bufc ^= kChunk * 4u;
+    pos = nxt;
+  }
+  cp_async_wait<0>();
+}
+
+// Prologue (first W blocks): N-stars / Poisson term.  Hot loop: every warp streams star-aligned
+// segments of the entry stream for all walkers.  Tail: reduction over stars (K3) and, with peers,
+// over GPUs.
 template <int NW, int MODE>
 __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars(K2Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int NQ = (NW + 1) / 2;
   constexpr int kK2Warps = k2_threads(NW) / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int Wpad = a.Wpad;
-  const uint32_t rowbytes = (uint32_t)Wpad * 8u;
+  constexpr int Wpad = 32 * NW;  // == a.Wpad
+  constexpr uint32_t rowbytes = (uint32_t)Wpad * 8u;
   const uint32_t lanebytes = (NW == 1 ? lane : 2 * lane) * 8u;
 
-  // smem layout: [stage: warps x 2 x kChunk entries (also the Poisson / reduction scratch)]
+  // smem layout: [stage: warps x (2 x 32 weights + 2 x 32 codes); also Poisson / reduction scratch]
   //              [FA | FB tables at tab_off (FACTOR only)]
   const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
-  const uint32_t stage = smem0 + (uint32_t)warp * 2 * kChunk * (uint32_t)sizeof(Entry);
+  const uint32_t st_a = smem0 + (uint32_t)warp * kStageBytes;
+  const uint32_t st_c = st_a + 2 * kChunk * 8u;
   const uint32_t tabA = smem0 + (uint32_t)a.tab_off + lanebytes;
   const uint32_t tabB = tabA + (uint32_t)a.nA * rowbytes;
   if (MODE == kModeFactor) {
@@ -453,122 +620,25 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
       if (threadIdx.x == 0) a.out[(size_t)MB_OUT_POISSON * a.Wtot + a.w0 + w] = pois;
     }
   }
-  const char* Tlane = reinterpret_cast<const char*>(a.T) + lanebytes;
 
-  double run[NW], star[NW], fa[NW];
-  LogAcc acc[NW];
-#pragma unroll
-  for (int i = 0; i < NW; ++i) { run[i] = 0.0; star[i] = 0.0; fa[i] = 1.0; acc[i].init(); }
+  Lanes<NW, MODE> L;
+  L.init(tabA, tabB, reinterpret_cast<const char*>(a.T) + lanebytes);
 
-  // factors of one entry for this lane's walkers
-  auto load_factors = [&](uint32_t idx, double* f) {
-    if (MODE == kModeFactor) {
-      const uint32_t addr = idx * rowbytes + tabB;
-      if (NW == 1) f[0] = lds_f64(addr);
-      else {
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-          double2 v = lds_f64x2(addr + 512u * q);
-          f[2 * q] = v.x; f[2 * q + 1] = v.y;
-        }
-      }
-    } else {
-      const char* p = Tlane + (size_t)idx * rowbytes;
-      if (NW == 1) f[0] = __ldg(reinterpret_cast<const double*>(p));
-      else {
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-          double2 v = __ldg(reinterpret_cast<const double2*>(p + 512 * q));
-          f[2 * q] = v.x; f[2 * q + 1] = v.y;
-        }
-      }
-    }
-  };
-
-  // boundary before an entry: close the run (and the star) and fetch the new age factor
-  auto boundary = [&](uint32_t meta) {
-#pragma unroll
-    for (int i = 0; i < NW; ++i) { star[i] = fma(fa[i], run[i], star[i]); run[i] = 0.0; }
-    if (meta & kNewStar) {
-#pragma unroll
-      for (int i = 0; i < NW; ++i) { acc[i] = star_done(acc[i], star[i]); star[i] = 0.0; }
-    }
-    if (MODE == kModeFactor) {
-      const uint32_t addr = (meta & kAgeMask) * rowbytes + tabA;
-      if (NW == 1) fa[0] = lds_f64(addr);
-      else {
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-          double2 v = lds_f64x2(addr + 512u * q);
-          fa[2 * q] = v.x; fa[2 * q + 1] = v.y;
-        }
-      }
-    }
-  };
-
-  // Segments are claimed dynamically (one atomic per segment, issued a segment ahead): SMs that
-  // run faster take more.  The result does not depend on who processed what: each segment's
-  // value depends only on its own entries, and segment values are added as 64-bit fixed point.
+  // Segments: every warp starts with its own index (no atomic storm at kernel start); further
+  // ones are claimed from a shared counter, one atomic per segment issued a segment ahead.  The
+  // result does not depend on who processed what: a segment's value depends only on its own
+  // entries, and segment values are added as 64-bit fixed point.
   long long fix[NW];
 #pragma unroll
   for (int i = 0; i < NW; ++i) fix[i] = 0;
-  // every warp's first segment is its own index (no atomic storm at kernel start); later ones
-  // come from the shared counter, offset by the number of warps
   const int nwarps_total = (int)gridDim.x * kK2Warps;
   int s = (int)blockIdx.x * kK2Warps + warp, s_next = 0;
   while (s < a.nseg) {
     if (lane == 0) s_next = nwarps_total + (int)atomicAdd(a.counters + kCtrSegment, 1u);
-    int64_t pos = a.seg[s];
-    const int64_t end = a.seg[s + 1];
-    int buf = 0;
-    if (pos + lane < end) cp_async16(stage + lane * 16u, a.entries + pos + lane);
-    cp_async_commit();
-    while (pos < end) {
-      const int64_t nxt = pos + kChunk;
-      if (nxt + lane < end) cp_async16(stage + ((buf ^ 1) * kChunk + lane) * 16u, a.entries + nxt + lane);
-      cp_async_commit();
-      cp_async_wait<1>();
-      __syncwarp();
-      const uint32_t cur = stage + buf * kChunk * 16u;
-      const int n = (int)min((int64_t)kChunk, end - pos);
-      int j = 0;
-      constexpr int UN = MB_K2_UNROLL;
-      for (; j + UN <= n; j += UN) {
-        uint4 e[UN];
-        double f[UN][NW];
+    stream_range<NW, MODE>(L, a.ea, a.ec, a.seg[s], a.seg[s + 1], st_a, st_c, lane);
+    L.close();
 #pragma unroll
-        for (int u = 0; u < UN; ++u) e[u] = lds_entry(cur + (j + u) * 16u);
-#pragma unroll
-        for (int u = 0; u < UN; ++u) load_factors(e[u].z, f[u]);
-#pragma unroll
-        for (int u = 0; u < UN; ++u) {
-          if (e[u].w & kNewRun) boundary(e[u].w);  // warp-uniform
-          const double av = __hiloint2double(e[u].y, e[u].x);
-#pragma unroll
-          for (int i = 0; i < NW; ++i) run[i] = fma(av, f[u][i], run[i]);
-        }
-      }
-      for (; j < n; ++j) {
-        uint4 e = lds_entry(cur + j * 16u);
-        double f[NW];
-        load_factors(e.z, f);
-        if (e.w & kNewRun) boundary(e.w);
-        const double av = __hiloint2double(e.y, e.x);
-#pragma unroll
-        for (int i = 0; i < NW; ++i) run[i] = fma(av, f[i], run[i]);
-      }
-      __syncwarp();
-      buf ^= 1;
-      pos = nxt;
-    }
-    cp_async_wait<0>();
-    // a segment ends on a star boundary: close the last star, bank the segment's log-sum
-#pragma unroll
-    for (int i = 0; i < NW; ++i) {
-      acc[i] = star_done(acc[i], fma(fa[i], run[i], star[i]));
-      star[i] = 0.0; run[i] = 0.0;
-      fix[i] += __double2ll_rn(acc[i].take_value() * kFixScale);
-    }
+    for (int i = 0; i < NW; ++i) fix[i] += __double2ll_rn(L.acc[i].take_value() * kFixScale);
     s = __shfl_sync(0xffffffffu, s_next, 0);
   }
 
@@ -582,8 +652,8 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   for (int i = 0; i < NW; ++i) {
     int w = (NW == 1) ? lane : 64 * (i >> 1) + 2 * lane + (i & 1);
     atomicAdd(sacc + w, (unsigned long long)fix[i]);
-    if (acc[i].bad) atomicAdd(sacc + Wpad + w, (unsigned long long)acc[i].bad);
-    if (acc[i].isnan) atomicAdd(sacc + 2 * Wpad + w, 1ull);
+    if (L.acc[i].bad) atomicAdd(sacc + Wpad + w, (unsigned long long)L.acc[i].bad);
+    if (L.acc[i].isnan) atomicAdd(sacc + 2 * Wpad + w, 1ull);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 3 * Wpad; i += blockDim.x)
@@ -655,7 +725,8 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
 constexpr int kPixThreads = 384;
 constexpr int kPixWarps = kPixThreads / 32;
 struct KPixArgs {
-  const Entry* entries;
+  const double* ea;           // entry weights
+  const uint32_t* ec;         // entry codes (FACTOR layout)
   const int64_t* pix_seg;     // [P][kPixWarps + 1] entry offsets of the pixel's warp pieces
   const double* F;            // [P][nA + nB][Wpad]
   const int32_t* pix_nstars;  // [P] S of each pixel's Poisson term
@@ -730,32 +801,20 @@ __device__ void poisson_all_walkers(const PoissonArgs& pa, const double* sF, int
 template <int NW>
 __global__ void __launch_bounds__(kPixThreads, (NW <= 2 ? 2 : 1)) mb_k2_pixels(KPixArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int NQ = (NW + 1) / 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int Wpad = a.Wpad;
-  const uint32_t rowbytes = (uint32_t)Wpad * 8u;
+  constexpr int Wpad = 32 * NW;  // == a.Wpad
+  constexpr uint32_t rowbytes = (uint32_t)Wpad * 8u;
   const uint32_t lanebytes = (NW == 1 ? lane : 2 * lane) * 8u;
-  // smem: [front: entry stage (12 x 1 KB) / Poisson task scratch][tables][spois Wpad][sacc 3 x Wpad]
+  // smem: [front: entry stage / Poisson task scratch][tables][spois Wpad][sacc 3 x Wpad]
   const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
-  const uint32_t stage = smem0 + (uint32_t)warp * 2 * kChunk * (uint32_t)sizeof(Entry);
+  const uint32_t st_a = smem0 + (uint32_t)warp * kStageBytes;
+  const uint32_t st_c = st_a + 2 * kChunk * 8u;
   double* sF = reinterpret_cast<double*>(smem_raw + a.tab_off);
   double* spois = sF + (size_t)(a.nA + a.nB) * Wpad;
   unsigned long long* sacc = reinterpret_cast<unsigned long long*>(spois + Wpad);
   const uint32_t tabA = smem0 + (uint32_t)a.tab_off + lanebytes;
   const uint32_t tabB = tabA + (uint32_t)a.nA * rowbytes;
   __shared__ int cur_pixel;
-
-  auto load_factors = [&](uint32_t idx, double* f) {
-    const uint32_t addr = idx * rowbytes + tabB;
-    if (NW == 1) f[0] = lds_f64(addr);
-    else {
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        double2 v = lds_f64x2(addr + 512u * q);
-        f[2 * q] = v.x; f[2 * q + 1] = v.y;
-      }
-    }
-  };
 
   bool first = true;
   while (true) {
@@ -782,79 +841,19 @@ __global__ void __launch_bounds__(kPixThreads, (NW <= 2 ? 2 : 1)) mb_k2_pixels(K
       __syncthreads();
     }
 
-    // ---- this warp's piece of the pixel's entry stream (same inner loop as mb_k2_stars) ----------
-    double run[NW], star[NW], fa[NW];
-    LogAcc acc[NW];
-#pragma unroll
-    for (int i = 0; i < NW; ++i) { run[i] = 0.0; star[i] = 0.0; fa[i] = 1.0; acc[i].init(); }
-    auto boundary = [&](uint32_t meta) {
-#pragma unroll
-      for (int i = 0; i < NW; ++i) { star[i] = fma(fa[i], run[i], star[i]); run[i] = 0.0; }
-      if (meta & kNewStar) {
-#pragma unroll
-        for (int i = 0; i < NW; ++i) { acc[i] = star_done(acc[i], star[i]); star[i] = 0.0; }
-      }
-      const uint32_t addr = (meta & kAgeMask) * rowbytes + tabA;
-      if (NW == 1) fa[0] = lds_f64(addr);
-      else {
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-          double2 v = lds_f64x2(addr + 512u * q);
-          fa[2 * q] = v.x; fa[2 * q + 1] = v.y;
-        }
-      }
-    };
-    int64_t pos = a.pix_seg[(size_t)pix * (kPixWarps + 1) + warp];
-    const int64_t end = a.pix_seg[(size_t)pix * (kPixWarps + 1) + warp + 1];
-    int buf = 0;
-    if (pos + lane < end) cp_async16(stage + lane * 16u, a.entries + pos + lane);
-    cp_async_commit();
-    while (pos < end) {
-      const int64_t nxt = pos + kChunk;
-      if (nxt + lane < end) cp_async16(stage + ((buf ^ 1) * kChunk + lane) * 16u, a.entries + nxt + lane);
-      cp_async_commit();
-      cp_async_wait<1>();
-      __syncwarp();
-      const uint32_t cur = stage + buf * kChunk * 16u;
-      const int n = (int)min((int64_t)kChunk, end - pos);
-      int j = 0;
-      for (; j + 4 <= n; j += 4) {
-        uint4 e[4];
-        double f[4][NW];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) e[u] = lds_entry(cur + (j + u) * 16u);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) load_factors(e[u].z, f[u]);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (e[u].w & kNewRun) boundary(e[u].w);
-          const double av = __hiloint2double(e[u].y, e[u].x);
-#pragma unroll
-          for (int i = 0; i < NW; ++i) run[i] = fma(av, f[u][i], run[i]);
-        }
-      }
-      for (; j < n; ++j) {
-        uint4 e = lds_entry(cur + j * 16u);
-        double f[NW];
-        load_factors(e.z, f);
-        if (e.w & kNewRun) boundary(e.w);
-        const double av = __hiloint2double(e.y, e.x);
-#pragma unroll
-        for (int i = 0; i < NW; ++i) run[i] = fma(av, f[i], run[i]);
-      }
-      __syncwarp();
-      buf ^= 1;
-      pos = nxt;
-    }
-    cp_async_wait<0>();
+    // this warp's piece of the pixel's entry stream (same inner loop as mb_k2_stars)
+    Lanes<NW, kModeFactor> L;
+    L.init(tabA, tabB, nullptr);
+    stream_range<NW, kModeFactor>(L, a.ea, a.ec, a.pix_seg[(size_t)pix * (kPixWarps + 1) + warp],
+                                  a.pix_seg[(size_t)pix * (kPixWarps + 1) + warp + 1], st_a, st_c, lane);
+    L.close();
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
-      acc[i] = star_done(acc[i], fma(fa[i], run[i], star[i]));
       const int w = (NW == 1) ? lane : 64 * (i >> 1) + 2 * lane + (i & 1);
-      const long long fixv = __double2ll_rn(acc[i].take_value() * kFixScale);
+      const long long fixv = __double2ll_rn(L.acc[i].take_value() * kFixScale);
       if (fixv) atomicAdd(sacc + w, (unsigned long long)fixv);
-      if (acc[i].bad) atomicAdd(sacc + Wpad + w, (unsigned long long)acc[i].bad);
-      if (acc[i].isnan) atomicAdd(sacc + 2 * Wpad + w, 1ull);
+      if (L.acc[i].bad) atomicAdd(sacc + Wpad + w, (unsigned long long)L.acc[i].bad);
+      if (L.acc[i].isnan) atomicAdd(sacc + 2 * Wpad + w, 1ull);
     }
     __syncthreads();
     double* out = a.out + (size_t)pix * MB_OUT_ROWS * a.W;
