@@ -52,7 +52,7 @@ struct mb_handle {
   mb_model_desc model{};
   ModelDev mdev{};
   std::vector<double> clsx[MB_NPARAM];
-  int nA = 1, nB = 1, nbins = 0, nseg = 0, ncls_total = 0;
+  int nA = 1, nB = 1, nbins = 0, nseg[2] = {0, 0}, ncls_total = 0;
   int64_t G = 0, S_local = 0, S_total = 0, n_entries = 0, n_entries_raw = 0, U = 0;
   int64_t device_bytes = 0;
   // parity hook (host copies)
@@ -61,7 +61,7 @@ struct mb_handle {
   double* d_clsx = nullptr;
   double* d_ea = nullptr;       // entry weights
   uint32_t* d_ec = nullptr;     // entry codes
-  int64_t* d_seg = nullptr;
+  int64_t* d_seg[2] = {nullptr, nullptr};  // segment tables: [0] 768-thread kernels, [1] 512-thread kernel
   uint32_t* d_rowcode = nullptr;
   double* d_H = nullptr;
   double* d_coef = nullptr;
@@ -235,7 +235,7 @@ extern "C" void mb_destroy(mb_handle* h) {
   cudaSetDevice(h->device);
   if (h->peer_world > 1) mb_peer_disconnect(h);
   if (h->d_xbuf) cudaFree(h->d_xbuf);
-  void* ptrs[] = {h->d_clsx, h->d_ea, h->d_ec, h->d_seg, h->d_rowcode, h->d_H, h->d_coef,
+  void* ptrs[] = {h->d_clsx, h->d_ea, h->d_ec, h->d_seg[0], h->d_seg[1], h->d_rowcode, h->d_H, h->d_coef,
                   h->d_bin_agecls, h->d_phi, h->d_tab[0], h->d_tab[1], h->d_tab[2], h->d_tab[3],
                   h->d_F, h->d_counter, h->d_gacc, h->d_T, h->d_out, h->d_pix_seg, h->d_pix_nstars, h->d_Fpix};
   for (void* p : ptrs)
@@ -468,25 +468,28 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
     ++next_pix;
   }
 
-  // ---- segments: star aligned, about four per resident warp ---------------------------------------
-  const int64_t resident_warps = (int64_t)h->sm_count * 24;
-  // measured on B200 (config 3 and its 1/2, 1/8 shards): 1 segment per warp beats 2, 4, 8 by 3-4 %
-  // -- per-segment costs (pipeline restart, one log) outweigh what dynamic balancing recovers
+  // ---- segments: star aligned, one table per block shape ---------------------------------------------
+  // measured on B200 (config 3 and its 1/2, 1/8 shards): 1 segment per resident warp beats 2, 4, 8
+  // by 3-4 % -- per-segment costs (pipeline restart, one log) outweigh what dynamic balancing
+  // recovers -- so the segment count must match the warps the launch really has: one table for
+  // the 768-thread kernels (up to 64 walkers per pass) and one for the 512-thread kernel (128).
   const int spw = o.segments_per_warp > 0 ? o.segments_per_warp : 1;
-  // `want` star-aligned segments of equal entry count (at least 64 entries each): boundary i is the
-  // first star end at or after i * n / want, so every resident warp gets its share
-  int64_t want = std::max<int64_t>(1, std::min<int64_t>(resident_warps * spw, h->n_entries / 64));
-  std::vector<int64_t> seg(1, 0);
-  {
+  std::vector<int64_t> seg[2];
+  for (int t = 0; t < 2; ++t) {
+    const int64_t resident_warps = (int64_t)h->sm_count * (k2_threads(t == 0 ? 2 : 4) / 32);
+    // `want` star-aligned segments of equal entry count (at least 64 entries each): boundary i is
+    // the first star end at or after i * n / want, so every resident warp gets its share
+    int64_t want = std::max<int64_t>(1, std::min<int64_t>(resident_warps * spw, h->n_entries / 64));
+    seg[t].assign(1, 0);
     size_t j = 0;
     for (int64_t i = 1; i <= want && j < star_end_pos.size(); ++i) {
       const int64_t goal = (h->n_entries * i + want - 1) / want;
       while (j < star_end_pos.size() && star_end_pos[j] < goal) ++j;
-      if (j < star_end_pos.size() && star_end_pos[j] > seg.back()) seg.push_back(star_end_pos[j]);
+      if (j < star_end_pos.size() && star_end_pos[j] > seg[t].back()) seg[t].push_back(star_end_pos[j]);
     }
+    if (h->n_entries > 0 && seg[t].back() != h->n_entries) seg[t].push_back(h->n_entries);
+    h->nseg[t] = (int)seg[t].size() - 1;
   }
-  if (h->n_entries > 0 && seg.back() != h->n_entries) seg.push_back(h->n_entries);
-  h->nseg = (int)seg.size() - 1;
 
   // ---- upload ----------------------------------------------------------------------------------------
   std::vector<double> clsx_all;
@@ -500,7 +503,8 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
     if (dev_upload(h, &h->d_ea, wts)) return 1;
     if (dev_upload(h, &h->d_ec, codes)) return 1;
   }
-  if (dev_upload(h, &h->d_seg, seg)) return 1;
+  if (dev_upload(h, &h->d_seg[0], seg[0])) return 1;
+  if (dev_upload(h, &h->d_seg[1], seg[1])) return 1;
   if (mode == MB_MODE_TABLE_GRID && dev_upload(h, &h->d_rowcode, rowcode)) return 1;
   if (h->poisson) {
     if (dev_upload(h, &h->d_H, H)) return 1;
@@ -791,10 +795,10 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     const int kK2Warps = k2_threads(NW) / 32;
     // at least one block even without entries: the Poisson prologue and the result rows live in K2
     int grid = std::min(h->sm_count * per_sm,
-                        std::max(h->poisson ? wp : 1, (h->nseg + kK2Warps - 1) / kK2Warps));
+                        std::max(h->poisson ? wp : 1, (h->nseg[NW == 4] + kK2Warps - 1) / kK2Warps));
     grid = std::min(grid, h->max_blocks);
     K2Args k2{};
-    k2.ea = h->d_ea; k2.ec = h->d_ec; k2.seg = h->d_seg; k2.nseg = h->nseg; k2.FA = FA; k2.T = h->d_T;
+    k2.ea = h->d_ea; k2.ec = h->d_ec; k2.seg = h->d_seg[NW == 4]; k2.nseg = h->nseg[NW == 4]; k2.FA = FA; k2.T = h->d_T;
     k2.gacc = h->d_gacc; k2.counters = h->d_counter; k2.out = d_out;
     k2.nA = h->nA; k2.nB = h->nB; k2.Wpad = Wpad; k2.W = wp; k2.w0 = w0; k2.Wtot = W;
     k2.tab_off = (int32_t)k2_front_bytes(h->nbins, Wpad);

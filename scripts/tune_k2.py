@@ -16,9 +16,11 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "build_variants")
 VARIANTS = {
-    "t768_u4": ["MB_K2_THREADS_LO=768", "MB_K2_UNROLL=4"],
-    "t768_u2": ["MB_K2_THREADS_LO=768", "MB_K2_UNROLL=2"],
-    "t512_u4": ["MB_K2_THREADS_LO=512", "MB_K2_UNROLL=4"],
+    "t768": ["MB_K2_THREADS_LO=768"],
+    "t640": ["MB_K2_THREADS_LO=640"],
+    "t512": ["MB_K2_THREADS_LO=512"],
+    "t896": ["MB_K2_THREADS_LO=896"],
+    "t1024": ["MB_K2_THREADS_LO=1024"],
 }
 
 
@@ -44,6 +46,7 @@ def one(lib, workload, index_mode):
 
     settings, moddata, stars, cfg = synth.make_problem(workload, mode=index_mode)
     model = MB_Model(copy.deepcopy(settings))
+    cfg = dict(cfg, W=int(os.environ.get("MB_WALKERS", cfg["W"])))
     phis = synth.make_walkers(model, cfg["W"], seed=3)
     sh = ShardedLikelihood(model, stars, moddata, device=0)
     dev = torch.device("cuda", 0)
