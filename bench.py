@@ -362,15 +362,17 @@ def run_ours(args):
     sm_mhz = clocks.get("sm_mhz") or 0
     onchip = None
     if mode == "factor" and sm_mhz:
-        # shared-memory wavefronts K2 must issue per entry for W walkers
-        nq = Wpad // 64 if Wpad >= 64 else 1
-        lds_bytes = n_ent * (12 + 8 * Wpad)
-        smem_peak = 128.0 * info["sm_count"] * sm_mhz * 1e6 / 1e9
-        onchip = {"bound": "smem", "bytes_per_launch": lds_bytes,
-                  "achieved": lds_bytes / (kms["k2_stars"] * 1e-3) / 1e9, "peak": smem_peak,
-                  "unit": "GB/s", "frac": lds_bytes / (kms["k2_stars"] * 1e-3) / 1e9 / smem_peak,
-                  "note": f"factor-table loads (8 B x {Wpad} walkers) + 12 B entry broadcast per entry; "
-                          f"peak = 128 B/clk/SM x {info['sm_count']} SMs x {sm_mhz:.0f} MHz"}
+        # shared-memory wavefronts K2 must issue (measured in lds_mix.cu): per
+        # entry 2*NW for the Wpad*8-byte factor row + 1.5 for the broadcast of weight and code
+        nw = Wpad // 32
+        wavefronts = n_ent * (2.0 * nw + 1.5)
+        peak_wf = info["sm_count"] * sm_mhz * 1e6 / 1e9
+        ach = wavefronts / (kms["k2_stars"] * 1e-3) / 1e9
+        onchip = {"bound": "smem", "wavefronts_per_launch": wavefronts, "achieved": ach, "peak": peak_wf,
+                  "unit": "Gwavefront/s", "frac": ach / peak_wf,
+                  "note": f"model count ({2 * nw} factor + 1.5 broadcast wavefronts per entry); peak = 1 "
+                          f"wavefront/clk/SM x {info['sm_count']} SMs x {sm_mhz:.0f} MHz; ncu's measured "
+                          "l1tex data-pipe utilisation for the same kernel is in profiles/"}
     # the north_star's own yardstick: the materialised-physmod design's compulsory bytes per step
     G = len(moddata["Av"])
     P = sum(1 for p in ("logA", "Av", "Rv", "fA") if sharded.spec.kinds[p] != "fixed")

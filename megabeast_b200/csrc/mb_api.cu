@@ -80,7 +80,8 @@ struct mb_handle {
   double* d_T = nullptr;  int64_t cap_T = 0;
   int max_blocks = 0;
   double* d_out = nullptr;  int64_t cap_out = 0;
-  double* h_pin = nullptr;  int64_t cap_pin = 0;
+  double* h_pin = nullptr;  int64_t cap_pin = 0;  // mapped pinned host buffer: phi | result rows
+  double* d_pin = nullptr;                         // its device address
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[MB_NKERNELS + 1] = {};
   int profiling = 0;
@@ -857,18 +858,19 @@ extern "C" int mb_lnlike_begin(mb_handle* h, const double* phi, int32_t W, int32
   if (ndim > 0 && !phi) return fail("mb_lnlike: phi is NULL");
   CK(cudaSetDevice(h->device));
   const int64_t nphi = (int64_t)W * std::max(1, ndim), nout = (int64_t)MB_OUT_ROWS * W;
-  if (ensure(h, &h->d_phi, &h->cap_phi, nphi)) return 1;
-  if (ensure(h, &h->d_out, &h->cap_out, nout)) return 1;
+  // phi (a few KB) and the result rows (3 W doubles) travel through MAPPED pinned host memory:
+  // K0 reads phi over PCIe, K2 writes the rows back, no separate copy operations in the stream
   if (nphi + nout > h->cap_pin) {
+    CK(cudaStreamSynchronize(h->stream));
     if (h->h_pin) CK(cudaFreeHost(h->h_pin));
     h->h_pin = nullptr; h->cap_pin = 0;
-    CK(cudaMallocHost((void**)&h->h_pin, sizeof(double) * (size_t)(nphi + nout)));
+    CK(cudaHostAlloc((void**)&h->h_pin, sizeof(double) * (size_t)(nphi + nout), cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void**)&h->d_pin, h->h_pin, 0));
     h->cap_pin = nphi + nout;
   }
   double* hp = h->h_pin;
   double* ho = h->h_pin + nphi;
   if (ndim > 0) memcpy(hp, phi, sizeof(double) * (size_t)W * ndim);
-  CK(cudaMemcpyAsync(h->d_phi, hp, sizeof(double) * (size_t)nphi, cudaMemcpyHostToDevice, h->stream));
   const double* dtab[MB_NPARAM] = {nullptr, nullptr, nullptr, nullptr};
   for (int p = 0; p < MB_NPARAM; ++p) {
     if (h->model.kind[p] != MB_TABULATED) continue;
@@ -878,8 +880,7 @@ extern "C" int mb_lnlike_begin(mb_handle* h, const double* phi, int32_t W, int32
     CK(cudaMemcpyAsync(h->d_tab[p], tab[p], sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
     dtab[p] = h->d_tab[p];
   }
-  if (eval_device(h, h->d_phi, W, ndim, dtab, h->d_out, h->stream)) return 1;
-  CK(cudaMemcpyAsync(ho, h->d_out, sizeof(double) * (size_t)nout, cudaMemcpyDeviceToHost, h->stream));
+  if (eval_device(h, h->d_pin, W, ndim, dtab, h->d_pin + nphi, h->stream)) return 1;
   h->pending_W = W;
   h->pending_out = ho;
   return 0;
@@ -939,7 +940,8 @@ extern "C" int mb_lnlike_pixels(mb_handle* h, const double* phi, int32_t W, int3
   if (nphi + nout > h->cap_pin) {
     if (h->h_pin) CK(cudaFreeHost(h->h_pin));
     h->h_pin = nullptr; h->cap_pin = 0;
-    CK(cudaMallocHost((void**)&h->h_pin, sizeof(double) * (size_t)(nphi + nout)));
+    CK(cudaHostAlloc((void**)&h->h_pin, sizeof(double) * (size_t)(nphi + nout), cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void**)&h->d_pin, h->h_pin, 0));
     h->cap_pin = nphi + nout;
   }
   double* hp = h->h_pin;
