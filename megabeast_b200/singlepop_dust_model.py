@@ -296,8 +296,10 @@ def lnprob(phi, megabeast_model, star_lnpgriddata, beast_moddata):
             return -np.inf
         return ln_prior + megabeast_model.lnlike(phi, star_lnpgriddata, beast_moddata)
     ln_prior = np.asarray(megabeast_model.lnprior(phi), dtype=np.float64)
-    out = np.full(phi.shape[0], -np.inf)
     inside = np.isfinite(ln_prior)
+    if inside.all():  # the usual case late in a chain: no masking, no copies
+        return ln_prior + megabeast_model.lnlike(phi, star_lnpgriddata, beast_moddata)
+    out = np.full(phi.shape[0], -np.inf)
     if inside.any():
         out[inside] = ln_prior[inside] + megabeast_model.lnlike(
             phi[inside], star_lnpgriddata, beast_moddata
