@@ -111,7 +111,8 @@ typedef struct {
   int32_t keep_indices;    /* retain the gathered grid rows for mb_gathered_indices */
   int32_t merge_duplicates;/* pre-sum a star's entries that share all class codes (FACTOR/TABLE_UNIQUE) */
   int32_t segments_per_warp;/* scheduling granularity of K2: entry-stream segments per resident warp (0 -> 1) */
-  int32_t reserved[11];
+  int32_t tail_percent;    /* percent of the entries cut into small dynamically claimed segments (0 -> none) */
+  int32_t reserved[10];
 } mb_options;
 
 typedef struct {
@@ -233,6 +234,12 @@ int mb_gathered_indices(const mb_handle* h, int64_t* rows, int64_t rows_cap, int
 #define MB_NKERNELS 4
 int mb_set_profiling(mb_handle* h, int32_t on);
 int mb_last_kernel_ms(const mb_handle* h, float ms[MB_NKERNELS]);
+/* With profiling on, the last K2 launch also leaves per-block phase stamps (%globaltimer, in
+ * microseconds since the first block started): us[block][6] = start, tables staged, Poisson
+ * prologue done, star loop done, block reduced, end (last block only; -1 elsewhere).  Returns the
+ * number of blocks written (at most cap_blocks), 0 if there is no timeline, -1 on error. */
+#define MB_TIMELINE_POINTS 6
+int mb_last_k2_timeline(const mb_handle* h, double* us, int32_t cap_blocks);
 
 /* One-time ingest (helpers.py:33-41 get_likelihoods): vals[k,s] = exp(lnp[k,s]) /
  * prior_weight[indxs[k,s]] on finite entries, in place on the host array, computed on `device`. */

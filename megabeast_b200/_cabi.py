@@ -100,7 +100,8 @@ class Options(ctypes.Structure):
         ("keep_indices", ctypes.c_int32),
         ("merge_duplicates", ctypes.c_int32),
         ("segments_per_warp", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 11),
+        ("tail_percent", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 10),
     ]
 
 
@@ -184,6 +185,7 @@ SIGNATURES = {
     "mb_gathered_indices": (ctypes.c_int, [ctypes.c_void_p, c_int64_p, ctypes.c_int64, c_int64_p]),
     "mb_set_profiling": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     "mb_last_kernel_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float * MB_NKERNELS)]),
+    "mb_last_k2_timeline": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int32]),
     "mb_likelihoods_from_lnp": (
         ctypes.c_int,
         [ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, c_int64_p, c_double_p, ctypes.c_int64,

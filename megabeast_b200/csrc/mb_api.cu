@@ -73,6 +73,8 @@ struct mb_handle {
   double* d_F = nullptr;    // [nA+nB][128]
   unsigned int* d_counter = nullptr;
   unsigned long long* d_gacc = nullptr;
+  unsigned long long* d_timeline = nullptr;    // K2 phase stamps, allocated when profiling is on
+  int timeline_blocks = 0;
   unsigned long long* d_xbuf = nullptr;        // this GPU's exchange buffer (cudaMalloc: IPC-exportable)
   unsigned long long* peer_xbuf[MB_MAX_PEERS] = {};
   int peer_world = 1, peer_rank = 0;
@@ -174,7 +176,8 @@ static size_t k2_front_bytes(int nbins, int Wpad) {
   const int threads = k2_threads(Wpad / 32);
   size_t stage = (size_t)(threads / 32) * kStageBytes;
   size_t pois = nbins > 0 ? (size_t)(poisson_nslice(threads, nbins) + 1) * nbins * 16 : 0;
-  return (std::max(stage, pois) + 15) & ~(size_t)15;
+  size_t slabs = (size_t)(threads / 32) * 3 * Wpad * 8;  // block reduction: one slab per warp
+  return (std::max(std::max(stage, pois), slabs) + 15) & ~(size_t)15;
 }
 static size_t k2_smem_bytes(int mode, int nA, int nB, int nbins, int Wpad) {
   size_t tables = mode == kModeFactor ? (size_t)(nA + nB) * Wpad * sizeof(double) : 0;
@@ -238,7 +241,8 @@ extern "C" void mb_destroy(mb_handle* h) {
   if (h->d_xbuf) cudaFree(h->d_xbuf);
   void* ptrs[] = {h->d_clsx, h->d_ea, h->d_ec, h->d_seg[0], h->d_seg[1], h->d_rowcode, h->d_H, h->d_coef,
                   h->d_bin_agecls, h->d_phi, h->d_tab[0], h->d_tab[1], h->d_tab[2], h->d_tab[3],
-                  h->d_F, h->d_counter, h->d_gacc, h->d_T, h->d_out, h->d_pix_seg, h->d_pix_nstars, h->d_Fpix};
+                  h->d_F, h->d_counter, h->d_gacc, h->d_T, h->d_out, h->d_pix_seg, h->d_pix_nstars, h->d_Fpix,
+                  h->d_timeline};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -475,20 +479,28 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
   // recovers -- so the segment count must match the warps the launch really has: one table for
   // the 768-thread kernels (up to 64 walkers per pass) and one for the 512-thread kernel (128).
   const int spw = o.segments_per_warp > 0 ? o.segments_per_warp : 1;
+  // ... optionally plus a tail pool: the last tail_percent of the entries cut into small segments
+  // that warps claim dynamically after their own big one.  Measured on B200 (4-16 %, config 3 and
+  // its 1/8 shard): no gain over none, so the default is none.
+  const double tail_frac = o.tail_percent > 0 ? std::min(50, o.tail_percent) / 100.0 : 0.0;
   std::vector<int64_t> seg[2];
   for (int t = 0; t < 2; ++t) {
     const int64_t resident_warps = (int64_t)h->sm_count * (k2_threads(t == 0 ? 2 : 4) / 32);
     // `want` star-aligned segments of equal entry count (at least 64 entries each): boundary i is
-    // the first star end at or after i * n / want, so every resident warp gets its share
-    int64_t want = std::max<int64_t>(1, std::min<int64_t>(resident_warps * spw, h->n_entries / 64));
+    // the first star end at or after its goal, so every resident warp gets its share
+    const int64_t n = h->n_entries;
+    int64_t want = std::max<int64_t>(1, std::min<int64_t>(resident_warps * spw, n / 64));
+    const int64_t n_main = want >= resident_warps ? (int64_t)((1.0 - tail_frac) * (double)n) : n;
+    const int64_t want_tail = n_main < n ? std::max<int64_t>(1, (n - n_main) / 96) : 0;
     seg[t].assign(1, 0);
     size_t j = 0;
-    for (int64_t i = 1; i <= want && j < star_end_pos.size(); ++i) {
-      const int64_t goal = (h->n_entries * i + want - 1) / want;
+    for (int64_t i = 1; i <= want + want_tail && j < star_end_pos.size(); ++i) {
+      const int64_t goal = i <= want ? (n_main * i + want - 1) / want
+                                     : n_main + ((n - n_main) * (i - want) + want_tail - 1) / want_tail;
       while (j < star_end_pos.size() && star_end_pos[j] < goal) ++j;
       if (j < star_end_pos.size() && star_end_pos[j] > seg[t].back()) seg[t].push_back(star_end_pos[j]);
     }
-    if (h->n_entries > 0 && seg[t].back() != h->n_entries) seg[t].push_back(h->n_entries);
+    if (n > 0 && seg[t].back() != n) seg[t].push_back(n);
     h->nseg[t] = (int)seg[t].size() - 1;
   }
 
@@ -706,7 +718,30 @@ extern "C" int mb_gathered_indices(const mb_handle* h, int64_t* rows, int64_t ca
 extern "C" int mb_set_profiling(mb_handle* h, int32_t on) {
   if (!h) return fail("null handle");
   h->profiling = on;
+  if (on && !h->d_timeline) {
+    CK(cudaSetDevice(h->device));
+    if (dev_alloc(h, &h->d_timeline, (int64_t)h->max_blocks * kTimelinePoints)) return 1;
+  }
   return 0;
+}
+
+extern "C" int mb_last_k2_timeline(const mb_handle* h, double* us, int32_t cap_blocks) {
+  if (!h || !us) { fail("mb_last_k2_timeline: null argument"); return -1; }
+  if (!h->d_timeline || h->timeline_blocks <= 0) return 0;
+  const int nb = std::min(h->timeline_blocks, (int)cap_blocks);
+  std::vector<unsigned long long> t((size_t)h->timeline_blocks * kTimelinePoints);
+  if (cudaMemcpy(t.data(), h->d_timeline, sizeof(unsigned long long) * t.size(), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    fail("mb_last_k2_timeline: copy failed");
+    return -1;
+  }
+  unsigned long long t0 = ~0ull;
+  for (int b = 0; b < h->timeline_blocks; ++b) t0 = std::min(t0, t[(size_t)b * kTimelinePoints]);
+  for (int b = 0; b < nb; ++b)
+    for (int k = 0; k < kTimelinePoints; ++k) {
+      unsigned long long v = t[(size_t)b * kTimelinePoints + k];
+      us[(size_t)b * kTimelinePoints + k] = v >= t0 && v != 0 ? (double)(v - t0) * 1e-3 : -1.0;
+    }
+  return nb;
 }
 extern "C" int mb_last_kernel_ms(const mb_handle* h, float ms[MB_NKERNELS]) {
   if (!h) return fail("null handle");
@@ -714,12 +749,24 @@ extern "C" int mb_last_kernel_ms(const mb_handle* h, float ms[MB_NKERNELS]) {
   return 0;
 }
 
+// K2 is launched with programmatic stream serialization: its blocks may be placed while the
+// preceding kernel (K0 / K1) is still running and wait inside the kernel (griddepcontrol.wait)
 template <int MODE>
-static void launch_k2(int NW, int grid, size_t smem, cudaStream_t st, const K2Args& a) {
+static cudaError_t launch_k2(int NW, int grid, size_t smem, cudaStream_t st, const K2Args& a) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)k2_threads(NW));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
   switch (NW) {
-    case 1: mb_k2_stars<1, MODE><<<grid, k2_threads(1), smem, st>>>(a); break;
-    case 2: mb_k2_stars<2, MODE><<<grid, k2_threads(2), smem, st>>>(a); break;
-    default: mb_k2_stars<4, MODE><<<grid, k2_threads(4), smem, st>>>(a); break;
+    case 1: return cudaLaunchKernelEx(&cfg, mb_k2_stars<1, MODE>, a);
+    case 2: return cudaLaunchKernelEx(&cfg, mb_k2_stars<2, MODE>, a);
+    default: return cudaLaunchKernelEx(&cfg, mb_k2_stars<4, MODE>, a);
   }
 }
 
@@ -806,14 +853,20 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     k2.pois.Ht = h->d_H; k2.pois.bin_agecls = h->d_bin_agecls; k2.pois.coef = h->d_coef;
     k2.pois.n_stars = (double)h->S_total; k2.pois.nbins = h->poisson ? h->nbins : 0;
     k2.pois.nslice = poisson_nslice(k2_threads(NW), h->nbins);
+    k2.timeline = nullptr;
+    if (prof && h->d_timeline) {
+      CK(cudaMemsetAsync(h->d_timeline, 0, sizeof(unsigned long long) * (size_t)grid * kTimelinePoints, st));
+      k2.timeline = h->d_timeline;
+      h->timeline_blocks = grid;
+    }
     k2.peer.world = h->peer_world; k2.peer.rank = h->peer_rank;
     if (h->peer_world > 1) {
       k2.peer.seq = ++h->peer_seq;
       for (int p = 0; p < h->peer_world; ++p) k2.peer.xbuf[p] = h->peer_xbuf[p];
     }
-    if (kmode == kModeFactor) launch_k2<kModeFactor>(NW, grid, smem, st, k2);
-    else if (kmode == kModeTable) launch_k2<kModeTable>(NW, grid, smem, st, k2);
-    else launch_k2<kModeTableGrid>(NW, grid, smem, st, k2);
+    if (kmode == kModeFactor) CK(launch_k2<kModeFactor>(NW, grid, smem, st, k2));
+    else if (kmode == kModeTable) CK(launch_k2<kModeTable>(NW, grid, smem, st, k2));
+    else CK(launch_k2<kModeTableGrid>(NW, grid, smem, st, k2));
     ++launches;
     if (prof) {
       CK(cudaEventRecord(h->ev[4], st));

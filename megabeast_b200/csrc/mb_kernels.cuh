@@ -134,6 +134,9 @@ constexpr int kK0Threads = 128;
 
 __global__ void __launch_bounds__(kK0Threads) mb_k0_factors(const __grid_constant__ K0Args a) {
   extern __shared__ double lut[];  // [sum of ncls over the parameters], offsets = model.clsoff
+  // programmatic dependent launch: K2's blocks may be scheduled while this grid still runs; they
+  // wait (griddepcontrol.wait) for this grid's completion before touching the tables
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const ModelDev& m = a.model;
   const int pix = blockIdx.x / a.Wpad, w = blockIdx.x - pix * a.Wpad;
   const int wr = w < a.W ? w : a.W - 1;
@@ -384,7 +387,16 @@ struct K2Args {
   int32_t tab_off;           // byte offset of the factor tables in dynamic shared memory
   PoissonArgs pois;          // N-stars term, computed by the first W blocks before the star loop
   PeerArgs peer;             // cross-GPU reduction of the shard totals
+  unsigned long long* timeline;  // optional [gridDim.x][kTimelinePoints] %globaltimer stamps (profiling)
 };
+constexpr int kTimelinePoints = 6;  // start, tables staged, Poisson done, stars done, block reduced, end
+__device__ __forceinline__ void stamp(unsigned long long* timeline, int point) {
+  if (timeline && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    timeline[(size_t)blockIdx.x * kTimelinePoints + point] = t;
+  }
+}
 
 // block shape: ONE block per SM -- 768 threads (<= 85 registers) for up to 64 walkers per pass,
 // 512 threads (<= 128 registers) for 128; one copy of the factor tables per SM
@@ -600,6 +612,9 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   const uint32_t st_c = st_a + 2 * kChunk * 8u;
   const uint32_t tabA = smem0 + (uint32_t)a.tab_off + lanebytes;
   const uint32_t tabB = tabA + (uint32_t)a.nA * rowbytes;
+  stamp(a.timeline, 0);
+  // launched with programmatic stream serialization: wait here for K0 (the tables) to complete
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (MODE == kModeFactor) {
     const int n2 = (a.nA + a.nB) * Wpad / 2;
     const double2* src = reinterpret_cast<const double2*>(a.FA);
@@ -607,6 +622,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     for (int i = threadIdx.x; i < n2; i += blockDim.x) dst[i] = __ldg(src + i);
     __syncthreads();
   }
+  stamp(a.timeline, 1);
   // Poisson prologue: block b computes the N-stars term of walkers b, b + gridDim.x, ... from the
   // tables it just staged; dynamic segment scheduling absorbs the few microseconds it starts late
   {
@@ -621,6 +637,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     }
   }
 
+  stamp(a.timeline, 2);
   Lanes<NW, MODE> L;
   L.init(tabA, tabB, reinterpret_cast<const char*>(a.T) + lanebytes);
 
@@ -645,24 +662,30 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   // ---- K3 (fused): warp -> block (shared atomics) -> grid (global atomics) reduction over stars,
   // all in integers; the last block to finish converts and writes the result rows.
   __syncthreads();
-  unsigned long long* sacc = reinterpret_cast<unsigned long long*>(smem_raw);  // [3][Wpad], reuses stage
-  for (int i = threadIdx.x; i < 3 * Wpad; i += blockDim.x) sacc[i] = 0ull;
-  __syncthreads();
+  stamp(a.timeline, 3);
+  // every warp parks its per-walker integers in its own slab of the (now idle) stage, then
+  // 3 * Wpad threads add the slabs: no shared-memory atomics (64-bit ones are CAS loops)
+  unsigned long long* slab = reinterpret_cast<unsigned long long*>(smem_raw);  // [warps][3][Wpad]
 #pragma unroll
   for (int i = 0; i < NW; ++i) {
-    int w = (NW == 1) ? lane : 64 * (i >> 1) + 2 * lane + (i & 1);
-    atomicAdd(sacc + w, (unsigned long long)fix[i]);
-    if (L.acc[i].bad) atomicAdd(sacc + Wpad + w, (unsigned long long)L.acc[i].bad);
-    if (L.acc[i].isnan) atomicAdd(sacc + 2 * Wpad + w, 1ull);
+    const int w = (NW == 1) ? lane : 64 * (i >> 1) + 2 * lane + (i & 1);
+    slab[((size_t)warp * 3 + 0) * Wpad + w] = (unsigned long long)fix[i];
+    slab[((size_t)warp * 3 + 1) * Wpad + w] = (unsigned long long)L.acc[i].bad;
+    slab[((size_t)warp * 3 + 2) * Wpad + w] = (unsigned long long)L.acc[i].isnan;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 3 * Wpad; i += blockDim.x)
-    if (sacc[i] != 0ull) atomicAdd(a.gacc + i, sacc[i]);
+  unsigned long long mine = 0ull;
+  if (threadIdx.x < 3 * Wpad) {
+    for (int wp = 0; wp < kK2Warps; ++wp) mine += slab[(size_t)wp * 3 * Wpad + threadIdx.x];
+    if (mine != 0ull) atomicAdd(a.gacc + threadIdx.x, mine);
+  }
+  unsigned long long* sacc = slab;  // scratch for the last block below
   __shared__ unsigned int ticket;
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) ticket = atomicAdd(a.counters + kCtrBlocks, 1u);
   __syncthreads();
+  stamp(a.timeline, 4);
   if (ticket != gridDim.x - 1) return;
   __threadfence();
   // last block of this GPU: take the shard totals, leave the accumulators zero for the next launch
@@ -713,6 +736,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     a.out[(size_t)MB_OUT_STARSUM * a.Wtot + a.w0 + w] = (nnan || timed_out) ? nan("") : (double)f / kFixScale;
     a.out[(size_t)MB_OUT_NONFINITE * a.Wtot + a.w0 + w] = timed_out ? -1.0 : (double)nbad;
   }
+  stamp(a.timeline, 5);
 }
 
 // ---- pixel batches: many independent small ensembles over one shared grid -----------------------

@@ -146,6 +146,7 @@ class LikelihoodEngine:
                 opt.keep_indices = int(bool(keep_indices))
                 opt.merge_duplicates = int(bool(merge_duplicates))
                 opt.segments_per_warp = int(os.environ.get("MB_SEGMENTS_PER_WARP", segments_per_warp))
+                opt.tail_percent = int(os.environ.get("MB_TAIL_PERCENT", 0))
                 h = ctypes.c_void_p()
                 if pixel_offsets is not None:
                     _cabi.check(
@@ -235,6 +236,16 @@ class LikelihoodEngine:
         ms = (ctypes.c_float * _cabi.MB_NKERNELS)()
         _cabi.check(self.lib.mb_last_kernel_ms(self.handles[i], ctypes.byref(ms)))
         return dict(zip(_cabi.KERNEL_NAMES, list(ms)))
+
+    def last_k2_timeline(self, i=0):
+        """Per-block phase stamps of the last K2 launch (profiling on): array [blocks][6] in
+        microseconds -- start, tables staged, Poisson done, star loop done, block reduced, end."""
+        cap = 1024
+        us = np.empty((cap, 6))
+        n = self.lib.mb_last_k2_timeline(self.handles[i], _cabi.dptr(us), cap)
+        if n < 0:
+            _cabi.check(1)
+        return us[:n]
 
     # -- evaluation ------------------------------------------------------------------------------
     def _tabs(self, tabs, W):
