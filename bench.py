@@ -338,7 +338,6 @@ def run_ours(args):
     alg = {
         "k0_factors": 8 * W * ndim + 8 * (nA + nB) * Wpad,
         "k1_expand": (4 * U if mode == "table_grid" else 0) + 8 * U * Wpad,
-        "unused": 0,
         "k2_stars": 12 * n_ent + 16 * info["n_bins"] * nB + (8 * (nA + nB) * Wpad if mode == "factor"
                                   else 8 * Wpad * (touched if touched is not None else U)),
     }

@@ -229,9 +229,9 @@ int mb_class_values(const mb_handle* h, int32_t param, double* out, int32_t cap)
 int mb_gathered_indices(const mb_handle* h, int64_t* rows, int64_t rows_cap, int64_t* offsets);
 
 /* Per-kernel device time (ms) of the last evaluation, measured with CUDA events when
- * profiling was enabled with mb_set_profiling(h, 1).  Order: K0 factors + Poisson term, K1 expand
- * (TABLE modes), (unused), K2 stars (its tail is the K3 reduction over stars). */
-#define MB_NKERNELS 4
+ * profiling was enabled with mb_set_profiling(h, 1).  Order: K0 factor tables, K1 expand (TABLE
+ * modes, else ~0), K2 stars (Poisson prologue + star loop + its tail, the K3 reduction). */
+#define MB_NKERNELS 3
 int mb_set_profiling(mb_handle* h, int32_t on);
 int mb_last_kernel_ms(const mb_handle* h, float ms[MB_NKERNELS]);
 /* With profiling on, the last K2 launch also leaves per-block phase stamps (%globaltimer, in

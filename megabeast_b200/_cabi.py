@@ -12,7 +12,7 @@ from . import build as _build
 MB_ABI_VERSION = 1
 MB_NPARAM = 4
 MB_MAX_NODES = 64
-MB_NKERNELS = 4
+MB_NKERNELS = 3
 MB_OUT_ROWS = 3
 PARAMS = ("logA", "Av", "Rv", "fA")  # enum mb_param order
 
@@ -37,7 +37,7 @@ KIND_VARNAMES = {
 }
 MODE = {"auto": 0, "factor": 1, "table_unique": 2, "table_grid": 3}
 MODE_NAME = {v: k for k, v in MODE.items()}
-KERNEL_NAMES = ("k0_factors", "k1_expand", "unused", "k2_stars")
+KERNEL_NAMES = ("k0_factors", "k1_expand", "k2_stars")
 
 STATUS_NONFINITE_STAR = 1
 STATUS_TOTAL_ZERO = 2

@@ -621,7 +621,7 @@ static int eval_pixels_device(mb_handle* h, const double* d_phi, int W, int ndim
   k0.model = h->mdev; k0.clsx = h->d_clsx; k0.phi = d_phi; k0.F = h->d_Fpix;
   k0.nA = h->nA; k0.nB = h->nB; k0.W = W; k0.Wpad = Wpad; k0.ndim = ndim; k0.ncls_total = h->ncls_total;
   mb_k0_factors<<<(unsigned)(h->P * Wpad), kK0Threads, sizeof(double) * std::max(1, h->ncls_total), st>>>(k0);
-  if (prof) { CK(cudaEventRecord(h->ev[1], st)); CK(cudaEventRecord(h->ev[2], st)); CK(cudaEventRecord(h->ev[3], st)); }
+  if (prof) { CK(cudaEventRecord(h->ev[1], st)); CK(cudaEventRecord(h->ev[2], st)); }
   KPixArgs ka{};
   ka.ea = h->d_ea; ka.ec = h->d_ec; ka.pix_seg = h->d_pix_seg; ka.F = h->d_Fpix; ka.pix_nstars = h->d_pix_nstars;
   ka.out = d_out; ka.counters = h->d_counter;
@@ -643,8 +643,8 @@ static int eval_pixels_device(mb_handle* h, const double* d_phi, int W, int ndim
     default: mb_k2_pixels<4><<<grid, kPixThreads, smem, st>>>(ka); break;
   }
   if (prof) {
-    CK(cudaEventRecord(h->ev[4], st));
-    CK(cudaEventSynchronize(h->ev[4]));
+    CK(cudaEventRecord(h->ev[3], st));
+    CK(cudaEventSynchronize(h->ev[3]));
     for (int i = 0; i < MB_NKERNELS; ++i) CK(cudaEventElapsedTime(&h->last_ms[i], h->ev[i], h->ev[i + 1]));
   }
   CK(cudaGetLastError());
@@ -792,7 +792,7 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
   CK(cudaSetDevice(h->device));
   const int kmode = h->mode == MB_MODE_FACTOR ? kModeFactor : h->mode == MB_MODE_TABLE_UNIQUE ? kModeTable : kModeTableGrid;
   const bool prof = h->profiling != 0;
-  float acc_ms[MB_NKERNELS] = {0, 0, 0, 0};
+  float acc_ms[MB_NKERNELS] = {0, 0, 0};
   int launches = 0;
   for (int w0 = 0; w0 < W;) {
     int rem = W - w0;
@@ -830,7 +830,6 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
       ++launches;
     }
     if (prof) CK(cudaEventRecord(h->ev[2], st));
-    if (prof) CK(cudaEventRecord(h->ev[3], st));
     size_t smem = k2_smem_bytes(kmode, h->nA, h->nB, h->nbins, Wpad);
     // occupancy query cached per pass shape (it costs microseconds of host time per call)
     int& cached = h->occ_cache[NW == 1 ? 0 : NW == 2 ? 1 : 2];
@@ -869,8 +868,8 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     else CK(launch_k2<kModeTableGrid>(NW, grid, smem, st, k2));
     ++launches;
     if (prof) {
-      CK(cudaEventRecord(h->ev[4], st));
-      CK(cudaEventSynchronize(h->ev[4]));
+      CK(cudaEventRecord(h->ev[3], st));
+      CK(cudaEventSynchronize(h->ev[3]));
       for (int i = 0; i < MB_NKERNELS; ++i) {
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));

@@ -12,14 +12,15 @@
 //
 //     physmod[g,w] = FA[cA(g)][w] * FB[cB(g)][w]       FA: age (logA) factor, FB: dust factor
 //
-// K0  mb_k0_factors      per-walker factor tables FA, FB from phi (tiny)
+// K0  mb_k0_factors      one block per walker: prior models on the classes -> factor tables FA, FB
 // K1  mb_k1_expand       TABLE modes: physmod table T[u][w] = FA*FB          (HBM write bound)
 // K2  mb_k2_stars<..>    prologue (first W blocks): N-stars sufficient statistics x FB -> per-bin
 //                        sums -> expected N -> Poisson term.  Then the hot loop:
-//                        stream (weight, table row) entries once for all walkers,
-//                        look the factors up (smem) or gather T rows (L2/HBM), per-star fp64
-//                        sum, log via mantissa/exponent product; K3 is fused into its tail:
-//                        warp -> block -> grid reduction over stars in 64-bit fixed point
+//                        stream (weight, code) entries once for all walkers, look the factors up
+//                        (smem) or gather T rows (L2/HBM), per-star fp64 sum, log via
+//                        mantissa/exponent product.  K3 is fused into its tail: warp -> block ->
+//                        grid (-> GPUs over NVLink peer memory) reduction in 64-bit fixed point
+// KPX mb_k2_pixels<..>   pixel batches: one block per pixel at a time, same inner loop
 //
 // Lanes of a warp are WALKERS, a warp walks one star's entries at a time, so every control
 // decision in K2 (run boundary, end of star) is warp-uniform.

@@ -66,10 +66,6 @@ class ModelSpec:
         return m
 
 
-def _col(moddata, key):
-    return np.ascontiguousarray(moddata[key], dtype=np.float64)
-
-
 class LikelihoodEngine:
     def __init__(self, spec, star_lnpgriddata, beast_moddata, massmult=None, devices=None,
                  mode="auto", star_range=None, n_stars_total=None, keep_indices=False,
