@@ -112,7 +112,11 @@ typedef struct {
   int32_t merge_duplicates;/* pre-sum a star's entries that share all class codes (FACTOR/TABLE_UNIQUE) */
   int32_t segments_per_warp;/* scheduling granularity of K2: entry-stream segments per resident warp (0 -> 1) */
   int32_t tail_percent;    /* percent of the entries cut into small dynamically claimed segments (0 -> none) */
-  int32_t reserved[10];
+  int32_t table_precision; /* FACTOR mode: 0 = fp64 factor tables (default, the 1e-9 parity mode); 1 = 32-bit
+                              tables in shared memory (the high word of each fp64 factor, rounded to 21
+                              significant bits; all sums still fp64): half the shared-memory traffic, ~8 %
+                              faster, measured error 7e-9 relative on lnlike, stated tolerance 1e-7 */
+  int32_t reserved[9];
 } mb_options;
 
 typedef struct {

@@ -101,7 +101,8 @@ class Options(ctypes.Structure):
         ("merge_duplicates", ctypes.c_int32),
         ("segments_per_warp", ctypes.c_int32),
         ("tail_percent", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 10),
+        ("table_precision", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 9),
     ]
 
 

@@ -90,6 +90,7 @@ struct mb_handle {
   float last_ms[MB_NKERNELS] = {};
   int last_wp = 0, last_launches = 0;
   int pending_W = 0;
+  int table_bytes = 8;   // FACTOR-mode shared-memory table element: 8 = fp64, 4 = fp32
   int occ_cache[3] = {0, 0, 0};
   size_t occ_smem[3] = {0, 0, 0};
   // pixel batches
@@ -179,8 +180,8 @@ static size_t k2_front_bytes(int nbins, int Wpad) {
   size_t slabs = (size_t)(threads / 32) * 3 * Wpad * 8;  // block reduction: one slab per warp
   return (std::max(std::max(stage, pois), slabs) + 15) & ~(size_t)15;
 }
-static size_t k2_smem_bytes(int mode, int nA, int nB, int nbins, int Wpad) {
-  size_t tables = mode == kModeFactor ? (size_t)(nA + nB) * Wpad * sizeof(double) : 0;
+static size_t k2_smem_bytes(int mode, int nA, int nB, int nbins, int Wpad, int elem_bytes = 8) {
+  size_t tables = mode == kModeFactor ? (size_t)(nA + nB) * Wpad * elem_bytes : 0;
   return k2_front_bytes(nbins, Wpad) + tables;
 }
 
@@ -271,6 +272,8 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
   struct Guard { mb_handle* h; bool ok = false; ~Guard() { if (!ok) mb_destroy(h); } } guard{h};
   h->device = o.device;
   h->model = *model;
+  if (o.table_precision != 0 && o.table_precision != 1) return fail("table_precision must be 0 (fp64) or 1 (fp32)");
+  h->table_bytes = o.table_precision == 1 ? 4 : 8;
   CK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, o.device));
   CK(cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, o.device));
   h->max_smem -= 1024;  // room for the kernels' few bytes of static shared memory
@@ -336,7 +339,7 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
 
   // ---- mode ----------------------------------------------------------------------------------------
   int mode = o.mode;
-  const bool factor_fits = k2_smem_bytes(kModeFactor, h->nA, h->nB, mm ? mm->n_ages * mm->n_mets : 0, 32) <= (size_t)h->max_smem;
+  const bool factor_fits = k2_smem_bytes(kModeFactor, h->nA, h->nB, mm ? mm->n_ages * mm->n_mets : 0, 32, h->table_bytes) <= (size_t)h->max_smem;
   if (mode == MB_MODE_AUTO) mode = factor_fits ? MB_MODE_FACTOR : MB_MODE_TABLE_UNIQUE;
   if (mode == MB_MODE_FACTOR && !factor_fits)
     return fail("factor tables (%d + %d classes) do not fit shared memory; use a TABLE mode", h->nA, h->nB);
@@ -539,6 +542,9 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
     int big = h->max_smem;
 #define MB_OPTIN(NW, MODE) CK(cudaFuncSetAttribute(mb_k2_stars<NW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, big))
     MB_OPTIN(1, kModeFactor); MB_OPTIN(2, kModeFactor); MB_OPTIN(4, kModeFactor);
+    CK(cudaFuncSetAttribute(mb_k2_stars<1, kModeFactor, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(mb_k2_stars<2, kModeFactor, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK(cudaFuncSetAttribute(mb_k2_stars<4, kModeFactor, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     MB_OPTIN(1, kModeTable); MB_OPTIN(2, kModeTable); MB_OPTIN(4, kModeTable);
     MB_OPTIN(1, kModeTableGrid); MB_OPTIN(2, kModeTableGrid); MB_OPTIN(4, kModeTableGrid);
 #undef MB_OPTIN
@@ -751,7 +757,7 @@ extern "C" int mb_last_kernel_ms(const mb_handle* h, float ms[MB_NKERNELS]) {
 
 // K2 is launched with programmatic stream serialization: its blocks may be placed while the
 // preceding kernel (K0 / K1) is still running and wait inside the kernel (griddepcontrol.wait)
-template <int MODE>
+template <int MODE, typename TF = double>
 static cudaError_t launch_k2(int NW, int grid, size_t smem, cudaStream_t st, const K2Args& a) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
@@ -764,23 +770,24 @@ static cudaError_t launch_k2(int NW, int grid, size_t smem, cudaStream_t st, con
   cfg.attrs = &attr;
   cfg.numAttrs = 1;
   switch (NW) {
-    case 1: return cudaLaunchKernelEx(&cfg, mb_k2_stars<1, MODE>, a);
-    case 2: return cudaLaunchKernelEx(&cfg, mb_k2_stars<2, MODE>, a);
-    default: return cudaLaunchKernelEx(&cfg, mb_k2_stars<4, MODE>, a);
+    case 1: return cudaLaunchKernelEx(&cfg, mb_k2_stars<1, MODE, TF>, a);
+    case 2: return cudaLaunchKernelEx(&cfg, mb_k2_stars<2, MODE, TF>, a);
+    default: return cudaLaunchKernelEx(&cfg, mb_k2_stars<4, MODE, TF>, a);
   }
 }
 
-template <int MODE>
+template <int MODE, typename TF = double>
 static int k2_occ(int NW, size_t smem) {
   int n = 0;
   switch (NW) {
-    case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<1, MODE>, k2_threads(1), smem); break;
-    case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<2, MODE>, k2_threads(2), smem); break;
-    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<4, MODE>, k2_threads(4), smem); break;
+    case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<1, MODE, TF>, k2_threads(1), smem); break;
+    case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<2, MODE, TF>, k2_threads(2), smem); break;
+    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<4, MODE, TF>, k2_threads(4), smem); break;
   }
   return n;
 }
-static int k2_blocks_per_sm(int kmode, int NW, size_t smem) {
+static int k2_blocks_per_sm(int kmode, int NW, size_t smem, int table_bytes) {
+  if (kmode == kModeFactor && table_bytes == 4) return k2_occ<kModeFactor, float>(NW, smem);
   return kmode == kModeFactor ? k2_occ<kModeFactor>(NW, smem)
          : kmode == kModeTable ? k2_occ<kModeTable>(NW, smem) : k2_occ<kModeTableGrid>(NW, smem);
 }
@@ -797,7 +804,7 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
   for (int w0 = 0; w0 < W;) {
     int rem = W - w0;
     int NW = rem <= 32 ? 1 : rem <= 64 ? 2 : 4;
-    while (NW > 1 && k2_smem_bytes(kmode, h->nA, h->nB, h->nbins, 32 * NW) > (size_t)h->max_smem) NW >>= 1;
+    while (NW > 1 && k2_smem_bytes(kmode, h->nA, h->nB, h->nbins, 32 * NW, h->table_bytes) > (size_t)h->max_smem) NW >>= 1;
     const int Wpad = 32 * NW;
     const int wp = std::min(rem, Wpad);
     h->last_wp = wp;
@@ -830,11 +837,11 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
       ++launches;
     }
     if (prof) CK(cudaEventRecord(h->ev[2], st));
-    size_t smem = k2_smem_bytes(kmode, h->nA, h->nB, h->nbins, Wpad);
+    size_t smem = k2_smem_bytes(kmode, h->nA, h->nB, h->nbins, Wpad, h->table_bytes);
     // occupancy query cached per pass shape (it costs microseconds of host time per call)
     int& cached = h->occ_cache[NW == 1 ? 0 : NW == 2 ? 1 : 2];
     if (cached <= 0 || h->occ_smem[NW == 1 ? 0 : NW == 2 ? 1 : 2] != smem) {
-      cached = k2_blocks_per_sm(kmode, NW, smem);
+      cached = k2_blocks_per_sm(kmode, NW, smem, h->table_bytes);
       h->occ_smem[NW == 1 ? 0 : NW == 2 ? 1 : 2] = smem;
     }
     int per_sm = cached;
@@ -863,7 +870,8 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
       k2.peer.seq = ++h->peer_seq;
       for (int p = 0; p < h->peer_world; ++p) k2.peer.xbuf[p] = h->peer_xbuf[p];
     }
-    if (kmode == kModeFactor) CK(launch_k2<kModeFactor>(NW, grid, smem, st, k2));
+    if (kmode == kModeFactor && h->table_bytes == 4) CK((launch_k2<kModeFactor, float>(NW, grid, smem, st, k2)));
+    else if (kmode == kModeFactor) CK(launch_k2<kModeFactor>(NW, grid, smem, st, k2));
     else if (kmode == kModeTable) CK(launch_k2<kModeTable>(NW, grid, smem, st, k2));
     else CK(launch_k2<kModeTableGrid>(NW, grid, smem, st, k2));
     ++launches;

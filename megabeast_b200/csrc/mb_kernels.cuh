@@ -407,7 +407,11 @@ __device__ __forceinline__ void stamp(unsigned long long* timeline, int point) {
 __host__ __device__ constexpr int k2_threads(int NW) { return NW <= 2 ? MB_K2_THREADS_LO : 512; }
 __host__ __device__ constexpr int k2_min_blocks(int NW) { return 1; }
 constexpr int kChunk = 32;                          // entries staged per warp per step
-constexpr int kStageBytes = 2 * kChunk * (8 + 4);   // per warp: double-buffered weights + codes
+#ifndef MB_K2_STAGES
+#define MB_K2_STAGES 4
+#endif
+constexpr int kStages = MB_K2_STAGES;                    // chunks in flight per warp (ring of buffers)
+constexpr int kStageBytes = kStages * kChunk * (8 + 4);  // per warp: weights ring + codes ring
 
 __device__ __forceinline__ void cp_async8(uint32_t smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem), "l"(gmem));
@@ -452,6 +456,22 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
   asm("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ uint2 lds_u32x2(uint32_t addr) {
+  uint2 v;
+  asm("ld.shared.v2.u32 {%0,%1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(addr));
+  return v;
+}
+// high word of a double rounded to 21 significant bits (round to nearest on the dropped word)
+__device__ __forceinline__ uint32_t round_to_hi_word(double v) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  if (((b >> 52) & 0x7ff) != 0x7ff) b += 0x80000000ull;  // leave inf / nan alone
+  return (uint32_t)(b >> 32);
+}
 
 // Launder a loop-invariant address through an opaque move: without it ptxas, short of registers,
 // re-derives the shared-memory addresses from %tid / %cgaid / kernel parameters inside the hot
@@ -465,11 +485,20 @@ __device__ __forceinline__ uint32_t keep_in_register(uint32_t x) {
 // Per-lane state of the NW walkers a lane owns while its warp walks stars.
 // Walker mapping: NW == 1: w = lane;  NW >= 2: for q < NW/2, w = 64 q + 2 lane + {0,1}
 // (one 16-byte shared/global load per q, conflict free).
-template <int NW, int MODE>
+// TF = element type of the FACTOR-mode tables in shared memory: double (default, exact) or a
+// 32-bit type (optional: half the shared-memory traffic; the element is the HIGH WORD of the
+// factor rounded to 21 significant bits, so it is used as a double without any conversion
+// instruction -- F2F.F64.F32 runs on the quarter-rate XU pipe and made a true fp32 table no
+// faster than the fp64 one; sums are still fp64).
+template <int NW, int MODE, typename TF = double>
 struct Lanes {
   static constexpr int NQ = (NW + 1) / 2;
-  static constexpr uint32_t rowbytes = 32u * NW * 8u;  // one table row: Wpad = 32 NW walkers
-  double run[NW], star[NW], fa[NW];
+  static constexpr bool kF32 = sizeof(TF) == 4;
+  static_assert(!kF32 || MODE == 1, "float tables exist in FACTOR mode only");
+  // one table row: Wpad = 32 NW walkers
+  static constexpr uint32_t rowbytes = 32u * NW * (MODE == 1 ? (uint32_t)sizeof(TF) : 8u);
+  double run[NW], run2[NW];       // two partial sums of the current run (halves the DFMA chain)
+  double star[NW], fa[NW];
   LogAcc acc[NW];
   uint32_t tabA, tabB;            // FACTOR: shared-memory byte addresses (lane offset included)
   const char* Tlane;              // TABLE*: global table base + lane offset
@@ -480,9 +509,18 @@ struct Lanes {
     for (int i = 0; i < NW; ++i) { run[i] = 0.0; star[i] = 0.0; fa[i] = 1.0; acc[i].init(); }
   }
   // factors of one entry for this lane's walkers
-  __device__ __forceinline__ void load_factors(uint32_t code, double* f) const {
-    if (MODE == kModeFactor) {
-      const uint32_t addr = (code & kDustMask) * rowbytes + tabB;
+  // FACTOR: one table row element pair / element of this lane (byte address given)
+  __device__ __forceinline__ static void lds_row(uint32_t addr, double* f) {
+    if (kF32) {  // 32-bit elements = high words of the (rounded) doubles: no conversion needed
+      if (NW == 1) f[0] = __hiloint2double((int)lds_u32(addr), 0);
+      else {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          uint2 v = lds_u32x2(addr + 256u * q);
+          f[2 * q] = __hiloint2double((int)v.x, 0); f[2 * q + 1] = __hiloint2double((int)v.y, 0);
+        }
+      }
+    } else {
       if (NW == 1) f[0] = lds_f64(addr);
       else {
 #pragma unroll
@@ -491,6 +529,11 @@ struct Lanes {
           f[2 * q] = v.x; f[2 * q + 1] = v.y;
         }
       }
+    }
+  }
+  __device__ __forceinline__ void load_factors(uint32_t code, double* f) const {
+    if (MODE == kModeFactor) {
+      lds_row((code & kDustMask) * rowbytes + tabB, f);
     } else {
       const char* p = Tlane + (size_t)(code & kRowMask) * rowbytes;
       if (NW == 1) f[0] = __ldg(reinterpret_cast<const double*>(p));
@@ -506,26 +549,20 @@ struct Lanes {
   // boundary before an entry (warp-uniform): close the run (and the star), fetch the new age factor
   __device__ __forceinline__ void boundary(uint32_t code) {
 #pragma unroll
-    for (int i = 0; i < NW; ++i) { star[i] = fma(fa[i], run[i], star[i]); run[i] = 0.0; }
+    for (int i = 0; i < NW; ++i) { star[i] = fma(fa[i], run[i] + run2[i], star[i]); run[i] = 0.0; run2[i] = 0.0; }
     if (MODE != kModeFactor || (code & kNewStar)) {
 #pragma unroll
       for (int i = 0; i < NW; ++i) { star_done(acc[i], star[i]); star[i] = 0.0; }
     }
-    if (MODE == kModeFactor) {
-      const uint32_t addr = ((code >> kAgeShift) & kAgeMask) * rowbytes + tabA;
-      if (NW == 1) fa[0] = lds_f64(addr);
-      else {
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-          double2 v = lds_f64x2(addr + 512u * q);
-          fa[2 * q] = v.x; fa[2 * q + 1] = v.y;
-        }
-      }
-    }
+    if (MODE == kModeFactor) lds_row(((code >> kAgeShift) & kAgeMask) * rowbytes + tabA, fa);
   }
   __device__ __forceinline__ void mac(double a, const double* f) {
 #pragma unroll
     for (int i = 0; i < NW; ++i) run[i] = fma(a, f[i], run[i]);
+  }
+  __device__ __forceinline__ void mac2(double a, const double* f) {
+#pragma unroll
+    for (int i = 0; i < NW; ++i) run2[i] = fma(a, f[i], run2[i]);
   }
   __device__ __forceinline__ void step(double a, uint32_t code, const double* f) {
     if ((int32_t)code < 0) boundary(code);  // bit 31, warp-uniform
@@ -535,8 +572,8 @@ struct Lanes {
   __device__ __forceinline__ void close() {
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
-      star_done(acc[i], fma(fa[i], run[i], star[i]));
-      star[i] = 0.0; run[i] = 0.0;
+      star_done(acc[i], fma(fa[i], run[i] + run2[i], star[i]));
+      star[i] = 0.0; run[i] = 0.0; run2[i] = 0.0;
     }
   }
 };
@@ -545,38 +582,41 @@ struct Lanes {
 // st_c) and fold them into L.  Per group of four entries the warp issues three broadcast loads
 // (four codes; two weight pairs) = 1.5 shared-memory wavefronts per entry, then per entry one
 // IMAD (table row address), NW/2 x LDS.128 (factors), NW x DFMA and one sign test.
-template <int NW, int MODE>
-__device__ __forceinline__ void stream_range(Lanes<NW, MODE>& L, const double* __restrict__ ga,
+template <int NW, int MODE, typename TF>
+__device__ __forceinline__ void stream_range(Lanes<NW, MODE, TF>& L, const double* __restrict__ ga,
                                              const uint32_t* __restrict__ gc, int64_t pos, const int64_t end,
                                              const uint32_t st_a, const uint32_t st_c, const int lane) {
   const uint32_t sa = keep_in_register(st_a), sc = keep_in_register(st_c);
   const uint32_t sa_lane = keep_in_register(st_a + lane * 8u), sc_lane = keep_in_register(st_c + lane * 4u);
-  uint32_t bufa = 0, bufc = 0;  // byte offsets of the current buffer (0 or one buffer)
-  if (pos + lane < end) {
-    cp_async8(sa_lane, ga + pos + lane);
-    cp_async4(sc_lane, gc + pos + lane);
-  }
-  cp_async_commit();
-  while (pos < end) {
-    const int64_t nxt = pos + kChunk;
-    if (nxt + lane < end) {
-      cp_async8(sa_lane + (bufa ^ (kChunk * 8u)), ga + nxt + lane);
-      cp_async4(sc_lane + (bufc ^ (kChunk * 4u)), gc + nxt + lane);
+  // ring of kStages chunk buffers: kStages - 1 chunks are in flight while one is processed
+  auto issue = [&](int64_t p, int slot) {
+    if (p + lane < end) {
+      cp_async8(sa_lane + slot * (kChunk * 8u), ga + p + lane);
+      cp_async4(sc_lane + slot * (kChunk * 4u), gc + p + lane);
     }
     cp_async_commit();
-    cp_async_wait<1>();
+  };
+#pragma unroll
+  for (int k = 0; k < kStages - 1; ++k) issue(pos + (int64_t)k * kChunk, k);
+  int slot = 0;
+  while (pos < end) {
+    int ahead = slot + kStages - 1;
+    if (ahead >= kStages) ahead -= kStages;
+    issue(pos + (int64_t)(kStages - 1) * kChunk, ahead);
+    cp_async_wait<kStages - 1>();
     __syncwarp();
-    uint32_t pa = sa + bufa, pc = sc + bufc;
+    uint32_t pa = sa + slot * (kChunk * 8u), pc = sc + slot * (kChunk * 4u);
     int n = (int)min((int64_t)kChunk, end - pos);
     for (; n >= 4; n -= 4, pa += 32u, pc += 16u) {
       const uint4 c = lds_stage_u4(pc);
       const double2 a01 = lds_stage_d2(pa), a23 = lds_stage_d2(pa + 16u);
       double f0[NW], f1[NW], f2[NW], f3[NW];
       L.load_factors(c.x, f0); L.load_factors(c.y, f1); L.load_factors(c.z, f2); L.load_factors(c.w, f3);
-      if ((int32_t)(c.x | c.y | c.z | c.w) < 0) {  // a run / star boundary somewhere in the group
+      // (the vote makes the uniformity of the branch visible to the compiler: no BSSY/BSYNC pair)
+      if (__any_sync(0xffffffffu, (int32_t)(c.x | c.y | c.z | c.w) < 0)) {  // a run / star boundary in the group
         L.step(a01.x, c.x, f0); L.step(a01.y, c.y, f1); L.step(a23.x, c.z, f2); L.step(a23.y, c.w, f3);
       } else {                                     // common case: four plain multiply-adds
-        L.mac(a01.x, f0); L.mac(a01.y, f1); L.mac(a23.x, f2); L.mac(a23.y, f3);
+        L.mac(a01.x, f0); L.mac2(a01.y, f1); L.mac(a23.x, f2); L.mac2(a23.y, f3);
       }
     }
     for (; n > 0; --n, pa += 8u, pc += 4u) {
@@ -587,9 +627,8 @@ __device__ __forceinline__ void stream_range(Lanes<NW, MODE>& L, const double* _
       L.step(a, c, f);
     }
     __syncwarp();
-    bufa ^= kChunk * 8u;
-    bufc ^= kChunk * 4u;
-    pos = nxt;
+    if (++slot == kStages) slot = 0;
+    pos += kChunk;
   }
   cp_async_wait<0>();
 }
@@ -597,20 +636,21 @@ __device__ __forceinline__ void stream_range(Lanes<NW, MODE>& L, const double* _
 // Prologue (first W blocks): N-stars / Poisson term.  Hot loop: every warp streams star-aligned
 // segments of the entry stream for all walkers.  Tail: reduction over stars (K3) and, with peers,
 // over GPUs.
-template <int NW, int MODE>
+template <int NW, int MODE, typename TF = double>
 __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars(K2Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int kK2Warps = k2_threads(NW) / 32;
+  constexpr bool kF32 = sizeof(TF) == 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int Wpad = 32 * NW;  // == a.Wpad
-  constexpr uint32_t rowbytes = (uint32_t)Wpad * 8u;
-  const uint32_t lanebytes = (NW == 1 ? lane : 2 * lane) * 8u;
+  constexpr uint32_t rowbytes = Lanes<NW, MODE, TF>::rowbytes;
+  const uint32_t lanebytes = (NW == 1 ? lane : 2 * lane) * (MODE == kModeFactor ? (uint32_t)sizeof(TF) : 8u);
 
   // smem layout: [stage: warps x (2 x 32 weights + 2 x 32 codes); also Poisson / reduction scratch]
   //              [FA | FB tables at tab_off (FACTOR only)]
   const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
   const uint32_t st_a = smem0 + (uint32_t)warp * kStageBytes;
-  const uint32_t st_c = st_a + 2 * kChunk * 8u;
+  const uint32_t st_c = st_a + kStages * kChunk * 8u;
   const uint32_t tabA = smem0 + (uint32_t)a.tab_off + lanebytes;
   const uint32_t tabB = tabA + (uint32_t)a.nA * rowbytes;
   stamp(a.timeline, 0);
@@ -619,8 +659,16 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   if (MODE == kModeFactor) {
     const int n2 = (a.nA + a.nB) * Wpad / 2;
     const double2* src = reinterpret_cast<const double2*>(a.FA);
-    double2* dst = reinterpret_cast<double2*>(smem_raw + a.tab_off);
-    for (int i = threadIdx.x; i < n2; i += blockDim.x) dst[i] = __ldg(src + i);
+    if (kF32) {
+      uint2* dst = reinterpret_cast<uint2*>(smem_raw + a.tab_off);
+      for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        const double2 v = __ldg(src + i);
+        dst[i] = make_uint2(round_to_hi_word(v.x), round_to_hi_word(v.y));
+      }
+    } else {
+      double2* dst = reinterpret_cast<double2*>(smem_raw + a.tab_off);
+      for (int i = threadIdx.x; i < n2; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
     __syncthreads();
   }
   stamp(a.timeline, 1);
@@ -628,7 +676,8 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   // tables it just staged; dynamic segment scheduling absorbs the few microseconds it starts late
   {
     __shared__ double pscratch[k2_threads(NW) / 32];
-    const double* Ftab = (MODE == kModeFactor) ? reinterpret_cast<const double*>(smem_raw + a.tab_off) : a.FA;
+    // the Poisson term always uses the fp64 tables (from shared memory when they are there)
+    const double* Ftab = (MODE == kModeFactor && !kF32) ? reinterpret_cast<const double*>(smem_raw + a.tab_off) : a.FA;
     for (int w = blockIdx.x; w < a.W; w += gridDim.x) {
       double pois = 0.0;
       if (a.pois.nbins > 0)
@@ -639,7 +688,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   }
 
   stamp(a.timeline, 2);
-  Lanes<NW, MODE> L;
+  Lanes<NW, MODE, TF> L;
   L.init(tabA, tabB, reinterpret_cast<const char*>(a.T) + lanebytes);
 
   // Segments: every warp starts with its own index (no atomic storm at kernel start); further
@@ -653,7 +702,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   int s = (int)blockIdx.x * kK2Warps + warp, s_next = 0;
   while (s < a.nseg) {
     if (lane == 0) s_next = nwarps_total + (int)atomicAdd(a.counters + kCtrSegment, 1u);
-    stream_range<NW, MODE>(L, a.ea, a.ec, a.seg[s], a.seg[s + 1], st_a, st_c, lane);
+    stream_range<NW, MODE, TF>(L, a.ea, a.ec, a.seg[s], a.seg[s + 1], st_a, st_c, lane);
     L.close();
 #pragma unroll
     for (int i = 0; i < NW; ++i) fix[i] += __double2ll_rn(L.acc[i].take_value() * kFixScale);
@@ -833,7 +882,7 @@ __global__ void __launch_bounds__(kPixThreads, (NW <= 2 ? 2 : 1)) mb_k2_pixels(K
   // smem: [front: entry stage / Poisson task scratch][tables][spois Wpad][sacc 3 x Wpad]
   const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
   const uint32_t st_a = smem0 + (uint32_t)warp * kStageBytes;
-  const uint32_t st_c = st_a + 2 * kChunk * 8u;
+  const uint32_t st_c = st_a + kStages * kChunk * 8u;
   double* sF = reinterpret_cast<double*>(smem_raw + a.tab_off);
   double* spois = sF + (size_t)(a.nA + a.nB) * Wpad;
   unsigned long long* sacc = reinterpret_cast<unsigned long long*>(spois + Wpad);
@@ -867,9 +916,9 @@ __global__ void __launch_bounds__(kPixThreads, (NW <= 2 ? 2 : 1)) mb_k2_pixels(K
     }
 
     // this warp's piece of the pixel's entry stream (same inner loop as mb_k2_stars)
-    Lanes<NW, kModeFactor> L;
+    Lanes<NW, kModeFactor, double> L;
     L.init(tabA, tabB, nullptr);
-    stream_range<NW, kModeFactor>(L, a.ea, a.ec, a.pix_seg[(size_t)pix * (kPixWarps + 1) + warp],
+    stream_range<NW, kModeFactor, double>(L, a.ea, a.ec, a.pix_seg[(size_t)pix * (kPixWarps + 1) + warp],
                                   a.pix_seg[(size_t)pix * (kPixWarps + 1) + warp + 1], st_a, st_c, lane);
     L.close();
 #pragma unroll

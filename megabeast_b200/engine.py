@@ -69,7 +69,7 @@ class ModelSpec:
 class LikelihoodEngine:
     def __init__(self, spec, star_lnpgriddata, beast_moddata, massmult=None, devices=None,
                  mode="auto", star_range=None, n_stars_total=None, keep_indices=False,
-                 merge_duplicates=True, segments_per_warp=0, pixel_offsets=None):
+                 merge_duplicates=True, segments_per_warp=0, pixel_offsets=None, table_precision="fp64"):
         self.lib = _cabi.load()
         self._mb_lnlike = self.lib.mb_lnlike
         self._bufs = {}
@@ -143,6 +143,7 @@ class LikelihoodEngine:
                 opt.merge_duplicates = int(bool(merge_duplicates))
                 opt.segments_per_warp = int(os.environ.get("MB_SEGMENTS_PER_WARP", segments_per_warp))
                 opt.tail_percent = int(os.environ.get("MB_TAIL_PERCENT", 0))
+                opt.table_precision = {"fp64": 0, "fp32": 1}[table_precision]
                 h = ctypes.c_void_p()
                 if pixel_offsets is not None:
                     _cabi.check(

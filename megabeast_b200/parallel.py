@@ -88,7 +88,8 @@ class ShardedLikelihood:
         self.star_range = shard_bounds(S, self.world, self.rank)
         self.engine = LikelihoodEngine(self.spec, star_lnpgriddata, beast_moddata, massmult=mm,
                                        devices=[self.device], mode=mode,
-                                       star_range=self.star_range, n_stars_total=S)
+                                       star_range=self.star_range, n_stars_total=S,
+                                       table_precision=getattr(model, "table_precision", "fp64"))
         # how the shard partials are added: "p2p" = inside the likelihood kernel over NVLink peer
         # memory (mb_peer_connect), "nccl" = one all-reduce after it; "auto" tries p2p first
         self.reduce = "none" if self.world == 1 else self._setup_reduce(reduce)

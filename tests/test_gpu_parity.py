@@ -265,3 +265,19 @@ def test_pixel_batch_fit_runs_all_pixels_at_once():
     again = pe.lnprob(best[:, None, :])[:, 0]
     assert_close(again, best_lp, 1e-12)
     pe.close()
+
+
+def test_fp32_table_mode_stated_tolerance():
+    """Optional mode: 32-bit factor tables on chip (21 significant bits), sums in fp64.  Stated
+    tolerance 1e-7 relative on lnprob (the fp64 default is held to 1e-9 everywhere else)."""
+    settings, moddata, stars, _ = synth.make_problem("cfg1", seeds=(41, 42, 43))
+    pm = port.PortModel(copy.deepcopy(settings))
+    for W in (7, 45, 100):
+        phis = synth.make_walkers(pm, W, seed=43)
+        want = c_oracle.lnprob_batch(pm, phis, stars, moddata)
+        model = MB_Model(copy.deepcopy(settings), table_precision="fp32")
+        got = lnprob(phis, model, stars, moddata)
+        err = np.max(np.abs(got - want) / np.abs(want))
+        assert err < 1e-7, err
+        exact = lnprob(phis, MB_Model(copy.deepcopy(settings)), stars, moddata)
+        assert np.max(np.abs(exact - want) / np.abs(want)) < RTOL
