@@ -171,6 +171,14 @@ int mb_get_info(const mb_handle* h, mb_info* out);
 int mb_lnlike(mb_handle* h, const double* phi, int32_t W, int32_t ndim, double* lnlike,
               int32_t* status);
 
+/* replaces: lnprob(phi, ...) (singlepop_dust_model.py:277-304) for a batch when every prior is a
+ * flat box (the only kind MB_Model.lnprior accepts, :255-273): lnprob[w] = -inf for a walker with
+ * any phi outside [lo, hi] (its likelihood is not evaluated, :302-303), else 0 + lnlike.  lo/hi:
+ * [ndim] in phi order.  last_inside (optional): index of the last walker that was evaluated, -1 if
+ * none -- the walker whose phi the reference leaves in the model dictionaries. */
+int mb_lnprob_box(mb_handle* h, const double* phi, int32_t W, int32_t ndim, const double* lo,
+                  const double* hi, double* lnprob, int32_t* status, int32_t* last_inside);
+
 /* Same with host-evaluated tables for MB_TABULATED parameters: tab[p] is [W][n_classes[p]]
  * (values of the parameter's callable at mb_class_values), NULL for analytic parameters. */
 int mb_lnlike_tabulated(mb_handle* h, const double* phi, int32_t W, int32_t ndim,

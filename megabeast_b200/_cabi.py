@@ -149,6 +149,11 @@ SIGNATURES = {
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p],
     ),
+    "mb_lnprob_box": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+         ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32)],
+    ),
     "mb_lnlike_tabulated": (
         ctypes.c_int,
         [ctypes.c_void_p, c_double_p, ctypes.c_int32, ctypes.c_int32, TabArray, c_double_p, c_int32_p],

@@ -90,6 +90,8 @@ struct mb_handle {
   float last_ms[MB_NKERNELS] = {};
   int last_wp = 0, last_launches = 0;
   int pending_W = 0;
+  std::vector<int32_t> scratch_idx, scratch_st;
+  std::vector<double> scratch_phi, scratch_rows, scratch_val;
   int table_bytes = 8;   // FACTOR-mode shared-memory table element: 8 = fp64, 4 = fp32
   int occ_cache[3] = {0, 0, 0};
   size_t occ_smem[3] = {0, 0, 0};
@@ -983,6 +985,49 @@ extern "C" int mb_lnlike_tabulated(mb_handle* h, const double* phi, int32_t W, i
 extern "C" int mb_lnlike(mb_handle* h, const double* phi, int32_t W, int32_t ndim, double* lnlike,
                          int32_t* status) {
   return mb_lnlike_tabulated(h, phi, W, ndim, nullptr, lnlike, status);
+}
+
+// lnprob of the reference (singlepop_dust_model.py:277-304) for a batch with flat (box) priors:
+// 0 inside [lo, hi] and -inf outside (:255-271; a NaN compares false on both sides and passes, as
+// upstream); the likelihood is evaluated only for the walkers inside the box (:302-303).
+extern "C" int mb_lnprob_box(mb_handle* h, const double* phi, int32_t W, int32_t ndim, const double* lo,
+                             const double* hi, double* lnprob, int32_t* status, int32_t* last_inside) {
+  if (!h || !lnprob || !status) return fail("mb_lnprob_box: null argument");
+  if (W <= 0) return 0;
+  if (ndim != h->ndim) return fail("phi has %d columns, the model has %d free variables", ndim, h->ndim);
+  if (ndim > 0 && (!phi || !lo || !hi)) return fail("mb_lnprob_box: null array");
+  std::vector<int32_t>& idx = h->scratch_idx;
+  idx.clear();
+  for (int w = 0; w < W; ++w) {
+    const double* p = phi + (size_t)w * ndim;
+    bool inside = true;
+    for (int k = 0; k < ndim; ++k)
+      if (p[k] < lo[k] || p[k] > hi[k]) { inside = false; break; }
+    if (inside) idx.push_back(w);
+    lnprob[w] = -INFINITY;
+    status[w] = MB_STATUS_OK;
+  }
+  if (last_inside) *last_inside = idx.empty() ? -1 : idx.back();
+  const int Win = (int)idx.size();
+  if (Win == 0) return 0;
+  const double* src = phi;
+  if (Win != W) {  // compact the walkers that are evaluated
+    h->scratch_phi.resize((size_t)Win * ndim);
+    for (int i = 0; i < Win; ++i)
+      memcpy(&h->scratch_phi[(size_t)i * ndim], phi + (size_t)idx[(size_t)i] * ndim, sizeof(double) * ndim);
+    src = h->scratch_phi.data();
+  }
+  if (mb_lnlike_begin(h, src, Win, ndim, nullptr)) return 1;
+  h->scratch_rows.resize((size_t)MB_OUT_ROWS * Win);
+  if (mb_lnlike_end(h, h->scratch_rows.data())) return 1;
+  h->scratch_val.resize((size_t)Win);
+  h->scratch_st.resize((size_t)Win);
+  mb_combine(h->scratch_rows.data(), Win, h->scratch_val.data(), h->scratch_st.data());
+  for (int i = 0; i < Win; ++i) {
+    lnprob[idx[(size_t)i]] = 0.0 + h->scratch_val[(size_t)i];
+    status[idx[(size_t)i]] = h->scratch_st[(size_t)i];
+  }
+  return 0;
 }
 
 extern "C" int mb_lnlike_pixels(mb_handle* h, const double* phi, int32_t W, int32_t ndim, double* lnlike,

@@ -319,6 +319,23 @@ class LikelihoodEngine:
         _cabi.check(self.lib.mb_lnlike_pixels_device(self.handles[0], ctypes.c_void_p(d_phi), W, ndim,
                                                      ctypes.c_void_p(d_out), ctypes.c_void_p(stream)))
 
+    def lnprob_box(self, phis, lo, hi):
+        """(lnprob[W], status[W], last_inside) for flat box priors, one C call (``mb_lnprob_box``):
+        -inf outside the box without evaluating the likelihood.  Single device, analytic models.
+        The returned arrays are reused by the next call with the same W."""
+        if not (phis.dtype == np.float64 and phis.flags.c_contiguous):
+            phis = np.ascontiguousarray(phis, dtype=np.float64)
+        W, ndim = phis.shape
+        buf = self._bufs.get(("box", W))
+        if buf is None:
+            out, status = np.empty(W), np.empty(W, dtype=np.int32)
+            buf = self._bufs[("box", W)] = (out, status, out.ctypes.data, status.ctypes.data, ctypes.c_int32(-1))
+        out, status, p_out, p_status, last = buf
+        if self.lib.mb_lnprob_box(self.handles[0], phis.ctypes.data, W, ndim, lo.ctypes.data, hi.ctypes.data,
+                                  p_out, p_status, ctypes.byref(last)):
+            _cabi.check(1)
+        return out, status, last.value
+
     def lnlike_device(self, d_phi, W, ndim, d_out, stream=0, i=0):
         """Asynchronous device-pointer form (``mb_lnlike_device``): ``d_phi`` [W][ndim] and
         ``d_out`` [3][W] are raw device addresses, ``stream`` a raw ``cudaStream_t``."""

@@ -146,6 +146,10 @@ class ShardedLikelihood:
 
     def lnlike_rows(self, phis):
         """Host phi (W, ndim in device order) -> reduced host rows [3][W]."""
+        if self.reduce in ("p2p", "none"):
+            # one C call: phi and the rows go through mapped pinned memory, the kernels run on the
+            # handle's own stream and (p2p) add the shards over NVLink themselves -- no torch ops
+            return self.engine.lnlike_rows(phis)
         t = self.torch
         phis = np.ascontiguousarray(phis, dtype=np.float64)
         W = phis.shape[0]

@@ -168,9 +168,13 @@ class MB_Model:
         return ModelSpec(kinds, nodes), np.asarray(perm, dtype=np.intp), ndim
 
     # -- device-resident data ------------------------------------------------------------------------
+    @staticmethod
+    def _data_key(star_lnpgriddata, beast_moddata):
+        return (id(star_lnpgriddata), id(beast_moddata), id(star_lnpgriddata["indxs"]),
+                id(star_lnpgriddata["vals"]), id(beast_moddata["prior_weight"]))
+
     def _engine_for(self, star_lnpgriddata, beast_moddata):
-        key = (id(star_lnpgriddata), id(beast_moddata), id(star_lnpgriddata["indxs"]),
-               id(star_lnpgriddata["vals"]), id(beast_moddata["prior_weight"]))
+        key = self._data_key(star_lnpgriddata, beast_moddata)
         hit = self._engines.get(key)
         if hit is not None:
             return hit[0], hit[1]
@@ -269,6 +273,29 @@ class MB_Model:
         self._box_cache = (np.asarray(lows, dtype=np.float64), np.asarray(highs, dtype=np.float64))
         return self._box_cache
 
+    def _lnprob_batch(self, phis, star_lnpgriddata, beast_moddata):
+        """Batched lnprob in one C call (box check, compaction of the in-box walkers, likelihood,
+        scatter).  Returns None when the general path is needed (tabulated models, several
+        devices, permuted variables)."""
+        hit = self._engines.get(self._data_key(star_lnpgriddata, beast_moddata))
+        if hit is None:  # first call on this data: the general path builds the device data if needed
+            return None
+        engine, (spec, perm, ndim) = hit[0], hit[1]
+        if perm is not None or spec.tabulated or len(engine.handles) != 1 or phis.shape[1] != ndim:
+            return None
+        lows, highs = self._box()
+        vals, status, last = engine.lnprob_box(phis, lows, highs)
+        if last >= 0:
+            self._store_phi(phis[last])
+        if status.any():
+            if np.any(status & _cabi.STATUS_PEER_TIMEOUT):
+                raise RuntimeError("a peer GPU did not deliver its star shard (timeout)")
+            if np.any(status & _cabi.STATUS_NONFINITE_STAR):
+                raise ValueError(_NONFINITE_MSG)
+            print(0.0)
+            raise SystemExit
+        return vals.copy()
+
     def lnprior(self, phi):
         """0 inside the flat-prior box, -inf outside (:231-274).  A 1-D phi gives the
         reference's Python float; a 2-D phi gives one value per row from one array compare."""
@@ -300,6 +327,11 @@ def lnprob(phi, megabeast_model, star_lnpgriddata, beast_moddata):
         if not np.isfinite(ln_prior):
             return -np.inf
         return ln_prior + megabeast_model.lnlike(phi, star_lnpgriddata, beast_moddata)
+    fast = getattr(megabeast_model, "_lnprob_batch", None)
+    if fast is not None:
+        out = fast(phi, star_lnpgriddata, beast_moddata)
+        if out is not None:
+            return out
     ln_prior = np.asarray(megabeast_model.lnprior(phi), dtype=np.float64)
     inside = np.isfinite(ln_prior)
     if inside.all():  # the usual case late in a chain: no masking, no copies
