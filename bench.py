@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3")
     ap.add_argument("--index-mode", default="uniform", choices=["uniform", "clustered"])
-    ap.add_argument("--mode", default="auto", choices=["auto", "factor", "table_unique", "table_grid"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "factor", "table_unique", "table_grid", "elementwise"])
     ap.add_argument("--walkers", type=int, default=0, help="override the config's walker count")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=4, help="walkers the CPU baseline evaluates")
@@ -440,7 +440,7 @@ def run_ours(args):
                           "status_flags": int(status_dev.max())}
     if args.all_modes and world == 1:
         others = {}
-        for m in ("factor", "table_unique", "table_grid"):
+        for m in ("factor", "table_unique", "table_grid", "elementwise"):
             if m == mode:
                 continue
             mdl = MB_Model(copy.deepcopy(settings), devices=[local], mode=m)

@@ -99,10 +99,15 @@ typedef struct {
 } mb_massmult_desc;
 
 enum mb_mode {
-  MB_MODE_AUTO = 0,        /* FACTOR when the factor tables fit shared memory, else TABLE_UNIQUE */
+  MB_MODE_AUTO = 0,        /* FACTOR when the factor tables fit shared memory, else TABLE_UNIQUE; ELEMENTWISE for
+                              grids whose columns cannot be class-coded (> 4096 distinct values) */
   MB_MODE_FACTOR = 1,      /* per-(star,point) class codes + per-walker factor tables in smem */
   MB_MODE_TABLE_UNIQUE = 2,/* physmod materialised over the distinct parameter combinations */
-  MB_MODE_TABLE_GRID = 3   /* physmod[G][W] materialised over every grid row, gathered by index */
+  MB_MODE_TABLE_GRID = 3,  /* physmod[G][W] materialised over every grid row, gathered by index */
+  MB_MODE_ELEMENTWISE = 4  /* physmod[G][W] by evaluating the prior models ELEMENTWISE over the grid's physics
+                              columns (singlepop_dust_model.py:131-148 literally), N-stars sums over the grid
+                              rows, gathered by index: no class coding, works for any grid.  AUTO falls back to
+                              it when a free parameter's column has too many distinct values to class-code. */
 };
 
 typedef struct {

@@ -35,7 +35,7 @@ KIND_VARNAMES = {
     "bins_interp": ("values",),
     "exponential": ("tau",),
 }
-MODE = {"auto": 0, "factor": 1, "table_unique": 2, "table_grid": 3}
+MODE = {"auto": 0, "factor": 1, "table_unique": 2, "table_grid": 3, "elementwise": 4}
 MODE_NAME = {v: k for k, v in MODE.items()}
 KERNEL_NAMES = ("k0_factors", "k1_expand", "k2_stars")
 

@@ -63,6 +63,18 @@ struct mb_handle {
   uint32_t* d_ec = nullptr;     // entry codes
   int64_t* d_seg[2] = {nullptr, nullptr};  // segment tables: [0] 768-thread kernels, [1] 512-thread kernel
   uint32_t* d_rowcode = nullptr;
+  // ELEMENTWISE mode: the physics columns themselves, bin-sorted row list for the N-stars sums
+  double* d_col[MB_NPARAM] = {nullptr, nullptr, nullptr, nullptr};
+  double* d_gw = nullptr;
+  double* d_compl = nullptr;
+  int32_t* d_binrows = nullptr;      // grid rows in (age, Z)-bin order
+  int64_t* d_tile_start = nullptr;   // K1e tiles over that list, never straddling a bin
+  int64_t* d_bin_tile = nullptr;     // [nbins + 1] first tile of every bin
+  double* d_partial = nullptr;       // [ntiles][128][2] per-tile partial bin sums
+  int64_t ntiles = 0;
+  double* d_bin_age = nullptr;
+  double* d_Fage = nullptr;     // [nbins][128] age factor per bin, written by K1e
+  double* d_SC = nullptr;       // [nbins][128][2] bin sums, written by K1b
   double* d_H = nullptr;
   double* d_coef = nullptr;
   int32_t* d_bin_agecls = nullptr;
@@ -130,6 +142,9 @@ extern "C" int mb_device_count(void) {
 }
 
 // class code of every grid row for one parameter
+// Returns 0 on success, 1 on error, 2 when the column has more than kMaxClassesPerColumn distinct
+// values (not a Cartesian axis: the caller switches to the ELEMENTWISE mode or reports it).
+static const size_t kMaxClassesPerColumn = 4096;
 static int classify(const mb_model_desc& m, int p, const double* col, int64_t G,
                     std::vector<double>& clsx, std::vector<int32_t>& code) {
   code.resize((size_t)G);
@@ -156,7 +171,11 @@ static int classify(const mb_model_desc& m, int p, const double* col, int64_t G,
     if (x != x) return fail("NaN in a physics-parameter column (row %lld)", (long long)g);
     auto it = std::lower_bound(uniq.begin(), uniq.end(), x);
     if (it == uniq.end() || *it != x) {
-      if (uniq.size() >= (1u << 20)) return fail("parameter column has more than 2^20 distinct values");
+      if (uniq.size() >= kMaxClassesPerColumn) {
+        fail("parameter column %d has more than %zu distinct values: not class-codable, use the ELEMENTWISE mode",
+             p, kMaxClassesPerColumn);
+        return 2;
+      }
       uniq.insert(it, x);
     }
   }
@@ -173,6 +192,11 @@ static int poisson_nslice(int threads, int nbins) {
   int ns = std::max(1, threads / nbins);
   while (ns > 1 && (size_t)(ns + 1) * nbins * 16 > 48 * 1024) --ns;
   return ns;
+}
+static size_t k1e_smem_bytes(int Wpad, int ndim) {
+  return sizeof(double) * ((size_t)Wpad * std::max(1, ndim) + (size_t)MB_NPARAM * Wpad * kK1eWalkerVals +
+                           2 * (size_t)MB_NPARAM * kK1eRows + 2 * (size_t)kK1eRows + 4 * (size_t)kK1eThreads) +
+         sizeof(int) * ((size_t)MB_NPARAM * kK1eRows + kK1eRows) + 16;
 }
 // front region of K2's dynamic shared memory: entry stage, reused as Poisson / reduction scratch
 static size_t k2_front_bytes(int nbins, int Wpad) {
@@ -245,7 +269,8 @@ extern "C" void mb_destroy(mb_handle* h) {
   void* ptrs[] = {h->d_clsx, h->d_ea, h->d_ec, h->d_seg[0], h->d_seg[1], h->d_rowcode, h->d_H, h->d_coef,
                   h->d_bin_agecls, h->d_phi, h->d_tab[0], h->d_tab[1], h->d_tab[2], h->d_tab[3],
                   h->d_F, h->d_counter, h->d_gacc, h->d_T, h->d_out, h->d_pix_seg, h->d_pix_nstars, h->d_Fpix,
-                  h->d_timeline};
+                  h->d_timeline, h->d_col[0], h->d_col[1], h->d_col[2], h->d_col[3], h->d_gw, h->d_compl,
+                  h->d_binrows, h->d_tile_start, h->d_bin_tile, h->d_partial, h->d_bin_age, h->d_Fage, h->d_SC};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -306,6 +331,9 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
     return fail("mass multipliers given but the logA prior is fixed (no N-stars term, :71-74)");
 
   // ---- class codes per grid row ------------------------------------------------------------------
+  // ELEMENTWISE (requested, or AUTO on a grid whose columns are not class-codable): no class codes
+  // at all, the prior models are evaluated on every grid row (mb_k1_elementwise)
+  bool elementwise = o.mode == MB_MODE_ELEMENTWISE;
   std::vector<int32_t> code[MB_NPARAM];
   int clsoff = 0;
   for (int p = 0; p < MB_NPARAM; ++p) {
@@ -314,24 +342,56 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
     md.radix[p] = 0;
     if (model->kind[p] == MB_FIXED) continue;
     if (!grid->col[p]) return fail("column of free parameter %d is NULL", p);
-    if (classify(*model, p, grid->col[p], G, h->clsx[p], code[p])) return 1;
+    if (elementwise) continue;
+    const int rc = classify(*model, p, grid->col[p], G, h->clsx[p], code[p]);
+    if (rc == 2 && o.mode == MB_MODE_AUTO && n_pixels == 0) { elementwise = true; continue; }
+    if (rc) return 1;
     md.ncls[p] = (int)h->clsx[p].size();
     clsoff += md.ncls[p];
   }
-  h->ncls_total = clsoff;
-  if (clsoff > 4096) return fail("more than 4096 classes in total (%d): K0 look-up table too large", clsoff);
   int64_t nB = 1;
-  for (int p = MB_P_AV; p < MB_NPARAM; ++p) {
-    if (model->kind[p] == MB_FIXED) continue;
-    md.radix[p] = (int)nB;
-    nB *= md.ncls[p];
-    if (nB > (int64_t)kDustMask + 1) return fail("more than 2^20 distinct dust-parameter combinations");
+  if (!elementwise) {
+    for (int p = MB_P_AV; p < MB_NPARAM; ++p) {
+      if (model->kind[p] == MB_FIXED) continue;
+      md.radix[p] = (int)nB;
+      nB *= md.ncls[p];
+      if (nB > (int64_t)kDustMask + 1) {
+        if (o.mode == MB_MODE_AUTO && n_pixels == 0) { elementwise = true; break; }
+        return fail("more than 2^20 distinct dust-parameter combinations");
+      }
+    }
+    if (clsoff > 4096 && !elementwise) {
+      if (o.mode == MB_MODE_AUTO && n_pixels == 0) elementwise = true;
+      else return fail("more than 4096 classes in total (%d): K0 look-up table too large", clsoff);
+    }
   }
+  if (elementwise) {
+    if (n_pixels > 0) return fail("pixel batches need class-codable columns (FACTOR mode)");
+    for (int p = 0; p < MB_NPARAM; ++p) {
+      md.ncls[p] = 1; md.clsoff[p] = 0; md.radix[p] = 0; h->clsx[p].clear(); code[p].clear();
+      if (model->kind[p] == MB_FIXED) continue;
+      if (model->kind[p] == MB_TABULATED)
+        return fail("tabulated prior models need class-codable columns (not available in ELEMENTWISE mode)");
+      const double* col = grid->col[p];
+      const int n = model->nnodes[p];
+      for (int64_t g = 0; g < G; ++g) {
+        if (col[g] != col[g]) return fail("NaN in a physics-parameter column (row %lld)", (long long)g);
+        if (model->kind[p] == MB_BINS_HISTO && !(col[g] >= model->nodes[p][0] && col[g] <= model->nodes[p][n - 1]))
+          return fail("requested x outside of model x range");
+      }
+      if (model->kind[p] == MB_BINS_HISTO)
+        for (int i = 1; i < n; ++i)
+          if (!(model->nodes[p][i] > model->nodes[p][i - 1])) return fail("bins_histo nodes must be strictly increasing");
+    }
+    clsoff = 0;
+    nB = 1;
+  }
+  h->ncls_total = clsoff;
   h->nB = (int)nB;
   h->nA = md.ncls[MB_P_LOGA];
   if (h->nA > (int)kAgeMask + 1) return fail("more than 1024 distinct age classes");
-  std::vector<uint32_t> rowcode((size_t)G);
-  for (int64_t g = 0; g < G; ++g) {
+  std::vector<uint32_t> rowcode(elementwise ? 0 : (size_t)G);
+  for (int64_t g = 0; g < G && !elementwise; ++g) {
     uint32_t cA = model->kind[MB_P_LOGA] == MB_FIXED ? 0u : (uint32_t)code[MB_P_LOGA][(size_t)g];
     uint32_t cB = 0;
     for (int p = MB_P_AV; p < MB_NPARAM; ++p)
@@ -340,20 +400,61 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
   }
 
   // ---- mode ----------------------------------------------------------------------------------------
-  int mode = o.mode;
+  int mode = elementwise ? MB_MODE_ELEMENTWISE : o.mode;
   const bool factor_fits = k2_smem_bytes(kModeFactor, h->nA, h->nB, mm ? mm->n_ages * mm->n_mets : 0, 32, h->table_bytes) <= (size_t)h->max_smem;
   if (mode == MB_MODE_AUTO) mode = factor_fits ? MB_MODE_FACTOR : MB_MODE_TABLE_UNIQUE;
   if (mode == MB_MODE_FACTOR && !factor_fits)
     return fail("factor tables (%d + %d classes) do not fit shared memory; use a TABLE mode", h->nA, h->nB);
   if (mode == MB_MODE_TABLE_UNIQUE && (int64_t)h->nA * h->nB > (1LL << 27)) mode = MB_MODE_TABLE_GRID;
-  if (mode < MB_MODE_FACTOR || mode > MB_MODE_TABLE_GRID) return fail("unknown mode %d", mode);
+  if (mode < MB_MODE_FACTOR || mode > MB_MODE_ELEMENTWISE) return fail("unknown mode %d", mode);
   h->mode = mode;
-  h->U = mode == MB_MODE_TABLE_GRID ? G : (int64_t)h->nA * h->nB;
+  h->U = (mode == MB_MODE_TABLE_GRID || elementwise) ? G : (int64_t)h->nA * h->nB;
 
   // ---- N-stars sufficient statistics (helpers.py:133-162) ----------------------------------------
-  std::vector<double> H, coef;
-  std::vector<int32_t> bin_agecls;
-  if (h->poisson) {
+  std::vector<double> H, coef, bin_age;
+  std::vector<int32_t> bin_agecls, binrows;
+  std::vector<int64_t> binoff, tile_start, bin_tile;
+  if (h->poisson && elementwise) {
+    // ELEMENTWISE: no statistics can be folded ahead of time; K1b sums physmod * grid_weight
+    // (* completeness) over each bin's rows, listed here in bin order
+    if (!grid->logA || !grid->Z) return fail("logA and Z columns are required for the N-stars term");
+    if (mm->n_ages < 1 || mm->n_mets < 1 || !mm->ages || !mm->mets || !mm->massmult)
+      return fail("invalid mass-multiplier description");
+    const int nAg = mm->n_ages, nZ = mm->n_mets;
+    h->nbins = nAg * nZ;
+    if (h->nbins > 2048) return fail("N-stars term: more than 2048 (age, Z) bins (%d)", h->nbins);
+    std::vector<int32_t> rowbin((size_t)G);
+    binoff.assign((size_t)h->nbins + 1, 0);
+    for (int64_t g = 0; g < G; ++g) {
+      const double* ia = std::lower_bound(mm->ages, mm->ages + nAg, grid->logA[g]);
+      const double* iz = std::lower_bound(mm->mets, mm->mets + nZ, grid->Z[g]);
+      if (ia == mm->ages + nAg || *ia != grid->logA[g] || iz == mm->mets + nZ || *iz != grid->Z[g])
+        return fail("grid row %lld has (logA, Z) outside the mass-multiplier bins", (long long)g);
+      const int32_t b = (int32_t)((ia - mm->ages) * nZ + (iz - mm->mets));
+      rowbin[(size_t)g] = b;
+      ++binoff[(size_t)b + 1];
+    }
+    for (int b = 0; b < h->nbins; ++b) binoff[(size_t)b + 1] += binoff[(size_t)b];
+    binrows.resize((size_t)G);
+    std::vector<int64_t> fill(binoff.begin(), binoff.end() - 1);
+    for (int64_t g = 0; g < G; ++g) binrows[(size_t)fill[(size_t)rowbin[(size_t)g]]++] = (int32_t)g;
+    // K1e tiles: at most kK1eRows consecutive positions of the bin-ordered list, inside one bin
+    bin_tile.assign(1, 0);
+    for (int b = 0; b < h->nbins; ++b) {
+      for (int64_t i = binoff[(size_t)b]; i < binoff[(size_t)b + 1]; i += kK1eRows) tile_start.push_back(i);
+      bin_tile.push_back((int64_t)tile_start.size());
+    }
+    tile_start.push_back(G);
+    h->ntiles = (int64_t)tile_start.size() - 1;
+    coef.resize((size_t)h->nbins);
+    bin_age.resize((size_t)h->nbins);
+    const double metprior = 1.0 / (double)nZ;
+    for (int i = 0; i < nAg; ++i)
+      for (int j = 0; j < nZ; ++j) {
+        coef[(size_t)i * nZ + j] = metprior * mm->massmult[(size_t)i * nZ + j] / mm->avemass;
+        bin_age[(size_t)i * nZ + j] = mm->ages[i];
+      }
+  } else if (h->poisson) {
     if (!grid->logA || !grid->Z) return fail("logA and Z columns are required for the N-stars term");
     if (mm->n_ages < 1 || mm->n_mets < 1 || !mm->ages || !mm->mets || !mm->massmult)
       return fail("invalid mass-multiplier description");
@@ -430,7 +531,7 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
                     (long long)stars->indxs[kk * S + s], (long long)G, (long long)s);
       Entry e;
       e.a = v * grid->prior_weight[r] * grid->grid_weight[r] * grid->completeness[r];
-      const uint32_t rc = rowcode[(size_t)r];
+      const uint32_t rc = elementwise ? 0u : rowcode[(size_t)r];
       const uint32_t cA = (rc >> kAgeShift) & kAgeMask, cB = rc & kDustMask;
       e.meta = cA;
       e.idx = mode == MB_MODE_FACTOR ? cB : mode == MB_MODE_TABLE_UNIQUE ? cA * (uint32_t)h->nB + cB : (uint32_t)r;
@@ -524,7 +625,29 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
   if (dev_upload(h, &h->d_seg[0], seg[0])) return 1;
   if (dev_upload(h, &h->d_seg[1], seg[1])) return 1;
   if (mode == MB_MODE_TABLE_GRID && dev_upload(h, &h->d_rowcode, rowcode)) return 1;
-  if (h->poisson) {
+  if (elementwise) {
+    for (int p = 0; p < MB_NPARAM; ++p) {
+      if (model->kind[p] == MB_FIXED) continue;
+      CK(cudaMalloc((void**)&h->d_col[p], sizeof(double) * (size_t)G));
+      h->device_bytes += 8 * G;
+      CK(cudaMemcpy(h->d_col[p], grid->col[p], sizeof(double) * (size_t)G, cudaMemcpyHostToDevice));
+    }
+    if (h->poisson) {
+      CK(cudaMalloc((void**)&h->d_gw, sizeof(double) * (size_t)G));
+      CK(cudaMalloc((void**)&h->d_compl, sizeof(double) * (size_t)G));
+      h->device_bytes += 16 * G;
+      CK(cudaMemcpy(h->d_gw, grid->grid_weight, sizeof(double) * (size_t)G, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(h->d_compl, grid->completeness, sizeof(double) * (size_t)G, cudaMemcpyHostToDevice));
+      if (dev_upload(h, &h->d_binrows, binrows)) return 1;
+      if (dev_upload(h, &h->d_tile_start, tile_start)) return 1;
+      if (dev_upload(h, &h->d_bin_tile, bin_tile)) return 1;
+      if (dev_alloc(h, &h->d_partial, h->ntiles * 128 * 2)) return 1;
+      if (dev_upload(h, &h->d_bin_age, bin_age)) return 1;
+      if (dev_upload(h, &h->d_coef, coef)) return 1;
+      if (dev_alloc(h, &h->d_Fage, (int64_t)h->nbins * 128)) return 1;
+      if (dev_alloc(h, &h->d_SC, (int64_t)h->nbins * 128 * 2)) return 1;
+    }
+  } else if (h->poisson) {
     if (dev_upload(h, &h->d_H, H)) return 1;
     if (dev_upload(h, &h->d_coef, coef)) return 1;
     if (dev_upload(h, &h->d_bin_agecls, bin_agecls)) return 1;
@@ -550,6 +673,11 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
     MB_OPTIN(1, kModeTable); MB_OPTIN(2, kModeTable); MB_OPTIN(4, kModeTable);
     MB_OPTIN(1, kModeTableGrid); MB_OPTIN(2, kModeTableGrid); MB_OPTIN(4, kModeTableGrid);
 #undef MB_OPTIN
+  }
+  if (elementwise) {
+    const size_t need = k1e_smem_bytes(128, h->ndim);
+    if (need > (size_t)h->max_smem) return fail("ELEMENTWISE: %d free variables do not fit shared memory", h->ndim);
+    CK(cudaFuncSetAttribute(mb_k1_elementwise, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
   }
   if (n_pixels > 0) {
     if (mode != MB_MODE_FACTOR) return fail("pixel batches need the factor tables in shared memory (FACTOR mode)");
@@ -704,7 +832,7 @@ extern "C" int mb_gathered_indices(const mb_handle* h, int64_t* rows, int64_t ca
   if (!h) return fail("null handle");
   if (h->kept_offs.empty()) return fail("handle was created without keep_indices");
   if ((int64_t)h->kept_rows.size() > cap) return fail("rows buffer too small (%lld needed)", (long long)h->kept_rows.size());
-  if (h->mode == MB_MODE_TABLE_GRID && h->n_entries == h->n_entries_raw) {
+  if ((h->mode == MB_MODE_TABLE_GRID || h->mode == MB_MODE_ELEMENTWISE) && h->n_entries == h->n_entries_raw) {
     // TABLE_GRID gathers by grid row: report what the device actually holds (round trip)
     std::vector<uint32_t> back((size_t)h->n_entries);
     if (h->n_entries) CK(cudaMemcpy(back.data(), h->d_ec, sizeof(uint32_t) * back.size(), cudaMemcpyDeviceToHost));
@@ -800,6 +928,7 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
   if (ndim != h->ndim) return fail("phi has %d columns, the model has %d free variables", ndim, h->ndim);
   CK(cudaSetDevice(h->device));
   const int kmode = h->mode == MB_MODE_FACTOR ? kModeFactor : h->mode == MB_MODE_TABLE_UNIQUE ? kModeTable : kModeTableGrid;
+  const bool elementwise = h->mode == MB_MODE_ELEMENTWISE;  // K1e (+ K1b) instead of K0 + K1; K2 gathers by grid row
   const bool prof = h->profiling != 0;
   float acc_ms[MB_NKERNELS] = {0, 0, 0};
   int launches = 0;
@@ -814,14 +943,16 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     double* FB = h->d_F + (size_t)h->nA * Wpad;
 
     if (prof) CK(cudaEventRecord(h->ev[0], st));
-    K0Args k0{};
-    k0.model = h->mdev; k0.clsx = h->d_clsx; k0.phi = d_phi + (size_t)w0 * ndim;
-    for (int p = 0; p < MB_NPARAM; ++p)
-      k0.tab[p] = (d_tab && d_tab[p]) ? d_tab[p] + (size_t)w0 * h->mdev.ncls[p] : nullptr;
-    k0.F = h->d_F; k0.nA = h->nA; k0.nB = h->nB; k0.W = wp; k0.Wpad = Wpad; k0.ndim = ndim;
-    k0.ncls_total = h->ncls_total;
-    mb_k0_factors<<<Wpad, kK0Threads, sizeof(double) * std::max(1, h->ncls_total), st>>>(k0);
-    ++launches;
+    if (!elementwise) {
+      K0Args k0{};
+      k0.model = h->mdev; k0.clsx = h->d_clsx; k0.phi = d_phi + (size_t)w0 * ndim;
+      for (int p = 0; p < MB_NPARAM; ++p)
+        k0.tab[p] = (d_tab && d_tab[p]) ? d_tab[p] + (size_t)w0 * h->mdev.ncls[p] : nullptr;
+      k0.F = h->d_F; k0.nA = h->nA; k0.nB = h->nB; k0.W = wp; k0.Wpad = Wpad; k0.ndim = ndim;
+      k0.ncls_total = h->ncls_total;
+      mb_k0_factors<<<Wpad, kK0Threads, sizeof(double) * std::max(1, h->ncls_total), st>>>(k0);
+      ++launches;
+    }
     if (prof) CK(cudaEventRecord(h->ev[1], st));
     if (kmode != kModeFactor) {
       int64_t need = h->U * Wpad;
@@ -832,6 +963,29 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
         if (dev_alloc(h, &h->d_T, need)) return 1;
         h->cap_T = need;
       }
+    }
+    if (elementwise) {
+      K1eArgs k1{};
+      k1.model = h->mdev;
+      for (int p = 0; p < MB_NPARAM; ++p) k1.col[p] = h->d_col[p];
+      k1.phi = d_phi + (size_t)w0 * ndim; k1.T = h->d_T; k1.G = h->G;
+      k1.W = wp; k1.Wpad = Wpad; k1.ndim = ndim;
+      if (h->poisson) {
+        k1.rowlist = h->d_binrows; k1.tile_start = h->d_tile_start; k1.gw = h->d_gw; k1.compl_ = h->d_compl;
+        k1.partial = h->d_partial; k1.Fage = h->d_Fage; k1.bin_age = h->d_bin_age; k1.nbins = h->nbins;
+        k1.ntiles = h->ntiles;
+      } else {
+        k1.ntiles = (h->G + kK1eRows - 1) / kK1eRows;
+      }
+      const size_t sm1 = k1e_smem_bytes(Wpad, ndim);
+      const int blocks1 = (int)std::min<int64_t>(k1.ntiles, (int64_t)h->sm_count * 6);
+      mb_k1_elementwise<<<blocks1, kK1eThreads, sm1, st>>>(k1);
+      ++launches;
+      if (h->poisson) {
+        mb_k1b_binsums<<<h->nbins, kK1bThreads, 0, st>>>(h->d_partial, h->d_bin_tile, h->d_SC, Wpad);
+        ++launches;
+      }
+    } else if (kmode != kModeFactor) {
       int64_t total = h->U * (Wpad / 2);
       int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->sm_count * 16);
       mb_k1_expand<<<blocks, 256, 0, st>>>(FA, FB, h->mode == MB_MODE_TABLE_GRID ? h->d_rowcode : nullptr,
@@ -854,13 +1008,14 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
                         std::max(h->poisson ? wp : 1, (h->nseg[NW == 4] + kK2Warps - 1) / kK2Warps));
     grid = std::min(grid, h->max_blocks);
     K2Args k2{};
-    k2.ea = h->d_ea; k2.ec = h->d_ec; k2.seg = h->d_seg[NW == 4]; k2.nseg = h->nseg[NW == 4]; k2.FA = FA; k2.T = h->d_T;
+    k2.ea = h->d_ea; k2.ec = h->d_ec; k2.seg = h->d_seg[NW == 4]; k2.nseg = h->nseg[NW == 4]; k2.FA = elementwise ? h->d_Fage : FA; k2.T = h->d_T;
     k2.gacc = h->d_gacc; k2.counters = h->d_counter; k2.out = d_out;
     k2.nA = h->nA; k2.nB = h->nB; k2.Wpad = Wpad; k2.W = wp; k2.w0 = w0; k2.Wtot = W;
     k2.tab_off = (int32_t)k2_front_bytes(h->nbins, Wpad);
     k2.pois.Ht = h->d_H; k2.pois.bin_agecls = h->d_bin_agecls; k2.pois.coef = h->d_coef;
     k2.pois.n_stars = (double)h->S_total; k2.pois.nbins = h->poisson ? h->nbins : 0;
     k2.pois.nslice = poisson_nslice(k2_threads(NW), h->nbins);
+    k2.pois.SC = elementwise ? h->d_SC : nullptr;
     k2.timeline = nullptr;
     if (prof && h->d_timeline) {
       CK(cudaMemsetAsync(h->d_timeline, 0, sizeof(unsigned long long) * (size_t)grid * kTimelinePoints, st));

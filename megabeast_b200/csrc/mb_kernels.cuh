@@ -189,6 +189,7 @@ struct PoissonArgs {
   double n_stars;             // S of the fit (:183-185)
   int32_t nbins;              // 0: no N-stars term
   int32_t nslice;             // slices of the dust classes per bin (host: fits the scratch)
+  const double* SC;           // ELEMENTWISE: bin sums [nbins][Wpad][2] already formed by K1b (else null)
 };
 
 // F: this pass's factor tables (shared or global), element (c, w) at F[c * Wpad + w].
@@ -198,6 +199,24 @@ __device__ double poisson_term(const PoissonArgs& pa, const double* F, int nA, i
                                double* part, double* scratch) {
   const int nbins = pa.nbins, nslice = pa.nslice;
   double* sc = part + (size_t)nslice * nbins * 2;  // [nbins][2]
+  if (pa.SC) {
+    // ELEMENTWISE: S and C were summed over the grid rows themselves (mb_k1b_binsums)
+    double part_nrm = 0.0;
+    for (int b = threadIdx.x; b < nbins; b += THREADS) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(pa.SC) + (size_t)b * Wpad + w);
+      sc[2 * b] = v.x; sc[2 * b + 1] = v.y;
+      part_nrm += v.x;
+    }
+    const double nrm = block_sum<THREADS>(part_nrm, scratch);
+    double part_pred = 0.0;
+    for (int b = threadIdx.x; b < nbins; b += THREADS) {
+      const double sb = sc[2 * b] / nrm;
+      if (sb > 0.0) part_pred += (F[(size_t)b * Wpad + w] * pa.coef[b]) * (sc[2 * b + 1] / nrm) / sb;
+    }
+    const double pred = block_sum<THREADS>(part_pred, scratch);
+    __syncthreads();
+    return pa.n_stars * log(pred) - pred - lgamma(pa.n_stars + 1.0);
+  }
   const double2* Ht = reinterpret_cast<const double2*>(pa.Ht);
   const double* FB = F + (size_t)nA * Wpad + w;
   for (int item = threadIdx.x; item < nbins * nslice; item += THREADS) {
@@ -258,26 +277,262 @@ __global__ void __launch_bounds__(256) mb_k1_expand(const double* __restrict__ F
                                                     const uint32_t* __restrict__ rowcode,
                                                     double* __restrict__ T, int64_t U, int nB,
                                                     int Wpad) {
-  // one thread = one (row, walker pair): 16-byte stores, walker minor -> fully coalesced
-  const int half = Wpad >> 1;
-  int64_t total = U * half;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t u = i / half;
-    int w2 = (int)(i - u * half) * 2;
+  // one thread = one (row, walker pair): 16-byte stores, walker minor -> fully coalesced.
+  // Wpad/2 is 16, 32 or 64: shifts and masks, no 64-bit division in the loop
+  const int half = Wpad >> 1, hshift = 31 - __clz(half);
+  const int w2 = (threadIdx.x & (half - 1)) * 2;
+  const int64_t rows_per_step = ((int64_t)gridDim.x * blockDim.x) >> hshift;
+  const double2* FA2 = reinterpret_cast<const double2*>(FA + w2);
+  const double2* FB2 = reinterpret_cast<const double2*>(FB + w2);
+  for (int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> hshift; u < U; u += rows_per_step) {
     uint32_t cA, cB;
     if (rowcode) {
       uint32_t code = __ldg(rowcode + u);
       cA = (code >> kAgeShift) & kAgeMask;
       cB = code & kDustMask;
     } else {
-      cA = (uint32_t)(u / nB);
-      cB = (uint32_t)(u - (int64_t)cA * nB);
+      cA = (uint32_t)u / (uint32_t)nB;          // U = nA * nB <= 2^27 here
+      cB = (uint32_t)u - cA * (uint32_t)nB;
     }
-    double2 fa = __ldg(reinterpret_cast<const double2*>(FA + (size_t)cA * Wpad + w2));
-    double2 fb = __ldg(reinterpret_cast<const double2*>(FB + (size_t)cB * Wpad + w2));
-    double2 t = make_double2(fa.x * fb.x, fa.y * fb.y);
-    __stcs(reinterpret_cast<double2*>(T + (size_t)u * Wpad + w2), t);
+    const double2 fa = __ldg(FA2 + (size_t)cA * half);
+    const double2 fb = __ldg(FB2 + (size_t)cB * half);
+    __stcs(reinterpret_cast<double2*>(T + (size_t)u * Wpad + w2), make_double2(fa.x * fb.x, fa.y * fb.y));
+  }
+}
+
+// ---- K1e / K1b: the prior weights evaluated ELEMENTWISE over the grid's physics columns ---------------
+// singlepop_dust_model.py:131-148 taken literally: physmod[g][w] = prod_p f_p(col_p[g]; theta_p(phi_w))
+// for every grid row, no class coding -- the path for grids whose columns are not a small set of
+// distinct values (non-Cartesian grids).  A block owns tiles of kK1eRows rows:
+//   phase 1  one thread per (row, parameter): what depends on the row only -- ln x and 1/x for the
+//            lognormals, the interval (and offset) for the binned models, 10^x for the exponential;
+//            column loads are coalesced along the rows
+//   phase 2  one thread per (row, walker pair): the per-walker part (one fp64 exp per lognormal),
+//            product in the reference's left-to-right order, 16-byte streaming stores, walker minor
+// Per-walker constants (mu, 1/sigma, inv_sqrt_2pi/sigma, ...) are derived from phi once per block.
+// Reads 8 P bytes per row, writes 8 Wpad bytes per row: HBM-write / fp64-exp bound.
+constexpr int kK1eThreads = 256;
+constexpr int kK1eRows = 64;
+constexpr int kK1eWalkerVals = 6;   // per (parameter, walker) derived constants
+struct K1eArgs {
+  ModelDev model;
+  const double* col[MB_NPARAM];  // device columns of the free parameters [G]
+  const double* phi;             // [W][ndim]
+  double* T;                     // [G][Wpad]
+  // N-stars term (helpers.py:133-162), optional: rows are visited in (age, Z)-bin order through
+  // `rowlist`, tiles never straddle a bin, and every tile leaves its partial bin sums
+  //   partial[tile][w] = (sum physmod grid_weight, sum physmod grid_weight completeness)
+  // so the table is never read back; mb_k1b_binsums adds the tiles of each bin in fixed order
+  const int32_t* rowlist;        // [G] grid rows in bin order (null: natural order, no partial sums)
+  const int64_t* tile_start;     // [ntiles + 1] positions in rowlist (null: tiles of kK1eRows rows)
+  const double* gw;              // grid_weight [G]
+  const double* compl_;          // completeness [G]
+  double* partial;               // [ntiles][Wpad][2]
+  double* Fage;                  // [nbins][Wpad]: age factor of each (age, Z) bin
+  const double* bin_age;         // [nbins] logA of the bin
+  int64_t G, ntiles;
+  int32_t W, Wpad, ndim, nbins;
+};
+
+// derived per-walker constants of parameter p -> c[0..5]
+__device__ __forceinline__ void k1e_walker_consts(const ModelDev& m, int p, const double* th, double* c) {
+  const double inv_sqrt_2pi = 0.3989422804014326779399460599343819;
+  switch (m.kind[p]) {
+    case MB_LOGNORMAL:
+      c[0] = log(th[0]) + th[1] * th[1]; c[1] = 1.0 / th[1]; c[2] = inv_sqrt_2pi / th[1];
+      break;
+    case MB_TWO_LOGNORMAL: {
+      const double n1 = 1.0 - 1.0 / (th[4] + 1.0), n2 = 1.0 / (th[4] + 1.0);
+      c[0] = log(th[0]) + th[2] * th[2]; c[1] = 1.0 / th[2]; c[2] = n1 * inv_sqrt_2pi / th[2];
+      c[3] = log(th[1]) + th[3] * th[3]; c[4] = 1.0 / th[3]; c[5] = n2 * inv_sqrt_2pi / th[3];
+      break;
+    }
+    case MB_EXPONENTIAL:
+      c[0] = th[0] * 1e9;
+      break;
+    default:
+      break;
+  }
+}
+// row part: two doubles and an interval index / validity flag
+__device__ __forceinline__ void k1e_row_part(const ModelDev& m, int p, double x, double* r0, double* r1, int* ri) {
+  *r0 = 0.0; *r1 = 0.0; *ri = 0;
+  switch (m.kind[p]) {
+    case MB_LOGNORMAL: case MB_TWO_LOGNORMAL:
+      if (x > 0.0) { *r0 = log(x); *r1 = 1.0 / x; *ri = 1; }
+      break;
+    case MB_BINS_HISTO: {
+      int n = m.nnodes[p], i = 0;
+      while (i + 1 < n && x >= m.nodes[p][i + 1]) ++i;
+      *ri = i;
+      break;
+    }
+    case MB_BINS_INTERP: {
+      int n = m.nnodes[p];
+      if (x <= m.nodes[p][0]) { *ri = 0; *r1 = -1.0; }               // th[0]
+      else if (x >= m.nodes[p][n - 1]) { *ri = n - 1; *r1 = -1.0; }  // th[n-1]
+      else {
+        int i = 0;
+        while (x >= m.nodes[p][i + 1]) ++i;
+        *ri = i; *r0 = x - m.nodes[p][i]; *r1 = m.nodes[p][i + 1] - m.nodes[p][i];
+      }
+      break;
+    }
+    case MB_EXPONENTIAL:
+      *r0 = pow(10.0, x);
+      break;
+    default:
+      break;
+  }
+}
+__device__ __forceinline__ double k1e_eval(int kind, const double* th, const double* c, double r0, double r1, int ri) {
+  switch (kind) {
+    case MB_LOGNORMAL: {
+      if (!ri) return 0.0;
+      const double t = (r0 - c[0]) * c[1];
+      return (c[2] * r1) * exp(-0.5 * (t * t));
+    }
+    case MB_TWO_LOGNORMAL: {
+      if (!ri) return 0.0;
+      const double t1 = (r0 - c[0]) * c[1], t2 = (r0 - c[3]) * c[4];
+      return (c[2] * r1) * exp(-0.5 * (t1 * t1)) + (c[5] * r1) * exp(-0.5 * (t2 * t2));
+    }
+    case MB_BINS_HISTO:
+      return th[ri];
+    case MB_BINS_INTERP:
+      if (r1 < 0.0) return th[ri];
+      return (th[ri + 1] - th[ri]) / r1 * r0 + th[ri];
+    case MB_EXPONENTIAL:
+      return exp(-1.0 * r0 / c[0]);
+    default:  // MB_FLAT
+      return 1.0;
+  }
+}
+
+__global__ void __launch_bounds__(kK1eThreads) mb_k1_elementwise(const __grid_constant__ K1eArgs a) {
+  extern __shared__ __align__(16) double k1e_smem[];
+  const ModelDev& m = a.model;
+  const int Wpad = a.Wpad, ndim = a.ndim;
+  // smem: phi [Wpad][ndim] | consts [NPARAM][Wpad][6] | row parts r0, r1 [NPARAM][rows] | weights
+  // gw, gw*compl [rows] | combine [threads][4] | ri [NPARAM][rows] | rows [rows]
+  double* sphi = k1e_smem;
+  double* scon = sphi + (size_t)Wpad * ndim;
+  double* sr0 = scon + (size_t)MB_NPARAM * Wpad * kK1eWalkerVals;
+  double* sr1 = sr0 + MB_NPARAM * kK1eRows;
+  double* sgw = sr1 + MB_NPARAM * kK1eRows;
+  double* sgc = sgw + kK1eRows;
+  double* scomb = sgc + kK1eRows;
+  int* sri = reinterpret_cast<int*>(scomb + 4 * kK1eThreads);
+  int* srow = sri + MB_NPARAM * kK1eRows;
+  for (int i = threadIdx.x; i < Wpad * ndim; i += kK1eThreads) {
+    const int w = i / ndim, k = i - w * ndim;
+    sphi[i] = a.phi[(size_t)(w < a.W ? w : a.W - 1) * ndim + k];  // padding columns repeat the last walker
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < MB_NPARAM * Wpad; i += kK1eThreads) {
+    const int p = i / Wpad, w = i - p * Wpad;
+    if (m.kind[p] != MB_FIXED) k1e_walker_consts(m, p, sphi + (size_t)w * ndim + m.voff[p], scon + (size_t)i * kK1eWalkerVals);
+  }
+  __syncthreads();
+  // age factor of every (age, Z) bin for the Poisson term (block 0 only; tiny)
+  if (a.Fage && blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < a.nbins * Wpad; i += kK1eThreads) {
+      const int b = i / Wpad, w = i - b * Wpad;
+      double v = 1.0;
+      if (m.kind[MB_P_LOGA] != MB_FIXED) {
+        double r0, r1; int ri;
+        k1e_row_part(m, MB_P_LOGA, a.bin_age[b], &r0, &r1, &ri);
+        v = k1e_eval(m.kind[MB_P_LOGA], sphi + (size_t)w * ndim + m.voff[MB_P_LOGA],
+                     scon + ((size_t)MB_P_LOGA * Wpad + w) * kK1eWalkerVals, r0, r1, ri);
+      }
+      a.Fage[i] = v;
+    }
+  }
+  const int half = Wpad >> 1;
+  const int rows_per_pass = kK1eThreads / half;
+  const int pair = threadIdx.x % half, rlane = threadIdx.x / half;
+  int kinds[MB_NPARAM];
+#pragma unroll
+  for (int p = 0; p < MB_NPARAM; ++p) kinds[p] = m.kind[p];
+  for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    const int64_t i0 = a.tile_start ? a.tile_start[tile] : tile * kK1eRows;
+    const int nrows = (int)((a.tile_start ? a.tile_start[tile + 1] : min(a.G, i0 + kK1eRows)) - i0);
+    __syncthreads();  // row parts of the previous tile are no longer read
+    for (int r = threadIdx.x; r < nrows; r += kK1eThreads) {
+      const int g = a.rowlist ? __ldg(a.rowlist + i0 + r) : (int)(i0 + r);
+      srow[r] = g;
+      if (a.partial) {
+        const double w = __ldg(a.gw + g);
+        sgw[r] = w; sgc[r] = w * __ldg(a.compl_ + g);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < MB_NPARAM * kK1eRows; i += kK1eThreads) {
+      const int p = i / kK1eRows, r = i - p * kK1eRows;
+      if (m.kind[p] != MB_FIXED && r < nrows) {
+        double r0, r1; int ri;
+        k1e_row_part(m, p, __ldg(a.col[p] + srow[r]), &r0, &r1, &ri);
+        sr0[i] = r0; sr1[i] = r1; sri[i] = ri;
+      }
+    }
+    __syncthreads();
+    double s0 = 0.0, s1 = 0.0, c0 = 0.0, c1 = 0.0;
+    for (int r = rlane; r < nrows; r += rows_per_pass) {
+      double v0 = 1.0, v1 = 1.0;
+#pragma unroll
+      for (int p = 0; p < MB_NPARAM; ++p) {  // logA, Av, Rv, fA: the reference's `cur_physmod *=` order
+        if (kinds[p] == MB_FIXED) continue;
+        const int i = p * kK1eRows + r;
+        const double* th0 = sphi + (size_t)(2 * pair) * ndim + m.voff[p];
+        const double* cc = scon + ((size_t)p * Wpad + 2 * pair) * kK1eWalkerVals;
+        const double r0 = sr0[i], r1 = sr1[i];
+        const int ri = sri[i];
+        v0 *= k1e_eval(kinds[p], th0, cc, r0, r1, ri);
+        v1 *= k1e_eval(kinds[p], th0 + ndim, cc + kK1eWalkerVals, r0, r1, ri);
+      }
+      __stcs(reinterpret_cast<double2*>(a.T + (size_t)srow[r] * Wpad + 2 * pair), make_double2(v0, v1));
+      if (a.partial) {
+        s0 = fma(v0, sgw[r], s0); s1 = fma(v1, sgw[r], s1);
+        c0 = fma(v0, sgc[r], c0); c1 = fma(v1, sgc[r], c1);
+      }
+    }
+    if (a.partial) {  // combine the row lanes in fixed order -> this tile's partial bin sums
+      double* mine = scomb + 4 * threadIdx.x;
+      mine[0] = s0; mine[1] = s1; mine[2] = c0; mine[3] = c1;
+      __syncthreads();
+      if (rlane == 0) {
+        for (int l = 1; l < rows_per_pass; ++l) {
+          const double* o = scomb + 4 * (l * half + pair);
+          s0 += o[0]; s1 += o[1]; c0 += o[2]; c1 += o[3];
+        }
+        double2* out = reinterpret_cast<double2*>(a.partial) + (size_t)tile * Wpad + 2 * pair;
+        out[0] = make_double2(s0, c0);
+        out[1] = make_double2(s1, c1);
+      }
+    }
+  }
+}
+
+// K1b: bin sums S, C (helpers.py:133-162) = the tiles' partial sums added per bin in tile order.
+// One block per bin, thread = (walker, tile lane); lanes combined in fixed order.
+constexpr int kK1bThreads = 256;
+__global__ void __launch_bounds__(kK1bThreads) mb_k1b_binsums(const double* __restrict__ partial,
+                                                              const int64_t* __restrict__ bin_tile,
+                                                              double* __restrict__ SC, int Wpad) {
+  __shared__ double2 part[kK1bThreads];
+  const int b = blockIdx.x;
+  const int w = threadIdx.x % Wpad, lane = threadIdx.x / Wpad, nlanes = kK1bThreads / Wpad;
+  const double2* P = reinterpret_cast<const double2*>(partial);
+  double s = 0.0, c = 0.0;
+  for (int64_t t = bin_tile[b] + lane; t < bin_tile[b + 1]; t += nlanes) {
+    const double2 v = __ldg(P + (size_t)t * Wpad + w);
+    s += v.x; c += v.y;
+  }
+  part[threadIdx.x] = make_double2(s, c);
+  __syncthreads();
+  if (lane == 0) {
+    for (int l = 1; l < nlanes; ++l) { s += part[l * Wpad + w].x; c += part[l * Wpad + w].y; }
+    reinterpret_cast<double2*>(SC)[(size_t)b * Wpad + w] = make_double2(s, c);
   }
 }
 

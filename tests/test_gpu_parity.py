@@ -16,7 +16,7 @@ from oracle import c_oracle
 from oracle import lnprob_port as port
 
 pytestmark = pytest.mark.gpu
-MODES = ["factor", "table_unique", "table_grid"]
+MODES = ["factor", "table_unique", "table_grid", "elementwise"]
 RTOL = 1e-9
 
 
@@ -45,6 +45,8 @@ def _eval(model, phis, stars, moddata, batch):
 def test_golden_one_walker_at_a_time(name, mode, capsys):
     settings, moddata, stars, phis, expect, kind = load_golden(name)
     model = MB_Model(copy.deepcopy(settings), mode=mode)
+    if mode == "elementwise" and model._spec()[0].tabulated:
+        pytest.skip("host-tabulated prior models need class-coded columns")
     got, gkind = _eval(model, phis, stars, moddata, batch=False)
     assert np.array_equal(gkind, kind)
     ok = kind == 0
@@ -74,7 +76,7 @@ def test_return_types_and_side_effects():
     assert lnprob(phis[1] * 0 - 1.0, model, stars, moddata) == -np.inf
 
 
-@pytest.mark.parametrize("mode", ["factor", "table_grid"])
+@pytest.mark.parametrize("mode", ["factor", "table_grid", "elementwise"])
 def test_gathered_indices_bit_exact(mode):
     settings, moddata, stars, phis, expect, kind = load_golden("masked_and_zero_stars")
     model = MB_Model(copy.deepcopy(settings))
@@ -109,6 +111,42 @@ def test_synthetic_vs_c_oracle(cfg, mode, W, engine_mode):
     assert_close(v, expect, RTOL)
     eng.close()
     assert abs(lnprob(phis[3], model, stars, moddata) - expect[3]) <= RTOL * abs(expect[3])
+
+
+def _jittered(moddata, rng, frac=1e-3):
+    """A NON-Cartesian grid: every row gets its own Av and Rv value (no small set of classes)."""
+    out = dict(moddata)
+    for key in ("Av", "Rv"):
+        out[key] = moddata[key] * (1.0 + frac * rng.standard_normal(moddata[key].size))
+    return out
+
+
+@pytest.mark.parametrize("cfg,W", [("small", 16), ("cfg1", 45), ("cfg1", 130)])
+def test_non_cartesian_grid_auto_elementwise(cfg, W):
+    """Columns with ~G distinct values cannot be class-coded: AUTO must pick the elementwise
+    evaluation over the grid's physics columns (singlepop_dust_model.py:131-148 literally) and
+    still match the oracle; the class-coded modes must refuse such a grid."""
+    settings, moddata, stars, _ = synth.make_problem(cfg, seeds=(21, 22, 23))
+    moddata = _jittered(moddata, np.random.default_rng(5))
+    assert np.unique(moddata["Av"]).size > 4096
+    pm = port.PortModel(copy.deepcopy(settings))
+    phis = synth.make_walkers(pm, W, seed=23)
+    expect = c_oracle.lnprob_batch(pm, phis, stars, moddata)
+    model = MB_Model(copy.deepcopy(settings))
+    got = lnprob(phis, model, stars, moddata)
+    assert model.engine_info()["mode"] == "elementwise"
+    assert_close(got, expect, RTOL)
+    assert abs(lnprob(phis[2], model, stars, moddata) - expect[2]) <= RTOL * abs(expect[2])
+    with pytest.raises(Exception, match="distinct values"):
+        lnprob(phis, MB_Model(copy.deepcopy(settings), mode="factor"), stars, moddata)
+
+
+def test_elementwise_matches_class_coded_on_cartesian_grid():
+    settings, moddata, stars, _ = synth.make_problem("cfg1", mode="clustered", seeds=(41, 42, 43))
+    phis = synth.make_walkers(MB_Model(copy.deepcopy(settings)), 64, seed=43)
+    a = lnprob(phis, MB_Model(copy.deepcopy(settings), mode="factor"), stars, moddata)
+    b = lnprob(phis, MB_Model(copy.deepcopy(settings), mode="elementwise"), stars, moddata)
+    assert_close(b, a, RTOL)
 
 
 def test_cfg1_golden_expect():
