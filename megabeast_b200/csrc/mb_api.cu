@@ -63,6 +63,7 @@ struct mb_handle {
   uint32_t* d_ec = nullptr;     // entry codes
   int64_t* d_seg[2] = {nullptr, nullptr};  // segment tables: [0] 768-thread kernels, [1] 512-thread kernel
   uint32_t* d_rowcode = nullptr;
+  uint16_t* d_rowlut = nullptr;  // [nB][4] look-up rows of every dust class's digits (K2 builds the tables itself)
   // ELEMENTWISE mode: the physics columns themselves, bin-sorted row list for the N-stars sums
   double* d_col[MB_NPARAM] = {nullptr, nullptr, nullptr, nullptr};
   double* d_gw = nullptr;
@@ -105,6 +106,7 @@ struct mb_handle {
   std::vector<int32_t> scratch_idx, scratch_st;
   std::vector<double> scratch_phi, scratch_rows, scratch_val;
   int table_bytes = 8;   // FACTOR-mode shared-memory table element: 8 = fp64, 4 = fp32
+  int no_fuse = 0;       // keep K0 as a separate launch (MB_NO_FUSE=1: A/B measurements)
   int occ_cache[3] = {0, 0, 0};
   size_t occ_smem[3] = {0, 0, 0};
   // pixel batches
@@ -270,7 +272,7 @@ extern "C" void mb_destroy(mb_handle* h) {
                   h->d_bin_agecls, h->d_phi, h->d_tab[0], h->d_tab[1], h->d_tab[2], h->d_tab[3],
                   h->d_F, h->d_counter, h->d_gacc, h->d_T, h->d_out, h->d_pix_seg, h->d_pix_nstars, h->d_Fpix,
                   h->d_timeline, h->d_col[0], h->d_col[1], h->d_col[2], h->d_col[3], h->d_gw, h->d_compl,
-                  h->d_binrows, h->d_tile_start, h->d_bin_tile, h->d_partial, h->d_bin_age, h->d_Fage, h->d_SC};
+                  h->d_rowlut, h->d_binrows, h->d_tile_start, h->d_bin_tile, h->d_partial, h->d_bin_age, h->d_Fage, h->d_SC};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -301,6 +303,7 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
   h->model = *model;
   if (o.table_precision != 0 && o.table_precision != 1) return fail("table_precision must be 0 (fp64) or 1 (fp32)");
   h->table_bytes = o.table_precision == 1 ? 4 : 8;
+  if (const char* nf = getenv("MB_NO_FUSE")) h->no_fuse = atoi(nf);
   CK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, o.device));
   CK(cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, o.device));
   h->max_smem -= 1024;  // room for the kernels' few bytes of static shared memory
@@ -625,6 +628,14 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
   if (dev_upload(h, &h->d_seg[0], seg[0])) return 1;
   if (dev_upload(h, &h->d_seg[1], seg[1])) return 1;
   if (mode == MB_MODE_TABLE_GRID && dev_upload(h, &h->d_rowcode, rowcode)) return 1;
+  if (mode == MB_MODE_FACTOR) {
+    std::vector<uint16_t> rowlut((size_t)h->nB * 4, (uint16_t)0xffff);
+    for (int cb = 0; cb < h->nB; ++cb)
+      for (int p = MB_P_AV; p < MB_NPARAM; ++p)
+        if (model->kind[p] != MB_FIXED)
+          rowlut[(size_t)cb * 4 + (p - MB_P_AV)] = (uint16_t)(md.clsoff[p] + (cb / md.radix[p]) % md.ncls[p]);
+    if (dev_upload(h, &h->d_rowlut, rowlut)) return 1;
+  }
   if (elementwise) {
     for (int p = 0; p < MB_NPARAM; ++p) {
       if (model->kind[p] == MB_FIXED) continue;
@@ -922,8 +933,10 @@ static int k2_blocks_per_sm(int kmode, int NW, size_t smem, int table_bytes) {
          : kmode == kModeTable ? k2_occ<kModeTable>(NW, smem) : k2_occ<kModeTableGrid>(NW, smem);
 }
 
+// h_phi (optional): host copy of phi, carried in K2's kernel parameters when the tables are built
+// inside K2 and it is small enough; d_phi must then still be readable by the device (mapped memory)
 static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const double* const d_tab[MB_NPARAM],
-                       double* d_out, cudaStream_t st) {
+                       double* d_out, cudaStream_t st, const double* h_phi = nullptr) {
   if (W <= 0) return 0;
   if (ndim != h->ndim) return fail("phi has %d columns, the model has %d free variables", ndim, h->ndim);
   CK(cudaSetDevice(h->device));
@@ -942,8 +955,17 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     double* FA = h->d_F;
     double* FB = h->d_F + (size_t)h->nA * Wpad;
 
+    // FACTOR mode with fp64 tables and analytic models: K2 builds the factor tables in its own
+    // prologue (look-up table in the stage area), no K0 launch
+    const size_t fuse_scratch = 8 * ((size_t)h->ncls_total * (Wpad + 1) + 2 * (size_t)MB_NPARAM * Wpad);
+    // host phi travels in the kernel parameters and is staged in shared memory; a batch too large
+    // for that keeps K0 (one read of the mapped host memory per walker instead of one per block)
+    const bool inline_phi = h_phi && (int64_t)wp * ndim <= kPhiInline &&
+                            fuse_scratch + 8 * (size_t)wp * ndim <= k2_front_bytes(h->nbins, Wpad);
+    bool fused = kmode == kModeFactor && h->table_bytes == 8 && !d_tab && !h->no_fuse && h->ncls_total < 0xffff &&
+                 fuse_scratch <= k2_front_bytes(h->nbins, Wpad) && (!h_phi || inline_phi);
     if (prof) CK(cudaEventRecord(h->ev[0], st));
-    if (!elementwise) {
+    if (!elementwise && !fused) {
       K0Args k0{};
       k0.model = h->mdev; k0.clsx = h->d_clsx; k0.phi = d_phi + (size_t)w0 * ndim;
       for (int p = 0; p < MB_NPARAM; ++p)
@@ -1016,6 +1038,16 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     k2.pois.n_stars = (double)h->S_total; k2.pois.nbins = h->poisson ? h->nbins : 0;
     k2.pois.nslice = poisson_nslice(k2_threads(NW), h->nbins);
     k2.pois.SC = elementwise ? h->d_SC : nullptr;
+    k2.build_tables = fused ? 1 : 0;
+    if (fused) {
+      k2.model = h->mdev; k2.clsx = h->d_clsx; k2.ndim = ndim; k2.ncls_total = h->ncls_total;
+      k2.rowlut = h->d_rowlut;
+      k2.phi = d_phi + (size_t)w0 * ndim;
+      if (inline_phi) {
+        k2.phi_inline = 1;
+        memcpy(k2.phi_in, h_phi + (size_t)w0 * ndim, sizeof(double) * (size_t)wp * ndim);
+      }
+    }
     k2.timeline = nullptr;
     if (prof && h->d_timeline) {
       CK(cudaMemsetAsync(h->d_timeline, 0, sizeof(unsigned long long) * (size_t)grid * kTimelinePoints, st));
@@ -1097,7 +1129,9 @@ extern "C" int mb_lnlike_begin(mb_handle* h, const double* phi, int32_t W, int32
     CK(cudaMemcpyAsync(h->d_tab[p], tab[p], sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
     dtab[p] = h->d_tab[p];
   }
-  if (eval_device(h, h->d_pin, W, ndim, dtab, h->d_pin + nphi, h->stream)) return 1;
+  bool any_tab = false;
+  for (int p = 0; p < MB_NPARAM; ++p) any_tab |= dtab[p] != nullptr;
+  if (eval_device(h, h->d_pin, W, ndim, any_tab ? dtab : nullptr, h->d_pin + nphi, h->stream, hp)) return 1;
   h->pending_W = W;
   h->pending_out = ho;
   return 0;

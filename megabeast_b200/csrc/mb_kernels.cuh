@@ -70,6 +70,16 @@ __device__ __forceinline__ double lognorm(double x, double mode, double sigma, d
   return amp * norm * exp(-0.5 * (t * t));
 }
 
+// the same with ln x and mu = ln(mode) + sigma^2 taken beforehand (identical operations, so the
+// result is bitwise the one of lognorm)
+__device__ __forceinline__ double lognorm_pre(double x, double lx, double mu, double sigma, double amp) {
+  if (!(x > 0.0)) return 0.0;
+  const double inv_sqrt_2pi = 0.3989422804014326779399460599343819;
+  double norm = inv_sqrt_2pi / (x * sigma);
+  double t = (lx - mu) / sigma;
+  return amp * norm * exp(-0.5 * (t * t));
+}
+
 __device__ double prior_eval(const ModelDev& m, int p, const double* __restrict__ th, double x) {
   switch (m.kind[p]) {
     case MB_LOGNORMAL:
@@ -629,6 +639,7 @@ struct PeerArgs {
   unsigned long long* xbuf[MB_MAX_PEERS];  // exchange buffer of every rank, as mapped on THIS GPU
 };
 
+constexpr int kPhiInline = 1152;  // doubles of phi carried in K2's kernel parameters (e.g. 128 walkers x 9)
 struct K2Args {
   const double* ea;     // entry weights  [n_entries]
   const uint32_t* ec;   // entry codes    [n_entries]
@@ -644,6 +655,16 @@ struct K2Args {
   PoissonArgs pois;          // N-stars term, computed by the first W blocks before the star loop
   PeerArgs peer;             // cross-GPU reduction of the shard totals
   unsigned long long* timeline;  // optional [gridDim.x][kTimelinePoints] %globaltimer stamps (profiling)
+  // FACTOR mode, fp64 tables, analytic models: every block builds the factor tables itself in its
+  // prologue (K0 fused into K2: no separate launch, no dependent-kernel gap); phi comes with the
+  // kernel parameters when it is small enough, else from `phi` (device or mapped host memory)
+  int32_t build_tables, phi_inline, ndim, ncls_total;
+  const double* clsx;        // class values [ncls_total]
+  const uint16_t* rowlut;    // [nB][4] look-up rows (class offsets included) of a dust class's Av, Rv, fA
+                             // digits; 0xffff = parameter fixed
+  const double* phi;         // [W][ndim], already offset to this pass's first walker
+  ModelDev model;
+  double phi_in[kPhiInline];
 };
 constexpr int kTimelinePoints = 6;  // start, tables staged, Poisson done, stars done, block reduced, end
 __device__ __forceinline__ void stamp(unsigned long long* timeline, int point) {
@@ -892,7 +913,7 @@ __device__ __forceinline__ void stream_range(Lanes<NW, MODE, TF>& L, const doubl
 // segments of the entry stream for all walkers.  Tail: reduction over stars (K3) and, with peers,
 // over GPUs.
 template <int NW, int MODE, typename TF = double>
-__global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars(K2Args a) {
+__global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars(const __grid_constant__ K2Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int kK2Warps = k2_threads(NW) / 32;
   constexpr bool kF32 = sizeof(TF) == 4;
@@ -911,7 +932,82 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   stamp(a.timeline, 0);
   // launched with programmatic stream serialization: wait here for K0 (the tables) to complete
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (MODE == kModeFactor) {
+  if (MODE == kModeFactor && !kF32 && a.build_tables) {
+    // K0 fused: the prior models on the classes (singlepop_dust_model.py:146-148 restricted to the
+    // distinct column values) for all walkers of the pass -> look-up table in the (still idle) stage
+    // area, then the FA / FB rows straight into shared memory.  Same arithmetic as mb_k0_factors;
+    // the logarithms (one per class, one or two per lognormal and walker) are taken first, once.
+    const ModelDev& m = a.model;
+    double* lut = reinterpret_cast<double*>(smem_raw);              // [ncls_total][Wpad]
+    double* tab = reinterpret_cast<double*>(smem_raw + a.tab_off);  // [nA + nB][Wpad]
+    const int ncls = a.ncls_total, nlut = ncls * Wpad;
+    double* lxs = lut + nlut;                                       // [ncls] ln(class value)
+    double* cmu = lxs + ncls;                                       // [NPARAM][Wpad][2] mu of the lognormals
+    // phi: carried in the kernel parameters (copied to shared memory with indexed constant loads --
+    // reads of the parameter space through a generic pointer are slow) or in device memory
+    const double* ph = a.phi;
+    if (a.phi_inline) {
+      double* sphi = cmu + 2 * MB_NPARAM * Wpad;
+      const int n = a.W * a.ndim;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) sphi[i] = a.phi_in[i];
+      __syncthreads();
+      ph = sphi;
+    }
+    for (int idx = threadIdx.x; idx < ncls + MB_NPARAM * Wpad; idx += blockDim.x) {
+      if (idx < ncls) {
+        const double x = __ldg(a.clsx + idx);
+        lxs[idx] = x > 0.0 ? log(x) : 0.0;
+      } else {
+        const int j = idx - ncls, p = j / Wpad, w = j - p * Wpad;
+        const double* th = ph + (size_t)(w < a.W ? w : a.W - 1) * a.ndim + m.voff[p];
+        if (m.kind[p] == MB_LOGNORMAL) {
+          cmu[2 * j] = log(th[0]) + th[1] * th[1];
+        } else if (m.kind[p] == MB_TWO_LOGNORMAL) {
+          cmu[2 * j] = log(th[0]) + th[2] * th[2];
+          cmu[2 * j + 1] = log(th[1]) + th[3] * th[3];
+        }
+      }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nlut; idx += blockDim.x) {
+      const int i = idx / Wpad, w = idx - i * Wpad;
+      int p = 0;
+#pragma unroll
+      for (int q = 1; q < MB_NPARAM; ++q)
+        if (i >= m.clsoff[q]) p = q;
+      const double* th = ph + (size_t)(w < a.W ? w : a.W - 1) * a.ndim + m.voff[p];  // padding repeats the last walker
+      const double x = __ldg(a.clsx + i);
+      double v = 1.0;
+      if (m.kind[p] == MB_LOGNORMAL) {
+        v = lognorm_pre(x, lxs[i], cmu[2 * (p * Wpad + w)], th[1], 1.0);
+      } else if (m.kind[p] == MB_TWO_LOGNORMAL) {
+        const double n1 = 1.0 - 1.0 / (th[4] + 1.0), n2 = 1.0 / (th[4] + 1.0);
+        v = lognorm_pre(x, lxs[i], cmu[2 * (p * Wpad + w)], th[2], n1) +
+            lognorm_pre(x, lxs[i], cmu[2 * (p * Wpad + w) + 1], th[3], n2);
+      } else if (m.kind[p] != MB_FIXED) {
+        v = prior_eval(m, p, th, x);
+      }
+      lut[idx] = v;
+    }
+    __syncthreads();
+    const int ntab = (a.nA + a.nB) * Wpad;
+    for (int idx = threadIdx.x; idx < ntab; idx += blockDim.x) {
+      const int c = idx / Wpad, w = idx - c * Wpad;
+      double v = 1.0;
+      if (c < a.nA) {
+        if (m.kind[MB_P_LOGA] != MB_FIXED) v = lut[(m.clsoff[MB_P_LOGA] + c) * Wpad + w];
+      } else {
+        // look-up rows of the dust class's digits (precomputed: no integer divisions here), multiplied
+        // in the reference's left-to-right order (`cur_physmod *=`, :146-148)
+        const ushort4 r = __ldg(reinterpret_cast<const ushort4*>(a.rowlut) + (c - a.nA));
+        if (r.x != 0xffff) v *= lut[r.x * Wpad + w];
+        if (r.y != 0xffff) v *= lut[r.y * Wpad + w];
+        if (r.z != 0xffff) v *= lut[r.z * Wpad + w];
+      }
+      tab[idx] = v;
+    }
+    __syncthreads();
+  } else if (MODE == kModeFactor) {
     const int n2 = (a.nA + a.nB) * Wpad / 2;
     const double2* src = reinterpret_cast<const double2*>(a.FA);
     if (kF32) {

@@ -65,7 +65,7 @@ class ShardedLikelihood:
     """
 
     def __init__(self, model, star_lnpgriddata, beast_moddata, device=None, mode="auto", group=None,
-                 reduce="auto"):
+                 reduce="auto", star_range=None, n_stars_total=None):
         import torch
 
         from .helpers import precompute_mass_multipliers
@@ -85,10 +85,13 @@ class ShardedLikelihood:
             model.compute_massmult = False
             mm = model.massmultipliers
         S = np.asarray(star_lnpgriddata["indxs"]).shape[1]
-        self.star_range = shard_bounds(S, self.world, self.rank)
+        # default: the arrays hold the whole job and this rank takes its contiguous share; a rank
+        # whose arrays hold only its own stars passes star_range=(0, S_local) and the job's total
+        self.star_range = shard_bounds(S, self.world, self.rank) if star_range is None else tuple(star_range)
         self.engine = LikelihoodEngine(self.spec, star_lnpgriddata, beast_moddata, massmult=mm,
                                        devices=[self.device], mode=mode,
-                                       star_range=self.star_range, n_stars_total=S,
+                                       star_range=self.star_range,
+                                       n_stars_total=S if n_stars_total is None else int(n_stars_total),
                                        table_precision=getattr(model, "table_precision", "fp64"))
         # how the shard partials are added: "p2p" = inside the likelihood kernel over NVLink peer
         # memory (mb_peer_connect), "nccl" = one all-reduce after it; "auto" tries p2p first

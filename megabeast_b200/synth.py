@@ -42,6 +42,8 @@ CONFIGS = {
     "cfg3_half": dict(axes=(41, 4, 61, 20, 5, 1), S=50_000, K=50, W=64),
     "cfg3_quarter": dict(axes=(41, 4, 61, 20, 5, 1), S=25_000, K=50, W=64),
     "cfg3_eighth": dict(axes=(41, 4, 61, 20, 5, 1), S=12_500, K=50, W=64),
+    # one GPU's share of the PHAT-scale config 4 on 8 GPUs
+    "cfg4_eighth": dict(axes=(41, 4, 61, 20, 10, 1), S=125_000, K=50, W=128),
 }
 
 _STELLAR = {

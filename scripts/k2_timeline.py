@@ -32,9 +32,10 @@ for name in sys.argv[1:] or ["cfg3", "cfg3_eighth"]:
     kms = sh.engine.last_kernel_ms()
     names = ["start", "tables", "poisson", "stars", "blockred", "end"]
     print(f"== {name}: entries {sh.engine.info()['n_entries']}, blocks {len(t)}, k2 event ms {kms['k2_stars']:.4f}")
-    pois = t[:64]
-    rest = t[64:]
-    for label, grp in (("blocks 0-63 (Poisson)", pois), ("blocks 64+", rest)):
+    nw = min(len(phis), len(t))
+    pois = t[:nw]
+    rest = t[nw:]
+    for label, grp in ((f"blocks 0-{nw - 1} (Poisson)", pois), (f"blocks {nw}+", rest)):
         if len(grp):
             print(f"  {label:22s} " + "  ".join(f"{n}={np.mean(grp[:, k]):6.2f}" for k, n in enumerate(names[:5])))
     print(f"  max over blocks        " + "  ".join(f"{n}={np.max(t[:, k]):6.2f}" for k, n in enumerate(names[:5]))
