@@ -362,15 +362,20 @@ def run_ours(args):
     n_ent = info["n_entries"]
     nA, nB = info["n_age_classes"], info["n_dust_classes"]
     mode = info["mode"]
-    U = len(moddata["Av"]) if mode == "table_grid" else nA * nB
+    by_row = mode in ("table_grid", "elementwise")  # physmod materialised over every grid row
+    U = len(moddata["Av"]) if by_row else nA * nB
+    nfree = sum(1 for p in ("logA", "Av", "Rv", "fA") if sharded.spec.kinds[p] != "fixed")
     touched = None
-    if mode == "table_grid":
+    if by_row:
         lo, hi = sharded.star_range
         sub_i, sub_v = stars["indxs"][:, lo:hi], stars["vals"][:, lo:hi]
         touched = int(np.unique(sub_i[np.isfinite(sub_v)]).size)
     alg = {
         "k0_factors": 8 * W * ndim + 8 * (nA + nB) * Wpad,
-        "k1_expand": (4 * U if mode == "table_grid" else 0) + 8 * U * Wpad,
+        # table_grid: row codes in, table out; elementwise: the free columns + grid_weight and
+        # completeness (N-stars partial sums) in, table out
+        "k1_expand": (4 * U if mode == "table_grid" else (8 * nfree + 16) * U if mode == "elementwise" else 0)
+                     + 8 * U * Wpad,
         "k2_stars": 12 * n_ent + 16 * info["n_bins"] * nB + (8 * (nA + nB) * Wpad if mode == "factor"
                                   else 8 * Wpad * (touched if touched is not None else U)),
     }
@@ -389,7 +394,9 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": alg[dom], "avg_launch_ms": kms[dom],
                 "traffic_source": traffic_src,
                 "note": "this kernel is bounded by the shared-memory/L1 data pipe, not HBM: see `onchip` and DESIGN.md section 5"
-                        if mode == "factor" else "HBM-bound gather of the materialised table"}
+                        if mode == "factor" else
+                        "K1e is bound by the fp64 exp of the lognormal priors (one per parameter, row and walker), not by HBM"
+                        if (mode == "elementwise" and dom == "k1_expand") else "HBM-bound: materialised table written / gathered"}
     clocks = sampler.summary()
     sm_mhz = clocks.get("sm_mhz") or 0
     onchip = None
