@@ -107,6 +107,13 @@ struct mb_handle {
   std::vector<double> scratch_phi, scratch_rows, scratch_val;
   int table_bytes = 8;   // FACTOR-mode shared-memory table element: 8 = fp64, 4 = fp32
   int no_fuse = 0;       // keep K0 as a separate launch (MB_NO_FUSE=1: A/B measurements)
+  // segment tables are rebuilt when the number of blocks that compute a Poisson term changes
+  std::vector<int64_t> star_end_pos;  // entry count after each non-empty star
+  int spw = 1;
+  double tail_frac = 0.0;
+  int pois_balance = 1;               // MB_POIS_BALANCE=0: equal segments for every warp
+  int seg_npois[2] = {0, 0}, seg_nw[2] = {0, 0};
+  int64_t seg_cap[2] = {0, 0};
   int occ_cache[3] = {0, 0, 0};
   size_t occ_smem[3] = {0, 0, 0};
   // pixel batches
@@ -280,6 +287,44 @@ extern "C" void mb_destroy(mb_handle* h) {
     if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
+}
+
+// Star-aligned segments of the entry stream, one per resident warp of block shape t (0: the
+// 768-thread kernels, 1: the 512-thread kernel), equal entry counts: boundary i is the first
+// star end at or after its goal.  With npois > 0 the warps of the first npois blocks -- the blocks that
+// compute a walker's N-stars / Poisson term before they start streaming -- get `delta` entries
+// fewer and the others correspondingly more, so that all blocks finish together.  delta comes from
+// a fixed model of this kernel on B200 (deterministic: the same data always gives the same
+// segments): the prologue costs ~2.2 us + 0.8 us per batch of eight L2 loads, a warp streams one
+// entry per (2 NW + 2.3) shared-memory wavefronts x resident warps / (0.9 x 1.9 GHz).
+static void build_segments(const mb_handle* h, int t, int npois, int NW, std::vector<int64_t>& seg) {
+  const std::vector<int64_t>& ends = h->star_end_pos;
+  const int threads = k2_threads(t == 0 ? 2 : 4), kw = threads / 32;
+  const int64_t resident_warps = (int64_t)h->sm_count * kw;
+  const int64_t n = h->n_entries;
+  int64_t want = std::max<int64_t>(1, std::min<int64_t>(resident_warps * h->spw, n / 64));
+  const int64_t n_main = want >= resident_warps ? (int64_t)((1.0 - h->tail_frac) * (double)n) : n;
+  const int64_t want_tail = n_main < n ? std::max<int64_t>(1, (n - n_main) / 96) : 0;
+  double delta = 0.0;
+  if (npois > 0 && npois < h->sm_count && want == resident_warps && want_tail == 0 && h->nbins > 0) {
+    const int nslice = poisson_nslice(threads, h->nbins);
+    const double t_pois_ns = 2200.0 + 800.0 * std::ceil(std::ceil((double)h->nB / nslice) / 8.0);
+    const double t_entry_ns = (2.0 * NW + 2.3) * kw / (0.9 * 1.9);
+    delta = std::min(t_pois_ns / t_entry_ns, 0.5 * (double)n / (double)want);
+  }
+  // entries per warp: x for the plain blocks, x - delta for the Poisson blocks
+  const double x = ((double)n_main + (double)npois * kw * delta) / (double)want;
+  seg.assign(1, 0);
+  size_t j = 0;
+  for (int64_t i = 1; i <= want + want_tail && j < ends.size(); ++i) {
+    int64_t goal;
+    if (i > want) goal = n_main + ((n - n_main) * (i - want) + want_tail - 1) / want_tail;
+    else if (delta > 0.0) goal = i == want ? n_main : (int64_t)std::ceil(x * (double)i - delta * (double)std::min<int64_t>(i, (int64_t)npois * kw));
+    else goal = (n_main * i + want - 1) / want;
+    while (j < ends.size() && ends[j] < goal) ++j;
+    if (j < ends.size() && ends[j] > seg.back()) seg.push_back(ends[j]);
+  }
+  if (n > 0 && seg.back() != n) seg.push_back(n);
 }
 
 static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
@@ -587,30 +632,18 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
   // by 3-4 % -- per-segment costs (pipeline restart, one log) outweigh what dynamic balancing
   // recovers -- so the segment count must match the warps the launch really has: one table for
   // the 768-thread kernels (up to 64 walkers per pass) and one for the 512-thread kernel (128).
-  const int spw = o.segments_per_warp > 0 ? o.segments_per_warp : 1;
+  h->spw = o.segments_per_warp > 0 ? o.segments_per_warp : 1;
   // ... optionally plus a tail pool: the last tail_percent of the entries cut into small segments
   // that warps claim dynamically after their own big one.  Measured on B200 (4-16 %, config 3 and
   // its 1/8 shard): no gain over none, so the default is none.
-  const double tail_frac = o.tail_percent > 0 ? std::min(50, o.tail_percent) / 100.0 : 0.0;
+  h->tail_frac = o.tail_percent > 0 ? std::min(50, o.tail_percent) / 100.0 : 0.0;
+  if (const char* pb = getenv("MB_POIS_BALANCE")) h->pois_balance = atoi(pb);
+  h->star_end_pos = std::move(star_end_pos);
   std::vector<int64_t> seg[2];
   for (int t = 0; t < 2; ++t) {
-    const int64_t resident_warps = (int64_t)h->sm_count * (k2_threads(t == 0 ? 2 : 4) / 32);
-    // `want` star-aligned segments of equal entry count (at least 64 entries each): boundary i is
-    // the first star end at or after its goal, so every resident warp gets its share
-    const int64_t n = h->n_entries;
-    int64_t want = std::max<int64_t>(1, std::min<int64_t>(resident_warps * spw, n / 64));
-    const int64_t n_main = want >= resident_warps ? (int64_t)((1.0 - tail_frac) * (double)n) : n;
-    const int64_t want_tail = n_main < n ? std::max<int64_t>(1, (n - n_main) / 96) : 0;
-    seg[t].assign(1, 0);
-    size_t j = 0;
-    for (int64_t i = 1; i <= want + want_tail && j < star_end_pos.size(); ++i) {
-      const int64_t goal = i <= want ? (n_main * i + want - 1) / want
-                                     : n_main + ((n - n_main) * (i - want) + want_tail - 1) / want_tail;
-      while (j < star_end_pos.size() && star_end_pos[j] < goal) ++j;
-      if (j < star_end_pos.size() && star_end_pos[j] > seg[t].back()) seg[t].push_back(star_end_pos[j]);
-    }
-    if (n > 0 && seg[t].back() != n) seg[t].push_back(n);
+    build_segments(h, t, 0, 0, seg[t]);
     h->nseg[t] = (int)seg[t].size() - 1;
+    h->seg_cap[t] = (int64_t)seg[t].size();
   }
 
   // ---- upload ----------------------------------------------------------------------------------------
@@ -697,6 +730,7 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
     std::vector<int32_t> pns((size_t)n_pixels);
     for (int64_t p = 0; p < n_pixels; ++p) {
       const int64_t e0 = pix_ent[(size_t)p], e1 = pix_ent[(size_t)p + 1];
+      const std::vector<int64_t>& star_end_pos = h->star_end_pos;
       size_t j = (size_t)pix_se[(size_t)p];
       const size_t j1 = (size_t)pix_se[(size_t)p + 1];
       int64_t* row = &pseg[(size_t)p * (kPixWarps + 1)];
@@ -1025,6 +1059,25 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     int per_sm = cached;
     if (per_sm < 1) return fail("K2 cannot be resident with %zu bytes of shared memory", smem);
     const int kK2Warps = k2_threads(NW) / 32;
+    {  // segments balanced for the number of blocks that run a Poisson prologue in this pass
+      const int t = NW == 4 ? 1 : 0;
+      const int npois = (h->poisson && h->pois_balance && kmode == kModeFactor && wp < h->sm_count) ? wp : 0;
+      if (npois != h->seg_npois[t] || (npois > 0 && NW != h->seg_nw[t])) {
+        std::vector<int64_t> seg;
+        build_segments(h, t, npois, NW, seg);
+        CK(cudaStreamSynchronize(st));  // the previous launch may still read the old table
+        if ((int64_t)seg.size() > h->seg_cap[t]) {
+          CK(cudaFree(h->d_seg[t]));
+          h->d_seg[t] = nullptr;
+          CK(cudaMalloc((void**)&h->d_seg[t], sizeof(int64_t) * seg.size()));
+          h->seg_cap[t] = (int64_t)seg.size();
+        }
+        CK(cudaMemcpy(h->d_seg[t], seg.data(), sizeof(int64_t) * seg.size(), cudaMemcpyHostToDevice));
+        h->nseg[t] = (int)seg.size() - 1;
+        h->seg_npois[t] = npois;
+        h->seg_nw[t] = NW;
+      }
+    }
     // at least one block even without entries: the Poisson prologue and the result rows live in K2
     int grid = std::min(h->sm_count * per_sm,
                         std::max(h->poisson ? wp : 1, (h->nseg[NW == 4] + kK2Warps - 1) / kK2Warps));

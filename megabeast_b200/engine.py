@@ -326,13 +326,16 @@ class LikelihoodEngine:
         if not (phis.dtype == np.float64 and phis.flags.c_contiguous):
             phis = np.ascontiguousarray(phis, dtype=np.float64)
         W, ndim = phis.shape
-        buf = self._bufs.get(("box", W))
-        if buf is None:
-            out, status = np.empty(W), np.empty(W, dtype=np.int32)
-            buf = self._bufs[("box", W)] = (out, status, out.ctypes.data, status.ctypes.data, ctypes.c_int32(-1))
-        out, status, p_out, p_status, last = buf
-        if self.lib.mb_lnprob_box(self.handles[0], phis.ctypes.data, W, ndim, lo.ctypes.data, hi.ctypes.data,
-                                  p_out, p_status, ctypes.byref(last)):
+        buf = self._bufs.get(-W)
+        if buf is None or buf[5] is not lo or buf[6] is not hi:
+            out, status, last = np.empty(W), np.empty(W, dtype=np.int32), ctypes.c_int32(-1)
+            # everything that does not change between calls is converted to ctypes once
+            buf = self._bufs[-W] = (out, status, last, self.lib.mb_lnprob_box,
+                                    (ctypes.c_void_p(lo.ctypes.data), ctypes.c_void_p(hi.ctypes.data),
+                                     ctypes.c_void_p(out.ctypes.data), ctypes.c_void_p(status.ctypes.data),
+                                     ctypes.byref(last)), lo, hi)
+        out, status, last, fn, (p_lo, p_hi, p_out, p_status, p_last) = buf[:5]
+        if fn(self.handles[0], phis.__array_interface__["data"][0], W, ndim, p_lo, p_hi, p_out, p_status, p_last):
             _cabi.check(1)
         return out, status, last.value
 

@@ -93,6 +93,8 @@ class MB_Model:
         # the model structure (which priors are free, their boxes) is fixed at construction
         self._layout_cache = None
         self._box_cache = None
+        self._store_targets = None
+        self._last_data = None  # (star dict, grid dict, indxs, vals, prior_weight, engine entry)
 
     # ------------------------------------------------------------------------------------------
     def start_params(self):
@@ -133,13 +135,18 @@ class MB_Model:
 
     def _store_phi(self, phi):
         """The reference leaves the last evaluated phi in ``physics_model`` (:136-143)."""
-        layout, _ = self._layout()
-        for p, vname, k, n in layout:
-            if n > 1:
-                for j in range(n):
-                    self.physics_model[p][vname][j] = phi[k + j]
-            else:
-                self.physics_model[p][vname] = phi[k]
+        targets = self._store_targets
+        if targets is None:  # (container, key) per phi column, resolved once
+            targets = []
+            for p, vname, k, n in self._layout()[0]:
+                mod = self.physics_model[p]
+                if n > 1:
+                    targets.extend((mod[vname], j) for j in range(n))
+                else:
+                    targets.append((mod, vname))
+            self._store_targets = targets
+        for (box, key), v in zip(targets, phi):
+            box[key] = v
 
     def _spec(self):
         """Device model description + the column permutation from reference phi order."""
@@ -200,6 +207,7 @@ class MB_Model:
             raise
         for old in list(self._engines.values()):  # one resident data set at a time
             old[0].close()
+        self._last_data = None
         if self._identity_perm(perm, ndim):
             perm = None  # device order == reference order (the usual case): no column shuffle
         self._engines = {key: (engine, (spec, perm, ndim), (star_lnpgriddata, beast_moddata))}
@@ -277,9 +285,17 @@ class MB_Model:
         """Batched lnprob in one C call (box check, compaction of the in-box walkers, likelihood,
         scatter).  Returns None when the general path is needed (tabulated models, several
         devices, permuted variables)."""
-        hit = self._engines.get(self._data_key(star_lnpgriddata, beast_moddata))
-        if hit is None:  # first call on this data: the general path builds the device data if needed
-            return None
+        last = self._last_data
+        if (last is not None and last[0] is star_lnpgriddata and last[1] is beast_moddata
+                and last[2] is star_lnpgriddata["indxs"] and last[3] is star_lnpgriddata["vals"]
+                and last[4] is beast_moddata["prior_weight"]):
+            hit = last[5]  # same objects as on the previous call (the sampler's steady state)
+        else:
+            hit = self._engines.get(self._data_key(star_lnpgriddata, beast_moddata))
+            if hit is None:  # first call on this data: the general path builds the device data if needed
+                return None
+            self._last_data = (star_lnpgriddata, beast_moddata, star_lnpgriddata["indxs"],
+                               star_lnpgriddata["vals"], beast_moddata["prior_weight"], hit)
         engine, (spec, perm, ndim) = hit[0], hit[1]
         if perm is not None or spec.tabulated or len(engine.handles) != 1 or phis.shape[1] != ndim:
             return None
