@@ -969,6 +969,8 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
       }
     }
     __syncthreads();
+    // (independent iterations, unrolled so that the fp64 divide / exp chains of a thread's items overlap)
+#pragma unroll 4
     for (int idx = threadIdx.x; idx < nlut; idx += blockDim.x) {
       const int i = idx / Wpad, w = idx - i * Wpad;
       int p = 0;
@@ -991,6 +993,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     }
     __syncthreads();
     const int ntab = (a.nA + a.nB) * Wpad;
+#pragma unroll 4
     for (int idx = threadIdx.x; idx < ntab; idx += blockDim.x) {
       const int c = idx / Wpad, w = idx - c * Wpad;
       double v = 1.0;

@@ -98,6 +98,8 @@ class ShardedLikelihood:
         self.reduce = "none" if self.world == 1 else self._setup_reduce(reduce)
         self._cap = 0
         self._ensure(64)
+        # device variable order == reference order (the usual case): lnprob can be one C call
+        self._fast_ok = self.perm.size == self.ndim and np.array_equal(self.perm, np.arange(self.ndim))
 
     def _setup_reduce(self, want):
         import torch.distributed as dist
@@ -172,12 +174,23 @@ class ShardedLikelihood:
         phi = np.asarray(phi, dtype=np.float64)
         single = phi.ndim == 1
         phis = phi[None, :] if single else phi
-        lp = np.asarray(self.model.lnprior(phis), dtype=np.float64)
-        out = np.full(len(phis), -np.inf)
-        inside = np.isfinite(lp)
-        if inside.any():
-            rows = self.lnlike_rows(phis[inside][:, self.perm])
-            vals, status = combine_rows(rows)
+        if self.reduce in ("p2p", "none") and self._fast_ok and phis.shape[1] == self.ndim:
+            # one C call per rank (mb_lnprob_box): prior box, likelihood of the in-box walkers on
+            # this rank's shard, shard totals added inside the kernel over NVLink, combine.  Every
+            # rank holds the same phi, so every rank launches (or skips) the same kernels.
+            lo, hi = self.model._box()
+            vals, status, _ = self.engine.lnprob_box(phis, lo, hi)
+            out = vals.copy()
+        else:
+            lp = np.asarray(self.model.lnprior(phis), dtype=np.float64)
+            out = np.full(len(phis), -np.inf)
+            inside = np.isfinite(lp)
+            status = np.zeros(1, dtype=np.int32)
+            if inside.any():
+                rows = self.lnlike_rows(phis[inside][:, self.perm])
+                vals, status = combine_rows(rows)
+                out[inside] = lp[inside] + vals
+        if status.any():
             if np.any(status & _cabi.STATUS_PEER_TIMEOUT):
                 raise RuntimeError("a peer GPU did not deliver its star shard (timeout)")
             if np.any(status & _cabi.STATUS_NONFINITE_STAR):
@@ -185,7 +198,6 @@ class ShardedLikelihood:
             if np.any(status & _cabi.STATUS_TOTAL_ZERO):
                 print(0.0)
                 raise SystemExit
-            out[inside] = lp[inside] + vals
         return out[0] if single else out
 
     def close(self):

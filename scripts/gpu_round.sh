@@ -9,7 +9,7 @@ python -c "import __graft_entry__ as g; g.build(); g.smoke()" > $OUT/${TAG}_smok
 timeout 900 python -m pytest tests -x -q -m gpu > $OUT/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -2 $OUT/${TAG}_pytest.log
 timeout 900 python bench.py --all-modes > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"
 tail -c 6000 $OUT/${TAG}_bench.json
-SHORT="python bench.py --steps 3 --warmup 3 --no-cpu-baseline"
+SHORT="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-clustered"
 timeout 600 $SHORT > $OUT/${TAG}_plain.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file $OUT/${TAG}_launches.csv $SHORT > $OUT/${TAG}_ncu_launches.log 2>&1
