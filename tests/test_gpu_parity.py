@@ -149,6 +149,30 @@ def test_elementwise_matches_class_coded_on_cartesian_grid():
     assert_close(b, a, RTOL)
 
 
+def test_many_walkers_run_as_several_passes():
+    """300 walkers = passes of 128 + 128 + 44: every pass builds its own tables inside K2."""
+    settings, moddata, stars, _ = synth.make_problem("small", seeds=(51, 52, 53))
+    pm = port.PortModel(copy.deepcopy(settings))
+    phis = synth.make_walkers(pm, 300, seed=53)
+    expect = c_oracle.lnprob_batch(pm, phis, stars, moddata)
+    for mode in ("factor", "table_unique", "elementwise"):
+        assert_close(lnprob(phis, MB_Model(copy.deepcopy(settings), mode=mode), stars, moddata), expect, RTOL)
+
+
+def test_phi_too_large_for_the_kernel_parameters():
+    """11 free variables x 128 walkers do not fit the 1,152 doubles K2 carries in its parameters:
+    the host path then keeps the separate K0 launch; results are the same as for a small batch."""
+    settings, moddata, stars, phis0, expect0, kind = load_golden("two_lognormal_bins_interp")
+    pm = port.PortModel(copy.deepcopy(settings))
+    phis = synth.make_walkers(pm, 128, seed=7)
+    expect = c_oracle.lnprob_batch(pm, phis, stars, moddata)
+    model = MB_Model(copy.deepcopy(settings), mode="factor")
+    assert_close(lnprob(phis, model, stars, moddata), expect, RTOL)
+    assert model.engine_info()["launches_last_eval"] == 2          # K0 + K2
+    assert_close(lnprob(phis[:64], model, stars, moddata), expect[:64], RTOL)
+    assert model.engine_info()["launches_last_eval"] == 1          # tables built inside K2
+
+
 def test_cfg1_golden_expect():
     phis, expect, kind = load_cfg1_expect()
     settings, moddata, stars, _ = synth.make_problem("cfg1")
