@@ -207,17 +207,34 @@ static size_t k1e_smem_bytes(int Wpad, int ndim) {
                            2 * (size_t)MB_NPARAM * kK1eRows + 2 * (size_t)kK1eRows + 4 * (size_t)kK1eThreads) +
          sizeof(int) * ((size_t)MB_NPARAM * kK1eRows + kK1eRows) + 16;
 }
-// front region of K2's dynamic shared memory: entry stage, reused as Poisson / reduction scratch
-static size_t k2_front_bytes(int nbins, int Wpad) {
-  const int threads = k2_threads(Wpad / 32);
-  size_t stage = (size_t)(threads / 32) * kStageBytes;
-  size_t pois = nbins > 0 ? (size_t)(poisson_nslice(threads, nbins) + 1) * nbins * 16 : 0;
-  size_t slabs = (size_t)(threads / 32) * 3 * Wpad * 8;  // block reduction: one slab per warp
-  return (std::max(std::max(stage, pois), slabs) + 15) & ~(size_t)15;
-}
-static size_t k2_smem_bytes(int mode, int nA, int nB, int nbins, int Wpad, int elem_bytes = 8) {
-  size_t tables = mode == kModeFactor ? (size_t)(nA + nB) * Wpad * elem_bytes : 0;
-  return k2_front_bytes(nbins, Wpad) + tables;
+// K2's dynamic shared memory: [front][factor tables (FACTOR mode)].  The front region holds the
+// per-warp entry stage and is reused as scratch: the in-kernel table build (look-up table, optional),
+// the Poisson prologue, and the block-reduction slabs -- which move over the tables (dead after
+// the star loop) when the tables are larger than they are, so that they never size the front.
+struct K2Smem {
+  size_t front = 0, tables = 0, total = 0, slab_off = 0;
+  bool fuse_fits = false;   // the look-up table of the in-kernel table build fits as well
+};
+static K2Smem k2_smem_plan(int kmode, int nA, int nB, int nbins, int Wpad, int elem_bytes, int max_smem,
+                           size_t fuse_scratch = 0) {
+  K2Smem p;
+  const int NW = Wpad / 32, threads = k2_threads(NW);
+  const size_t stage = (size_t)(threads / 32) * k2_stage_bytes(NW);
+  const size_t pois = nbins > 0 ? (size_t)(poisson_nslice(threads, nbins) + 1) * nbins * 16 : 0;
+  const size_t slabs = (size_t)(threads / 32) * 3 * Wpad * 8;  // block reduction: one slab per warp
+  p.tables = kmode == kModeFactor ? (size_t)(nA + nB) * Wpad * elem_bytes : 0;
+  const bool slabs_over_tables = p.tables >= slabs;
+  size_t front = std::max(stage, pois);
+  if (!slabs_over_tables) front = std::max(front, slabs);
+  front = (front + 15) & ~(size_t)15;
+  if (fuse_scratch > 0) {
+    const size_t with_fuse = (std::max(front, fuse_scratch) + 15) & ~(size_t)15;
+    if (with_fuse + p.tables <= (size_t)max_smem) { front = with_fuse; p.fuse_fits = true; }
+  }
+  p.front = front;
+  p.slab_off = slabs_over_tables ? front : 0;
+  p.total = front + p.tables;
+  return p;
 }
 
 extern "C" int mb_peer_disconnect(mb_handle* h) {
@@ -449,7 +466,8 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
 
   // ---- mode ----------------------------------------------------------------------------------------
   int mode = elementwise ? MB_MODE_ELEMENTWISE : o.mode;
-  const bool factor_fits = k2_smem_bytes(kModeFactor, h->nA, h->nB, mm ? mm->n_ages * mm->n_mets : 0, 32, h->table_bytes) <= (size_t)h->max_smem;
+  const bool factor_fits = k2_smem_plan(kModeFactor, h->nA, h->nB, mm ? mm->n_ages * mm->n_mets : 0, 32, h->table_bytes,
+                                        h->max_smem).total <= (size_t)h->max_smem;
   if (mode == MB_MODE_AUTO) mode = factor_fits ? MB_MODE_FACTOR : MB_MODE_TABLE_UNIQUE;
   if (mode == MB_MODE_FACTOR && !factor_fits)
     return fail("factor tables (%d + %d classes) do not fit shared memory; use a TABLE mode", h->nA, h->nB);
@@ -982,7 +1000,7 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
   for (int w0 = 0; w0 < W;) {
     int rem = W - w0;
     int NW = rem <= 32 ? 1 : rem <= 64 ? 2 : 4;
-    while (NW > 1 && k2_smem_bytes(kmode, h->nA, h->nB, h->nbins, 32 * NW, h->table_bytes) > (size_t)h->max_smem) NW >>= 1;
+    while (NW > 1 && k2_smem_plan(kmode, h->nA, h->nB, h->nbins, 32 * NW, h->table_bytes, h->max_smem).total > (size_t)h->max_smem) NW >>= 1;
     const int Wpad = 32 * NW;
     const int wp = std::min(rem, Wpad);
     h->last_wp = wp;
@@ -991,13 +1009,16 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
 
     // FACTOR mode with fp64 tables and analytic models: K2 builds the factor tables in its own
     // prologue (look-up table in the stage area), no K0 launch
-    const size_t fuse_scratch = 8 * ((size_t)h->ncls_total * (Wpad + 1) + 2 * (size_t)MB_NPARAM * Wpad);
     // host phi travels in the kernel parameters and is staged in shared memory; a batch too large
     // for that keeps K0 (one read of the mapped host memory per walker instead of one per block)
-    const bool inline_phi = h_phi && (int64_t)wp * ndim <= kPhiInline &&
-                            fuse_scratch + 8 * (size_t)wp * ndim <= k2_front_bytes(h->nbins, Wpad);
-    bool fused = kmode == kModeFactor && h->table_bytes == 8 && !d_tab && !h->no_fuse && h->ncls_total < 0xffff &&
-                 fuse_scratch <= k2_front_bytes(h->nbins, Wpad) && (!h_phi || inline_phi);
+    const bool inline_phi = h_phi && (int64_t)wp * ndim <= kPhiInline;
+    const size_t fuse_scratch = 8 * ((size_t)h->ncls_total * (Wpad + 1) + 2 * (size_t)MB_NPARAM * Wpad +
+                                     (inline_phi ? (size_t)wp * ndim : 0));
+    const bool may_fuse = kmode == kModeFactor && h->table_bytes == 8 && !d_tab && !h->no_fuse &&
+                          h->ncls_total < 0xffff && (!h_phi || inline_phi);
+    const K2Smem plan = k2_smem_plan(kmode, h->nA, h->nB, h->nbins, Wpad, h->table_bytes, h->max_smem,
+                                     may_fuse ? fuse_scratch : 0);
+    const bool fused = may_fuse && plan.fuse_fits;
     if (prof) CK(cudaEventRecord(h->ev[0], st));
     if (!elementwise && !fused) {
       K0Args k0{};
@@ -1049,7 +1070,7 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
       ++launches;
     }
     if (prof) CK(cudaEventRecord(h->ev[2], st));
-    size_t smem = k2_smem_bytes(kmode, h->nA, h->nB, h->nbins, Wpad, h->table_bytes);
+    size_t smem = plan.total;
     // occupancy query cached per pass shape (it costs microseconds of host time per call)
     int& cached = h->occ_cache[NW == 1 ? 0 : NW == 2 ? 1 : 2];
     if (cached <= 0 || h->occ_smem[NW == 1 ? 0 : NW == 2 ? 1 : 2] != smem) {
@@ -1086,7 +1107,8 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     k2.ea = h->d_ea; k2.ec = h->d_ec; k2.seg = h->d_seg[NW == 4]; k2.nseg = h->nseg[NW == 4]; k2.FA = elementwise ? h->d_Fage : FA; k2.T = h->d_T;
     k2.gacc = h->d_gacc; k2.counters = h->d_counter; k2.out = d_out;
     k2.nA = h->nA; k2.nB = h->nB; k2.Wpad = Wpad; k2.W = wp; k2.w0 = w0; k2.Wtot = W;
-    k2.tab_off = (int32_t)k2_front_bytes(h->nbins, Wpad);
+    k2.tab_off = (int32_t)plan.front;
+    k2.slab_off = (int32_t)plan.slab_off;
     k2.pois.Ht = h->d_H; k2.pois.bin_agecls = h->d_bin_agecls; k2.pois.coef = h->d_coef;
     k2.pois.n_stars = (double)h->S_total; k2.pois.nbins = h->poisson ? h->nbins : 0;
     k2.pois.nslice = poisson_nslice(k2_threads(NW), h->nbins);

@@ -652,6 +652,7 @@ struct K2Args {
   double* out;          // [MB_OUT_ROWS][Wtot], written at columns w0 .. w0+W-1
   int32_t nA, nB, Wpad, W, w0, Wtot;
   int32_t tab_off;           // byte offset of the factor tables in dynamic shared memory
+  int32_t slab_off;          // byte offset of the block-reduction slabs (0, or tab_off: over the dead tables)
   PoissonArgs pois;          // N-stars term, computed by the first W blocks before the star loop
   PeerArgs peer;             // cross-GPU reduction of the shard totals
   unsigned long long* timeline;  // optional [gridDim.x][kTimelinePoints] %globaltimer stamps (profiling)
@@ -688,6 +689,11 @@ constexpr int kChunk = 32;                          // entries staged per warp p
 #endif
 constexpr int kStages = MB_K2_STAGES;                    // chunks in flight per warp (ring of buffers)
 constexpr int kStageBytes = kStages * kChunk * (8 + 4);  // per warp: weights ring + codes ring
+// The 128-walker kernel issues twice the factor loads per entry, so two chunks in flight hide the
+// stream as well as four (measured on B200: 215 us with 2, 3 or 4) -- and the smaller ring lets
+// 128 walkers x 200 dust classes (config 4: 210 KB of tables) run as ONE pass.
+__host__ __device__ constexpr int k2_stages(int NW) { return NW == 4 ? 2 : kStages; }
+__host__ __device__ constexpr int k2_stage_bytes(int NW) { return k2_stages(NW) * kChunk * (8 + 4); }
 
 __device__ __forceinline__ void cp_async8(uint32_t smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem), "l"(gmem));
@@ -858,13 +864,13 @@ struct Lanes {
 // st_c) and fold them into L.  Per group of four entries the warp issues three broadcast loads
 // (four codes; two weight pairs) = 1.5 shared-memory wavefronts per entry, then per entry one
 // IMAD (table row address), NW/2 x LDS.128 (factors), NW x DFMA and one sign test.
-template <int NW, int MODE, typename TF>
+template <int NW, int MODE, typename TF, int STAGES = kStages>
 __device__ __forceinline__ void stream_range(Lanes<NW, MODE, TF>& L, const double* __restrict__ ga,
                                              const uint32_t* __restrict__ gc, int64_t pos, const int64_t end,
                                              const uint32_t st_a, const uint32_t st_c, const int lane) {
   const uint32_t sa = keep_in_register(st_a), sc = keep_in_register(st_c);
   const uint32_t sa_lane = keep_in_register(st_a + lane * 8u), sc_lane = keep_in_register(st_c + lane * 4u);
-  // ring of kStages chunk buffers: kStages - 1 chunks are in flight while one is processed
+  // ring of STAGES chunk buffers: STAGES - 1 chunks are in flight while one is processed
   auto issue = [&](int64_t p, int slot) {
     if (p + lane < end) {
       cp_async8(sa_lane + slot * (kChunk * 8u), ga + p + lane);
@@ -873,13 +879,13 @@ __device__ __forceinline__ void stream_range(Lanes<NW, MODE, TF>& L, const doubl
     cp_async_commit();
   };
 #pragma unroll
-  for (int k = 0; k < kStages - 1; ++k) issue(pos + (int64_t)k * kChunk, k);
+  for (int k = 0; k < STAGES - 1; ++k) issue(pos + (int64_t)k * kChunk, k);
   int slot = 0;
   while (pos < end) {
-    int ahead = slot + kStages - 1;
-    if (ahead >= kStages) ahead -= kStages;
-    issue(pos + (int64_t)(kStages - 1) * kChunk, ahead);
-    cp_async_wait<kStages - 1>();
+    int ahead = slot + STAGES - 1;
+    if (ahead >= STAGES) ahead -= STAGES;
+    issue(pos + (int64_t)(STAGES - 1) * kChunk, ahead);
+    cp_async_wait<STAGES - 1>();
     __syncwarp();
     uint32_t pa = sa + slot * (kChunk * 8u), pc = sc + slot * (kChunk * 4u);
     int n = (int)min((int64_t)kChunk, end - pos);
@@ -903,7 +909,7 @@ __device__ __forceinline__ void stream_range(Lanes<NW, MODE, TF>& L, const doubl
       L.step(a, c, f);
     }
     __syncwarp();
-    if (++slot == kStages) slot = 0;
+    if (++slot == STAGES) slot = 0;
     pos += kChunk;
   }
   cp_async_wait<0>();
@@ -925,8 +931,9 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   // smem layout: [stage: warps x (2 x 32 weights + 2 x 32 codes); also Poisson / reduction scratch]
   //              [FA | FB tables at tab_off (FACTOR only)]
   const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
-  const uint32_t st_a = smem0 + (uint32_t)warp * kStageBytes;
-  const uint32_t st_c = st_a + kStages * kChunk * 8u;
+  constexpr int STAGES = k2_stages(NW);
+  const uint32_t st_a = smem0 + (uint32_t)warp * k2_stage_bytes(NW);
+  const uint32_t st_c = st_a + STAGES * kChunk * 8u;
   const uint32_t tabA = smem0 + (uint32_t)a.tab_off + lanebytes;
   const uint32_t tabB = tabA + (uint32_t)a.nA * rowbytes;
   stamp(a.timeline, 0);
@@ -1056,7 +1063,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   int s = (int)blockIdx.x * kK2Warps + warp, s_next = 0;
   while (s < a.nseg) {
     if (lane == 0) s_next = nwarps_total + (int)atomicAdd(a.counters + kCtrSegment, 1u);
-    stream_range<NW, MODE, TF>(L, a.ea, a.ec, a.seg[s], a.seg[s + 1], st_a, st_c, lane);
+    stream_range<NW, MODE, TF, STAGES>(L, a.ea, a.ec, a.seg[s], a.seg[s + 1], st_a, st_c, lane);
     L.close();
 #pragma unroll
     for (int i = 0; i < NW; ++i) fix[i] += __double2ll_rn(L.acc[i].take_value() * kFixScale);
@@ -1069,7 +1076,8 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   stamp(a.timeline, 3);
   // every warp parks its per-walker integers in its own slab of the (now idle) stage, then
   // 3 * Wpad threads add the slabs: no shared-memory atomics (64-bit ones are CAS loops)
-  unsigned long long* slab = reinterpret_cast<unsigned long long*>(smem_raw);  // [warps][3][Wpad]
+  // (in the front region, or -- when that is too small -- over the factor tables, dead by now)
+  unsigned long long* slab = reinterpret_cast<unsigned long long*>(smem_raw + a.slab_off);  // [warps][3][Wpad]
 #pragma unroll
   for (int i = 0; i < NW; ++i) {
     const int w = (NW == 1) ? lane : 64 * (i >> 1) + 2 * lane + (i & 1);
