@@ -1,6 +1,7 @@
 // megabeast_b200 host side of the C ABI (include/megabeast_b200.h): one-time ingest of the
 // reference's data dictionaries into device-resident class-coded form, and the per-step launch
-// sequence K0 -> (K1) -> K1b -> K2 -> K3.  No torch, no CPU fallback.
+// sequence: K2 alone (FACTOR mode), K0 -> K1 -> K2 (TABLE modes) or K1e -> K1b -> K2
+// (ELEMENTWISE); the reduction over stars (K3) is K2's tail.  No torch, no CPU fallback.
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>

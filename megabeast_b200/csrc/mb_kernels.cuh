@@ -13,9 +13,15 @@
 //     physmod[g,w] = FA[cA(g)][w] * FB[cB(g)][w]       FA: age (logA) factor, FB: dust factor
 //
 // K0  mb_k0_factors      one block per walker: prior models on the classes -> factor tables FA, FB
+//                        (TABLE modes, tabulated models, pixel batches; in FACTOR mode K2 builds
+//                        the tables itself in its prologue and K0 is not launched)
 // K1  mb_k1_expand       TABLE modes: physmod table T[u][w] = FA*FB          (HBM write bound)
-// K2  mb_k2_stars<..>    prologue (first W blocks): N-stars sufficient statistics x FB -> per-bin
-//                        sums -> expected N -> Poisson term.  Then the hot loop:
+// K1e mb_k1_elementwise  ELEMENTWISE mode: physmod[g][w] from the grid's physics columns, row by
+//                        row (any grid, no class coding); K1b mb_k1b_binsums adds its per-tile
+//                        N-stars partial sums per (age, Z) bin
+// K2  mb_k2_stars<..>    prologue: (FACTOR) the factor tables, built in shared memory; (first W
+//                        blocks) N-stars sufficient statistics x FB -> per-bin sums -> expected N ->
+//                        Poisson term.  Then the hot loop:
 //                        stream (weight, code) entries once for all walkers, look the factors up
 //                        (smem) or gather T rows (L2/HBM), per-star fp64 sum, log via
 //                        mantissa/exponent product.  K3 is fused into its tail: warp -> block ->

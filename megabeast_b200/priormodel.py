@@ -4,7 +4,7 @@ Host-side prior-model callables with the interface ``MB_Model`` expects from
 55-67,146-148``): built from a parameter dictionary, keeps a reference to it, evaluates
 ``ndarray -> ndarray`` with whatever values the dictionary holds at call time.
 
-They are NOT on the likelihood hot path -- the CUDA kernel ``mb_k0_factors`` evaluates the
+They are NOT on the likelihood hot path -- the CUDA kernels (``prior_eval`` in mb_kernels.cuh) evaluate the
 same formulas on the device.  The host versions serve three cold uses: the IMF integral of
 ``precompute_mass_multipliers`` (once per fit), the ``physics_model[...]["model"]`` entries
 other code may call, and the construction-time cross-check of the device formulas.
