@@ -740,7 +740,8 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
   if (elementwise) {
     const size_t need = k1e_smem_bytes(128, h->ndim);
     if (need > (size_t)h->max_smem) return fail("ELEMENTWISE: %d free variables do not fit shared memory", h->ndim);
-    CK(cudaFuncSetAttribute(mb_k1_elementwise, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    CK(cudaFuncSetAttribute(mb_k1_elementwise<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    CK(cudaFuncSetAttribute(mb_k1_elementwise<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
   }
   if (n_pixels > 0) {
     if (mode != MB_MODE_FACTOR) return fail("pixel batches need the factor tables in shared memory (FACTOR mode)");
@@ -1057,7 +1058,11 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
       }
       const size_t sm1 = k1e_smem_bytes(Wpad, ndim);
       const int blocks1 = (int)std::min<int64_t>(k1.ntiles, (int64_t)h->sm_count * 6);
-      mb_k1_elementwise<<<blocks1, kK1eThreads, sm1, st>>>(k1);
+      bool ln = true;  // every free dust parameter a single lognormal: the register-resident fast path
+      for (int p = MB_P_AV; p < MB_NPARAM; ++p)
+        ln = ln && (h->mdev.kind[p] == MB_FIXED || h->mdev.kind[p] == MB_LOGNORMAL);
+      if (ln) mb_k1_elementwise<true><<<blocks1, kK1eThreads, sm1, st>>>(k1);
+      else mb_k1_elementwise<false><<<blocks1, kK1eThreads, sm1, st>>>(k1);
       ++launches;
       if (h->poisson) {
         mb_k1b_binsums<<<h->nbins, kK1bThreads, 0, st>>>(h->d_partial, h->d_bin_tile, h->d_SC, Wpad);

@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(256) mb_k1_expand(const double* __restrict__ F
 // Per-walker constants (mu, 1/sigma, inv_sqrt_2pi/sigma, ...) are derived from phi once per block.
 // Reads 8 P bytes per row, writes 8 Wpad bytes per row: HBM-write / fp64-exp bound.
 constexpr int kK1eThreads = 256;
-constexpr int kK1eRows = 64;
+constexpr int kK1eRows = 256;
 constexpr int kK1eWalkerVals = 6;   // per (parameter, walker) derived constants
 struct K1eArgs {
   ModelDev model;
@@ -349,6 +349,36 @@ struct K1eArgs {
   int64_t G, ntiles;
   int32_t W, Wpad, ndim, nbins;
 };
+
+// exp(x) for x <= 0 (K1e's arguments are -t^2/2), NaN passed through.  The library's scheme --
+// k = round(x / ln 2), r = x - k ln 2 in two parts, exp(r) by a degree-13 polynomial (|r| <= 0.347:
+// truncation 4e-18), scaled by 2^k in one or two exact steps so that results below 2^-1022 round
+// once into the subnormals -- with the coefficients held in REGISTERS by the caller: K1e evaluates
+// four of these per (row, walker pair), and the inlined library exp re-materialised its constants
+// each time (a third of that kernel's instructions).  Against numpy's exp on 2 x 10^6 arguments
+// in [-746, 0]: <= 1 ulp in the normal range, <= 1 unit in the subnormals, the same exact zeros.
+struct ExpCoef { double c[14]; };
+__constant__ double kExpPoly[14] = {
+    1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
+    1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0};
+__device__ __forceinline__ double exp_nonpos(double x, const ExpCoef& e) {
+  // branch free: arguments below -746 are clamped (the two-step scaling then rounds p 2^-1076 to
+  // exactly zero, as exp underflows below -745.14); NaN is restored by a select at the end
+  const double xc = fmax(x, -746.0);
+  const double shifter = 6755399441055744.0;    // 1.5 * 2^52: the low word of x*log2e + shifter is round(x*log2e)
+  const double t = fma(xc, 1.4426950408889634074, shifter);
+  const int k = __double2loint(t);
+  const double kd = t - shifter;
+  double r = fma(-kd, 6.93147180369123816490e-01, xc);
+  r = fma(-kd, 1.90821492927058770002e-10, r);
+  double p = e.c[13];
+#pragma unroll
+  for (int i = 12; i >= 0; --i) p = fma(p, r, e.c[i]);
+  // 2^k in two exact power-of-two factors: only the last multiply can round (into the subnormals)
+  const int k1 = k >> 1, k2 = k - k1;
+  const double res = (p * __hiloint2double((k1 + 1023) << 20, 0)) * __hiloint2double((k2 + 1023) << 20, 0);
+  return x != x ? x : res;
+}
 
 // derived per-walker constants of parameter p -> c[0..5]
 __device__ __forceinline__ void k1e_walker_consts(const ModelDev& m, int p, const double* th, double* c) {
@@ -425,7 +455,11 @@ __device__ __forceinline__ double k1e_eval(int kind, const double* th, const dou
   }
 }
 
-__global__ void __launch_bounds__(kK1eThreads) mb_k1_elementwise(const __grid_constant__ K1eArgs a) {
+// LN = the common shape (docs example): every free dust parameter is a single lognormal.  Its
+// per-walker constants then live in registers for the whole kernel (no shared-memory reads, no
+// dispatch on the model kind per evaluation) and exp runs with register-resident coefficients.
+template <bool LN>
+__global__ void __launch_bounds__(kK1eThreads, LN ? 2 : 3) mb_k1_elementwise(const __grid_constant__ K1eArgs a) {
   extern __shared__ __align__(16) double k1e_smem[];
   const ModelDev& m = a.model;
   const int Wpad = a.Wpad, ndim = a.ndim;
@@ -470,6 +504,22 @@ __global__ void __launch_bounds__(kK1eThreads) mb_k1_elementwise(const __grid_co
   int kinds[MB_NPARAM];
 #pragma unroll
   for (int p = 0; p < MB_NPARAM; ++p) kinds[p] = m.kind[p];
+  // LN: this thread's two walkers' lognormal constants (mu, 1/sigma, inv_sqrt_2pi/sigma) per dust
+  // parameter, and the exp coefficients
+  double lc[LN ? 3 : 1][2][3];
+  ExpCoef ec;
+  if (LN) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int w = 0; w < 2; ++w)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          lc[LN ? j : 0][w][k] = kinds[MB_P_AV + j] == MB_LOGNORMAL
+                                     ? scon[((size_t)(MB_P_AV + j) * Wpad + 2 * pair + w) * kK1eWalkerVals + k] : 0.0;
+#pragma unroll
+    for (int i = 0; i < 14; ++i) ec.c[i] = kExpPoly[i];
+  }
   for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
     const int64_t i0 = a.tile_start ? a.tile_start[tile] : tile * kK1eRows;
     const int nrows = (int)((a.tile_start ? a.tile_start[tile + 1] : min(a.G, i0 + kK1eRows)) - i0);
@@ -499,6 +549,20 @@ __global__ void __launch_bounds__(kK1eThreads) mb_k1_elementwise(const __grid_co
       for (int p = 0; p < MB_NPARAM; ++p) {  // logA, Av, Rv, fA: the reference's `cur_physmod *=` order
         if (kinds[p] == MB_FIXED) continue;
         const int i = p * kK1eRows + r;
+        if (LN && p == MB_P_LOGA && kinds[p] == MB_BINS_HISTO) {  // step function: the row's interval picks the height
+          const double* th = sphi + (size_t)(2 * pair) * ndim + m.voff[MB_P_LOGA] + sri[i];
+          v0 = th[0]; v1 = th[ndim];
+          continue;
+        }
+        if (LN && p >= MB_P_AV) {
+          const double lx = sr0[i], rx = sr1[i];
+          const double (&c)[2][3] = lc[LN ? p - MB_P_AV : 0];
+          // x <= 0: the row part holds ln x = 0 and 1/x = 0, so the factor is exactly 0 as it must be
+          const double t0 = (lx - c[0][0]) * c[0][1], t1 = (lx - c[1][0]) * c[1][1];
+          v0 *= (c[0][2] * rx) * exp_nonpos(-0.5 * (t0 * t0), ec);
+          v1 *= (c[1][2] * rx) * exp_nonpos(-0.5 * (t1 * t1), ec);
+          continue;
+        }
         const double* th0 = sphi + (size_t)(2 * pair) * ndim + m.voff[p];
         const double* cc = scon + ((size_t)p * Wpad + 2 * pair) * kK1eWalkerVals;
         const double r0 = sr0[i], r1 = sr1[i];
