@@ -1088,7 +1088,10 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     const int kK2Warps = k2_threads(NW) / 32;
     {  // segments balanced for the number of blocks that run a Poisson prologue in this pass
       const int t = NW == 4 ? 1 : 0;
-      const int npois = (h->poisson && h->pois_balance && kmode == kModeFactor && wp < h->sm_count) ? wp : 0;
+      // (rounded up to a multiple of eight: a sampler that alternates between half-ensembles of 22
+      // and 23 walkers must not trigger a rebuild on every call)
+      const int npois = (h->poisson && h->pois_balance && kmode == kModeFactor && wp < h->sm_count)
+                            ? std::min((wp + 7) & ~7, h->sm_count - 1) : 0;
       if (npois != h->seg_npois[t] || (npois > 0 && NW != h->seg_nw[t])) {
         std::vector<int64_t> seg;
         build_segments(h, t, npois, NW, seg);
