@@ -45,6 +45,20 @@ def test_library_exports_every_declared_symbol():
     assert lib.mb_abi_version() == _cabi.MB_ABI_VERSION
 
 
+def test_enum_maps_match_the_header():
+    """The ctypes mirror's mode / prior-kind / status numbers are the header's."""
+    header = open(os.path.join(ROOT, "include", "megabeast_b200.h")).read()
+    modes = dict(re.findall(r"MB_MODE_([A-Z_]+) = (\d+)", header))
+    assert {k.lower(): int(v) for k, v in modes.items()} == _cabi.MODE
+    kinds = dict(re.findall(r"^  MB_([A-Z_]+) = (\d+)", header, flags=re.M))
+    kinds = {k.lower(): int(v) for k, v in kinds.items() if not k.startswith(("MODE_", "OUT_", "P_"))}
+    assert kinds == _cabi.KIND
+    status = {k: int(v) for k, v in re.findall(r"#define MB_STATUS_([A-Z_]+) (\d+)", header)}
+    assert status["NONFINITE_STAR"] == _cabi.STATUS_NONFINITE_STAR
+    assert status["TOTAL_ZERO"] == _cabi.STATUS_TOTAL_ZERO
+    assert status["PEER_TIMEOUT"] == _cabi.STATUS_PEER_TIMEOUT
+
+
 def test_struct_layouts_match_header_sizes():
     # sizes computed by hand from the header's field lists (LP64)
     assert ctypes.sizeof(_cabi.ModelDesc) == 4 * 4 + 4 * 4 + 4 * 64 * 8
