@@ -1014,7 +1014,7 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     // host phi travels in the kernel parameters and is staged in shared memory; a batch too large
     // for that keeps K0 (one read of the mapped host memory per walker instead of one per block)
     const bool inline_phi = h_phi && (int64_t)wp * ndim <= kPhiInline;
-    const size_t fuse_scratch = 8 * ((size_t)h->ncls_total * (Wpad + 1) + 2 * (size_t)MB_NPARAM * Wpad +
+    const size_t fuse_scratch = 8 * ((size_t)h->ncls_total * (Wpad + 2) + 6 * (size_t)MB_NPARAM * Wpad + (size_t)h->nB +
                                      (inline_phi ? (size_t)wp * ndim : 0));
     const bool may_fuse = kmode == kModeFactor && h->table_bytes == 8 && !d_tab && !h->no_fuse &&
                           h->ncls_total < 0xffff && (!h_phi || inline_phi);

@@ -76,16 +76,6 @@ __device__ __forceinline__ double lognorm(double x, double mode, double sigma, d
   return amp * norm * exp(-0.5 * (t * t));
 }
 
-// the same with ln x and mu = ln(mode) + sigma^2 taken beforehand (identical operations, so the
-// result is bitwise the one of lognorm)
-__device__ __forceinline__ double lognorm_pre(double x, double lx, double mu, double sigma, double amp) {
-  if (!(x > 0.0)) return 0.0;
-  const double inv_sqrt_2pi = 0.3989422804014326779399460599343819;
-  double norm = inv_sqrt_2pi / (x * sigma);
-  double t = (lx - mu) / sigma;
-  return amp * norm * exp(-0.5 * (t * t));
-}
-
 __device__ double prior_eval(const ModelDev& m, int p, const double* __restrict__ th, double x) {
   switch (m.kind[p]) {
     case MB_LOGNORMAL:
@@ -1012,65 +1002,83 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   if (MODE == kModeFactor && !kF32 && a.build_tables) {
     // K0 fused: the prior models on the classes (singlepop_dust_model.py:146-148 restricted to the
     // distinct column values) for all walkers of the pass -> look-up table in the (still idle) stage
-    // area, then the FA / FB rows straight into shared memory.  Same arithmetic as mb_k0_factors;
-    // the logarithms (one per class, one or two per lognormal and walker) are taken first, once.
+    // area, then the FA / FB rows straight into shared memory.  The fp64 pipe bounds this prologue
+    // (every block repeats it), so the lognormals are arranged for few operations: ln x and 1/x once
+    // per class, mu = ln(mode) + sigma^2, 1/sigma and amp/(sigma sqrt(2 pi)) once per walker, then
+    // one multiply-add chain and one branch-free exp per (class, walker) -- no divisions there.
+    // (mb_k0_factors evaluates the textbook form; the two agree to an ulp or two.)
     const ModelDev& m = a.model;
     double* lut = reinterpret_cast<double*>(smem_raw);              // [ncls_total][Wpad]
     double* tab = reinterpret_cast<double*>(smem_raw + a.tab_off);  // [nA + nB][Wpad]
     const int ncls = a.ncls_total, nlut = ncls * Wpad;
-    double* lxs = lut + nlut;                                       // [ncls] ln(class value)
-    double* cmu = lxs + ncls;                                       // [NPARAM][Wpad][2] mu of the lognormals
+    double* lxs = lut + nlut;                                       // [ncls][2] ln x, 1/x of the class value
+    double* cw = lxs + 2 * ncls;                                    // [NPARAM][Wpad][6] per-walker lognormal constants
+    ushort4* srow = reinterpret_cast<ushort4*>(cw + 6 * MB_NPARAM * Wpad);  // [nB] look-up rows of a dust class's digits
     // phi: carried in the kernel parameters (copied to shared memory with indexed constant loads --
     // reads of the parameter space through a generic pointer are slow) or in device memory
     const double* ph = a.phi;
     if (a.phi_inline) {
-      double* sphi = cmu + 2 * MB_NPARAM * Wpad;
+      double* sphi = reinterpret_cast<double*>(srow + a.nB);
       const int n = a.W * a.ndim;
       for (int i = threadIdx.x; i < n; i += blockDim.x) sphi[i] = a.phi_in[i];
       __syncthreads();
       ph = sphi;
     }
+    const double inv_sqrt_2pi = 0.3989422804014326779399460599343819;
+    // (the digit rows ride along with the first phase: their L2 latency hides behind the logarithms)
+    for (int i = (int)blockDim.x - 1 - (int)threadIdx.x; i < a.nB; i += blockDim.x)
+      srow[i] = __ldg(reinterpret_cast<const ushort4*>(a.rowlut) + i);
     for (int idx = threadIdx.x; idx < ncls + MB_NPARAM * Wpad; idx += blockDim.x) {
       if (idx < ncls) {
         const double x = __ldg(a.clsx + idx);
-        lxs[idx] = x > 0.0 ? log(x) : 0.0;
+        lxs[2 * idx] = x > 0.0 ? log(x) : 0.0;
+        lxs[2 * idx + 1] = x > 0.0 ? 1.0 / x : 0.0;  // x <= 0: the lognormal is exactly 0 there
       } else {
         const int j = idx - ncls, p = j / Wpad, w = j - p * Wpad;
         const double* th = ph + (size_t)(w < a.W ? w : a.W - 1) * a.ndim + m.voff[p];
+        double* c = cw + 6 * j;
         if (m.kind[p] == MB_LOGNORMAL) {
-          cmu[2 * j] = log(th[0]) + th[1] * th[1];
+          const double isig = 1.0 / th[1];
+          c[0] = log(th[0]) + th[1] * th[1]; c[1] = isig; c[2] = inv_sqrt_2pi * isig;
         } else if (m.kind[p] == MB_TWO_LOGNORMAL) {
-          cmu[2 * j] = log(th[0]) + th[2] * th[2];
-          cmu[2 * j + 1] = log(th[1]) + th[3] * th[3];
+          const double n1 = 1.0 - 1.0 / (th[4] + 1.0), n2 = 1.0 / (th[4] + 1.0);
+          const double isig1 = 1.0 / th[2], isig2 = 1.0 / th[3];
+          c[0] = log(th[0]) + th[2] * th[2]; c[1] = isig1; c[2] = n1 * inv_sqrt_2pi * isig1;
+          c[3] = log(th[1]) + th[3] * th[3]; c[4] = isig2; c[5] = n2 * inv_sqrt_2pi * isig2;
         }
       }
     }
     __syncthreads();
-    // (independent iterations, unrolled so that the fp64 divide / exp chains of a thread's items overlap)
-#pragma unroll 4
-    for (int idx = threadIdx.x; idx < nlut; idx += blockDim.x) {
-      const int i = idx / Wpad, w = idx - i * Wpad;
-      int p = 0;
+    {
+      ExpCoef ec;
 #pragma unroll
-      for (int q = 1; q < MB_NPARAM; ++q)
-        if (i >= m.clsoff[q]) p = q;
-      const double* th = ph + (size_t)(w < a.W ? w : a.W - 1) * a.ndim + m.voff[p];  // padding repeats the last walker
-      const double x = __ldg(a.clsx + i);
-      double v = 1.0;
-      if (m.kind[p] == MB_LOGNORMAL) {
-        v = lognorm_pre(x, lxs[i], cmu[2 * (p * Wpad + w)], th[1], 1.0);
-      } else if (m.kind[p] == MB_TWO_LOGNORMAL) {
-        const double n1 = 1.0 - 1.0 / (th[4] + 1.0), n2 = 1.0 / (th[4] + 1.0);
-        v = lognorm_pre(x, lxs[i], cmu[2 * (p * Wpad + w)], th[2], n1) +
-            lognorm_pre(x, lxs[i], cmu[2 * (p * Wpad + w) + 1], th[3], n2);
-      } else if (m.kind[p] != MB_FIXED) {
-        v = prior_eval(m, p, th, x);
+      for (int i = 0; i < 14; ++i) ec.c[i] = kExpPoly[i];
+#pragma unroll 3
+      for (int idx = threadIdx.x; idx < nlut; idx += blockDim.x) {
+        const int i = idx / Wpad, w = idx - i * Wpad;
+        int p = 0;
+#pragma unroll
+        for (int q = 1; q < MB_NPARAM; ++q)
+          if (i >= m.clsoff[q]) p = q;
+        const double* c = cw + 6 * (p * Wpad + w);
+        const double lx = lxs[2 * i], rx = lxs[2 * i + 1];
+        double v = 1.0;
+        if (m.kind[p] == MB_LOGNORMAL) {
+          const double t = (lx - c[0]) * c[1];
+          v = (c[2] * rx) * exp_nonpos(-0.5 * (t * t), ec);
+        } else if (m.kind[p] == MB_TWO_LOGNORMAL) {
+          const double t1 = (lx - c[0]) * c[1], t2 = (lx - c[3]) * c[4];
+          v = (c[2] * rx) * exp_nonpos(-0.5 * (t1 * t1), ec) + (c[5] * rx) * exp_nonpos(-0.5 * (t2 * t2), ec);
+        } else if (m.kind[p] != MB_FIXED) {
+          // padding columns repeat the last walker
+          v = prior_eval(m, p, ph + (size_t)(w < a.W ? w : a.W - 1) * a.ndim + m.voff[p], __ldg(a.clsx + i));
+        }
+        lut[idx] = v;
       }
-      lut[idx] = v;
     }
     __syncthreads();
     const int ntab = (a.nA + a.nB) * Wpad;
-#pragma unroll 4
+#pragma unroll 3
     for (int idx = threadIdx.x; idx < ntab; idx += blockDim.x) {
       const int c = idx / Wpad, w = idx - c * Wpad;
       double v = 1.0;
@@ -1079,7 +1087,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
       } else {
         // look-up rows of the dust class's digits (precomputed: no integer divisions here), multiplied
         // in the reference's left-to-right order (`cur_physmod *=`, :146-148)
-        const ushort4 r = __ldg(reinterpret_cast<const ushort4*>(a.rowlut) + (c - a.nA));
+        const ushort4 r = srow[c - a.nA];
         if (r.x != 0xffff) v *= lut[r.x * Wpad + w];
         if (r.y != 0xffff) v *= lut[r.y * Wpad + w];
         if (r.z != 0xffff) v *= lut[r.z * Wpad + w];
