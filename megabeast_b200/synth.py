@@ -42,6 +42,9 @@ CONFIGS = {
     "cfg3_half": dict(axes=(41, 4, 61, 20, 5, 1), S=50_000, K=50, W=64),
     "cfg3_quarter": dict(axes=(41, 4, 61, 20, 5, 1), S=25_000, K=50, W=64),
     "cfg3_eighth": dict(axes=(41, 4, 61, 20, 5, 1), S=12_500, K=50, W=64),
+    # production-like dust axes (A(V) 0-10 in steps of 0.1, 9 R(V), 5 f_A: 4,500 dust classes, too many
+    # for shared memory -> `table_unique`, the class table gathered from L2)
+    "fine_dust": dict(axes=(41, 4, 10, 100, 9, 5), S=100_000, K=50, W=64),
     # one GPU's share of the PHAT-scale config 4 on 8 GPUs
     "cfg4_eighth": dict(axes=(41, 4, 61, 20, 10, 1), S=125_000, K=50, W=128),
 }
