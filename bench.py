@@ -378,7 +378,7 @@ def run_ours(args):
         # completeness (N-stars partial sums) in, table out
         "k1_expand": (4 * U if mode == "table_grid" else (8 * nfree + 16) * U if mode == "elementwise" else 0)
                      + 8 * U * Wpad,
-        "k2_stars": 12 * n_ent + 16 * info["n_bins"] * nB + (8 * (nA + nB) * Wpad if mode == "factor"
+        "k2_stars": (8 + info["code_bytes"]) * n_ent + 16 * info["n_bins"] * nB + (8 * (nA + nB) * Wpad if mode == "factor"
                                   else 8 * Wpad * (touched if touched is not None else U)),
     }
     dur_s = kms[dom] * 1e-3
@@ -406,12 +406,13 @@ def run_ours(args):
         # shared-memory wavefronts K2 must issue (measured in lds_mix.cu): per
         # entry 2*NW for the Wpad*8-byte factor row + 1.5 for the broadcast of weight and code
         nw = Wpad // 32
-        wavefronts = n_ent * (2.0 * nw + 1.5)
+        bcast = 1.5 if info["code_bytes"] == 4 else 1.25  # four codes: one 16-byte or one 8-byte broadcast
+        wavefronts = n_ent * (2.0 * nw + bcast)
         peak_wf = info["sm_count"] * sm_mhz * 1e6 / 1e9
         ach = wavefronts / (kms["k2_stars"] * 1e-3) / 1e9
         onchip = {"bound": "smem", "wavefronts_per_launch": wavefronts, "achieved": ach, "peak": peak_wf,
                   "unit": "Gwavefront/s", "frac": ach / peak_wf,
-                  "note": f"model count ({2 * nw} factor + 1.5 broadcast wavefronts per entry); peak = 1 "
+                  "note": f"model count ({2 * nw} factor + {bcast} broadcast wavefronts per entry); peak = 1 "
                           f"wavefront/clk/SM x {info['sm_count']} SMs x {sm_mhz:.0f} MHz; ncu's measured "
                           "l1tex data-pipe utilisation for the same kernel is in profiles/"}
     # the north_star's own yardstick: the materialised-physmod design's compulsory bytes per step

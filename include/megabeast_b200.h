@@ -143,7 +143,8 @@ typedef struct {
   int64_t n_entries;       /* finite (star, point) entries held on the device */
   int64_t n_entries_raw;   /* before merging duplicates */
   int64_t device_bytes;
-  int64_t reserved[8];
+  int64_t code_bytes;      /* bytes of an entry's code word on the device: 4, or 2 (FACTOR mode, <= 16 age classes) */
+  int64_t reserved[7];
 } mb_info;
 
 /* Device result layout of mb_lnlike_device: three rows of W doubles.  The two rows that add over

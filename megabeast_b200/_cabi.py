@@ -126,7 +126,8 @@ class Info(ctypes.Structure):
         ("n_entries", ctypes.c_int64),
         ("n_entries_raw", ctypes.c_int64),
         ("device_bytes", ctypes.c_int64),
-        ("reserved", ctypes.c_int64 * 8),
+        ("code_bytes", ctypes.c_int64),
+        ("reserved", ctypes.c_int64 * 7),
     ]
 
 

@@ -61,7 +61,9 @@ struct mb_handle {
   // device, static
   double* d_clsx = nullptr;
   double* d_ea = nullptr;       // entry weights
-  uint32_t* d_ec = nullptr;     // entry codes
+  uint32_t* d_ec = nullptr;     // entry codes (32-bit), or ...
+  uint16_t* d_ec16 = nullptr;   // ... 16-bit codes: FACTOR mode, fp64 tables, <= 16 age classes (see Lanes)
+  int c16 = 0;
   int64_t* d_seg[2] = {nullptr, nullptr};  // segment tables: [0] 768-thread kernels, [1] 512-thread kernel
   uint32_t* d_rowcode = nullptr;
   uint16_t* d_rowlut = nullptr;  // [nB][4] look-up rows of every dust class's digits (K2 builds the tables itself)
@@ -293,7 +295,7 @@ extern "C" void mb_destroy(mb_handle* h) {
   cudaSetDevice(h->device);
   if (h->peer_world > 1) mb_peer_disconnect(h);
   if (h->d_xbuf) cudaFree(h->d_xbuf);
-  void* ptrs[] = {h->d_clsx, h->d_ea, h->d_ec, h->d_seg[0], h->d_seg[1], h->d_rowcode, h->d_H, h->d_coef,
+  void* ptrs[] = {h->d_clsx, h->d_ea, h->d_ec, h->d_ec16, h->d_seg[0], h->d_seg[1], h->d_rowcode, h->d_H, h->d_coef,
                   h->d_bin_agecls, h->d_phi, h->d_tab[0], h->d_tab[1], h->d_tab[2], h->d_tab[3],
                   h->d_F, h->d_counter, h->d_gacc, h->d_T, h->d_out, h->d_pix_seg, h->d_pix_nstars, h->d_Fpix,
                   h->d_timeline, h->d_col[0], h->d_col[1], h->d_col[2], h->d_col[3], h->d_gw, h->d_compl,
@@ -651,6 +653,8 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
   // by 3-4 % -- per-segment costs (pipeline restart, one log) outweigh what dynamic balancing
   // recovers -- so the segment count must match the warps the launch really has: one table for
   // the 768-thread kernels (up to 64 walkers per pass) and one for the 512-thread kernel (128).
+  h->c16 = mode == MB_MODE_FACTOR && h->table_bytes == 8 && n_pixels == 0 && h->nA <= 16 && h->nB <= 1024 &&
+           !getenv("MB_CODES32");
   h->spw = o.segments_per_warp > 0 ? o.segments_per_warp : 1;
   // ... optionally plus a tail pool: the last tail_percent of the entries cut into small segments
   // that warps claim dynamically after their own big one.  Measured on B200 (4-16 %, config 3 and
@@ -675,7 +679,15 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
     std::vector<double> wts(entries.size());
     for (size_t i = 0; i < entries.size(); ++i) wts[i] = entries[i].a;
     if (dev_upload(h, &h->d_ea, wts)) return 1;
-    if (dev_upload(h, &h->d_ec, codes)) return 1;
+    if (h->c16) {
+      std::vector<uint16_t> c16(codes.size() + 2, (uint16_t)0);  // padded: codes are fetched in pairs
+      for (size_t i = 0; i < codes.size(); ++i) {
+        const uint32_t c = codes[i];
+        c16[i] = (uint16_t)(((c & kNewRun) ? 0x8000u : 0u) | ((c & kNewStar) ? 0x4000u : 0u) |
+                            (((c >> kAgeShift) & kAgeMask) << 10) | (c & kDustMask));
+      }
+      if (dev_upload(h, &h->d_ec16, c16)) return 1;
+    } else if (dev_upload(h, &h->d_ec, codes)) return 1;
   }
   if (dev_upload(h, &h->d_seg[0], seg[0])) return 1;
   if (dev_upload(h, &h->d_seg[1], seg[1])) return 1;
@@ -733,6 +745,9 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
     CK(cudaFuncSetAttribute(mb_k2_stars<1, kModeFactor, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(mb_k2_stars<2, kModeFactor, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(mb_k2_stars<4, kModeFactor, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CK((cudaFuncSetAttribute(mb_k2_stars<1, kModeFactor, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
+    CK((cudaFuncSetAttribute(mb_k2_stars<2, kModeFactor, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
+    CK((cudaFuncSetAttribute(mb_k2_stars<4, kModeFactor, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
     MB_OPTIN(1, kModeTable); MB_OPTIN(2, kModeTable); MB_OPTIN(4, kModeTable);
     MB_OPTIN(1, kModeTableGrid); MB_OPTIN(2, kModeTableGrid); MB_OPTIN(4, kModeTableGrid);
 #undef MB_OPTIN
@@ -883,6 +898,7 @@ extern "C" int mb_get_info(const mb_handle* h, mb_info* out) {
   out->n_entries = h->n_entries;
   out->n_entries_raw = h->n_entries_raw;
   out->device_bytes = h->device_bytes;
+  out->code_bytes = h->c16 ? 2 : 4;
   return 0;
 }
 
@@ -952,7 +968,7 @@ extern "C" int mb_last_kernel_ms(const mb_handle* h, float ms[MB_NKERNELS]) {
 
 // K2 is launched with programmatic stream serialization: its blocks may be placed while the
 // preceding kernel (K0 / K1) is still running and wait inside the kernel (griddepcontrol.wait)
-template <int MODE, typename TF = double>
+template <int MODE, typename TF = double, bool C16 = false>
 static cudaError_t launch_k2(int NW, int grid, size_t smem, cudaStream_t st, const K2Args& a) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
@@ -965,23 +981,24 @@ static cudaError_t launch_k2(int NW, int grid, size_t smem, cudaStream_t st, con
   cfg.attrs = &attr;
   cfg.numAttrs = 1;
   switch (NW) {
-    case 1: return cudaLaunchKernelEx(&cfg, mb_k2_stars<1, MODE, TF>, a);
-    case 2: return cudaLaunchKernelEx(&cfg, mb_k2_stars<2, MODE, TF>, a);
-    default: return cudaLaunchKernelEx(&cfg, mb_k2_stars<4, MODE, TF>, a);
+    case 1: return cudaLaunchKernelEx(&cfg, mb_k2_stars<1, MODE, TF, C16>, a);
+    case 2: return cudaLaunchKernelEx(&cfg, mb_k2_stars<2, MODE, TF, C16>, a);
+    default: return cudaLaunchKernelEx(&cfg, mb_k2_stars<4, MODE, TF, C16>, a);
   }
 }
 
-template <int MODE, typename TF = double>
+template <int MODE, typename TF = double, bool C16 = false>
 static int k2_occ(int NW, size_t smem) {
   int n = 0;
   switch (NW) {
-    case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<1, MODE, TF>, k2_threads(1), smem); break;
-    case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<2, MODE, TF>, k2_threads(2), smem); break;
-    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<4, MODE, TF>, k2_threads(4), smem); break;
+    case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<1, MODE, TF, C16>, k2_threads(1), smem); break;
+    case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<2, MODE, TF, C16>, k2_threads(2), smem); break;
+    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<4, MODE, TF, C16>, k2_threads(4), smem); break;
   }
   return n;
 }
-static int k2_blocks_per_sm(int kmode, int NW, size_t smem, int table_bytes) {
+static int k2_blocks_per_sm(int kmode, int NW, size_t smem, int table_bytes, int c16) {
+  if (kmode == kModeFactor && c16) return k2_occ<kModeFactor, double, true>(NW, smem);
   if (kmode == kModeFactor && table_bytes == 4) return k2_occ<kModeFactor, float>(NW, smem);
   return kmode == kModeFactor ? k2_occ<kModeFactor>(NW, smem)
          : kmode == kModeTable ? k2_occ<kModeTable>(NW, smem) : k2_occ<kModeTableGrid>(NW, smem);
@@ -1080,7 +1097,7 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     // occupancy query cached per pass shape (it costs microseconds of host time per call)
     int& cached = h->occ_cache[NW == 1 ? 0 : NW == 2 ? 1 : 2];
     if (cached <= 0 || h->occ_smem[NW == 1 ? 0 : NW == 2 ? 1 : 2] != smem) {
-      cached = k2_blocks_per_sm(kmode, NW, smem, h->table_bytes);
+      cached = k2_blocks_per_sm(kmode, NW, smem, h->table_bytes, h->c16);
       h->occ_smem[NW == 1 ? 0 : NW == 2 ? 1 : 2] = smem;
     }
     int per_sm = cached;
@@ -1113,7 +1130,7 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
                         std::max(h->poisson ? wp : 1, (h->nseg[NW == 4] + kK2Warps - 1) / kK2Warps));
     grid = std::min(grid, h->max_blocks);
     K2Args k2{};
-    k2.ea = h->d_ea; k2.ec = h->d_ec; k2.seg = h->d_seg[NW == 4]; k2.nseg = h->nseg[NW == 4]; k2.FA = elementwise ? h->d_Fage : FA; k2.T = h->d_T;
+    k2.ea = h->d_ea; k2.ec = h->c16 ? (const void*)h->d_ec16 : (const void*)h->d_ec; k2.seg = h->d_seg[NW == 4]; k2.nseg = h->nseg[NW == 4]; k2.FA = elementwise ? h->d_Fage : FA; k2.T = h->d_T;
     k2.gacc = h->d_gacc; k2.counters = h->d_counter; k2.out = d_out;
     k2.nA = h->nA; k2.nB = h->nB; k2.Wpad = Wpad; k2.W = wp; k2.w0 = w0; k2.Wtot = W;
     k2.tab_off = (int32_t)plan.front;
@@ -1143,7 +1160,8 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
       k2.peer.seq = ++h->peer_seq;
       for (int p = 0; p < h->peer_world; ++p) k2.peer.xbuf[p] = h->peer_xbuf[p];
     }
-    if (kmode == kModeFactor && h->table_bytes == 4) CK((launch_k2<kModeFactor, float>(NW, grid, smem, st, k2)));
+    if (kmode == kModeFactor && h->c16) CK((launch_k2<kModeFactor, double, true>(NW, grid, smem, st, k2)));
+    else if (kmode == kModeFactor && h->table_bytes == 4) CK((launch_k2<kModeFactor, float>(NW, grid, smem, st, k2)));
     else if (kmode == kModeFactor) CK(launch_k2<kModeFactor>(NW, grid, smem, st, k2));
     else if (kmode == kModeTable) CK(launch_k2<kModeTable>(NW, grid, smem, st, k2));
     else CK(launch_k2<kModeTableGrid>(NW, grid, smem, st, k2));

@@ -702,7 +702,7 @@ struct PeerArgs {
 constexpr int kPhiInline = 1152;  // doubles of phi carried in K2's kernel parameters (e.g. 128 walkers x 9)
 struct K2Args {
   const double* ea;     // entry weights  [n_entries]
-  const uint32_t* ec;   // entry codes    [n_entries]
+  const void* ec;       // entry codes    [n_entries]: uint32, or uint16 for the C16 kernels (padded by one)
   const int64_t* seg;   // [nseg+1] entry offsets, star aligned
   int32_t nseg;
   const double* FA;     // FACTOR: [nA][Wpad] then [nB][Wpad], contiguous (staged to smem)
@@ -783,6 +783,16 @@ __device__ __forceinline__ double lds_stage_d(uint32_t addr) {
   asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ uint2 lds_stage_u2(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_stage_u16(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];\n" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ uint32_t lds_stage_u(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(addr) : "memory");
@@ -832,8 +842,18 @@ __device__ __forceinline__ uint32_t keep_in_register(uint32_t x) {
 // factor rounded to 21 significant bits, so it is used as a double without any conversion
 // instruction -- F2F.F64.F32 runs on the quarter-rate XU pipe and made a true fp32 table no
 // faster than the fp64 one; sums are still fp64).
-template <int NW, int MODE, typename TF = double>
+// C16: the FACTOR code word packed in 16 bits -- [15] new run, [14] new star, [13:10] age class,
+// [9:0] dust class (<= 16 age classes; 1,024 dust classes is more than shared memory can hold
+// anyway) -- so that four codes are ONE 8-byte broadcast load instead of a 16-byte one (one
+// shared-memory wavefront less per four entries).  An even entry's code arrives with the next one
+// in its upper half; the masks below never look there.
+template <int NW, int MODE, typename TF = double, bool C16 = false>
 struct Lanes {
+  static_assert(!C16 || (MODE == 1 && sizeof(TF) == 8), "16-bit codes: FACTOR mode with fp64 tables");
+  __device__ __forceinline__ static uint32_t dust(uint32_t code) { return C16 ? (code & 0x3ffu) : (code & kDustMask); }
+  __device__ __forceinline__ static uint32_t age(uint32_t code) { return C16 ? ((code >> 10) & 0xfu) : ((code >> kAgeShift) & kAgeMask); }
+  __device__ __forceinline__ static bool is_run(uint32_t code) { return C16 ? (code & 0x8000u) != 0 : (int32_t)code < 0; }
+  __device__ __forceinline__ static bool is_star(uint32_t code) { return C16 ? (code & 0x4000u) != 0 : (code & kNewStar) != 0; }
   static constexpr int NQ = (NW + 1) / 2;
   static constexpr bool kF32 = sizeof(TF) == 4;
   static_assert(!kF32 || MODE == 1, "float tables exist in FACTOR mode only");
@@ -875,7 +895,7 @@ struct Lanes {
   }
   __device__ __forceinline__ void load_factors(uint32_t code, double* f) const {
     if (MODE == kModeFactor) {
-      lds_row((code & kDustMask) * rowbytes + tabB, f);
+      lds_row(dust(code) * rowbytes + tabB, f);
     } else {
       const char* p = Tlane + (size_t)(code & kRowMask) * rowbytes;
       if (NW == 1) f[0] = __ldg(reinterpret_cast<const double*>(p));
@@ -892,11 +912,11 @@ struct Lanes {
   __device__ __forceinline__ void boundary(uint32_t code) {
 #pragma unroll
     for (int i = 0; i < NW; ++i) { star[i] = fma(fa[i], run[i] + run2[i], star[i]); run[i] = 0.0; run2[i] = 0.0; }
-    if (MODE != kModeFactor || (code & kNewStar)) {
+    if (MODE != kModeFactor || is_star(code)) {
 #pragma unroll
       for (int i = 0; i < NW; ++i) { star_done(acc[i], star[i]); star[i] = 0.0; }
     }
-    if (MODE == kModeFactor) lds_row(((code >> kAgeShift) & kAgeMask) * rowbytes + tabA, fa);
+    if (MODE == kModeFactor) lds_row(age(code) * rowbytes + tabA, fa);
   }
   __device__ __forceinline__ void mac(double a, const double* f) {
 #pragma unroll
@@ -907,7 +927,7 @@ struct Lanes {
     for (int i = 0; i < NW; ++i) run2[i] = fma(a, f[i], run2[i]);
   }
   __device__ __forceinline__ void step(double a, uint32_t code, const double* f) {
-    if ((int32_t)code < 0) boundary(code);  // bit 31, warp-uniform
+    if (is_run(code)) boundary(code);  // the new-run flag, warp-uniform
     mac(a, f);
   }
   // a streamed range ends on a star boundary: close the last star
@@ -924,18 +944,27 @@ struct Lanes {
 // st_c) and fold them into L.  Per group of four entries the warp issues three broadcast loads
 // (four codes; two weight pairs) = 1.5 shared-memory wavefronts per entry, then per entry one
 // IMAD (table row address), NW/2 x LDS.128 (factors), NW x DFMA and one sign test.
-template <int NW, int MODE, typename TF, int STAGES = kStages>
-__device__ __forceinline__ void stream_range(Lanes<NW, MODE, TF>& L, const double* __restrict__ ga,
-                                             const uint32_t* __restrict__ gc, int64_t pos, const int64_t end,
+template <int NW, int MODE, typename TF, int STAGES = kStages, bool C16 = false>
+__device__ __forceinline__ void stream_range(Lanes<NW, MODE, TF, C16>& L, const double* __restrict__ ga,
+                                             const void* __restrict__ gcodes, int64_t pos, const int64_t end,
                                              const uint32_t st_a, const uint32_t st_c, const int lane) {
+  constexpr uint32_t kCodeBytes = C16 ? 2u : 4u;
+  const uint32_t* gc = static_cast<const uint32_t*>(gcodes);          // 32-bit codes
+  const uint16_t* gc16 = static_cast<const uint16_t*>(gcodes);        // 16-bit codes, fetched in 4-byte aligned pairs
+  // 16-bit codes: chunks start on an even entry.  A range that starts on an odd one stages the
+  // entry before it too and skips it: the first chunk handles entries 1..3 one by one, then groups
+  int lead = C16 ? (int)(pos & 1) : 0;
+  pos -= lead;
   const uint32_t sa = keep_in_register(st_a), sc = keep_in_register(st_c);
   const uint32_t sa_lane = keep_in_register(st_a + lane * 8u), sc_lane = keep_in_register(st_c + lane * 4u);
   // ring of STAGES chunk buffers: STAGES - 1 chunks are in flight while one is processed
   auto issue = [&](int64_t p, int slot) {
     if (p + lane < end) {
       cp_async8(sa_lane + slot * (kChunk * 8u), ga + p + lane);
-      cp_async4(sc_lane + slot * (kChunk * 4u), gc + p + lane);
+      if (!C16) cp_async4(sc_lane + slot * (kChunk * 4u), gc + p + lane);
     }
+    if (C16 && lane < kChunk / 2 && p + 2 * lane < end)  // two codes per lane (the array is padded by one)
+      cp_async4(sc_lane + slot * (kChunk * 2u), gc16 + p + 2 * lane);
     cp_async_commit();
   };
 #pragma unroll
@@ -947,22 +976,42 @@ __device__ __forceinline__ void stream_range(Lanes<NW, MODE, TF>& L, const doubl
     issue(pos + (int64_t)(STAGES - 1) * kChunk, ahead);
     cp_async_wait<STAGES - 1>();
     __syncwarp();
-    uint32_t pa = sa + slot * (kChunk * 8u), pc = sc + slot * (kChunk * 4u);
+    uint32_t pa = sa + slot * (kChunk * 8u), pc = sc + slot * (kChunk * kCodeBytes);
     int n = (int)min((int64_t)kChunk, end - pos);
-    for (; n >= 4; n -= 4, pa += 32u, pc += 16u) {
-      const uint4 c = lds_stage_u4(pc);
+    if (C16 && lead) {
+      for (int i = 1; i < 4 && i < n; ++i) {
+        const uint32_t c = lds_stage_u16(pc + 2u * i);
+        const double a = lds_stage_d(pa + 8u * i);
+        double f[NW];
+        L.load_factors(c, f);
+        L.step(a, c, f);
+      }
+      n = n > 4 ? n - 4 : 0; pa += 32u; pc += 8u;
+      lead = 0;
+    }
+    for (; n >= 4; n -= 4, pa += 32u, pc += 4u * kCodeBytes) {
+      uint4 c;
+      bool any_boundary;
+      if (C16) {  // four codes in one 8-byte broadcast
+        const uint2 cc = lds_stage_u2(pc);
+        c = make_uint4(cc.x, cc.x >> 16, cc.y, cc.y >> 16);
+        any_boundary = ((cc.x | cc.y) & 0x80008000u) != 0;
+      } else {
+        c = lds_stage_u4(pc);
+        any_boundary = (int32_t)(c.x | c.y | c.z | c.w) < 0;
+      }
       const double2 a01 = lds_stage_d2(pa), a23 = lds_stage_d2(pa + 16u);
       double f0[NW], f1[NW], f2[NW], f3[NW];
       L.load_factors(c.x, f0); L.load_factors(c.y, f1); L.load_factors(c.z, f2); L.load_factors(c.w, f3);
       // (the vote makes the uniformity of the branch visible to the compiler: no BSSY/BSYNC pair)
-      if (__any_sync(0xffffffffu, (int32_t)(c.x | c.y | c.z | c.w) < 0)) {  // a run / star boundary in the group
+      if (__any_sync(0xffffffffu, any_boundary)) {  // a run / star boundary in the group
         L.step(a01.x, c.x, f0); L.step(a01.y, c.y, f1); L.step(a23.x, c.z, f2); L.step(a23.y, c.w, f3);
       } else {                                     // common case: four plain multiply-adds
         L.mac(a01.x, f0); L.mac2(a01.y, f1); L.mac(a23.x, f2); L.mac2(a23.y, f3);
       }
     }
-    for (; n > 0; --n, pa += 8u, pc += 4u) {
-      const uint32_t c = lds_stage_u(pc);
+    for (; n > 0; --n, pa += 8u, pc += kCodeBytes) {
+      const uint32_t c = C16 ? lds_stage_u16(pc) : lds_stage_u(pc);
       const double a = lds_stage_d(pa);
       double f[NW];
       L.load_factors(c, f);
@@ -978,14 +1027,14 @@ __device__ __forceinline__ void stream_range(Lanes<NW, MODE, TF>& L, const doubl
 // Prologue (first W blocks): N-stars / Poisson term.  Hot loop: every warp streams star-aligned
 // segments of the entry stream for all walkers.  Tail: reduction over stars (K3) and, with peers,
 // over GPUs.
-template <int NW, int MODE, typename TF = double>
+template <int NW, int MODE, typename TF = double, bool C16 = false>
 __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars(const __grid_constant__ K2Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int kK2Warps = k2_threads(NW) / 32;
   constexpr bool kF32 = sizeof(TF) == 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int Wpad = 32 * NW;  // == a.Wpad
-  constexpr uint32_t rowbytes = Lanes<NW, MODE, TF>::rowbytes;
+  constexpr uint32_t rowbytes = Lanes<NW, MODE, TF, C16>::rowbytes;
   const uint32_t lanebytes = (NW == 1 ? lane : 2 * lane) * (MODE == kModeFactor ? (uint32_t)sizeof(TF) : 8u);
 
   // smem layout: [stage: warps x (2 x 32 weights + 2 x 32 codes); also Poisson / reduction scratch]
@@ -1127,7 +1176,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   }
 
   stamp(a.timeline, 2);
-  Lanes<NW, MODE, TF> L;
+  Lanes<NW, MODE, TF, C16> L;
   L.init(tabA, tabB, reinterpret_cast<const char*>(a.T) + lanebytes);
 
   // Segments: every warp starts with its own index (no atomic storm at kernel start); further
@@ -1141,7 +1190,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   int s = (int)blockIdx.x * kK2Warps + warp, s_next = 0;
   while (s < a.nseg) {
     if (lane == 0) s_next = nwarps_total + (int)atomicAdd(a.counters + kCtrSegment, 1u);
-    stream_range<NW, MODE, TF, STAGES>(L, a.ea, a.ec, a.seg[s], a.seg[s + 1], st_a, st_c, lane);
+    stream_range<NW, MODE, TF, STAGES, C16>(L, a.ea, a.ec, a.seg[s], a.seg[s + 1], st_a, st_c, lane);
     L.close();
 #pragma unroll
     for (int i = 0; i < NW; ++i) fix[i] += __double2ll_rn(L.acc[i].take_value() * kFixScale);
