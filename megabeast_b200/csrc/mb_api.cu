@@ -110,6 +110,12 @@ struct mb_handle {
   std::vector<double> scratch_phi, scratch_rows, scratch_val;
   int table_bytes = 8;   // FACTOR-mode shared-memory table element: 8 = fp64, 4 = fp32
   int no_fuse = 0;       // keep K0 as a separate launch (MB_NO_FUSE=1: A/B measurements)
+  // host path: K2's last block raises a flag in mapped host memory after the result rows; the host
+  // polls it instead of going through cudaStreamSynchronize (MB_NO_FLAG=1: always synchronize)
+  int use_flag = 1;
+  unsigned long long flag_seq = 0;     // value the pending evaluation will publish (0: no flag armed)
+  volatile unsigned long long* h_flag = nullptr;
+  unsigned long long* d_flag = nullptr;
   // segment tables are rebuilt when the number of blocks that compute a Poisson term changes
   std::vector<int64_t> star_end_pos;  // entry count after each non-empty star
   int spw = 1;
@@ -369,6 +375,7 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
   if (o.table_precision != 0 && o.table_precision != 1) return fail("table_precision must be 0 (fp64) or 1 (fp32)");
   h->table_bytes = o.table_precision == 1 ? 4 : 8;
   if (const char* nf = getenv("MB_NO_FUSE")) h->no_fuse = atoi(nf);
+  if (const char* nf = getenv("MB_NO_FLAG")) h->use_flag = !atoi(nf);
   CK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, o.device));
   CK(cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, o.device));
   h->max_smem -= 1024;  // room for the kernels' few bytes of static shared memory
@@ -1007,7 +1014,8 @@ static int k2_blocks_per_sm(int kmode, int NW, size_t smem, int table_bytes, int
 // h_phi (optional): host copy of phi, carried in K2's kernel parameters when the tables are built
 // inside K2 and it is small enough; d_phi must then still be readable by the device (mapped memory)
 static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const double* const d_tab[MB_NPARAM],
-                       double* d_out, cudaStream_t st, const double* h_phi = nullptr) {
+                       double* d_out, cudaStream_t st, const double* h_phi = nullptr,
+                       unsigned long long* d_flag = nullptr, unsigned long long flag_seq = 0) {
   if (W <= 0) return 0;
   if (ndim != h->ndim) return fail("phi has %d columns, the model has %d free variables", ndim, h->ndim);
   CK(cudaSetDevice(h->device));
@@ -1139,6 +1147,7 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     k2.pois.n_stars = (double)h->S_total; k2.pois.nbins = h->poisson ? h->nbins : 0;
     k2.pois.nslice = poisson_nslice(k2_threads(NW), h->nbins);
     k2.pois.SC = elementwise ? h->d_SC : nullptr;
+    if (d_flag && w0 + wp >= W) { k2.done_flag = d_flag; k2.done_seq = flag_seq; }  // the last pass publishes
     k2.build_tables = fused ? 1 : 0;
     if (fused) {
       k2.model = h->mdev; k2.clsx = h->d_clsx; k2.ndim = ndim; k2.ncls_total = h->ncls_total;
@@ -1215,9 +1224,13 @@ extern "C" int mb_lnlike_begin(mb_handle* h, const double* phi, int32_t W, int32
     CK(cudaStreamSynchronize(h->stream));
     if (h->h_pin) CK(cudaFreeHost(h->h_pin));
     h->h_pin = nullptr; h->cap_pin = 0;
-    CK(cudaHostAlloc((void**)&h->h_pin, sizeof(double) * (size_t)(nphi + nout), cudaHostAllocMapped));
+    // (+ one 8-byte slot at the end: the completion flag)
+    CK(cudaHostAlloc((void**)&h->h_pin, sizeof(double) * (size_t)(nphi + nout + 1), cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer((void**)&h->d_pin, h->h_pin, 0));
     h->cap_pin = nphi + nout;
+    h->h_flag = reinterpret_cast<volatile unsigned long long*>(h->h_pin + h->cap_pin);
+    h->d_flag = reinterpret_cast<unsigned long long*>(h->d_pin + h->cap_pin);
+    *h->h_flag = 0ull;
   }
   double* hp = h->h_pin;
   double* ho = h->h_pin + nphi;
@@ -1233,7 +1246,11 @@ extern "C" int mb_lnlike_begin(mb_handle* h, const double* phi, int32_t W, int32
   }
   bool any_tab = false;
   for (int p = 0; p < MB_NPARAM; ++p) any_tab |= dtab[p] != nullptr;
-  if (eval_device(h, h->d_pin, W, ndim, any_tab ? dtab : nullptr, h->d_pin + nphi, h->stream, hp)) return 1;
+  const bool flag = h->use_flag && !h->profiling && h->h_flag;
+  const unsigned long long seq = flag ? ++h->flag_seq : 0ull;
+  if (eval_device(h, h->d_pin, W, ndim, any_tab ? dtab : nullptr, h->d_pin + nphi, h->stream, hp,
+                  flag ? h->d_flag : nullptr, seq)) return 1;
+  if (!flag) h->flag_seq = 0;  // mb_lnlike_end synchronizes the stream
   h->pending_W = W;
   h->pending_out = ho;
   return 0;
@@ -1245,7 +1262,23 @@ extern "C" int mb_lnlike_end(mb_handle* h, double* rows) {
   CK(cudaSetDevice(h->device));
   const int W = h->pending_W;
   h->pending_W = 0;
-  CK(cudaStreamSynchronize(h->stream));
+  bool seen = false;
+  if (h->flag_seq && h->h_flag) {
+    // poll the flag the kernel raises after its rows; look at the stream now and then so that a
+    // failed launch or a fault cannot leave us spinning
+    const unsigned long long want = h->flag_seq;
+    for (unsigned spins = 0;; ++spins) {
+      if (*h->h_flag == want) { seen = true; break; }
+      if ((spins & 0x3fffu) == 0x3fffu) {
+        cudaError_t q = cudaStreamQuery(h->stream);
+        if (q != cudaErrorNotReady) {  // finished (flag will be there) or failed
+          if (q != cudaSuccess) return fail("likelihood kernels failed: %s", cudaGetErrorString(q));
+          break;
+        }
+      }
+    }
+  }
+  if (!seen) CK(cudaStreamSynchronize(h->stream));
   memcpy(rows, h->pending_out, sizeof(double) * (size_t)MB_OUT_ROWS * W);
   return 0;
 }
@@ -1336,9 +1369,12 @@ extern "C" int mb_lnlike_pixels(mb_handle* h, const double* phi, int32_t W, int3
   if (nphi + nout > h->cap_pin) {
     if (h->h_pin) CK(cudaFreeHost(h->h_pin));
     h->h_pin = nullptr; h->cap_pin = 0;
-    CK(cudaHostAlloc((void**)&h->h_pin, sizeof(double) * (size_t)(nphi + nout), cudaHostAllocMapped));
+    CK(cudaHostAlloc((void**)&h->h_pin, sizeof(double) * (size_t)(nphi + nout + 1), cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer((void**)&h->d_pin, h->h_pin, 0));
     h->cap_pin = nphi + nout;
+    h->h_flag = reinterpret_cast<volatile unsigned long long*>(h->h_pin + h->cap_pin);  // (slot kept for mb_lnlike_begin)
+    h->d_flag = reinterpret_cast<unsigned long long*>(h->d_pin + h->cap_pin);
+    *h->h_flag = 0ull;
   }
   double* hp = h->h_pin;
   double* ho = h->h_pin + nphi;

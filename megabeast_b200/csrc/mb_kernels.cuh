@@ -719,6 +719,8 @@ struct K2Args {
   // FACTOR mode, fp64 tables, analytic models: every block builds the factor tables itself in its
   // prologue (K0 fused into K2: no separate launch, no dependent-kernel gap); phi comes with the
   // kernel parameters when it is small enough, else from `phi` (device or mapped host memory)
+  volatile unsigned long long* done_flag;  // optional (mapped host memory): set to done_seq after the rows
+  unsigned long long done_seq;
   int32_t build_tables, phi_inline, ndim, ncls_total;
   const double* clsx;        // class values [ncls_total]
   const uint16_t* rowlut;    // [nB][4] look-up rows (class offsets included) of a dust class's Av, Rv, fA
@@ -1274,6 +1276,13 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     const unsigned long long nbad = tot[Wpad + w], nnan = tot[2 * Wpad + w];
     a.out[(size_t)MB_OUT_STARSUM * a.Wtot + a.w0 + w] = (nnan || timed_out) ? nan("") : (double)f / kFixScale;
     a.out[(size_t)MB_OUT_NONFINITE * a.Wtot + a.w0 + w] = timed_out ? -1.0 : (double)nbad;
+  }
+  if (a.done_flag) {
+    // host path: the result rows live in mapped host memory; publish "rows complete" there so the
+    // host can pick them up without waiting for the stream's completion machinery
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) *a.done_flag = a.done_seq;
   }
   stamp(a.timeline, 5);
 }
