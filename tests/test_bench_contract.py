@@ -1,0 +1,42 @@
+"""
+bench.py's driver contract, checked without a GPU on the reference arm: exactly ONE line on
+stdout, valid JSON, the keys the driver reads.  (The GPU arm prints the same keys plus the
+device-side ones; profiles/r1_bench_cfg3_n1.json is such a line.)
+"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_reference_arm_prints_one_json_line():
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                          "--workload", "tiny", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, res.stdout
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference"
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["value"] > 0 and line["unit"] == "evals/s" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_committed_gpu_bench_line_has_the_contract_keys():
+    with open(os.path.join(ROOT, "profiles", "r1_bench_cfg3_n1.json")) as f:
+        line = json.loads(f.read().strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches",
+                "roofline", "cpu_baseline"):
+        assert key in line, key
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"])
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(line["cpu_baseline"])
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(line["e2e"])
+    assert line["gpu_launches"] == line["steps"]          # one launch per step
+    assert "workload" in line["config"]
