@@ -8,21 +8,27 @@ bench.py -- ensemble lnprob evaluations per second on BASELINE.json's headline w
 
 A "step" is one pass of the hot path over one batch of W = 64 walkers (one emcee proposal
 round).  N > 1 is launched by torchrun, one rank per GPU: the 100,000 stars are sharded over
-the ranks (grid replicated), one NCCL all-reduce of 2*W doubles per step -> "strong" scaling of
-the fixed-size job BASELINE.json names.  Rank 0 prints ONE JSON line.
+the ranks (grid replicated), the shard totals are added inside the likelihood kernel over NVLink
+peer memory (or by one NCCL all-reduce of 2*W doubles) -> "strong" scaling of the fixed-size job
+BASELINE.json names.  Rank 0 prints ONE JSON line.
 
 Keys beyond the base contract:
-  value        device-timed (CUDA events on the launching stream), phi resident in HBM
+  value        device-timed (CUDA events on the launching stream), phi resident in HBM; at N > 1 the
+               ranks are aligned by a device-side rendezvous (a tiny NCCL all-reduce enqueued after the
+               L2 flush, outside the timed events) so that the flush's skew is not billed to the step
   e2e          the same metric through the public API with HOST buffers: lnprob(phis, model,
-               star_lnpgriddata, beast_moddata) -- prior box on the host, pinned H2D of phi,
-               kernels, (all-reduce,) D2H of the result rows, exceptions checked
+               star_lnpgriddata, beast_moddata) -- prior box on the host, phi to the device,
+               kernels, (shard reduction,) result rows back, exceptions checked
   roofline     dominant kernel: algorithmic bytes per launch / its CUDA-event duration vs the
                measured HBM copy bandwidth (MEASURED_PEAKS.json).  See DESIGN.md section 5 for why
                the factor-mode hot kernel is bounded by shared-memory bandwidth instead, and
                `onchip` for that ceiling.
-  cpu_baseline the oracle's numpy port (the reference's algorithm, one core) on a bounded
-               sample of the same workload, timed on this box; its values double as a full-size
-               parity check of the GPU path (`parity`).
+  sustained    >= 2 s of back-to-back launches (L2 warm), clocks and power sampled under load
+  cpu_baseline the oracle's numpy port (the reference's algorithm) on a bounded sample of the same
+               workload, timed on this box's host cores; its values double as a full-size parity check
+               of the GPU path (`parity`, >= 8 walkers; at N > 1 against the C oracle, plus p2p == nccl)
+  secondary    (N = 8) BASELINE config 4 -- 1,000,000 stars x 50 points, 2,000,800-row grid, 128 walkers --
+               sharded over the same ranks: device-timed, end to end, parity
 """
 import argparse
 import json
@@ -49,13 +55,17 @@ def parse_args():
     ap.add_argument("--workload", default="cfg3")
     ap.add_argument("--index-mode", default="uniform", choices=["uniform", "clustered"])
     ap.add_argument("--mode", default="auto", choices=["auto", "factor", "table_unique", "table_grid", "elementwise"])
+    ap.add_argument("--split-inner", default="", help="FACTOR mode: dust parameters of the inner table, e.g. Av or Av,Rv")
     ap.add_argument("--walkers", type=int, default=0, help="override the config's walker count")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample", type=int, default=4, help="walkers the CPU baseline evaluates")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="walkers the CPU baseline / parity check evaluates")
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps (not the headline)")
     ap.add_argument("--all-modes", action="store_true", help="also time the other engine modes")
     ap.add_argument("--no-clustered", action="store_true",
                     help="skip the extra measurement with clustered (BEAST-like) sparse indices")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the 2 s back-to-back block")
+    ap.add_argument("--secondary", default="auto", choices=["auto", "cfg4", "none"],
+                    help="N > 1: also measure BASELINE config 4 sharded over the ranks (auto: at N = 8)")
     ap.add_argument("--table-precision", default="fp64", choices=["fp64", "fp32"],
                     help="fp32: 32-bit factor tables on chip, stated tolerance 1e-7 (not the headline)")
     ap.add_argument("--reduce", default="auto", choices=["auto", "p2p", "nccl"],
@@ -83,6 +93,13 @@ def metric_name(args, cfg, G, W):
     if args.workload == "cfg3" and W == 64:
         return METRIC
     return f"ensemble lnprob evals/sec ({cfg['S']} stars x {G} grid, {W} walkers)"
+
+
+def workload_config(args, cfg, G, W):
+    """The `config` object -- byte-identical in both arms (the driver compares them)."""
+    return {"workload": f"{args.workload}: {cfg['S']} stars x {cfg['K']} sparse points, {G}-row grid, "
+                        f"{W} walkers, docs-example model",
+            "index_mode": args.index_mode}
 
 
 def make_workload(args):
@@ -113,8 +130,6 @@ def run_reference(args):
         return  # the CPU arm is a one-process job; the other ranks have nothing to do
     import multiprocessing as mp
 
-    import numpy as np
-
     from megabeast_b200 import synth
     from oracle import lnprob_port as port
 
@@ -142,20 +157,18 @@ def run_reference(args):
             pool.map(_ref_eval, sel)
         dt = time.perf_counter() - t0
     value = per_step * steps / dt
+    G = len(moddata["Av"])
     sample = (f"each step = {per_step} of {W} walkers x all {cfg['S']} stars, one walker per core; "
               f"{steps} of the requested {args.steps} steps run to stay inside {budget_s:.0f} s")
     line = {
         "impl": "reference",
-        "metric": metric_name(args, cfg, len(moddata["Av"]), W), "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "metric": metric_name(args, cfg, G, W), "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm + 1, "ms_per_step": 1e3 * dt / steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {cfg['S']} stars x {cfg['K']} sparse points, "
-                               f"{len(moddata['Av'])}-row grid, {W} walkers, docs-example model",
-                   "index_mode": args.index_mode,
-                   "what": "oracle/lnprob_port.py loop=True: numpy restatement of the reference's "
-                           "lnprob (per-star Python loop, per-bin grid masks), walker-parallel "
-                           "over the host cores with multiprocessing"},
+        "config": workload_config(args, cfg, G, W),
+        "what": "oracle/lnprob_port.py loop=True: numpy restatement of the reference's lnprob (per-star "
+                "Python loop, per-bin grid masks), walker-parallel over the host cores with multiprocessing",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": per_step, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -167,12 +180,12 @@ def run_reference(args):
 # our arm
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+    """Samples SM clock / throttle reasons / power of one GPU through NVML while a tagged phase runs."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag, self.err = index, [], False, None
-        self.active = False
+        self.phase = None
 
     def run(self):
         try:
@@ -182,19 +195,21 @@ class ClockSampler(threading.Thread):
             h = nv.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
             while not self.stop_flag:
-                if self.active:
+                phase = self.phase
+                if phase is not None:
                     try:
                         reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                     except Exception:
                         reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                     self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), reasons,
-                                         nv.nvmlDeviceGetPowerUsage(h) / 1e3))
+                                         nv.nvmlDeviceGetPowerUsage(h) / 1e3, phase))
                 time.sleep(0.004)
         except Exception as exc:  # NVML missing: report, do not fail the bench
             self.err = repr(exc)
 
-    def summary(self):
-        if self.err or not self.samples:
+    def summary(self, phase=None):
+        sel = [s for s in self.samples if phase is None or s[3] == phase]
+        if self.err or not sel:
             return {"sm_mhz": None, "sm_max_mhz": getattr(self, "max_mhz", None), "reasons": [],
                     "note": self.err or "no samples"}
         import statistics
@@ -203,12 +218,43 @@ class ClockSampler(threading.Thread):
                  0x8: "hw_slowdown", 0x10: "sync_boost", 0x20: "sw_thermal_slowdown",
                  0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
         seen = 0
-        for _, r, _ in self.samples:
+        for _, r, _, _ in sel:
             seen |= r
         reasons = [n for b, n in names.items() if seen & b and n != "gpu_idle"]
-        return {"sm_mhz": statistics.median(s[0] for s in self.samples), "sm_max_mhz": self.max_mhz,
-                "reasons": reasons, "samples": len(self.samples),
-                "power_w_max": max(s[2] for s in self.samples)}
+        return {"sm_mhz": statistics.median(s[0] for s in sel), "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(sel),
+                "power_w_max": max(s[2] for s in sel), "power_w_median": statistics.median(s[2] for s in sel)}
+
+
+_CPU = {}
+
+
+def _cpu_eval(phi):
+    from oracle import lnprob_port as port
+
+    return port.lnprob(phi, _CPU["pm"], _CPU["stars"], _CPU["mod"], loop=True)
+
+
+def cpu_baseline_and_values(settings, moddata, stars, phis, n):
+    """The numpy port (reference algorithm, per-star Python loop) on n walkers, one per host core."""
+    import copy
+    import multiprocessing as mp
+
+    import numpy as np
+
+    from oracle import lnprob_port as port
+
+    pm = port.PortModel(copy.deepcopy(settings))
+    pm.massmultipliers = port.mass_multipliers(moddata, pm.physics_model["M_ini"])
+    _CPU.update(pm=pm, stars=stars, mod=moddata)
+    procs = max(1, min(host_cores(), n))
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        pool.map(_cpu_eval, [phis[0]] * procs)  # warm-up call in every worker
+        t0 = time.perf_counter()
+        vals = np.array(pool.map(_cpu_eval, list(phis[:n]), chunksize=1))
+        dt = time.perf_counter() - t0
+    return vals, dt, procs
 
 
 def run_ours(args):
@@ -224,6 +270,16 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    split = tuple(p for p in args.split_inner.split(",") if p) or None
+    settings, moddata, stars, cfg, W = make_workload(args)
+    model = MB_Model(copy.deepcopy(settings), devices=[local], mode=args.mode,
+                     table_precision=args.table_precision, split_inner=split)
+    phis = synth.make_walkers(model, W, seed=3)
+    # CPU baseline first: its worker processes are forked before this process holds a CUDA context
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        n_cpu = max(1, min(args.cpu_sample, W))
+        cpu = cpu_baseline_and_values(settings, moddata, stars, phis, n_cpu)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; megabeast_b200 has no CPU fallback")
     torch.cuda.set_device(local)
@@ -237,6 +293,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    tick = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def align_ranks():
+        """Device-side rendezvous on the current stream (asynchronous for the host): every rank's
+        next kernel starts when the slowest rank arrives.  Outside the timed events."""
+        if world > 1:
+            dist.all_reduce(tick)
+
     def max_over_ranks(x):
         if world == 1:
             return x
@@ -244,10 +308,6 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    settings, moddata, stars, cfg, W = make_workload(args)
-    model = MB_Model(copy.deepcopy(settings), devices=[local], mode=args.mode,
-                     table_precision=args.table_precision)
-    phis = synth.make_walkers(model, W, seed=3)
     t0 = time.perf_counter()
     sharded = ShardedLikelihood(model, stars, moddata, device=local, mode=args.mode, reduce=args.reduce)
     t_ingest = time.perf_counter() - t0
@@ -262,25 +322,44 @@ def run_ours(args):
         if not args.no_flush:
             flush.zero_()
 
+    def time_device(sh, rows, nsteps, nwarm):
+        for _ in range(nwarm):
+            flush_l2()
+            align_ranks()
+            sh.lnlike_device(d_phi, rows)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
+        barrier()
+        t_w = time.perf_counter()
+        for i in range(nsteps):
+            flush_l2()
+            align_ranks()
+            evs[i][0].record()
+            sh.lnlike_device(d_phi, rows)
+            evs[i][1].record()
+        barrier()
+        t_w = time.perf_counter() - t_w
+        return max_over_ranks(sum(a.elapsed_time(b) for a, b in evs)), t_w
+
+    def time_e2e(call, nsteps, nwarm):
+        for _ in range(nwarm):
+            flush_l2()
+            out = call()
+        barrier()
+        tot = 0.0
+        for i in range(nsteps):
+            flush_l2()
+            barrier()  # N > 1: a sampler's ranks leave step n together; the flush must not de-align them
+            t0 = time.perf_counter()
+            out = call()
+            tot += time.perf_counter() - t0
+        barrier()
+        return max_over_ranks(tot), out
+
     # ---- device-timed value ------------------------------------------------------------------------
-    for _ in range(max(3, args.warmup)):
-        flush_l2()
-        sharded.lnlike_device(d_phi, d_rows)
     sampler = ClockSampler(local)
     sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    barrier()
-    sampler.active = True
-    t_wall = time.perf_counter()
-    for i in range(K):
-        flush_l2()
-        ev[i][0].record()
-        sharded.lnlike_device(d_phi, d_rows)
-        ev[i][1].record()
-    barrier()
-    t_wall = time.perf_counter() - t_wall
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = max_over_ranks(sum(step_ms))
+    sampler.phase = "timed"
+    total_ms, t_wall = time_device(sharded, d_rows, K, max(3, args.warmup))
     launches = sharded.engine.info()["launches_last_eval"] * K
     rows_dev = d_rows.cpu().numpy()
     vals_dev, status_dev = combine_rows(rows_dev)
@@ -292,22 +371,30 @@ def run_ours(args):
     else:
         def e2e_call():
             return sharded.lnprob(phis)
-    for _ in range(max(3, args.warmup)):
-        flush_l2()
-        e2e_vals = e2e_call()
-    barrier()
-    e2e_s = 0.0
-    for i in range(K):
-        flush_l2()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        e2e_vals = e2e_call()
-        e2e_s += time.perf_counter() - t0
-    barrier()
-    sampler.active = False
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
-    e2e_s = max_over_ranks(e2e_s)
+    e2e_s, e2e_vals = time_e2e(e2e_call, K, max(3, args.warmup))
+    sampler.phase = None
+
+    # ---- sustained: back-to-back launches for >= 2 s, clocks and power sampled under load ---------------
+    sustained = None
+    if not args.no_sustained:
+        barrier()
+        step_s = total_ms * 1e-3 / K
+        n_sus = int(min(200000, max(200, 2.2 / max(step_s * 0.8, 1e-6))))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(20):
+            sharded.lnlike_device(d_phi, d_rows)
+        barrier()
+        sampler.phase = "sustained"
+        a.record()
+        for _ in range(n_sus):
+            sharded.lnlike_device(d_phi, d_rows)
+        b.record()
+        barrier()
+        sampler.phase = None
+        sus_ms = max_over_ranks(a.elapsed_time(b))
+        sustained = {"value": W * n_sus / (sus_ms * 1e-3), "unit": UNIT, "seconds": sus_ms * 1e-3, "steps": n_sus,
+                     "ms_per_step": sus_ms / n_sus, "l2": "warm (no flush between steps: launches back to back)",
+                     "clocks": sampler.summary("sustained")}
 
     # ---- weak scaling (N > 1): every rank holds a FULL 100k-star shard of an N x 100k-star job --------
     weak = None
@@ -316,18 +403,7 @@ def run_ours(args):
                                 device=local, mode=args.mode, reduce=args.reduce,
                                 star_range=(0, cfg["S"]), n_stars_total=world * cfg["S"])
         d_rows_w = torch.empty((3, W), dtype=torch.float64, device=dev)
-        for _ in range(max(3, args.warmup)):
-            flush_l2()
-            shw.lnlike_device(d_phi, d_rows_w)
-        evw = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        barrier()
-        for i in range(K):
-            flush_l2()
-            evw[i][0].record()
-            shw.lnlike_device(d_phi, d_rows_w)
-            evw[i][1].record()
-        barrier()
-        weak_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evw))
+        weak_ms, _ = time_device(shw, d_rows_w, K, max(3, args.warmup))
         # every rank holds the same stars: the job's star sum must be N x the single-copy one
         ratio = (d_rows_w[0] / (world * d_rows[0])).cpu().numpy()
         weak = {"stars_per_gpu": cfg["S"], "stars_total": world * cfg["S"],
@@ -340,20 +416,72 @@ def run_ours(args):
         shw.close()
 
     # ---- per-kernel times (CUDA events inside the library, same stream) ------------------------------
+    # N > 1: the ranks are aligned before every profiled launch, so a kernel's time holds its own work
+    # plus the wait for the slowest peer of THAT launch, never the skew of an earlier step
     eng = sharded.engine
     eng.set_profiling(True)
     kms = {}
     nprof = min(K, 50)
+    phases = None
     for _ in range(nprof):
         flush_l2()
+        barrier()
         sharded.lnlike_device(d_phi, d_rows)
         torch.cuda.synchronize()
         for k, v in eng.last_kernel_ms().items():
             kms[k] = kms.get(k, 0.0) + v / nprof
+        tl = eng.last_k2_timeline()
+        if len(tl):
+            ph = np.array([tl[:, 1].max(), tl[:, 2].max(), tl[:, 3].max(), tl[:, 4].max(), tl[:, 5].max()])
+            phases = ph / nprof if phases is None else phases + ph / nprof
     eng.set_profiling(False)
+    if world > 1:
+        t = torch.tensor([kms[k] for k in sorted(kms)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        kms = dict(zip(sorted(kms), [float(x) for x in t.cpu()]))
     dom = max(kms, key=kms.get)
 
+    # ---- N > 1: parity of the reduced values, and p2p == nccl bit for bit --------------------------------
+    parity = None
+    if world > 1:
+        n = max(1, min(args.cpu_sample, W))
+        other = "nccl" if sharded.reduce == "p2p" else "p2p"
+        bitwise = None
+        try:
+            sh2 = ShardedLikelihood(MB_Model(copy.deepcopy(settings), devices=[local], mode=args.mode), stars, moddata,
+                                    device=local, mode=args.mode, reduce=other)
+            rows2 = torch.empty((3, W), dtype=torch.float64, device=dev)
+            sh2.lnlike_device(d_phi, rows2)
+            torch.cuda.synchronize()
+            bitwise = bool(torch.equal(rows2[:2], d_rows[:2]))
+            sh2.close()
+        except Exception as exc:  # e.g. no peer access on this box: say so, do not fail the bench
+            bitwise = f"unavailable: {exc!r}"
+        if rank == 0:
+            from oracle import c_oracle
+            from oracle import lnprob_port as port
+
+            pm = port.PortModel(copy.deepcopy(settings))
+            t0 = time.perf_counter()
+            want = c_oracle.lnprob_batch(pm, phis[:n], stars, moddata)
+            t_or = time.perf_counter() - t0
+            rel = np.abs(vals_dev[:n] - want) / np.abs(want)
+            rel2 = np.abs(np.asarray(e2e_vals)[:n] - want) / np.abs(want)
+            parity = {"walkers_checked": n, "against": "oracle/mb_oracle.c (reference algorithm, all stars, "
+                      f"OpenMP over walkers; {t_or:.1f} s)",
+                      "max_rel_err_device_path": float(rel.max()), "max_rel_err_e2e_path": float(rel2.max()),
+                      "tolerance": 1e-9, "status_flags": int(status_dev.max()),
+                      f"{sharded.reduce}_equals_{other}_bitwise": bitwise}
+        barrier()
+
+    # ---- secondary (N = 8): BASELINE config 4, sharded over the same ranks ---------------------------------
+    secondary = None
+    want_secondary = args.secondary == "cfg4" or (args.secondary == "auto" and world == 8 and args.workload == "cfg3")
+    if world > 1 and want_secondary:
+        secondary = run_secondary_cfg4(args, world, rank, local, dev, barrier, max_over_ranks, align_ranks, flush_l2)
+
     if rank != 0:
+        sampler.stop_flag = True
         if world > 1:
             dist.destroy_process_group()
         return
@@ -363,6 +491,7 @@ def run_ours(args):
     Wpad = 32 * (1 if W <= 32 else 2 if W <= 64 else 4)
     n_ent = info["n_entries"]
     nA, nB = info["n_age_classes"], info["n_dust_classes"]
+    nO, nI = info["n_outer_rows"], info["n_inner_rows"]
     mode = info["mode"]
     by_row = mode in ("table_grid", "elementwise")  # physmod materialised over every grid row
     U = len(moddata["Av"]) if by_row else nA * nB
@@ -378,7 +507,7 @@ def run_ours(args):
         # completeness (N-stars partial sums) in, table out
         "k1_expand": (4 * U if mode == "table_grid" else (8 * nfree + 16) * U if mode == "elementwise" else 0)
                      + 8 * U * Wpad,
-        "k2_stars": (8 + info["code_bytes"]) * n_ent + 16 * info["n_bins"] * nB + (8 * (nA + nB) * Wpad if mode == "factor"
+        "k2_stars": (8 + info["code_bytes"]) * n_ent + 16 * info["n_bins"] * nB + (8 * (nO + nI) * Wpad if mode == "factor"
                                   else 8 * Wpad * (touched if touched is not None else U)),
     }
     dur_s = kms[dom] * 1e-3
@@ -397,29 +526,30 @@ def run_ours(args):
                 "traffic_source": traffic_src,
                 "note": "this kernel is bounded by the shared-memory/L1 data pipe, not HBM: see `onchip` and DESIGN.md section 5"
                         if mode == "factor" else
-                        "K1e is bound by the fp64 exp of the lognormal priors (one per parameter, row and walker), not by HBM"
+                        "K1e is bound by the fp64 exp of the lognormal priors, not by HBM"
                         if (mode == "elementwise" and dom == "k1_expand") else "HBM-bound: materialised table written / gathered"}
-    clocks = sampler.summary()
+    clocks = sampler.summary("timed")
+    sampler.stop_flag = True
     sm_mhz = clocks.get("sm_mhz") or 0
     onchip = None
     if mode == "factor" and sm_mhz:
         # shared-memory wavefronts K2 must issue (measured in lds_mix.cu): per
-        # entry 2*NW for the Wpad*8-byte factor row + 1.5 for the broadcast of weight and code
+        # entry 2*NW for the Wpad*8-byte inner-factor row + 1.5 (1.25 with 16-bit codes) for the broadcast
+        # of weight and code, per run 2*NW for the outer-factor row
         nw = Wpad // 32
         bcast = 1.5 if info["code_bytes"] == 4 else 1.25  # four codes: one 16-byte or one 8-byte broadcast
-        wavefronts = n_ent * (2.0 * nw + bcast)
+        wavefronts = n_ent * (2.0 * nw + bcast) + info["n_runs"] * 2.0 * nw
         peak_wf = info["sm_count"] * sm_mhz * 1e6 / 1e9
         ach = wavefronts / (kms["k2_stars"] * 1e-3) / 1e9
         onchip = {"bound": "smem", "wavefronts_per_launch": wavefronts, "achieved": ach, "peak": peak_wf,
                   "unit": "Gwavefront/s", "frac": ach / peak_wf,
-                  "note": f"model count ({2 * nw} factor + {bcast} broadcast wavefronts per entry); peak = 1 "
-                          f"wavefront/clk/SM x {info['sm_count']} SMs x {sm_mhz:.0f} MHz; ncu's measured "
-                          "l1tex data-pipe utilisation for the same kernel is in profiles/"}
+                  "note": f"model count ({2 * nw} inner-factor + {bcast} broadcast wavefronts per entry, {2 * nw} "
+                          f"outer-factor wavefronts per run); peak = 1 wavefront/clk/SM x {info['sm_count']} SMs x "
+                          f"{sm_mhz:.0f} MHz; ncu's measured l1tex data-pipe utilisation for the same kernel is in profiles/"}
     # the north_star's own yardstick: the materialised-physmod design's compulsory bytes per step
     G = len(moddata["Av"])
-    P = sum(1 for p in ("logA", "Av", "Rv", "fA") if sharded.spec.kinds[p] != "fixed")
     raw = info["n_entries_raw"]
-    survey_bytes = G * (8 * P + 18) + 8 * G * W + 12 * raw + 8 * W * min(G, raw) + 8 * W
+    survey_bytes = G * (8 * nfree + 18) + 8 * G * W + 12 * raw + 8 * W * min(G, raw) + 8 * W
     step_s = total_ms * 1e-3 / K
     survey = {"bytes_per_step": survey_bytes, "achieved": survey_bytes / step_s / 1e9, "peak": peak,
               "frac": survey_bytes / step_s / 1e9 / peak, "unit": "GB/s",
@@ -434,16 +564,18 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64" if args.table_precision == "fp64" else "f64 sums, 32-bit (21 significant bits) factor tables",
         "data": "synthetic",
-        "config": {
-            "workload": f"{args.workload}: {cfg['S']} stars x {cfg['K']} sparse points, {G}-row grid, "
-                        f"{W} walkers, docs-example model (9 parameters)",
-            "index_mode": args.index_mode, "engine_mode": mode,
+        "config": workload_config(args, cfg, G, W),
+        "engine": {
+            "engine_mode": mode, "n_free_parameters": ndim,
             "sharding": f"stars split over {world} rank(s), grid replicated; shard reduction: "
                         + {"none": "none (1 GPU)", "nccl": f"one NCCL all-reduce of {2 * W} doubles per step",
                            "p2p": "fused into K2's tail over NVLink peer memory (no collective launch)"}[sharded.reduce],
             "l2": "kept warm" if args.no_flush else f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB memset, outside the timed events)",
-            "entries": n_ent, "entries_raw": raw, "age_classes": nA, "dust_classes": nB,
-            "bins": info["n_bins"], "ingest_s": round(t_ingest, 3),
+            "rank_alignment": "none (1 GPU)" if world == 1 else
+                              "device-side rendezvous (4-byte NCCL all-reduce) enqueued after the flush, before the start event",
+            "entries": n_ent, "entries_raw": raw, "runs": info["n_runs"], "age_classes": nA, "dust_classes": nB,
+            "outer_rows": nO, "inner_rows": nI, "split_inner_mask": info["split_inner_mask"],
+            "code_bytes": info["code_bytes"], "bins": info["n_bins"], "ingest_s": round(t_ingest, 3),
         },
         "clocks": clocks,
         "e2e": {"value": W * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * W * ndim,
@@ -457,27 +589,33 @@ def run_ours(args):
         "north_star_equivalent": survey,
         "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,
     }
+    if phases is not None:
+        line["k2_phases_us"] = dict(zip(("tables_built", "nstars_bins_done", "star_loop_done", "block_reduced", "end"),
+                                        [round(float(x), 2) for x in phases]))
+        line["k2_phases_us"]["note"] = ("%globaltimer stamps inside K2, microseconds since its first block started, "
+                                        "max over blocks, mean over the profiled launches (rank 0)")
+    if sustained is not None:
+        line["sustained"] = sustained
     if weak is not None:
         line["weak_scaling"] = weak
+    if parity is not None:
+        line["parity"] = parity
+    if secondary is not None:
+        line["secondary"] = secondary
 
     # ---- CPU baseline + full-size parity ----------------------------------------------------------------
-    if world == 1 and not args.no_cpu_baseline:
-        from oracle import lnprob_port as port
-
-        pm = port.PortModel(copy.deepcopy(settings))
-        pm.massmultipliers = port.mass_multipliers(moddata, pm.physics_model["M_ini"])
-        n = max(1, min(args.cpu_sample, W))
-        port.lnprob(phis[0], pm, stars, moddata, loop=True)  # warm-up call
-        t0 = time.perf_counter()
-        cpu_vals = np.array([port.lnprob(p, pm, stars, moddata, loop=True) for p in phis[:n]])
-        dt = time.perf_counter() - t0
+    if cpu is not None:
+        n = n_cpu
+        cpu_vals, dt, procs = cpu
         line["cpu_baseline"] = {
-            "value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{n} of {W} walkers x all {cfg['S']} stars; oracle/lnprob_port.py loop=True "
-                      f"(numpy restatement of the reference's lnprob, per-star Python loop); {dt:.1f} s"}
+            "value": n / dt, "unit": UNIT, "cores": procs, "kind": "port",
+            "sample": f"{n} of {W} walkers x all {cfg['S']} stars, one walker per process on {procs} host cores; "
+                      f"oracle/lnprob_port.py loop=True (numpy restatement of the reference's lnprob, per-star "
+                      f"Python loop); {dt:.1f} s"}
         rel = np.abs(vals_dev[:n] - cpu_vals) / np.abs(cpu_vals)
         rel2 = np.abs(np.asarray(e2e_vals)[:n] - cpu_vals) / np.abs(cpu_vals)
-        line["parity"] = {"walkers_checked": n, "max_rel_err_device_path": float(rel.max()),
+        line["parity"] = {"walkers_checked": n, "against": "oracle/lnprob_port.py loop=True (numpy port of the reference)",
+                          "max_rel_err_device_path": float(rel.max()),
                           "max_rel_err_e2e_path": float(rel2.max()), "tolerance": 1e-9,
                           "status_flags": int(status_dev.max())}
     if world == 1 and args.index_mode == "uniform" and not args.no_clustered:
@@ -486,7 +624,8 @@ def run_ours(args):
         # kernels, with the top-K points clustered in grid-axis space
         t0 = time.perf_counter()
         _, mod_c, stars_c, _ = synth.make_problem(args.workload, mode="clustered")
-        mdl = MB_Model(copy.deepcopy(settings), devices=[local], mode=args.mode, table_precision=args.table_precision)
+        mdl = MB_Model(copy.deepcopy(settings), devices=[local], mode=args.mode, table_precision=args.table_precision,
+                       split_inner=split)
         shc = ShardedLikelihood(mdl, stars_c, mod_c, device=local, mode=args.mode)
         t_setup = time.perf_counter() - t0
         for _ in range(5):
@@ -513,7 +652,8 @@ def run_ours(args):
         ci = shc.engine.info()
         line["clustered_indices"] = {
             "value": W * nrep / (tot * 1e-3), "unit": UNIT, "ms_per_step": tot / nrep,
-            "e2e_value": W * nrep / e2e_c, "entries": ci["n_entries"], "entries_raw": ci["n_entries_raw"], "setup_s": round(t_setup, 1),
+            "e2e_value": W * nrep / e2e_c, "entries": ci["n_entries"], "entries_raw": ci["n_entries_raw"],
+            "runs": ci["n_runs"], "setup_s": round(t_setup, 1),
             "note": "same workload with each star's sparse points clustered around a centre in grid-axis "
                     "space (BEAST-like): duplicates of a star's class codes merge, fewer entries to stream"}
         shc.close()
@@ -549,6 +689,116 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_secondary_cfg4(args, world, rank, local, dev, barrier, max_over_ranks, align_ranks, flush_l2):
+    """BASELINE config 4 (PHAT scale: 1,000,000 stars x 50 points, 2,000,800-row grid, 128 walkers), star-sharded
+    over the ranks.  Every rank synthesises only ITS shard of stars (seed = 2 + 1000 * rank; the grid, seed 1,
+    is replicated), so the job is the concatenation of the shards.  Parity: every rank runs the C oracle on its
+    own shard (sum of ln L over its stars), the shard sums are added, rank 0 adds the N-stars term of the numpy port."""
+    import copy
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from megabeast_b200 import MB_Model, synth
+    from megabeast_b200.engine import shard_bounds
+    from megabeast_b200.parallel import ShardedLikelihood, combine_rows
+    from oracle import c_oracle
+    from oracle import lnprob_port as port
+
+    c4 = synth.CONFIGS["cfg4"]
+    S, K4, W4 = c4["S"], c4["K"], c4["W"]
+    t0 = time.perf_counter()
+    moddata = synth.make_grid(c4["axes"], seed=1)
+    lo, hi = shard_bounds(S, world, rank)
+    stars = synth.make_star_data(moddata, c4["axes"], hi - lo, K4, mode=args.index_mode, seed=2 + 1000 * rank)
+    settings = synth.docs_example_settings()
+    model = MB_Model(copy.deepcopy(settings), devices=[local], mode=args.mode)
+    phis = synth.make_walkers(model, W4, seed=3)
+    t_synth = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    sh = ShardedLikelihood(model, stars, moddata, device=local, mode=args.mode, reduce=args.reduce,
+                           star_range=(0, hi - lo), n_stars_total=S)
+    t_ingest = time.perf_counter() - t0
+    d_phi = torch.from_numpy(np.ascontiguousarray(phis[:, sh.perm])).to(dev)
+    d_rows = torch.empty((3, W4), dtype=torch.float64, device=dev)
+    nsteps, nwarm = max(10, min(args.steps, 50)), 5
+    for _ in range(nwarm):
+        flush_l2()
+        align_ranks()
+        sh.lnlike_device(d_phi, d_rows)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
+    barrier()
+    for i in range(nsteps):
+        flush_l2()
+        align_ranks()
+        evs[i][0].record()
+        sh.lnlike_device(d_phi, d_rows)
+        evs[i][1].record()
+    barrier()
+    dev_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
+    vals_dev, status_dev = combine_rows(d_rows.cpu().numpy())
+    for _ in range(nwarm):
+        flush_l2()
+        vals_e2e = sh.lnprob(phis)
+    e2e = 0.0
+    for _ in range(nsteps):
+        flush_l2()
+        barrier()
+        t0 = time.perf_counter()
+        vals_e2e = sh.lnprob(phis)
+        e2e += time.perf_counter() - t0
+    barrier()
+    e2e = max_over_ranks(e2e)
+    info = sh.engine.info()
+    # parity on n walkers: shard star sums from the C oracle (no N-stars term), added over the ranks
+    n = max(4, min(args.cpu_sample, W4))
+    pm = port.PortModel(copy.deepcopy(settings))
+    pm.compute_N_stars = False
+    t0 = time.perf_counter()
+    part, st = c_oracle.lnlike_batch(pm, phis[:n], stars, moddata)
+    t_or = time.perf_counter() - t0
+    t = torch.from_numpy(np.ascontiguousarray(part)).to(dev)
+    dist.all_reduce(t)
+    starsum = t.cpu().numpy()
+    out = None
+    if rank == 0:
+        from scipy.special import gammaln
+
+        pm2 = port.PortModel(copy.deepcopy(settings))
+        mm = port.mass_multipliers(moddata, pm2.physics_model["M_ini"])
+        want = np.empty(n)
+        for i in range(n):
+            physmod, mods = pm2.physmod(phis[i], moddata)
+            pred = port.predicted_num_stars(mm, moddata, physmod, mods["logA"], loop=False)
+            want[i] = S * np.log(pred) - pred - gammaln(S + 1) + starsum[i]
+        rel = np.abs(vals_dev[:n] - want) / np.abs(want)
+        rel2 = np.abs(np.asarray(vals_e2e)[:n] - want) / np.abs(want)
+        out = {
+            "workload": f"cfg4: {S} stars x {K4} sparse points, {len(moddata['Av'])}-row grid, {W4} walkers, "
+                        f"docs-example model; stars sharded over {world} ranks ({hi - lo} on rank 0), grid replicated",
+            "index_mode": args.index_mode,
+            "metric": f"ensemble lnprob evals/sec ({S} stars x {len(moddata['Av'])} grid, {W4} walkers)",
+            "value": W4 * nsteps / (dev_ms * 1e-3), "unit": UNIT, "ms_per_step": dev_ms / nsteps, "steps": nsteps,
+            "scaling": "strong",
+            "e2e": {"value": W4 * nsteps / e2e, "unit": UNIT, "ms_per_step": 1e3 * e2e / nsteps,
+                    "h2d_bytes_per_step": 8 * W4 * sh.ndim, "d2h_bytes_per_step": 8 * 3 * W4},
+            "engine": {"engine_mode": info["mode"], "reduce": sh.reduce, "entries_rank0": info["n_entries"],
+                       "dust_classes": info["n_dust_classes"], "walkers_per_pass": info["walkers_per_pass"],
+                       "launches_per_step": info["launches_last_eval"], "synth_s": round(t_synth, 1),
+                       "ingest_s": round(t_ingest, 2)},
+            "parity": {"walkers_checked": n, "max_rel_err_device_path": float(rel.max()),
+                       "max_rel_err_e2e_path": float(rel2.max()), "tolerance": 1e-9,
+                       "status_flags": int(status_dev.max()),
+                       "against": "oracle/mb_oracle.c on every rank's own shard (sum of ln L), added over the ranks, plus "
+                                  f"the numpy port's N-stars term on rank 0 ({t_or:.1f} s per rank)"},
+            "n1_reference": "profiles/r2_bench_cfg4_n1.json (same job on 1 GPU, builder-run)",
+        }
+    sh.close()
+    barrier()
+    return out
 
 
 def main():

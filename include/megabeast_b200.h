@@ -101,7 +101,11 @@ typedef struct {
 enum mb_mode {
   MB_MODE_AUTO = 0,        /* FACTOR when the factor tables fit shared memory, else TABLE_UNIQUE; ELEMENTWISE for
                               grids whose columns cannot be class-coded (> 4096 distinct values) */
-  MB_MODE_FACTOR = 1,      /* per-(star,point) class codes + per-walker factor tables in smem */
+  MB_MODE_FACTOR = 1,      /* per-(star,point) class codes + per-walker factor tables in smem: an OUTER table (age
+                              classes, times the dust parameters that do not fit inside) read once per run of a
+                              star's entries and an INNER table (the other dust parameters) read once per entry.
+                              The split is chosen at mb_create: all dust parameters inside when that fits (the
+                              classic age | dust split), else e.g. A(V) inside, age x R(V) outside */
   MB_MODE_TABLE_UNIQUE = 2,/* physmod materialised over the distinct parameter combinations */
   MB_MODE_TABLE_GRID = 3,  /* physmod[G][W] materialised over every grid row, gathered by index */
   MB_MODE_ELEMENTWISE = 4  /* physmod[G][W] by evaluating the prior models ELEMENTWISE over the grid's physics
@@ -121,7 +125,10 @@ typedef struct {
                               tables in shared memory (the high word of each fp64 factor, rounded to 21
                               significant bits; all sums still fp64): half the shared-memory traffic, ~8 %
                               faster, measured error 7e-9 relative on lnlike, stated tolerance 1e-7 */
-  int32_t reserved[9];
+  int32_t split_inner_mask;/* FACTOR mode: 0 = choose the table split automatically; else the dust parameters kept in
+                              the INNER table as a bit mask (1 = Av, 2 = Rv, 4 = fA), the others go to the outer
+                              table with the age classes.  For tests and measurements. */
+  int32_t reserved[8];
 } mb_options;
 
 typedef struct {
@@ -143,8 +150,12 @@ typedef struct {
   int64_t n_entries;       /* finite (star, point) entries held on the device */
   int64_t n_entries_raw;   /* before merging duplicates */
   int64_t device_bytes;
-  int64_t code_bytes;      /* bytes of an entry's code word on the device: 4, or 2 (FACTOR mode, <= 16 age classes) */
-  int64_t reserved[7];
+  int64_t code_bytes;      /* bytes of an entry's code word on the device: 4, or 2 (FACTOR mode, few enough classes) */
+  int64_t n_outer_rows;    /* FACTOR: rows of the outer factor table (age classes x outer dust combinations) */
+  int64_t n_inner_rows;    /* FACTOR: rows of the inner factor table */
+  int64_t split_inner_mask;/* dust parameters in the inner table (1 = Av, 2 = Rv, 4 = fA) */
+  int64_t n_runs;          /* runs of equal outer class in the entry stream (one outer-row read each) */
+  int64_t reserved[3];
 } mb_info;
 
 /* Device result layout of mb_lnlike_device: three rows of W doubles.  The two rows that add over
@@ -214,7 +225,8 @@ int mb_lnlike_device(mb_handle* h, const double* d_phi, int32_t W, int32_t ndim,
  *                    e.g. torch.distributed.all_gather) and maps the peers' buffers (CUDA IPC)
  * Afterwards every mb_lnlike* call on the handle returns rows STARSUM and NONFINITE already summed
  * over all ranks, identical on every rank, provided all ranks issue the same sequence of calls.
- * A rank that waits more than ~2 s for a peer reports MB_STATUS_PEER_TIMEOUT. */
+ * A rank that waits longer than the timeout for a peer (20 s; environment MB_PEER_TIMEOUT_MS at
+ * mb_create) reports MB_STATUS_PEER_TIMEOUT for every walker of that call. */
 #define MB_MAX_PEERS 16
 #define MB_PEER_HANDLE_BYTES 64
 int mb_peer_export(mb_handle* h, void* token);
@@ -245,6 +257,15 @@ int mb_class_values(const mb_handle* h, int32_t param, double* out, int32_t cap)
  * offsets has n_stars_local+1 entries.  Must equal indxs[:, s][isfinite(vals[:, s])]
  * (singlepop_dust_model.py:196-198) bit for bit. */
 int mb_gathered_indices(const mb_handle* h, int64_t* rows, int64_t rows_cap, int64_t* offsets);
+
+/* Parity hook: what the DEVICE holds.  Copies the class-coded entry stream back from device memory
+ * and decodes it: entry e of local star s (offsets[s] <= e < offsets[s+1], star-major, in the device's
+ * own order: sorted by class, duplicates merged unless merge_duplicates = 0) carries the class index
+ * cls[e*MB_NPARAM + p] of parameter p (index into mb_class_values(p); 0 for a fixed parameter) and the
+ * folded weight vals*prior_weight*grid_weight*completeness in weight[e].  Star boundaries come from
+ * the new-star flags of the device's code words.  FACTOR and TABLE_UNIQUE modes; needs keep_indices.
+ * cap = capacity of cls (in entries) and weight; offsets has n_stars_local+1 entries. */
+int mb_device_entries(const mb_handle* h, int64_t cap, int32_t* cls, double* weight, int64_t* offsets);
 
 /* Per-kernel device time (ms) of the last evaluation, measured with CUDA events when
  * profiling was enabled with mb_set_profiling(h, 1).  Order: K0 factor tables, K1 expand (TABLE

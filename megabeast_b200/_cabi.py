@@ -102,7 +102,8 @@ class Options(ctypes.Structure):
         ("segments_per_warp", ctypes.c_int32),
         ("tail_percent", ctypes.c_int32),
         ("table_precision", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 9),
+        ("split_inner_mask", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 8),
     ]
 
 
@@ -127,7 +128,11 @@ class Info(ctypes.Structure):
         ("n_entries_raw", ctypes.c_int64),
         ("device_bytes", ctypes.c_int64),
         ("code_bytes", ctypes.c_int64),
-        ("reserved", ctypes.c_int64 * 7),
+        ("n_outer_rows", ctypes.c_int64),
+        ("n_inner_rows", ctypes.c_int64),
+        ("split_inner_mask", ctypes.c_int64),
+        ("n_runs", ctypes.c_int64),
+        ("reserved", ctypes.c_int64 * 3),
     ]
 
 
@@ -190,6 +195,7 @@ SIGNATURES = {
     "mb_peer_disconnect": (ctypes.c_int, [ctypes.c_void_p]),
     "mb_class_values": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, c_double_p, ctypes.c_int32]),
     "mb_gathered_indices": (ctypes.c_int, [ctypes.c_void_p, c_int64_p, ctypes.c_int64, c_int64_p]),
+    "mb_device_entries": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_int32_p, c_double_p, c_int64_p]),
     "mb_set_profiling": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     "mb_last_kernel_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float * MB_NKERNELS)]),
     "mb_last_k2_timeline": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int32]),

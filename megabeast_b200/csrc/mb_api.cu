@@ -54,7 +54,12 @@ struct mb_handle {
   ModelDev mdev{};
   std::vector<double> clsx[MB_NPARAM];
   int nA = 1, nB = 1, nbins = 0, nseg[2] = {0, 0}, ncls_total = 0;
-  int64_t G = 0, S_local = 0, S_total = 0, n_entries = 0, n_entries_raw = 0, U = 0;
+  // FACTOR-mode table split: outer table = age classes x the dust parameters kept outside (nO = nA * nOd
+  // rows), inner table = the other dust parameters (nI rows).  Classic split: nOd = 1, nI = nB.
+  int nO = 1, nOd = 1, nI = 1, inner_mask = 0, nscratch = 0, age_slot = 0;
+  int ob = 0;                                // bits of outer class in a 16-bit code word (0: 32-bit codes)
+  uint32_t oradix[MB_NPARAM] = {0, 0, 0, 0}, iradix[MB_NPARAM] = {0, 0, 0, 0};
+  int64_t G = 0, S_local = 0, S_total = 0, n_entries = 0, n_entries_raw = 0, U = 0, n_runs = 0;
   int64_t device_bytes = 0;
   // parity hook (host copies)
   std::vector<int64_t> kept_rows, kept_offs;
@@ -66,7 +71,9 @@ struct mb_handle {
   int c16 = 0;
   int64_t* d_seg[2] = {nullptr, nullptr};  // segment tables: [0] 768-thread kernels, [1] 512-thread kernel
   uint32_t* d_rowcode = nullptr;
-  uint16_t* d_rowlut = nullptr;  // [nB][4] look-up rows of every dust class's digits (K2 builds the tables itself)
+  uint16_t* d_rowsrc = nullptr;   // [nO + nI][4] look-up rows multiplied into a table row (K0 and K2's own table build)
+  uint16_t* d_lutslot = nullptr;  // [ncls_total] where a look-up row lives during K2's table build
+  double* d_Pb = nullptr;         // [nbins][2][128] per-bin N-stars results of the running launch
   // ELEMENTWISE mode: the physics columns themselves, bin-sorted row list for the N-stars sums
   double* d_col[MB_NPARAM] = {nullptr, nullptr, nullptr, nullptr};
   double* d_gw = nullptr;
@@ -86,7 +93,7 @@ struct mb_handle {
   double* d_phi = nullptr;  int64_t cap_phi = 0;
   double* d_tab[MB_NPARAM] = {nullptr, nullptr, nullptr, nullptr};
   int64_t cap_tab[MB_NPARAM] = {0, 0, 0, 0};
-  double* d_F = nullptr;    // [nA+nB][128]
+  double* d_F = nullptr;    // [nO + nI + nA][128]: outer rows, inner rows, plain age rows
   unsigned int* d_counter = nullptr;
   unsigned long long* d_gacc = nullptr;
   unsigned long long* d_timeline = nullptr;    // K2 phase stamps, allocated when profiling is on
@@ -116,13 +123,10 @@ struct mb_handle {
   unsigned long long flag_seq = 0;     // value the pending evaluation will publish (0: no flag armed)
   volatile unsigned long long* h_flag = nullptr;
   unsigned long long* d_flag = nullptr;
-  // segment tables are rebuilt when the number of blocks that compute a Poisson term changes
   std::vector<int64_t> star_end_pos;  // entry count after each non-empty star
   int spw = 1;
   double tail_frac = 0.0;
-  int pois_balance = 1;               // MB_POIS_BALANCE=0: equal segments for every warp
-  int seg_npois[2] = {0, 0}, seg_nw[2] = {0, 0};
-  int64_t seg_cap[2] = {0, 0};
+  unsigned long long peer_timeout_ns = 20000000000ull;  // MB_PEER_TIMEOUT_MS (default 20 s)
   int occ_cache[3] = {0, 0, 0};
   size_t occ_smem[3] = {0, 0, 0};
   // pixel batches
@@ -203,46 +207,60 @@ static int classify(const mb_model_desc& m, int p, const double* col, int64_t G,
   return 0;
 }
 
-// slices of the dust classes per bin in the Poisson prologue: as many as the block has threads
-// for, as long as the scratch [(nslice + 1)][nbins][2] stays within 48 KB
-static int poisson_nslice(int threads, int nbins) {
-  if (nbins <= 0) return 1;
-  int ns = std::max(1, threads / nbins);
-  while (ns > 1 && (size_t)(ns + 1) * nbins * 16 > 48 * 1024) --ns;
-  return ns;
-}
 static size_t k1e_smem_bytes(int Wpad, int ndim) {
   return sizeof(double) * ((size_t)Wpad * std::max(1, ndim) + (size_t)MB_NPARAM * Wpad * kK1eWalkerVals +
                            2 * (size_t)MB_NPARAM * kK1eRows + 2 * (size_t)kK1eRows + 4 * (size_t)kK1eThreads) +
          sizeof(int) * ((size_t)MB_NPARAM * kK1eRows + kK1eRows) + 16;
 }
 // K2's dynamic shared memory: [front][factor tables (FACTOR mode)].  The front region holds the
-// per-warp entry stage and is reused as scratch: the in-kernel table build (look-up table, optional),
-// the Poisson prologue, and the block-reduction slabs -- which move over the tables (dead after
-// the star loop) when the tables are larger than they are, so that they never size the front.
+// per-warp entry stage and is reused as scratch: the in-kernel table build (look-up rows, optional),
+// the N-stars prologue (per-warp partial bin sums) and the block-reduction slabs -- which move over
+// the tables (dead after the star loop) when the tables are larger than they are, so that they never
+// size the front.
 struct K2Smem {
   size_t front = 0, tables = 0, total = 0, slab_off = 0;
-  bool fuse_fits = false;   // the look-up table of the in-kernel table build fits as well
+  size_t pois_off = 0;      // N-stars scratch: after the look-up rows when the tables are built in the kernel
+  int pois_warps = 0;       // warps whose partial sums fit
+  bool fuse_fits = false;   // the scratch of the in-kernel table build fits as well
 };
-static K2Smem k2_smem_plan(int kmode, int nA, int nB, int nbins, int Wpad, int elem_bytes, int max_smem,
-                           size_t fuse_scratch = 0) {
+// scratch of the in-kernel table build: look-up rows | ln x, 1/x per class | per-walker constants |
+// row lists | slots | phi
+static size_t k2_fuse_scratch(int nscratch, int ncls_total, int nrows, int Wpad, size_t phi_doubles) {
+  return 8 * ((size_t)nscratch * Wpad + 2 * (size_t)ncls_total + 6 * (size_t)MB_NPARAM * Wpad + (size_t)nrows +
+              (size_t)((ncls_total + 3) / 4) + phi_doubles);
+}
+static K2Smem k2_smem_plan(int kmode, int nO, int nI, int nbins, int Wpad, int elem_bytes, int max_smem,
+                           size_t fuse_scratch = 0, int nscratch = 0) {
   K2Smem p;
-  const int NW = Wpad / 32, threads = k2_threads(NW);
-  const size_t stage = (size_t)(threads / 32) * k2_stage_bytes(NW);
-  const size_t pois = nbins > 0 ? (size_t)(poisson_nslice(threads, nbins) + 1) * nbins * 16 : 0;
-  const size_t slabs = (size_t)(threads / 32) * 3 * Wpad * 8;  // block reduction: one slab per warp
-  p.tables = kmode == kModeFactor ? (size_t)(nA + nB) * Wpad * elem_bytes : 0;
+  const int NW = Wpad / 32, threads = k2_threads(NW), warps = threads / 32;
+  const size_t stage = (size_t)warps * k2_stage_bytes(NW);
+  const size_t slabs = (size_t)warps * kAccRows * Wpad * 8;  // block reduction: one slab per warp
+  const size_t pois_row = 2 * (size_t)Wpad * 8;              // one warp's partial (S, C) for all walkers
+  p.tables = kmode == kModeFactor ? (size_t)(nO + nI) * Wpad * elem_bytes : 0;
   const bool slabs_over_tables = p.tables >= slabs;
-  size_t front = std::max(stage, pois);
-  if (!slabs_over_tables) front = std::max(front, slabs);
-  front = (front + 15) & ~(size_t)15;
+  size_t base = stage;
+  if (!slabs_over_tables) base = std::max(base, slabs);
+  auto finish = [&](size_t front, size_t pois_off) {
+    int pw = 0;
+    if (nbins > 0) {
+      const size_t avail = (size_t)max_smem > p.tables + pois_off ? (size_t)max_smem - p.tables - pois_off : 0;
+      pw = (int)std::min<size_t>((size_t)warps, avail / pois_row);
+      front = std::max(front, pois_off + (size_t)std::max(pw, 1) * pois_row);
+    }
+    p.pois_off = pois_off;
+    p.pois_warps = pw;
+    p.front = (front + 15) & ~(size_t)15;
+  };
+  finish(base, 0);
   if (fuse_scratch > 0) {
-    const size_t with_fuse = (std::max(front, fuse_scratch) + 15) & ~(size_t)15;
-    if (with_fuse + p.tables <= (size_t)max_smem) { front = with_fuse; p.fuse_fits = true; }
+    const K2Smem plain = p;
+    finish(std::max(base, fuse_scratch), (size_t)nscratch * Wpad * 8);
+    if (p.front + p.tables <= (size_t)max_smem && (nbins == 0 || p.pois_warps >= 1)) p.fuse_fits = true;
+    else p = plain;
   }
-  p.front = front;
-  p.slab_off = slabs_over_tables ? front : 0;
-  p.total = front + p.tables;
+  p.slab_off = slabs_over_tables ? p.front : 0;
+  p.total = p.front + p.tables;
+  if (nbins > 0 && p.pois_warps < 1) p.total = (size_t)max_smem + 1;  // no room for the N-stars scratch
   return p;
 }
 
@@ -305,7 +323,7 @@ extern "C" void mb_destroy(mb_handle* h) {
                   h->d_bin_agecls, h->d_phi, h->d_tab[0], h->d_tab[1], h->d_tab[2], h->d_tab[3],
                   h->d_F, h->d_counter, h->d_gacc, h->d_T, h->d_out, h->d_pix_seg, h->d_pix_nstars, h->d_Fpix,
                   h->d_timeline, h->d_col[0], h->d_col[1], h->d_col[2], h->d_col[3], h->d_gw, h->d_compl,
-                  h->d_rowlut, h->d_binrows, h->d_tile_start, h->d_bin_tile, h->d_partial, h->d_bin_age, h->d_Fage, h->d_SC};
+                  h->d_rowsrc, h->d_lutslot, h->d_Pb, h->d_binrows, h->d_tile_start, h->d_bin_tile, h->d_partial, h->d_bin_age, h->d_Fage, h->d_SC};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -317,13 +335,9 @@ extern "C" void mb_destroy(mb_handle* h) {
 
 // Star-aligned segments of the entry stream, one per resident warp of block shape t (0: the
 // 768-thread kernels, 1: the 512-thread kernel), equal entry counts: boundary i is the first
-// star end at or after its goal.  With npois > 0 the warps of the first npois blocks -- the blocks that
-// compute a walker's N-stars / Poisson term before they start streaming -- get `delta` entries
-// fewer and the others correspondingly more, so that all blocks finish together.  delta comes from
-// a fixed model of this kernel on B200 (deterministic: the same data always gives the same
-// segments): the prologue costs ~2.2 us + 0.8 us per batch of eight L2 loads, a warp streams one
-// entry per (2 NW + 2.3) shared-memory wavefronts x resident warps / (0.9 x 1.9 GHz).
-static void build_segments(const mb_handle* h, int t, int npois, int NW, std::vector<int64_t>& seg) {
+// star end at or after its goal.  (Every block does the same prologue work now -- the N-stars bins
+// are spread over all blocks -- so all warps get equal shares.)
+static void build_segments(const mb_handle* h, int t, std::vector<int64_t>& seg) {
   const std::vector<int64_t>& ends = h->star_end_pos;
   const int threads = k2_threads(t == 0 ? 2 : 4), kw = threads / 32;
   const int64_t resident_warps = (int64_t)h->sm_count * kw;
@@ -331,21 +345,11 @@ static void build_segments(const mb_handle* h, int t, int npois, int NW, std::ve
   int64_t want = std::max<int64_t>(1, std::min<int64_t>(resident_warps * h->spw, n / 64));
   const int64_t n_main = want >= resident_warps ? (int64_t)((1.0 - h->tail_frac) * (double)n) : n;
   const int64_t want_tail = n_main < n ? std::max<int64_t>(1, (n - n_main) / 96) : 0;
-  double delta = 0.0;
-  if (npois > 0 && npois < h->sm_count && want == resident_warps && want_tail == 0 && h->nbins > 0) {
-    const int nslice = poisson_nslice(threads, h->nbins);
-    const double t_pois_ns = 2200.0 + 800.0 * std::ceil(std::ceil((double)h->nB / nslice) / 8.0);
-    const double t_entry_ns = (2.0 * NW + 2.3) * kw / (0.9 * 1.9);
-    delta = std::min(t_pois_ns / t_entry_ns, 0.5 * (double)n / (double)want);
-  }
-  // entries per warp: x for the plain blocks, x - delta for the Poisson blocks
-  const double x = ((double)n_main + (double)npois * kw * delta) / (double)want;
   seg.assign(1, 0);
   size_t j = 0;
   for (int64_t i = 1; i <= want + want_tail && j < ends.size(); ++i) {
     int64_t goal;
     if (i > want) goal = n_main + ((n - n_main) * (i - want) + want_tail - 1) / want_tail;
-    else if (delta > 0.0) goal = i == want ? n_main : (int64_t)std::ceil(x * (double)i - delta * (double)std::min<int64_t>(i, (int64_t)npois * kw));
     else goal = (n_main * i + want - 1) / want;
     while (j < ends.size() && ends[j] < goal) ++j;
     if (j < ends.size() && ends[j] > seg.back()) seg.push_back(ends[j]);
@@ -465,26 +469,125 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
   h->nB = (int)nB;
   h->nA = md.ncls[MB_P_LOGA];
   if (h->nA > (int)kAgeMask + 1) return fail("more than 1024 distinct age classes");
+  // ---- mode, and the split of the factor tables ----------------------------------------------------
+  // FACTOR keeps two factor tables in shared memory: outer (age classes x the dust parameters kept
+  // outside, one row read per RUN of a star's entries) and inner (the other dust parameters, one row
+  // read per ENTRY).  The classic split -- outer = age, inner = product over all dust parameters --
+  // gives the fewest runs and is taken whenever its tables fit; production dust axes (100-200 A(V)
+  // values x 9 R(V) ...) do not fit as one product table, so some dust parameters move to the outer
+  // table: among the splits that fit, the one with the fewest outer rows (fewest runs per star).
+  const int nbins_plan = mm ? mm->n_ages * mm->n_mets : 0;
+  auto fits = [&](int64_t nO, int64_t nI, int Wpad) {
+    return nO <= (int64_t)kAgeMask + 1 && nI <= (int64_t)kDustMask + 1 &&
+           k2_smem_plan(kModeFactor, (int)nO, (int)nI, nbins_plan, Wpad, h->table_bytes, h->max_smem).total <=
+               (size_t)h->max_smem;
+  };
+  std::vector<int> dust_free;
+  for (int p = MB_P_AV; p < MB_NPARAM; ++p)
+    if (model->kind[p] != MB_FIXED && !elementwise) dust_free.push_back(p);
+  int full_mask = 0;
+  for (int p : dust_free) full_mask |= 1 << (p - MB_P_AV);
+  auto split_sizes = [&](int inner_mask, int64_t& nOd, int64_t& nI) {
+    nOd = 1; nI = 1;
+    for (int p : dust_free) (((inner_mask >> (p - MB_P_AV)) & 1) ? nI : nOd) *= md.ncls[p];
+  };
+  int inner_mask = full_mask;   // classic
+  int mode = elementwise ? MB_MODE_ELEMENTWISE : o.mode;
+  if (mode < MB_MODE_AUTO || mode > MB_MODE_ELEMENTWISE) return fail("unknown mode %d", mode);
+  const int forced_mask = o.split_inner_mask & 7;
+  if (forced_mask && (forced_mask & ~full_mask))
+    return fail("split_inner_mask 0x%x names a dust parameter whose prior is fixed", forced_mask);
+  if (forced_mask && n_pixels > 0) return fail("pixel batches use the classic table split");
+  if ((mode == MB_MODE_AUTO || mode == MB_MODE_FACTOR) && !elementwise) {
+    bool found = false;
+    if (forced_mask) {
+      int64_t nOd, nI;
+      split_sizes(forced_mask, nOd, nI);
+      found = fits(h->nA * nOd, nI, 32);
+      inner_mask = forced_mask;
+    } else {
+      // walkers per pass the tables must fit for: 64 first (the usual batch), then 32
+      for (int Wpad : {64, 32}) {
+        if (fits(h->nA, h->nB, Wpad)) { inner_mask = full_mask; found = true; break; }
+        if (n_pixels > 0) continue;
+        int64_t best_nO = -1, best_rows = 0;
+        for (int m = 1; m < full_mask; ++m) {
+          if (m & ~full_mask) continue;
+          int64_t nOd, nI;
+          split_sizes(m, nOd, nI);
+          const int64_t nO = h->nA * nOd;
+          if (!fits(nO, nI, Wpad)) continue;
+          if (best_nO < 0 || nO < best_nO || (nO == best_nO && nO + nI < best_rows)) {
+            best_nO = nO; best_rows = nO + nI; inner_mask = m;
+          }
+        }
+        if (best_nO >= 0) { found = true; break; }
+      }
+    }
+    if (found) mode = MB_MODE_FACTOR;
+    else if (mode == MB_MODE_FACTOR || forced_mask)
+      return fail("factor tables (%d age x %d dust classes) do not fit shared memory in any split; use a TABLE mode",
+                  h->nA, h->nB);
+    else { mode = MB_MODE_TABLE_UNIQUE; inner_mask = full_mask; }
+  }
+  if (mode != MB_MODE_FACTOR) inner_mask = full_mask;
+  if (mode == MB_MODE_TABLE_UNIQUE && (int64_t)h->nA * h->nB > (1LL << 27)) mode = MB_MODE_TABLE_GRID;
+  h->mode = mode;
+  h->U = (mode == MB_MODE_TABLE_GRID || elementwise) ? G : (int64_t)h->nA * h->nB;
+  {
+    int64_t nOd = 1, nI = 1;
+    h->inner_mask = inner_mask;
+    for (int p : dust_free) {
+      if ((inner_mask >> (p - MB_P_AV)) & 1) { h->iradix[p] = (uint32_t)nI; nI *= md.ncls[p]; }
+      else { h->oradix[p] = (uint32_t)nOd; nOd *= md.ncls[p]; }
+    }
+    h->nOd = (int)nOd; h->nI = (int)nI; h->nO = h->nA * (int)nOd;
+  }
+  // grid-row class code: outer class (age class * nOd + outer-dust digit) << 20 | inner class
   std::vector<uint32_t> rowcode(elementwise ? 0 : (size_t)G);
   for (int64_t g = 0; g < G && !elementwise; ++g) {
     uint32_t cA = model->kind[MB_P_LOGA] == MB_FIXED ? 0u : (uint32_t)code[MB_P_LOGA][(size_t)g];
-    uint32_t cB = 0;
-    for (int p = MB_P_AV; p < MB_NPARAM; ++p)
-      if (model->kind[p] != MB_FIXED) cB += (uint32_t)code[p][(size_t)g] * (uint32_t)md.radix[p];
-    rowcode[(size_t)g] = (cA << kAgeShift) | cB;
+    uint32_t od = 0, ci = 0;
+    for (int p : dust_free) {
+      od += (uint32_t)code[p][(size_t)g] * h->oradix[p];
+      ci += (uint32_t)code[p][(size_t)g] * h->iradix[p];
+    }
+    rowcode[(size_t)g] = ((cA * (uint32_t)h->nOd + od) << kAgeShift) | ci;
   }
-
-  // ---- mode ----------------------------------------------------------------------------------------
-  int mode = elementwise ? MB_MODE_ELEMENTWISE : o.mode;
-  const bool factor_fits = k2_smem_plan(kModeFactor, h->nA, h->nB, mm ? mm->n_ages * mm->n_mets : 0, 32, h->table_bytes,
-                                        h->max_smem).total <= (size_t)h->max_smem;
-  if (mode == MB_MODE_AUTO) mode = factor_fits ? MB_MODE_FACTOR : MB_MODE_TABLE_UNIQUE;
-  if (mode == MB_MODE_FACTOR && !factor_fits)
-    return fail("factor tables (%d + %d classes) do not fit shared memory; use a TABLE mode", h->nA, h->nB);
-  if (mode == MB_MODE_TABLE_UNIQUE && (int64_t)h->nA * h->nB > (1LL << 27)) mode = MB_MODE_TABLE_GRID;
-  if (mode < MB_MODE_FACTOR || mode > MB_MODE_ELEMENTWISE) return fail("unknown mode %d", mode);
-  h->mode = mode;
-  h->U = (mode == MB_MODE_TABLE_GRID || elementwise) ? G : (int64_t)h->nA * h->nB;
+  // look-up rows behind every table row, and where a look-up row lives while K2 builds its tables:
+  // a parameter that is alone in its table is evaluated in place, the others in a scratch table
+  std::vector<uint16_t> rowsrc((size_t)(h->nO + h->nI) * 4, (uint16_t)0xffff);
+  std::vector<uint16_t> lutslot((size_t)std::max(1, clsoff), (uint16_t)0);
+  if (!elementwise) {
+    const bool age_free = model->kind[MB_P_LOGA] != MB_FIXED;
+    int n_outer_params = age_free ? 1 : 0, n_inner_params = 0;
+    for (int p : dust_free) (((inner_mask >> (p - MB_P_AV)) & 1) ? n_inner_params : n_outer_params)++;
+    for (int r = 0; r < h->nO; ++r) {
+      int k = 0;
+      if (age_free) rowsrc[(size_t)r * 4 + k++] = (uint16_t)(md.clsoff[MB_P_LOGA] + r / h->nOd);
+      for (int p : dust_free)
+        if (!((inner_mask >> (p - MB_P_AV)) & 1))
+          rowsrc[(size_t)r * 4 + k++] = (uint16_t)(md.clsoff[p] + ((r % h->nOd) / h->oradix[p]) % md.ncls[p]);
+    }
+    for (int r = 0; r < h->nI; ++r) {
+      int k = 0;
+      for (int p : dust_free)
+        if ((inner_mask >> (p - MB_P_AV)) & 1)
+          rowsrc[(size_t)(h->nO + r) * 4 + k++] = (uint16_t)(md.clsoff[p] + (r / h->iradix[p]) % md.ncls[p]);
+    }
+    int nscratch = 0;
+    for (int p = 0; p < MB_NPARAM; ++p) {
+      if (model->kind[p] == MB_FIXED) continue;
+      const bool inner = p != MB_P_LOGA && ((inner_mask >> (p - MB_P_AV)) & 1);
+      const bool alone = inner ? n_inner_params == 1 : n_outer_params == 1;
+      if (p == MB_P_LOGA) h->age_slot = alone ? -1 : nscratch;  // -1: the age rows are the outer table itself
+      for (int c = 0; c < md.ncls[p]; ++c)
+        lutslot[(size_t)md.clsoff[p] + c] =
+            alone ? (uint16_t)(0x8000u | (unsigned)((inner ? h->nO : 0) + c)) : (uint16_t)nscratch++;
+    }
+    h->nscratch = nscratch;
+    if (h->nO + h->nI >= 0x8000) return fail("more than 32767 factor-table rows");
+  }
 
   // ---- N-stars sufficient statistics (helpers.py:133-162) ----------------------------------------
   std::vector<double> H, coef, bin_age;
@@ -530,6 +633,8 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
         coef[(size_t)i * nZ + j] = metprior * mm->massmult[(size_t)i * nZ + j] / mm->avemass;
         bin_age[(size_t)i * nZ + j] = mm->ages[i];
       }
+    bin_agecls.resize((size_t)h->nbins);   // K1e leaves the age factor per BIN: row of `fage` = the bin itself
+    for (int b = 0; b < h->nbins; ++b) bin_agecls[(size_t)b] = b;
   } else if (h->poisson) {
     if (!grid->logA || !grid->Z) return fail("logA and Z columns are required for the N-stars term");
     if (mm->n_ages < 1 || mm->n_mets < 1 || !mm->ages || !mm->mets || !mm->massmult)
@@ -548,10 +653,14 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
       int i = (int)(ia - mm->ages), j = (int)(iz - mm->mets);
       if (age_first_row[(size_t)i] < 0) age_first_row[(size_t)i] = (int32_t)g;
       size_t b = (size_t)i * nZ + j;
-      uint32_t cB = rowcode[(size_t)g] & kDustMask;
+      const uint32_t rc = rowcode[(size_t)g];
+      // dust class in table order: outer-dust digit * nI + inner class
+      const size_t cD = (size_t)(((rc >> kAgeShift) & kAgeMask) % (uint32_t)h->nOd) * h->nI + (rc & kDustMask);
       double gw = grid->grid_weight[g];
-      H[((size_t)cB * h->nbins + b) * 2] += gw;       // Ht[cB][bin]: bin minor, read coalesced by KP
-      H[((size_t)cB * h->nbins + b) * 2 + 1] += gw * grid->completeness[g];
+      // K2 reads a bin's classes contiguously: Ht[bin][cD]; the pixel kernel (lanes = bins): Ht[cD][bin]
+      const size_t at = n_pixels > 0 ? (cD * h->nbins + b) * 2 : (b * (size_t)h->nB + cD) * 2;
+      H[at] += gw;
+      H[at + 1] += gw * grid->completeness[g];
     }
     coef.resize((size_t)h->nbins);
     bin_agecls.resize((size_t)h->nbins);
@@ -561,7 +670,7 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
         coef[(size_t)i * nZ + j] = metprior * mm->massmult[(size_t)i * nZ + j] / mm->avemass;
         // an age no grid row carries has empty bins (S = 0, skipped); any class will do
         int32_t r = age_first_row[(size_t)i];
-        bin_agecls[(size_t)i * nZ + j] = r < 0 ? 0 : (int32_t)((rowcode[(size_t)r] >> kAgeShift) & kAgeMask);
+        bin_agecls[(size_t)i * nZ + j] = r < 0 ? 0 : (int32_t)(((rowcode[(size_t)r] >> kAgeShift) & kAgeMask) / (uint32_t)h->nOd);
       }
   }
 
@@ -608,16 +717,17 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
       Entry e;
       e.a = v * grid->prior_weight[r] * grid->grid_weight[r] * grid->completeness[r];
       const uint32_t rc = elementwise ? 0u : rowcode[(size_t)r];
-      const uint32_t cA = (rc >> kAgeShift) & kAgeMask, cB = rc & kDustMask;
-      e.meta = cA;
-      e.idx = mode == MB_MODE_FACTOR ? cB : mode == MB_MODE_TABLE_UNIQUE ? cA * (uint32_t)h->nB + cB : (uint32_t)r;
+      // (TABLE modes always use the classic split: outer class = age class, inner class = dust class)
+      const uint32_t cO = (rc >> kAgeShift) & kAgeMask, cI = rc & kDustMask;
+      e.meta = cO;
+      e.idx = mode == MB_MODE_FACTOR ? cI : mode == MB_MODE_TABLE_UNIQUE ? cO * (uint32_t)h->nB + cI : (uint32_t)r;
       cur.push_back(e);
       if (o.keep_indices) h->kept_rows.push_back(r);
     }
     if (o.keep_indices) h->kept_offs.push_back((int64_t)h->kept_rows.size());
     h->n_entries_raw += (int64_t)cur.size();
     if (cur.empty()) continue;  // sums to 0.0 -> skipped by the reference too (:218-221)
-    // runs of equal age class (FACTOR reloads the age factor once per run); ties by table row
+    // runs of equal outer class (FACTOR reloads the outer factor once per run); ties by table row
     std::stable_sort(cur.begin(), cur.end(), [](const Entry& x, const Entry& y) {
       return x.meta != y.meta ? x.meta < y.meta : x.idx < y.idx;
     });
@@ -629,7 +739,7 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
       }
       entries.push_back(e);
     }
-    // device code words: FACTOR [31] new run, [30] new star, [29:20] age class, [19:0] dust class;
+    // device code words: FACTOR [31] new run, [30] new star, [29:20] outer class, [19:0] inner class;
     // TABLE modes read the full product from the table: [31] new star, [30:0] table row
     uint32_t prevA = 0xffffffffu;
     for (size_t i = first; i < entries.size(); ++i) {
@@ -639,6 +749,7 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
         code = (cA << kAgeShift) | entries[i].idx;
         if (i == first) code |= kNewRun | kNewStar;
         else if (cA != prevA) code |= kNewRun;
+        if (code & kNewRun) ++h->n_runs;
       } else {
         code = entries[i].idx;
         if (i == first) code |= kNewRun;
@@ -660,20 +771,24 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
   // by 3-4 % -- per-segment costs (pipeline restart, one log) outweigh what dynamic balancing
   // recovers -- so the segment count must match the warps the launch really has: one table for
   // the 768-thread kernels (up to 64 walkers per pass) and one for the 512-thread kernel (128).
-  h->c16 = mode == MB_MODE_FACTOR && h->table_bytes == 8 && n_pixels == 0 && h->nA <= 16 && h->nB <= 1024 &&
-           !getenv("MB_CODES32");
+  // 16-bit code words where the class counts allow: 4 + 10 or 6 + 8 bits of (outer, inner) class
+  h->ob = 0;
+  if (mode == MB_MODE_FACTOR && h->table_bytes == 8 && n_pixels == 0 && !getenv("MB_CODES32")) {
+    if (h->nO <= 16 && h->nI <= 1024) h->ob = 4;
+    else if (h->nO <= 64 && h->nI <= 256) h->ob = 6;
+  }
+  h->c16 = h->ob > 0;
   h->spw = o.segments_per_warp > 0 ? o.segments_per_warp : 1;
   // ... optionally plus a tail pool: the last tail_percent of the entries cut into small segments
   // that warps claim dynamically after their own big one.  Measured on B200 (4-16 %, config 3 and
   // its 1/8 shard): no gain over none, so the default is none.
   h->tail_frac = o.tail_percent > 0 ? std::min(50, o.tail_percent) / 100.0 : 0.0;
-  if (const char* pb = getenv("MB_POIS_BALANCE")) h->pois_balance = atoi(pb);
+  if (const char* pt = getenv("MB_PEER_TIMEOUT_MS")) h->peer_timeout_ns = (unsigned long long)std::max(1.0, atof(pt)) * 1000000ull;
   h->star_end_pos = std::move(star_end_pos);
   std::vector<int64_t> seg[2];
   for (int t = 0; t < 2; ++t) {
-    build_segments(h, t, 0, 0, seg[t]);
+    build_segments(h, t, seg[t]);
     h->nseg[t] = (int)seg[t].size() - 1;
-    h->seg_cap[t] = (int64_t)seg[t].size();
   }
 
   // ---- upload ----------------------------------------------------------------------------------------
@@ -691,7 +806,7 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
       for (size_t i = 0; i < codes.size(); ++i) {
         const uint32_t c = codes[i];
         c16[i] = (uint16_t)(((c & kNewRun) ? 0x8000u : 0u) | ((c & kNewStar) ? 0x4000u : 0u) |
-                            (((c >> kAgeShift) & kAgeMask) << 10) | (c & kDustMask));
+                            (((c >> kAgeShift) & kAgeMask) << (14 - h->ob)) | (c & kDustMask));
       }
       if (dev_upload(h, &h->d_ec16, c16)) return 1;
     } else if (dev_upload(h, &h->d_ec, codes)) return 1;
@@ -699,14 +814,11 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
   if (dev_upload(h, &h->d_seg[0], seg[0])) return 1;
   if (dev_upload(h, &h->d_seg[1], seg[1])) return 1;
   if (mode == MB_MODE_TABLE_GRID && dev_upload(h, &h->d_rowcode, rowcode)) return 1;
-  if (mode == MB_MODE_FACTOR) {
-    std::vector<uint16_t> rowlut((size_t)h->nB * 4, (uint16_t)0xffff);
-    for (int cb = 0; cb < h->nB; ++cb)
-      for (int p = MB_P_AV; p < MB_NPARAM; ++p)
-        if (model->kind[p] != MB_FIXED)
-          rowlut[(size_t)cb * 4 + (p - MB_P_AV)] = (uint16_t)(md.clsoff[p] + (cb / md.radix[p]) % md.ncls[p]);
-    if (dev_upload(h, &h->d_rowlut, rowlut)) return 1;
+  if (!elementwise) {
+    if (dev_upload(h, &h->d_rowsrc, rowsrc)) return 1;
+    if (dev_upload(h, &h->d_lutslot, lutslot)) return 1;
   }
+  if (h->poisson && dev_alloc(h, &h->d_Pb, (int64_t)h->nbins * 2 * 128)) return 1;
   if (elementwise) {
     for (int p = 0; p < MB_NPARAM; ++p) {
       if (model->kind[p] == MB_FIXED) continue;
@@ -726,6 +838,7 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
       if (dev_alloc(h, &h->d_partial, h->ntiles * 128 * 2)) return 1;
       if (dev_upload(h, &h->d_bin_age, bin_age)) return 1;
       if (dev_upload(h, &h->d_coef, coef)) return 1;
+      if (dev_upload(h, &h->d_bin_agecls, bin_agecls)) return 1;
       if (dev_alloc(h, &h->d_Fage, (int64_t)h->nbins * 128)) return 1;
       if (dev_alloc(h, &h->d_SC, (int64_t)h->nbins * 128 * 2)) return 1;
     }
@@ -734,11 +847,11 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
     if (dev_upload(h, &h->d_coef, coef)) return 1;
     if (dev_upload(h, &h->d_bin_agecls, bin_agecls)) return 1;
   }
-  if (dev_alloc(h, &h->d_F, (int64_t)(h->nA + h->nB) * 128)) return 1;
+  if (dev_alloc(h, &h->d_F, (int64_t)(h->nO + h->nI + h->nA) * 128)) return 1;
   if (dev_alloc(h, &h->d_counter, kCtrWords)) return 1;
   CK(cudaMemset(h->d_counter, 0, sizeof(unsigned int) * kCtrWords));
-  if (dev_alloc(h, &h->d_gacc, 3 * 128)) return 1;
-  CK(cudaMemset(h->d_gacc, 0, sizeof(unsigned long long) * 3 * 128));
+  if (dev_alloc(h, &h->d_gacc, kAccRows * 128)) return 1;
+  CK(cudaMemset(h->d_gacc, 0, sizeof(unsigned long long) * kAccRows * 128));
   h->max_blocks = h->sm_count * 4;
   CK(cudaMalloc((void**)&h->d_xbuf, kXBufBytes));
   CK(cudaMemset(h->d_xbuf, 0, kXBufBytes));
@@ -752,9 +865,12 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
     CK(cudaFuncSetAttribute(mb_k2_stars<1, kModeFactor, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(mb_k2_stars<2, kModeFactor, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CK(cudaFuncSetAttribute(mb_k2_stars<4, kModeFactor, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CK((cudaFuncSetAttribute(mb_k2_stars<1, kModeFactor, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
-    CK((cudaFuncSetAttribute(mb_k2_stars<2, kModeFactor, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
-    CK((cudaFuncSetAttribute(mb_k2_stars<4, kModeFactor, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
+    CK((cudaFuncSetAttribute(mb_k2_stars<1, kModeFactor, double, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
+    CK((cudaFuncSetAttribute(mb_k2_stars<2, kModeFactor, double, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
+    CK((cudaFuncSetAttribute(mb_k2_stars<4, kModeFactor, double, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
+    CK((cudaFuncSetAttribute(mb_k2_stars<1, kModeFactor, double, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
+    CK((cudaFuncSetAttribute(mb_k2_stars<2, kModeFactor, double, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
+    CK((cudaFuncSetAttribute(mb_k2_stars<4, kModeFactor, double, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)));
     MB_OPTIN(1, kModeTable); MB_OPTIN(2, kModeTable); MB_OPTIN(4, kModeTable);
     MB_OPTIN(1, kModeTableGrid); MB_OPTIN(2, kModeTableGrid); MB_OPTIN(4, kModeTableGrid);
 #undef MB_OPTIN
@@ -816,7 +932,7 @@ static size_t pix_front_bytes(int nbins, int Wpad) {
   return (std::max(stage, red) + 15) & ~(size_t)15;
 }
 static size_t pix_smem_bytes(int nA, int nB, int nbins, int Wpad) {
-  return pix_front_bytes(nbins, Wpad) + (size_t)(nA + nB) * Wpad * 8 + (size_t)Wpad * 8 + (size_t)3 * Wpad * 8;
+  return pix_front_bytes(nbins, Wpad) + (size_t)(nA + nB) * Wpad * 8 + (size_t)Wpad * 8 + (size_t)kAccRows * Wpad * 8;
 }
 
 static int eval_pixels_device(mb_handle* h, const double* d_phi, int W, int ndim, double* d_out, cudaStream_t st) {
@@ -830,7 +946,7 @@ static int eval_pixels_device(mb_handle* h, const double* d_phi, int W, int ndim
   const int Wpad = 32 * NW;
   const size_t smem = pix_smem_bytes(h->nA, h->nB, h->nbins, Wpad);
   if (smem > (size_t)h->max_smem) return fail("pixel kernel needs %zu bytes of shared memory", smem);
-  const int64_t needF = h->P * (int64_t)(h->nA + h->nB) * Wpad;
+  const int64_t needF = h->P * (int64_t)(h->nA + h->nB + h->nA) * Wpad;  // K0's layout: age, dust, plain age rows
   if (needF > h->cap_Fpix) {
     CK(cudaStreamSynchronize(st));
     if (h->d_Fpix) { CK(cudaFree(h->d_Fpix)); h->device_bytes -= h->cap_Fpix * 8; }
@@ -842,14 +958,15 @@ static int eval_pixels_device(mb_handle* h, const double* d_phi, int W, int ndim
   if (prof) CK(cudaEventRecord(h->ev[0], st));
   K0Args k0{};
   k0.model = h->mdev; k0.clsx = h->d_clsx; k0.phi = d_phi; k0.F = h->d_Fpix;
-  k0.nA = h->nA; k0.nB = h->nB; k0.W = W; k0.Wpad = Wpad; k0.ndim = ndim; k0.ncls_total = h->ncls_total;
+  k0.rowsrc = h->d_rowsrc; k0.nrows = h->nA + h->nB; k0.nAge = h->nA;
+  k0.W = W; k0.Wpad = Wpad; k0.ndim = ndim; k0.ncls_total = h->ncls_total;
   mb_k0_factors<<<(unsigned)(h->P * Wpad), kK0Threads, sizeof(double) * std::max(1, h->ncls_total), st>>>(k0);
   if (prof) { CK(cudaEventRecord(h->ev[1], st)); CK(cudaEventRecord(h->ev[2], st)); }
   KPixArgs ka{};
   ka.ea = h->d_ea; ka.ec = h->d_ec; ka.pix_seg = h->d_pix_seg; ka.F = h->d_Fpix; ka.pix_nstars = h->d_pix_nstars;
   ka.out = d_out; ka.counters = h->d_counter;
   ka.pois.Ht = h->d_H; ka.pois.bin_agecls = h->d_bin_agecls; ka.pois.coef = h->d_coef;
-  ka.pois.nbins = h->poisson ? h->nbins : 0; ka.pois.nslice = 1; ka.pois.n_stars = 0.0;
+  ka.pois.nbins = h->poisson ? h->nbins : 0; ka.pois.n_stars = 0.0;
   ka.P = (int)h->P; ka.nA = h->nA; ka.nB = h->nB; ka.Wpad = Wpad; ka.W = W;
   ka.tab_off = (int32_t)pix_front_bytes(h->nbins, Wpad);
   int per_sm = 0;
@@ -906,6 +1023,10 @@ extern "C" int mb_get_info(const mb_handle* h, mb_info* out) {
   out->n_entries_raw = h->n_entries_raw;
   out->device_bytes = h->device_bytes;
   out->code_bytes = h->c16 ? 2 : 4;
+  out->n_outer_rows = h->nO;
+  out->n_inner_rows = h->nI;
+  out->split_inner_mask = h->inner_mask;
+  out->n_runs = h->n_runs;
   return 0;
 }
 
@@ -936,6 +1057,67 @@ extern "C" int mb_gathered_indices(const mb_handle* h, int64_t* rows, int64_t ca
   // class-coded modes dereference the grid only at create time: the rows that were read then
   memcpy(rows, h->kept_rows.data(), sizeof(int64_t) * h->kept_rows.size());
   memcpy(offs, h->kept_offs.data(), sizeof(int64_t) * h->kept_offs.size());
+  return 0;
+}
+
+extern "C" int mb_device_entries(const mb_handle* h, int64_t cap, int32_t* cls, double* weight, int64_t* offs) {
+  if (!h || !cls || !weight || !offs) return fail("mb_device_entries: null argument");
+  if (h->kept_offs.empty()) return fail("handle was created without keep_indices");
+  if (h->mode != MB_MODE_FACTOR && h->mode != MB_MODE_TABLE_UNIQUE)
+    return fail("mb_device_entries: the device holds class codes in the FACTOR and TABLE_UNIQUE modes only");
+  if (h->n_entries > cap) return fail("entry buffers too small (%lld needed)", (long long)h->n_entries);
+  CK(cudaSetDevice(h->device));
+  const size_t n = (size_t)h->n_entries;
+  std::vector<uint32_t> code(n);
+  if (n) {
+    CK(cudaMemcpy(weight, h->d_ea, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (h->c16) {
+      std::vector<uint16_t> c16(n);
+      CK(cudaMemcpy(c16.data(), h->d_ec16, sizeof(uint16_t) * n, cudaMemcpyDeviceToHost));
+      const int ib = 14 - h->ob;
+      for (size_t i = 0; i < n; ++i) {  // back to the 32-bit layout
+        const uint32_t c = c16[i];
+        code[i] = ((c & 0x8000u) ? kNewRun : 0u) | ((c & 0x4000u) ? kNewStar : 0u) |
+                  (((c >> ib) & ((1u << h->ob) - 1u)) << kAgeShift) | (c & ((1u << ib) - 1u));
+      }
+    } else {
+      CK(cudaMemcpy(code.data(), h->d_ec, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+    }
+  }
+  const ModelDev& md = h->mdev;
+  size_t e = 0;
+  for (int64_t s = 0; s < h->S_local; ++s) {
+    offs[s] = (int64_t)e;
+    if (h->kept_offs[(size_t)s + 1] == h->kept_offs[(size_t)s]) continue;  // no finite entry: nothing on the device
+    // this star's entries: from its new-star flag up to the next one
+    bool first = true;
+    for (; e < n; ++e) {
+      const uint32_t c = code[e];
+      const bool new_star = h->mode == MB_MODE_FACTOR ? (c & kNewStar) != 0 : (c & kNewRun) != 0;
+      if (new_star && !first) break;
+      if (first && !new_star) return fail("mb_device_entries: star %lld does not start with a new-star flag", (long long)s);
+      first = false;
+      uint32_t cA, od, ci;
+      if (h->mode == MB_MODE_FACTOR) {
+        const uint32_t cO = (c >> kAgeShift) & kAgeMask;
+        cA = cO / (uint32_t)h->nOd; od = cO % (uint32_t)h->nOd; ci = c & kDustMask;
+      } else {
+        const uint32_t u = c & kRowMask;
+        cA = u / (uint32_t)h->nB; od = 0; ci = u % (uint32_t)h->nB;
+      }
+      int32_t* out = cls + e * MB_NPARAM;
+      out[MB_P_LOGA] = (int32_t)cA;
+      for (int p = MB_P_AV; p < MB_NPARAM; ++p) {
+        out[p] = 0;
+        if (md.kind[p] == MB_FIXED) continue;
+        out[p] = (h->inner_mask >> (p - MB_P_AV)) & 1 ? (int32_t)((ci / h->iradix[p]) % (uint32_t)md.ncls[p])
+                                                      : (int32_t)((od / h->oradix[p]) % (uint32_t)md.ncls[p]);
+      }
+    }
+    if (first) return fail("mb_device_entries: star %lld has no entries on the device", (long long)s);
+  }
+  offs[h->S_local] = (int64_t)e;
+  if (e != n) return fail("mb_device_entries: %lld entries left over after the last star", (long long)(n - e));
   return 0;
 }
 
@@ -975,7 +1157,7 @@ extern "C" int mb_last_kernel_ms(const mb_handle* h, float ms[MB_NKERNELS]) {
 
 // K2 is launched with programmatic stream serialization: its blocks may be placed while the
 // preceding kernel (K0 / K1) is still running and wait inside the kernel (griddepcontrol.wait)
-template <int MODE, typename TF = double, bool C16 = false>
+template <int MODE, typename TF = double, int OB = 0>
 static cudaError_t launch_k2(int NW, int grid, size_t smem, cudaStream_t st, const K2Args& a) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
@@ -988,24 +1170,25 @@ static cudaError_t launch_k2(int NW, int grid, size_t smem, cudaStream_t st, con
   cfg.attrs = &attr;
   cfg.numAttrs = 1;
   switch (NW) {
-    case 1: return cudaLaunchKernelEx(&cfg, mb_k2_stars<1, MODE, TF, C16>, a);
-    case 2: return cudaLaunchKernelEx(&cfg, mb_k2_stars<2, MODE, TF, C16>, a);
-    default: return cudaLaunchKernelEx(&cfg, mb_k2_stars<4, MODE, TF, C16>, a);
+    case 1: return cudaLaunchKernelEx(&cfg, mb_k2_stars<1, MODE, TF, OB>, a);
+    case 2: return cudaLaunchKernelEx(&cfg, mb_k2_stars<2, MODE, TF, OB>, a);
+    default: return cudaLaunchKernelEx(&cfg, mb_k2_stars<4, MODE, TF, OB>, a);
   }
 }
 
-template <int MODE, typename TF = double, bool C16 = false>
+template <int MODE, typename TF = double, int OB = 0>
 static int k2_occ(int NW, size_t smem) {
   int n = 0;
   switch (NW) {
-    case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<1, MODE, TF, C16>, k2_threads(1), smem); break;
-    case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<2, MODE, TF, C16>, k2_threads(2), smem); break;
-    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<4, MODE, TF, C16>, k2_threads(4), smem); break;
+    case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<1, MODE, TF, OB>, k2_threads(1), smem); break;
+    case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<2, MODE, TF, OB>, k2_threads(2), smem); break;
+    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, mb_k2_stars<4, MODE, TF, OB>, k2_threads(4), smem); break;
   }
   return n;
 }
-static int k2_blocks_per_sm(int kmode, int NW, size_t smem, int table_bytes, int c16) {
-  if (kmode == kModeFactor && c16) return k2_occ<kModeFactor, double, true>(NW, smem);
+static int k2_blocks_per_sm(int kmode, int NW, size_t smem, int table_bytes, int ob) {
+  if (kmode == kModeFactor && ob == 4) return k2_occ<kModeFactor, double, 4>(NW, smem);
+  if (kmode == kModeFactor && ob == 6) return k2_occ<kModeFactor, double, 6>(NW, smem);
   if (kmode == kModeFactor && table_bytes == 4) return k2_occ<kModeFactor, float>(NW, smem);
   return kmode == kModeFactor ? k2_occ<kModeFactor>(NW, smem)
          : kmode == kModeTable ? k2_occ<kModeTable>(NW, smem) : k2_occ<kModeTableGrid>(NW, smem);
@@ -1024,27 +1207,28 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
   const bool prof = h->profiling != 0;
   float acc_ms[MB_NKERNELS] = {0, 0, 0};
   int launches = 0;
+  const int nrows = h->nO + h->nI;
   for (int w0 = 0; w0 < W;) {
     int rem = W - w0;
     int NW = rem <= 32 ? 1 : rem <= 64 ? 2 : 4;
-    while (NW > 1 && k2_smem_plan(kmode, h->nA, h->nB, h->nbins, 32 * NW, h->table_bytes, h->max_smem).total > (size_t)h->max_smem) NW >>= 1;
+    while (NW > 1 && k2_smem_plan(kmode, h->nO, h->nI, h->nbins, 32 * NW, h->table_bytes, h->max_smem).total > (size_t)h->max_smem) NW >>= 1;
     const int Wpad = 32 * NW;
     const int wp = std::min(rem, Wpad);
     h->last_wp = wp;
-    double* FA = h->d_F;
-    double* FB = h->d_F + (size_t)h->nA * Wpad;
+    double* FO = h->d_F;                                // outer rows (TABLE modes: the age rows FA)
+    double* FI = h->d_F + (size_t)h->nO * Wpad;         // inner rows (TABLE modes: the dust rows FB)
+    double* Fage = h->d_F + (size_t)nrows * Wpad;       // plain age rows
 
     // FACTOR mode with fp64 tables and analytic models: K2 builds the factor tables in its own
-    // prologue (look-up table in the stage area), no K0 launch
+    // prologue (look-up rows in the stage area), no K0 launch
     // host phi travels in the kernel parameters and is staged in shared memory; a batch too large
     // for that keeps K0 (one read of the mapped host memory per walker instead of one per block)
     const bool inline_phi = h_phi && (int64_t)wp * ndim <= kPhiInline;
-    const size_t fuse_scratch = 8 * ((size_t)h->ncls_total * (Wpad + 2) + 6 * (size_t)MB_NPARAM * Wpad + (size_t)h->nB +
-                                     (inline_phi ? (size_t)wp * ndim : 0));
+    const size_t fuse_scratch = k2_fuse_scratch(h->nscratch, h->ncls_total, nrows, Wpad, inline_phi ? (size_t)wp * ndim : 0);
     const bool may_fuse = kmode == kModeFactor && h->table_bytes == 8 && !d_tab && !h->no_fuse &&
-                          h->ncls_total < 0xffff && (!h_phi || inline_phi);
-    const K2Smem plan = k2_smem_plan(kmode, h->nA, h->nB, h->nbins, Wpad, h->table_bytes, h->max_smem,
-                                     may_fuse ? fuse_scratch : 0);
+                          h->ncls_total < 0x7fff && (!h_phi || inline_phi);
+    const K2Smem plan = k2_smem_plan(kmode, h->nO, h->nI, h->nbins, Wpad, h->table_bytes, h->max_smem,
+                                     may_fuse ? fuse_scratch : 0, h->nscratch);
     const bool fused = may_fuse && plan.fuse_fits;
     if (prof) CK(cudaEventRecord(h->ev[0], st));
     if (!elementwise && !fused) {
@@ -1052,7 +1236,7 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
       k0.model = h->mdev; k0.clsx = h->d_clsx; k0.phi = d_phi + (size_t)w0 * ndim;
       for (int p = 0; p < MB_NPARAM; ++p)
         k0.tab[p] = (d_tab && d_tab[p]) ? d_tab[p] + (size_t)w0 * h->mdev.ncls[p] : nullptr;
-      k0.F = h->d_F; k0.nA = h->nA; k0.nB = h->nB; k0.W = wp; k0.Wpad = Wpad; k0.ndim = ndim;
+      k0.F = h->d_F; k0.rowsrc = h->d_rowsrc; k0.nrows = nrows; k0.nAge = h->nA; k0.W = wp; k0.Wpad = Wpad; k0.ndim = ndim;
       k0.ncls_total = h->ncls_total;
       mb_k0_factors<<<Wpad, kK0Threads, sizeof(double) * std::max(1, h->ncls_total), st>>>(k0);
       ++launches;
@@ -1096,7 +1280,7 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     } else if (kmode != kModeFactor) {
       int64_t total = h->U * (Wpad / 2);
       int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->sm_count * 16);
-      mb_k1_expand<<<blocks, 256, 0, st>>>(FA, FB, h->mode == MB_MODE_TABLE_GRID ? h->d_rowcode : nullptr,
+      mb_k1_expand<<<blocks, 256, 0, st>>>(FO, FI, h->mode == MB_MODE_TABLE_GRID ? h->d_rowcode : nullptr,
                                            h->d_T, h->U, h->nB, Wpad);
       ++launches;
     }
@@ -1105,53 +1289,40 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     // occupancy query cached per pass shape (it costs microseconds of host time per call)
     int& cached = h->occ_cache[NW == 1 ? 0 : NW == 2 ? 1 : 2];
     if (cached <= 0 || h->occ_smem[NW == 1 ? 0 : NW == 2 ? 1 : 2] != smem) {
-      cached = k2_blocks_per_sm(kmode, NW, smem, h->table_bytes, h->c16);
+      cached = k2_blocks_per_sm(kmode, NW, smem, h->table_bytes, h->ob);
       h->occ_smem[NW == 1 ? 0 : NW == 2 ? 1 : 2] = smem;
     }
     int per_sm = cached;
     if (per_sm < 1) return fail("K2 cannot be resident with %zu bytes of shared memory", smem);
     const int kK2Warps = k2_threads(NW) / 32;
-    {  // segments balanced for the number of blocks that run a Poisson prologue in this pass
-      const int t = NW == 4 ? 1 : 0;
-      // (rounded up to a multiple of eight: a sampler that alternates between half-ensembles of 22
-      // and 23 walkers must not trigger a rebuild on every call)
-      const int npois = (h->poisson && h->pois_balance && kmode == kModeFactor && wp < h->sm_count)
-                            ? std::min((wp + 7) & ~7, h->sm_count - 1) : 0;
-      if (npois != h->seg_npois[t] || (npois > 0 && NW != h->seg_nw[t])) {
-        std::vector<int64_t> seg;
-        build_segments(h, t, npois, NW, seg);
-        CK(cudaStreamSynchronize(st));  // the previous launch may still read the old table
-        if ((int64_t)seg.size() > h->seg_cap[t]) {
-          CK(cudaFree(h->d_seg[t]));
-          h->d_seg[t] = nullptr;
-          CK(cudaMalloc((void**)&h->d_seg[t], sizeof(int64_t) * seg.size()));
-          h->seg_cap[t] = (int64_t)seg.size();
-        }
-        CK(cudaMemcpy(h->d_seg[t], seg.data(), sizeof(int64_t) * seg.size(), cudaMemcpyHostToDevice));
-        h->nseg[t] = (int)seg.size() - 1;
-        h->seg_npois[t] = npois;
-        h->seg_nw[t] = NW;
-      }
-    }
-    // at least one block even without entries: the Poisson prologue and the result rows live in K2
+    // at least one block even without entries (the result rows are written by K2's last block), and
+    // enough blocks to spread the (age, Z) bins of the N-stars term
     int grid = std::min(h->sm_count * per_sm,
-                        std::max(h->poisson ? wp : 1, (h->nseg[NW == 4] + kK2Warps - 1) / kK2Warps));
-    grid = std::min(grid, h->max_blocks);
+                        std::max(h->poisson ? std::min(h->nbins, h->sm_count) : 1, (h->nseg[NW == 4] + kK2Warps - 1) / kK2Warps));
+    grid = std::max(1, std::min(grid, h->max_blocks));
     K2Args k2{};
-    k2.ea = h->d_ea; k2.ec = h->c16 ? (const void*)h->d_ec16 : (const void*)h->d_ec; k2.seg = h->d_seg[NW == 4]; k2.nseg = h->nseg[NW == 4]; k2.FA = elementwise ? h->d_Fage : FA; k2.T = h->d_T;
+    k2.ea = h->d_ea; k2.ec = h->c16 ? (const void*)h->d_ec16 : (const void*)h->d_ec; k2.seg = h->d_seg[NW == 4]; k2.nseg = h->nseg[NW == 4]; k2.FA = FO; k2.T = h->d_T;
     k2.gacc = h->d_gacc; k2.counters = h->d_counter; k2.out = d_out;
-    k2.nA = h->nA; k2.nB = h->nB; k2.Wpad = Wpad; k2.W = wp; k2.w0 = w0; k2.Wtot = W;
+    k2.nA = h->nO; k2.nB = h->nI; k2.nOd = h->nOd; k2.Wpad = Wpad; k2.W = wp; k2.w0 = w0; k2.Wtot = W;
     k2.tab_off = (int32_t)plan.front;
     k2.slab_off = (int32_t)plan.slab_off;
-    k2.pois.Ht = h->d_H; k2.pois.bin_agecls = h->d_bin_agecls; k2.pois.coef = h->d_coef;
+    k2.pois.Ht = h->d_H; k2.pois.bin_agecls = h->d_bin_agecls; k2.pois.coef = h->d_coef; k2.pois.Pb = h->d_Pb;
     k2.pois.n_stars = (double)h->S_total; k2.pois.nbins = h->poisson ? h->nbins : 0;
-    k2.pois.nslice = poisson_nslice(k2_threads(NW), h->nbins);
+    k2.pois.nwarps = plan.pois_warps; k2.pois.scratch_off = (int32_t)plan.pois_off;
     k2.pois.SC = elementwise ? h->d_SC : nullptr;
+    // plain age factors (the `ageprior` of helpers.py:135): K1e's per-bin rows, K0's rows in global
+    // memory, or -- tables built inside K2 -- the outer table itself / the scratch look-up rows
+    if (elementwise) k2.pois.fage = h->d_Fage;
+    else if (!fused) k2.pois.fage = Fage;
+    else {
+      k2.pois.fage = nullptr;
+      k2.pois.fage_smem_off = h->age_slot < 0 ? (int32_t)plan.front : (int32_t)((size_t)h->age_slot * Wpad * 8);
+    }
     if (d_flag && w0 + wp >= W) { k2.done_flag = d_flag; k2.done_seq = flag_seq; }  // the last pass publishes
     k2.build_tables = fused ? 1 : 0;
     if (fused) {
       k2.model = h->mdev; k2.clsx = h->d_clsx; k2.ndim = ndim; k2.ncls_total = h->ncls_total;
-      k2.rowlut = h->d_rowlut;
+      k2.rowsrc = h->d_rowsrc; k2.lutslot = h->d_lutslot; k2.nscratch = h->nscratch;
       k2.phi = d_phi + (size_t)w0 * ndim;
       if (inline_phi) {
         k2.phi_inline = 1;
@@ -1164,12 +1335,13 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
       k2.timeline = h->d_timeline;
       h->timeline_blocks = grid;
     }
-    k2.peer.world = h->peer_world; k2.peer.rank = h->peer_rank;
+    k2.peer.world = h->peer_world; k2.peer.rank = h->peer_rank; k2.peer.timeout_ns = h->peer_timeout_ns;
     if (h->peer_world > 1) {
       k2.peer.seq = ++h->peer_seq;
       for (int p = 0; p < h->peer_world; ++p) k2.peer.xbuf[p] = h->peer_xbuf[p];
     }
-    if (kmode == kModeFactor && h->c16) CK((launch_k2<kModeFactor, double, true>(NW, grid, smem, st, k2)));
+    if (kmode == kModeFactor && h->ob == 4) CK((launch_k2<kModeFactor, double, 4>(NW, grid, smem, st, k2)));
+    else if (kmode == kModeFactor && h->ob == 6) CK((launch_k2<kModeFactor, double, 6>(NW, grid, smem, st, k2)));
     else if (kmode == kModeFactor && h->table_bytes == 4) CK((launch_k2<kModeFactor, float>(NW, grid, smem, st, k2)));
     else if (kmode == kModeFactor) CK(launch_k2<kModeFactor>(NW, grid, smem, st, k2));
     else if (kmode == kModeTable) CK(launch_k2<kModeTable>(NW, grid, smem, st, k2));

@@ -10,7 +10,13 @@
 // column holds a few tens of distinct values ("classes"), and physmod[g,w] depends on the row
 // only through its class codes:
 //
-//     physmod[g,w] = FA[cA(g)][w] * FB[cB(g)][w]       FA: age (logA) factor, FB: dust factor
+//     physmod[g,w] = FO[cO(g)][w] * FI[cI(g)][w]
+//
+// FO = "outer" factor table (age class x the dust parameters kept outside), FI = "inner" factor
+// table (the remaining dust parameters).  The classic split is outer = age alone (FA), inner = all
+// dust parameters (FB); grids whose dust classes do not fit shared memory as ONE product table
+// (production BEAST grids: 100-200 A(V) values x 9 R(V)) keep the parameters separate: inner = A(V),
+// outer = age x R(V) (x f_A), and a star's entries are sorted into runs of equal outer class.
 //
 // K0  mb_k0_factors      one block per walker: prior models on the classes -> factor tables FA, FB
 //                        (TABLE modes, tabulated models, pixel batches; in FACTOR mode K2 builds
@@ -123,8 +129,9 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
 // One block per walker column.  Phase 1: every free parameter's prior model evaluated on its
 // classes (singlepop_dust_model.py:146-148 restricted to the distinct column values) into a
 // shared-memory look-up table -- a few tens of fp64 exp/log evaluations per walker.  Phase 2:
-// FA[c][w] (nA rows) and FB[c][w] (nB rows = products over the dust parameters, in the
-// reference's left-to-right order), walker minor.  Columns w >= W (padding up to the pass width)
+// the table rows (nrows = outer rows then inner rows), each the product of up to four look-up rows
+// listed in `rowsrc` (the reference's left-to-right order), then the nAge plain age-factor rows
+// (the `ageprior` of helpers.py:135), walker minor.  Columns w >= W (padding up to the pass width)
 // repeat the last real walker so no lane of K2 ever sees garbage.  The model description travels
 // in the kernel parameters (constant bank).  Pixel batches: P independent ensembles, tables laid
 // out [p][class][Wpad], phi [p][W][ndim].
@@ -134,8 +141,9 @@ struct K0Args {
   const double* clsx;
   const double* phi;          // [P][W][ndim], already offset to the pass's first walker
   const double* tab[MB_NPARAM];
-  double* F;                  // [P][nA + nB][Wpad]: FA rows then FB rows
-  int32_t nA, nB, W, Wpad, ndim, ncls_total;
+  double* F;                  // [P][nrows + nAge][Wpad]: outer rows, inner rows, plain age rows
+  const uint16_t* rowsrc;     // [nrows][4] look-up rows (class offsets included) multiplied into a table row; 0xffff = none
+  int32_t nrows, nAge, W, Wpad, ndim, ncls_total;
 };
 constexpr int kK0Threads = 128;
 
@@ -161,117 +169,172 @@ __global__ void __launch_bounds__(kK0Threads) mb_k0_factors(const __grid_constan
     lut[i] = v;
   }
   __syncthreads();
-  double* F = a.F + (size_t)pix * (a.nA + a.nB) * a.Wpad + w;
-  for (int c = threadIdx.x; c < a.nA + a.nB; c += kK0Threads) {
+  double* F = a.F + (size_t)pix * (a.nrows + a.nAge) * a.Wpad + w;
+  for (int c = threadIdx.x; c < a.nrows + a.nAge; c += kK0Threads) {
     double v = 1.0;
-    if (c < a.nA) {
-      if (m.kind[MB_P_LOGA] != MB_FIXED) v = lut[m.clsoff[MB_P_LOGA] + c];
-    } else {
-      const int cb = c - a.nA;
+    if (c < a.nrows) {
       // same left-to-right product order as the reference's `cur_physmod *=` loop (:146-148)
-#pragma unroll
-      for (int p = MB_P_AV; p < MB_NPARAM; ++p) {
-        if (m.kind[p] == MB_FIXED) continue;
-        v *= lut[m.clsoff[p] + (cb / m.radix[p]) % m.ncls[p]];
-      }
+      const ushort4 r = __ldg(reinterpret_cast<const ushort4*>(a.rowsrc) + c);
+      if (r.x != 0xffff) v *= lut[r.x];
+      if (r.y != 0xffff) v *= lut[r.y];
+      if (r.z != 0xffff) v *= lut[r.z];
+      if (r.w != 0xffff) v *= lut[r.w];
+    } else if (m.kind[MB_P_LOGA] != MB_FIXED) {
+      v = lut[m.clsoff[MB_P_LOGA] + (c - a.nrows)];
     }
     F[(size_t)c * a.Wpad] = v;
   }
 }
 
-// ---- N-stars / Poisson term of one walker, computed by a whole block ------------------------------
+// ---- N-stars / Poisson term, spread over the blocks of K2 by (age, Z) bin -------------------------
 // helpers.py:133-162 needs, per (age, Z) bin, S = sum_g physmod*grid_weight and
 // C = sum_g physmod*grid_weight*completeness over the bin's rows.  Inside a bin the age factor is
-// constant, so with the create-time statistics Ht[cB][bin] = (sum grid_weight, sum
-// grid_weight*completeness) over the bin's rows of dust class cB:
-//     S_bin = FA[age(bin)] * sum_cB Ht[cB][bin].x * FB[cB]      (C_bin with .y)
-// then: normalise by the grand total (:133-134), skip empty bins (:156), expected number of stars,
-// Poisson term (singlepop_dust_model.py:182-186).  Runs as a prologue of K2 (block b does walker
-// b, b + gridDim, ...) on the factor tables the block already holds.
+// constant, so with the create-time statistics Ht[bin][cD] = (sum grid_weight, sum
+// grid_weight*completeness) over the bin's rows of dust class cD = od * nI + i (outer-dust digit,
+// inner class):
+//     S_bin = sum_od FO[age(bin) * nOd + od] * sum_i Ht[bin][od * nI + i].x * FI[i]     (C_bin with .y)
+// Block b of K2 computes the bins b, b + gridDim.x, ... for ALL walkers of the pass (Ht is read
+// once per launch, not once per walker) and leaves (S_bin, term_bin) in `Pb`; the last block of the
+// launch adds the bins in fixed order: normalisation (:133-134; it cancels in C/S and only decides
+// the degenerate cases), skip of empty bins (:156), expected number of stars, Poisson term
+// (singlepop_dust_model.py:182-186).
 struct PoissonArgs {
-  const double* Ht;           // [nB][nbins][2]
-  const int32_t* bin_agecls;  // [nbins] FA row of the bin's age
+  const double* Ht;           // [nbins][nOd * nI][2]
+  const int32_t* bin_agecls;  // [nbins] row of `fage` holding the bin's plain age factor; also the age class
   const double* coef;         // [nbins] metprior * massmult / avemass   (helpers.py:148-151)
+  double* Pb;                 // [nbins][2][Wpad] scratch: S_bin, term_bin (rewritten by every launch)
+  const double* fage;         // plain age factors [..][Wpad] in global memory, or null: read them from the
+                              // tables / look-up rows in shared memory (fage_smem_off)
   double n_stars;             // S of the fit (:183-185)
   int32_t nbins;              // 0: no N-stars term
-  int32_t nslice;             // slices of the dust classes per bin (host: fits the scratch)
+  int32_t nwarps;             // warps of the block that take part (their partial sums must fit the scratch)
+  int32_t scratch_off;        // byte offset of the reduction scratch [nwarps][2][Wpad] in dynamic shared memory
+  int32_t fage_smem_off;      // byte offset of the plain age-factor rows in dynamic shared memory (fage == null)
   const double* SC;           // ELEMENTWISE: bin sums [nbins][Wpad][2] already formed by K1b (else null)
 };
 
-// F: this pass's factor tables (shared or global), element (c, w) at F[c * Wpad + w].
-// part: scratch [(nslice + 1)][nbins][2] doubles.  All threads of the block must call.
-template <int THREADS>
-__device__ double poisson_term(const PoissonArgs& pa, const double* F, int nA, int nB, int Wpad, int w,
-                               double* part, double* scratch) {
-  const int nbins = pa.nbins, nslice = pa.nslice;
-  double* sc = part + (size_t)nslice * nbins * 2;  // [nbins][2]
-  if (pa.SC) {
-    // ELEMENTWISE: S and C were summed over the grid rows themselves (mb_k1b_binsums)
-    double part_nrm = 0.0;
-    for (int b = threadIdx.x; b < nbins; b += THREADS) {
-      const double2 v = __ldg(reinterpret_cast<const double2*>(pa.SC) + (size_t)b * Wpad + w);
-      sc[2 * b] = v.x; sc[2 * b + 1] = v.y;
-      part_nrm += v.x;
-    }
-    const double nrm = block_sum<THREADS>(part_nrm, scratch);
-    double part_pred = 0.0;
-    for (int b = threadIdx.x; b < nbins; b += THREADS) {
-      const double sb = sc[2 * b] / nrm;
-      if (sb > 0.0) part_pred += (F[(size_t)b * Wpad + w] * pa.coef[b]) * (sc[2 * b + 1] / nrm) / sb;
-    }
-    const double pred = block_sum<THREADS>(part_pred, scratch);
-    __syncthreads();
-    return pa.n_stars * log(pred) - pred - lgamma(pa.n_stars + 1.0);
-  }
+// F: outer rows then inner rows, element (row, w) at F[row * Wpad + w]; shared memory (FACTOR mode with
+// fp64 tables) or global.  All threads of the block must call.  Lane l of a warp owns walkers
+// l, l + 32, ... (8-byte loads, conflict free).
+template <int NW, int THREADS>
+__device__ void poisson_bins(const PoissonArgs& pa, const double* F, int nO, int nOd, int nI,
+                             unsigned char* smem_raw) {
+  constexpr int Wpad = 32 * NW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pw = pa.nwarps;
+  double* red = reinterpret_cast<double*>(smem_raw + pa.scratch_off);  // [pw][2][Wpad]
+  const double* fage = pa.fage ? pa.fage : reinterpret_cast<const double*>(smem_raw + pa.fage_smem_off);
   const double2* Ht = reinterpret_cast<const double2*>(pa.Ht);
-  const double* FB = F + (size_t)nA * Wpad + w;
-  for (int item = threadIdx.x; item < nbins * nslice; item += THREADS) {
-    const int b = item % nbins, sl = item / nbins;
-    double s = 0.0, c = 0.0;
-    int cb = sl;
-    // batches of 8 independent L2 loads in flight, then the multiply-adds in class order
-    for (; cb + 7 * nslice < nB; cb += 8 * nslice) {
-      double2 h[8];
+  const double* FI = F + (size_t)nO * Wpad + lane;
+  for (int b = blockIdx.x; b < pa.nbins; b += gridDim.x) {
+    const int acls = __ldg(pa.bin_agecls + b);
+    if (warp < pw) {
+      double S[NW], C[NW];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) h[u] = __ldg(Ht + (size_t)(cb + u * nslice) * nbins + b);
+      for (int j = 0; j < NW; ++j) { S[j] = 0.0; C[j] = 0.0; }
+      if (pa.SC) {
+        // ELEMENTWISE: S and C were summed over the grid rows themselves (mb_k1b_binsums)
+        if (warp == 0) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const double f = FB[(size_t)(cb + u * nslice) * Wpad];
-        s = fma(h[u].x, f, s); c = fma(h[u].y, f, c);
+          for (int j = 0; j < NW; ++j) {
+            const double2 v = __ldg(reinterpret_cast<const double2*>(pa.SC) + (size_t)b * Wpad + lane + 32 * j);
+            S[j] = v.x; C[j] = v.y;
+          }
+        }
+      } else {
+        for (int od = 0; od < nOd; ++od) {
+          double s[NW], c[NW];
+#pragma unroll
+          for (int j = 0; j < NW; ++j) { s[j] = 0.0; c[j] = 0.0; }
+          const double2* hrow = Ht + ((size_t)b * nOd + od) * nI;
+          int i = warp;
+          // four independent (warp-uniform) loads of the statistics in flight, then the multiply-adds
+          for (; i + 3 * pw < nI; i += 4 * pw) {
+            double2 h[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) h[u] = __ldg(hrow + i + u * pw);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const double* f = FI + (size_t)(i + u * pw) * Wpad;
+#pragma unroll
+              for (int j = 0; j < NW; ++j) {
+                const double fv = f[32 * j];
+                s[j] = fma(h[u].x, fv, s[j]); c[j] = fma(h[u].y, fv, c[j]);
+              }
+            }
+          }
+          for (; i < nI; i += pw) {
+            const double2 h0 = __ldg(hrow + i);
+            const double* f = FI + (size_t)i * Wpad;
+#pragma unroll
+            for (int j = 0; j < NW; ++j) {
+              const double fv = f[32 * j];
+              s[j] = fma(h0.x, fv, s[j]); c[j] = fma(h0.y, fv, c[j]);
+            }
+          }
+          const double* fo = F + (size_t)(acls * nOd + od) * Wpad + lane;
+#pragma unroll
+          for (int j = 0; j < NW; ++j) {
+            const double fv = fo[32 * j];
+            S[j] = fma(fv, s[j], S[j]); C[j] = fma(fv, c[j], C[j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NW; ++j) {
+        red[((size_t)warp * 2 + 0) * Wpad + lane + 32 * j] = S[j];
+        red[((size_t)warp * 2 + 1) * Wpad + lane + 32 * j] = C[j];
       }
     }
-    for (; cb < nB; cb += nslice) {
-      double2 h0 = __ldg(Ht + (size_t)cb * nbins + b);
-      const double f = FB[(size_t)cb * Wpad];
-      s = fma(h0.x, f, s); c = fma(h0.y, f, c);
+    __syncthreads();
+    if (threadIdx.x < Wpad) {
+      const int w = threadIdx.x;
+      double Sb = 0.0, Cb = 0.0;
+      for (int wp = 0; wp < pw; ++wp) {  // fixed warp order
+        Sb += red[((size_t)wp * 2 + 0) * Wpad + w];
+        Cb += red[((size_t)wp * 2 + 1) * Wpad + w];
+      }
+      // helpers.py:152-162: ageprior * metprior * massmult / avemass * C / S, bins with S <= 0 skipped
+      const double fa = fage[(size_t)acls * Wpad + w];
+      const double term = Sb > 0.0 ? (fa * __ldg(pa.coef + b)) * (Cb / Sb) : 0.0;
+      pa.Pb[((size_t)b * 2 + 0) * Wpad + w] = Sb;
+      pa.Pb[((size_t)b * 2 + 1) * Wpad + w] = term;
     }
-    part[((size_t)sl * nbins + b) * 2] = s;
-    part[((size_t)sl * nbins + b) * 2 + 1] = c;
+    __syncthreads();  // the scratch is reused by the block's next bin
+  }
+}
+
+// Last block of the launch: add the bins in fixed order -> Poisson term of every walker of the pass.
+// psum: scratch [THREADS / Wpad][2][Wpad] doubles.  All threads of the block must call.
+template <int NW, int THREADS>
+__device__ void poisson_finish(const PoissonArgs& pa, double* psum, double* out_row, int W) {
+  constexpr int Wpad = 32 * NW, kParts = THREADS / Wpad;
+  const int w = threadIdx.x % Wpad, part = threadIdx.x / Wpad;
+  double nrm = 0.0, pred = 0.0;
+  if (part < kParts)
+    for (int b = part; b < pa.nbins; b += kParts) {
+      nrm += __ldcg(pa.Pb + ((size_t)b * 2 + 0) * Wpad + w);
+      pred += __ldcg(pa.Pb + ((size_t)b * 2 + 1) * Wpad + w);
+    }
+  if (part < kParts) {
+    psum[((size_t)part * 2 + 0) * Wpad + w] = nrm;
+    psum[((size_t)part * 2 + 1) * Wpad + w] = pred;
   }
   __syncthreads();
-  double part_nrm = 0.0;
-  for (int b = threadIdx.x; b < nbins; b += THREADS) {
-    double S = 0.0, C = 0.0;
-    for (int sl = 0; sl < nslice; ++sl) {  // fixed slice order
-      S += part[((size_t)sl * nbins + b) * 2];
-      C += part[((size_t)sl * nbins + b) * 2 + 1];
+  if (threadIdx.x < W) {
+    nrm = 0.0; pred = 0.0;
+    for (int p = 0; p < kParts; ++p) {  // fixed order
+      nrm += psum[((size_t)p * 2 + 0) * Wpad + threadIdx.x];
+      pred += psum[((size_t)p * 2 + 1) * Wpad + threadIdx.x];
     }
-    const double fa = F[(size_t)pa.bin_agecls[b] * Wpad + w];
-    S *= fa; C *= fa;
-    sc[2 * b] = S; sc[2 * b + 1] = C;
-    part_nrm += S;
+    // helpers.py:133-134 divides every weight by the grand total first: a total of 0 (0/0 = nan
+    // weights), nan or inf leaves no bin with S/total > 0 -> every bin skipped, pred = 0
+    if (!(nrm > 0.0) || !(nrm < INFINITY)) pred = 0.0;
+    double pois = 0.0;
+    if (pa.nbins > 0) pois = pa.n_stars * log(pred) - pred - lgamma(pa.n_stars + 1.0);  // :182-186
+    out_row[threadIdx.x] = pois;
   }
-  // helpers.py:133-134: weights are normalised by their grand total before the bin sums
-  const double nrm = block_sum<THREADS>(part_nrm, scratch);
-  double part_pred = 0.0;
-  for (int b = threadIdx.x; b < nbins; b += THREADS) {
-    const double sb = sc[2 * b] / nrm;
-    if (sb > 0.0)  // helpers.py:156 (false for NaN: 0/0 when every weight is zero)
-      part_pred += (F[(size_t)pa.bin_agecls[b] * Wpad + w] * pa.coef[b]) * (sc[2 * b + 1] / nrm) / sb;
-  }
-  const double pred = block_sum<THREADS>(part_pred, scratch);
-  __syncthreads();  // scratch / part are free again
-  return pa.n_stars * log(pred) - pred - lgamma(pa.n_stars + 1.0);  // :182-186
+  __syncthreads();
 }
 
 // ---- K1: materialise the prior-weight table (TABLE modes) -------------------------------------
@@ -634,11 +697,29 @@ struct LogAcc {
     return v;
   }
 };
-// Segment log-sums are accumulated as 64-bit fixed point (2^-32 resolution, range +-2.1e9):
-// integer addition is exact, so the total is independent of the order in which warps, blocks
-// and GPUs contribute -- bitwise reproducible under dynamic scheduling.  Rounding is 1.2e-10
-// absolute per segment, ~1e-8 over the ~1e4 segments of a 100k-star shard whose total is ~1e6.
-constexpr double kFixScale = 4294967296.0;
+// Segment log-sums are accumulated as TWO 64-bit fixed-point words: hi counts units of 2^-24, lo
+// the remainder in units of 2^-68 (|lo| <= 2^43 per segment).  Integer addition is exact, so the
+// total is independent of the order in which warps, blocks and GPUs contribute -- bitwise
+// reproducible under dynamic scheduling -- and the absolute resolution (3.4e-21 per segment) keeps
+// 1e-9 RELATIVE accuracy down to totals of ~1e-11.  Range: |total| < 2^39 = 5.5e11 in hi; a star's
+// ln L lies in [-745, 710], so that takes > 7e8 stars per job, more than 16 GPUs can hold; lo has
+// room for 2^20 segments (a launch has at most a few thousand per GPU).
+constexpr double kFixHiScale = 16777216.0;          // 2^24
+constexpr double kFixLoScale = 17592186044416.0;    // 2^44 (on top of 2^24)
+constexpr int kAccRows = 4;                         // hi, lo, non-finite stars, nan flags
+struct Fix2 { long long hi, lo; };
+__device__ __forceinline__ Fix2 to_fix2(double v) {
+  Fix2 f;
+  const double vs = v * kFixHiScale;                // exact (power of two)
+  f.hi = __double2ll_rn(vs);
+  f.lo = __double2ll_rn((vs - (double)f.hi) * kFixLoScale);  // the difference is exact
+  return f;
+}
+__device__ __forceinline__ double from_fix2(long long hi, long long lo) {
+  hi += lo >> 44;                                   // carry the whole units of lo (floor)
+  lo &= (1ll << 44) - 1;
+  return (double)hi * (1.0 / kFixHiScale) + (double)lo * (1.0 / (kFixHiScale * kFixLoScale));
+}
 enum { kCtrSegment = 0, kCtrBlocks = 1, kCtrWords = 2 };
 
 // Rare star outcomes, kept out of line: exact zero (skipped, :218-221), non-finite (counted ->
@@ -677,7 +758,7 @@ enum { kModeFactor = 1, kModeTable = 2, kModeTableGrid = 3 };
 
 // ---- star shards on several GPUs: reduction over NVLink peer memory, fused into K2's tail --------
 // Every GPU owns an exchange buffer (cudaMalloc, opened by the other ranks through CUDA IPC):
-//   data [2 parities][MB_MAX_PEERS sources][3 * 128] u64   fixed-point log-sum, non-finite, nan
+//   data [2 parities][MB_MAX_PEERS sources][4 * 128] u64   fixed-point log-sum (hi, lo), non-finite, nan
 //   flags[2 parities][MB_MAX_PEERS sources]         u32   sequence number of the data in the slot
 // The last block of rank r's K2 stores its shard totals into slot r of EVERY rank's buffer (plain
 // stores to peer addresses, NVLink), fences system-wide, publishes the launch's sequence number in
@@ -685,7 +766,7 @@ enum { kModeFactor = 1, kModeTable = 2, kModeTableGrid = 3 };
 // Integer sums: the order is irrelevant, every rank gets bitwise the same totals.  Two parities:
 // a rank can be at most one launch ahead of the slowest one (it needs everyone's flag of launch n
 // to leave launch n), so launch n + 2 never overwrites data of launch n that is still being read.
-constexpr int kXWords = 3 * 128;
+constexpr int kXWords = kAccRows * 128;
 __host__ __device__ constexpr size_t xbuf_data_off(int par, int src) {   // in u64 words
   return ((size_t)par * MB_MAX_PEERS + src) * kXWords;
 }
@@ -696,6 +777,7 @@ constexpr size_t kXBufBytes = 8 * (size_t)2 * MB_MAX_PEERS * kXWords + 4 * (size
 struct PeerArgs {
   int32_t world, rank;   // world <= 1: single shard, no exchange
   uint32_t seq;          // sequence number of this launch, identical on all ranks
+  unsigned long long timeout_ns;  // how long the last block waits for a peer's shard (MB_PEER_TIMEOUT_MS)
   unsigned long long* xbuf[MB_MAX_PEERS];  // exchange buffer of every rank, as mapped on THIS GPU
 };
 
@@ -705,15 +787,16 @@ struct K2Args {
   const void* ec;       // entry codes    [n_entries]: uint32, or uint16 for the C16 kernels (padded by one)
   const int64_t* seg;   // [nseg+1] entry offsets, star aligned
   int32_t nseg;
-  const double* FA;     // FACTOR: [nA][Wpad] then [nB][Wpad], contiguous (staged to smem)
+  const double* FA;     // FACTOR: outer rows [nA][Wpad] then inner rows [nB][Wpad], contiguous (staged to smem)
   const double* T;      // TABLE*: [U][Wpad]
-  unsigned long long* gacc;  // [3][Wpad] fixed-point log-sum, non-finite stars, nan flags (zero between launches)
+  unsigned long long* gacc;  // [kAccRows][Wpad] fixed-point log-sum (hi, lo), non-finite stars, nan flags (zero between launches)
   unsigned int* counters;    // [kCtrWords] next segment, blocks done (zero between launches)
   double* out;          // [MB_OUT_ROWS][Wtot], written at columns w0 .. w0+W-1
-  int32_t nA, nB, Wpad, W, w0, Wtot;
+  int32_t nA, nB, Wpad, W, w0, Wtot;   // nA = rows of the OUTER table (age classes x nOd), nB = rows of the INNER table
+  int32_t nOd;               // outer-dust combinations per age class (1: the classic age | dust split)
   int32_t tab_off;           // byte offset of the factor tables in dynamic shared memory
   int32_t slab_off;          // byte offset of the block-reduction slabs (0, or tab_off: over the dead tables)
-  PoissonArgs pois;          // N-stars term, computed by the first W blocks before the star loop
+  PoissonArgs pois;          // N-stars term: every block computes some (age, Z) bins before the star loop
   PeerArgs peer;             // cross-GPU reduction of the shard totals
   unsigned long long* timeline;  // optional [gridDim.x][kTimelinePoints] %globaltimer stamps (profiling)
   // FACTOR mode, fp64 tables, analytic models: every block builds the factor tables itself in its
@@ -723,8 +806,12 @@ struct K2Args {
   unsigned long long done_seq;
   int32_t build_tables, phi_inline, ndim, ncls_total;
   const double* clsx;        // class values [ncls_total]
-  const uint16_t* rowlut;    // [nB][4] look-up rows (class offsets included) of a dust class's Av, Rv, fA
-                             // digits; 0xffff = parameter fixed
+  const uint16_t* rowsrc;    // [nA + nB][4] look-up rows (class offsets included) multiplied into a table
+                             // row; 0xffff = none
+  const uint16_t* lutslot;   // [ncls_total] where a look-up row lives while the tables are built: bit 15 set =
+                             // row (& 0x7fff) of the tables themselves (a parameter alone in its table is
+                             // evaluated in place), else row of the scratch look-up table
+  int32_t nscratch;          // rows of the scratch look-up table
   const double* phi;         // [W][ndim], already offset to this pass's first walker
   ModelDev model;
   double phi_in[kPhiInline];
@@ -844,16 +931,20 @@ __device__ __forceinline__ uint32_t keep_in_register(uint32_t x) {
 // factor rounded to 21 significant bits, so it is used as a double without any conversion
 // instruction -- F2F.F64.F32 runs on the quarter-rate XU pipe and made a true fp32 table no
 // faster than the fp64 one; sums are still fp64).
-// C16: the FACTOR code word packed in 16 bits -- [15] new run, [14] new star, [13:10] age class,
-// [9:0] dust class (<= 16 age classes; 1,024 dust classes is more than shared memory can hold
-// anyway) -- so that four codes are ONE 8-byte broadcast load instead of a 16-byte one (one
-// shared-memory wavefront less per four entries).  An even entry's code arrives with the next one
-// in its upper half; the masks below never look there.
-template <int NW, int MODE, typename TF = double, bool C16 = false>
+// OB > 0: the FACTOR code word packed in 16 bits -- [15] new run, [14] new star, then OB bits of
+// outer class and 14 - OB bits of inner class (OB = 4: <= 16 outer x 1,024 inner classes, the classic
+// age | dust split; OB = 6: <= 64 x 256, the separable split of production dust axes) -- so that
+// four codes are ONE 8-byte broadcast load instead of a 16-byte one (one shared-memory wavefront
+// less per four entries).  An even entry's code arrives with the next one in its upper half; the
+// masks below never look there.  OB = 0: 32-bit code words.
+template <int NW, int MODE, typename TF = double, int OB = 0>
 struct Lanes {
+  static constexpr bool C16 = OB > 0;
+  static constexpr uint32_t kInnerBits16 = 14 - OB;
   static_assert(!C16 || (MODE == 1 && sizeof(TF) == 8), "16-bit codes: FACTOR mode with fp64 tables");
-  __device__ __forceinline__ static uint32_t dust(uint32_t code) { return C16 ? (code & 0x3ffu) : (code & kDustMask); }
-  __device__ __forceinline__ static uint32_t age(uint32_t code) { return C16 ? ((code >> 10) & 0xfu) : ((code >> kAgeShift) & kAgeMask); }
+  // dust() = inner class (row of the inner table), age() = outer class (row of the outer table)
+  __device__ __forceinline__ static uint32_t dust(uint32_t code) { return C16 ? (code & ((1u << kInnerBits16) - 1u)) : (code & kDustMask); }
+  __device__ __forceinline__ static uint32_t age(uint32_t code) { return C16 ? ((code >> kInnerBits16) & ((1u << OB) - 1u)) : ((code >> kAgeShift) & kAgeMask); }
   __device__ __forceinline__ static bool is_run(uint32_t code) { return C16 ? (code & 0x8000u) != 0 : (int32_t)code < 0; }
   __device__ __forceinline__ static bool is_star(uint32_t code) { return C16 ? (code & 0x4000u) != 0 : (code & kNewStar) != 0; }
   static constexpr int NQ = (NW + 1) / 2;
@@ -870,7 +961,7 @@ struct Lanes {
   __device__ __forceinline__ void init(uint32_t tabA_, uint32_t tabB_, const char* Tlane_) {
     tabA = keep_in_register(tabA_); tabB = keep_in_register(tabB_); Tlane = Tlane_;
 #pragma unroll
-    for (int i = 0; i < NW; ++i) { run[i] = 0.0; star[i] = 0.0; fa[i] = 1.0; acc[i].init(); }
+    for (int i = 0; i < NW; ++i) { run[i] = 0.0; run2[i] = 0.0; star[i] = 0.0; fa[i] = 1.0; acc[i].init(); }
   }
   // factors of one entry for this lane's walkers
   // FACTOR: one table row element pair / element of this lane (byte address given)
@@ -946,10 +1037,11 @@ struct Lanes {
 // st_c) and fold them into L.  Per group of four entries the warp issues three broadcast loads
 // (four codes; two weight pairs) = 1.5 shared-memory wavefronts per entry, then per entry one
 // IMAD (table row address), NW/2 x LDS.128 (factors), NW x DFMA and one sign test.
-template <int NW, int MODE, typename TF, int STAGES = kStages, bool C16 = false>
-__device__ __forceinline__ void stream_range(Lanes<NW, MODE, TF, C16>& L, const double* __restrict__ ga,
+template <int NW, int MODE, typename TF, int STAGES = kStages, int OB = 0>
+__device__ __forceinline__ void stream_range(Lanes<NW, MODE, TF, OB>& L, const double* __restrict__ ga,
                                              const void* __restrict__ gcodes, int64_t pos, const int64_t end,
                                              const uint32_t st_a, const uint32_t st_c, const int lane) {
+  constexpr bool C16 = OB > 0;
   constexpr uint32_t kCodeBytes = C16 ? 2u : 4u;
   const uint32_t* gc = static_cast<const uint32_t*>(gcodes);          // 32-bit codes
   const uint16_t* gc16 = static_cast<const uint16_t*>(gcodes);        // 16-bit codes, fetched in 4-byte aligned pairs
@@ -1026,21 +1118,21 @@ __device__ __forceinline__ void stream_range(Lanes<NW, MODE, TF, C16>& L, const 
   cp_async_wait<0>();
 }
 
-// Prologue (first W blocks): N-stars / Poisson term.  Hot loop: every warp streams star-aligned
-// segments of the entry stream for all walkers.  Tail: reduction over stars (K3) and, with peers,
-// over GPUs.
-template <int NW, int MODE, typename TF = double, bool C16 = false>
+// Prologue: factor tables (built in place or copied), then this block's (age, Z) bins of the N-stars
+// term.  Hot loop: every warp streams star-aligned segments of the entry stream for all walkers.
+// Tail: reduction over stars (K3), Poisson term and, with peers, the reduction over GPUs.
+template <int NW, int MODE, typename TF = double, int OB = 0>
 __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars(const __grid_constant__ K2Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int kK2Warps = k2_threads(NW) / 32;
   constexpr bool kF32 = sizeof(TF) == 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int Wpad = 32 * NW;  // == a.Wpad
-  constexpr uint32_t rowbytes = Lanes<NW, MODE, TF, C16>::rowbytes;
+  constexpr uint32_t rowbytes = Lanes<NW, MODE, TF, OB>::rowbytes;
   const uint32_t lanebytes = (NW == 1 ? lane : 2 * lane) * (MODE == kModeFactor ? (uint32_t)sizeof(TF) : 8u);
 
-  // smem layout: [stage: warps x (2 x 32 weights + 2 x 32 codes); also Poisson / reduction scratch]
-  //              [FA | FB tables at tab_off (FACTOR only)]
+  // smem layout: [front: per-warp entry stage; also table-build / Poisson / reduction scratch]
+  //              [outer | inner tables at tab_off (FACTOR only)]
   const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
   constexpr int STAGES = k2_stages(NW);
   const uint32_t st_a = smem0 + (uint32_t)warp * k2_stage_bytes(NW);
@@ -1050,35 +1142,48 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   stamp(a.timeline, 0);
   // launched with programmatic stream serialization: wait here for K0 (the tables) to complete
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  // this block's slices of the N-stars statistics: pull them into L2 while the tables are built
+  if (a.pois.nbins > 0 && !a.pois.SC) {
+    const int per_bin = a.nOd * a.nB * 16;  // bytes
+    for (int b = blockIdx.x; b < a.pois.nbins; b += gridDim.x) {
+      const char* base = reinterpret_cast<const char*>(a.pois.Ht) + (size_t)b * per_bin;
+      for (int o = threadIdx.x * 128; o < per_bin; o += blockDim.x * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
+    }
+  }
   if (MODE == kModeFactor && !kF32 && a.build_tables) {
     // K0 fused: the prior models on the classes (singlepop_dust_model.py:146-148 restricted to the
-    // distinct column values) for all walkers of the pass -> look-up table in the (still idle) stage
-    // area, then the FA / FB rows straight into shared memory.  The fp64 pipe bounds this prologue
-    // (every block repeats it), so the lognormals are arranged for few operations: ln x and 1/x once
-    // per class, mu = ln(mode) + sigma^2, 1/sigma and amp/(sigma sqrt(2 pi)) once per walker, then
-    // one multiply-add chain and one branch-free exp per (class, walker) -- no divisions there.
+    // distinct column values) for all walkers of the pass -> look-up rows (in the still idle stage
+    // area, or directly in the tables for a parameter that is alone in its table), then the product
+    // rows straight into shared memory.  The fp64 pipe bounds this prologue (every block repeats
+    // it), so the lognormals are arranged for few operations: ln x and 1/x once per class,
+    // mu = ln(mode) + sigma^2, 1/sigma and amp/(sigma sqrt(2 pi)) once per walker, then one
+    // multiply-add chain and one branch-free exp per (class, walker) -- no divisions there.
     // (mb_k0_factors evaluates the textbook form; the two agree to an ulp or two.)
     const ModelDev& m = a.model;
-    double* lut = reinterpret_cast<double*>(smem_raw);              // [ncls_total][Wpad]
+    double* lut = reinterpret_cast<double*>(smem_raw);              // [nscratch][Wpad]
     double* tab = reinterpret_cast<double*>(smem_raw + a.tab_off);  // [nA + nB][Wpad]
-    const int ncls = a.ncls_total, nlut = ncls * Wpad;
-    double* lxs = lut + nlut;                                       // [ncls][2] ln x, 1/x of the class value
+    const int ncls = a.ncls_total, nrows = a.nA + a.nB;
+    double* lxs = lut + (size_t)a.nscratch * Wpad;                  // [ncls][2] ln x, 1/x of the class value
     double* cw = lxs + 2 * ncls;                                    // [NPARAM][Wpad][6] per-walker lognormal constants
-    ushort4* srow = reinterpret_cast<ushort4*>(cw + 6 * MB_NPARAM * Wpad);  // [nB] look-up rows of a dust class's digits
+    ushort4* srow = reinterpret_cast<ushort4*>(cw + 6 * MB_NPARAM * Wpad);  // [nrows] look-up rows of a table row
+    unsigned short* sslot = reinterpret_cast<unsigned short*>(srow + nrows);  // [ncls] (padded to 8 bytes)
     // phi: carried in the kernel parameters (copied to shared memory with indexed constant loads --
     // reads of the parameter space through a generic pointer are slow) or in device memory
     const double* ph = a.phi;
     if (a.phi_inline) {
-      double* sphi = reinterpret_cast<double*>(srow + a.nB);
+      double* sphi = reinterpret_cast<double*>(sslot + ((ncls + 3) & ~3));
       const int n = a.W * a.ndim;
       for (int i = threadIdx.x; i < n; i += blockDim.x) sphi[i] = a.phi_in[i];
       __syncthreads();
       ph = sphi;
     }
     const double inv_sqrt_2pi = 0.3989422804014326779399460599343819;
-    // (the digit rows ride along with the first phase: their L2 latency hides behind the logarithms)
-    for (int i = (int)blockDim.x - 1 - (int)threadIdx.x; i < a.nB; i += blockDim.x)
-      srow[i] = __ldg(reinterpret_cast<const ushort4*>(a.rowlut) + i);
+    // (the row lists ride along with the first phase: their L2 latency hides behind the logarithms)
+    for (int i = (int)blockDim.x - 1 - (int)threadIdx.x; i < nrows; i += blockDim.x)
+      srow[i] = __ldg(reinterpret_cast<const ushort4*>(a.rowsrc) + i);
+    for (int i = (int)blockDim.x - 1 - (int)threadIdx.x; i < ncls; i += blockDim.x)
+      sslot[i] = __ldg(a.lutslot + i);
     for (int idx = threadIdx.x; idx < ncls + MB_NPARAM * Wpad; idx += blockDim.x) {
       if (idx < ncls) {
         const double x = __ldg(a.clsx + idx);
@@ -1104,6 +1209,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
       ExpCoef ec;
 #pragma unroll
       for (int i = 0; i < 14; ++i) ec.c[i] = kExpPoly[i];
+      const int nlut = ncls * Wpad;
 #pragma unroll 3
       for (int idx = threadIdx.x; idx < nlut; idx += blockDim.x) {
         const int i = idx / Wpad, w = idx - i * Wpad;
@@ -1124,25 +1230,28 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
           // padding columns repeat the last walker
           v = prior_eval(m, p, ph + (size_t)(w < a.W ? w : a.W - 1) * a.ndim + m.voff[p], __ldg(a.clsx + i));
         }
-        lut[idx] = v;
+        const unsigned slot = sslot[i];
+        ((slot & 0x8000u) ? tab + (size_t)(slot & 0x7fffu) * Wpad : lut + (size_t)slot * Wpad)[w] = v;
       }
     }
     __syncthreads();
-    const int ntab = (a.nA + a.nB) * Wpad;
-#pragma unroll 3
+    const int ntab = nrows * Wpad;
+#pragma unroll 2
     for (int idx = threadIdx.x; idx < ntab; idx += blockDim.x) {
-      const int c = idx / Wpad, w = idx - c * Wpad;
+      const int r = idx / Wpad, w = idx - r * Wpad;
+      // look-up rows of the table row (precomputed: no integer divisions here), multiplied in the
+      // reference's left-to-right order (`cur_physmod *=`, :146-148)
+      const ushort4 sr = srow[r];
+      if (sr.y == 0xffff && sr.x != 0xffff && sslot[sr.x] == (0x8000u | (unsigned)r)) continue;  // evaluated in place
       double v = 1.0;
-      if (c < a.nA) {
-        if (m.kind[MB_P_LOGA] != MB_FIXED) v = lut[(m.clsoff[MB_P_LOGA] + c) * Wpad + w];
-      } else {
-        // look-up rows of the dust class's digits (precomputed: no integer divisions here), multiplied
-        // in the reference's left-to-right order (`cur_physmod *=`, :146-148)
-        const ushort4 r = srow[c - a.nA];
-        if (r.x != 0xffff) v *= lut[r.x * Wpad + w];
-        if (r.y != 0xffff) v *= lut[r.y * Wpad + w];
-        if (r.z != 0xffff) v *= lut[r.z * Wpad + w];
-      }
+      auto lrow = [&](unsigned row) -> const double* {
+        const unsigned slot = sslot[row];
+        return (slot & 0x8000u) ? tab + (size_t)(slot & 0x7fffu) * Wpad : lut + (size_t)slot * Wpad;
+      };
+      if (sr.x != 0xffff) v *= lrow(sr.x)[w];
+      if (sr.y != 0xffff) v *= lrow(sr.y)[w];
+      if (sr.z != 0xffff) v *= lrow(sr.z)[w];
+      if (sr.w != 0xffff) v *= lrow(sr.w)[w];
       tab[idx] = v;
     }
     __syncthreads();
@@ -1162,66 +1271,63 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     __syncthreads();
   }
   stamp(a.timeline, 1);
-  // Poisson prologue: block b computes the N-stars term of walkers b, b + gridDim.x, ... from the
-  // tables it just staged; dynamic segment scheduling absorbs the few microseconds it starts late
-  {
-    __shared__ double pscratch[k2_threads(NW) / 32];
-    // the Poisson term always uses the fp64 tables (from shared memory when they are there)
+  // N-stars prologue: this block's (age, Z) bins for all walkers of the pass, on the tables it just
+  // staged (always the fp64 ones: from shared memory when they are there, else from global memory)
+  if (a.pois.nbins > 0) {
     const double* Ftab = (MODE == kModeFactor && !kF32) ? reinterpret_cast<const double*>(smem_raw + a.tab_off) : a.FA;
-    for (int w = blockIdx.x; w < a.W; w += gridDim.x) {
-      double pois = 0.0;
-      if (a.pois.nbins > 0)
-        pois = poisson_term<k2_threads(NW)>(a.pois, Ftab, a.nA, a.nB, Wpad, w,
-                                            reinterpret_cast<double*>(smem_raw), pscratch);
-      if (threadIdx.x == 0) a.out[(size_t)MB_OUT_POISSON * a.Wtot + a.w0 + w] = pois;
-    }
+    poisson_bins<NW, k2_threads(NW)>(a.pois, Ftab, a.nA, a.nOd, a.nB, smem_raw);
   }
 
   stamp(a.timeline, 2);
-  Lanes<NW, MODE, TF, C16> L;
+  Lanes<NW, MODE, TF, OB> L;
   L.init(tabA, tabB, reinterpret_cast<const char*>(a.T) + lanebytes);
 
   // Segments: every warp starts with its own index (no atomic storm at kernel start); further
   // ones are claimed from a shared counter, one atomic per segment issued a segment ahead.  The
   // result does not depend on who processed what: a segment's value depends only on its own
-  // entries, and segment values are added as 64-bit fixed point.
-  long long fix[NW];
+  // entries, and segment values are added as fixed point.
+  long long fixhi[NW], fixlo[NW];
 #pragma unroll
-  for (int i = 0; i < NW; ++i) fix[i] = 0;
+  for (int i = 0; i < NW; ++i) { fixhi[i] = 0; fixlo[i] = 0; }
   const int nwarps_total = (int)gridDim.x * kK2Warps;
   int s = (int)blockIdx.x * kK2Warps + warp, s_next = 0;
   while (s < a.nseg) {
     if (lane == 0) s_next = nwarps_total + (int)atomicAdd(a.counters + kCtrSegment, 1u);
-    stream_range<NW, MODE, TF, STAGES, C16>(L, a.ea, a.ec, a.seg[s], a.seg[s + 1], st_a, st_c, lane);
+    stream_range<NW, MODE, TF, STAGES, OB>(L, a.ea, a.ec, a.seg[s], a.seg[s + 1], st_a, st_c, lane);
     L.close();
 #pragma unroll
-    for (int i = 0; i < NW; ++i) fix[i] += __double2ll_rn(L.acc[i].take_value() * kFixScale);
+    for (int i = 0; i < NW; ++i) {
+      const Fix2 f = to_fix2(L.acc[i].take_value());
+      fixhi[i] += f.hi; fixlo[i] += f.lo;
+    }
     s = __shfl_sync(0xffffffffu, s_next, 0);
   }
 
-  // ---- K3 (fused): warp -> block (shared atomics) -> grid (global atomics) reduction over stars,
+  // ---- K3 (fused): warp -> block (slabs) -> grid (global atomics) reduction over stars,
   // all in integers; the last block to finish converts and writes the result rows.
+  __shared__ unsigned int ticket;
+  __shared__ int timed_out;
   __syncthreads();
   stamp(a.timeline, 3);
   // every warp parks its per-walker integers in its own slab of the (now idle) stage, then
-  // 3 * Wpad threads add the slabs: no shared-memory atomics (64-bit ones are CAS loops)
+  // kAccRows * Wpad threads add the slabs: no shared-memory atomics (64-bit ones are CAS loops)
   // (in the front region, or -- when that is too small -- over the factor tables, dead by now)
-  unsigned long long* slab = reinterpret_cast<unsigned long long*>(smem_raw + a.slab_off);  // [warps][3][Wpad]
+  unsigned long long* slab = reinterpret_cast<unsigned long long*>(smem_raw + a.slab_off);  // [warps][kAccRows][Wpad]
 #pragma unroll
   for (int i = 0; i < NW; ++i) {
     const int w = (NW == 1) ? lane : 64 * (i >> 1) + 2 * lane + (i & 1);
-    slab[((size_t)warp * 3 + 0) * Wpad + w] = (unsigned long long)fix[i];
-    slab[((size_t)warp * 3 + 1) * Wpad + w] = (unsigned long long)L.acc[i].bad;
-    slab[((size_t)warp * 3 + 2) * Wpad + w] = (unsigned long long)L.acc[i].isnan;
+    slab[((size_t)warp * kAccRows + 0) * Wpad + w] = (unsigned long long)fixhi[i];
+    slab[((size_t)warp * kAccRows + 1) * Wpad + w] = (unsigned long long)fixlo[i];
+    slab[((size_t)warp * kAccRows + 2) * Wpad + w] = (unsigned long long)L.acc[i].bad;
+    slab[((size_t)warp * kAccRows + 3) * Wpad + w] = (unsigned long long)L.acc[i].isnan;
   }
+  if (threadIdx.x == 0) timed_out = 0;
   __syncthreads();
   unsigned long long mine = 0ull;
-  if (threadIdx.x < 3 * Wpad) {
-    for (int wp = 0; wp < kK2Warps; ++wp) mine += slab[(size_t)wp * 3 * Wpad + threadIdx.x];
+  if (threadIdx.x < kAccRows * Wpad) {
+    for (int wp = 0; wp < kK2Warps; ++wp) mine += slab[(size_t)wp * kAccRows * Wpad + threadIdx.x];
     if (mine != 0ull) atomicAdd(a.gacc + threadIdx.x, mine);
   }
-  unsigned long long* sacc = slab;  // scratch for the last block below
-  __shared__ unsigned int ticket;
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) ticket = atomicAdd(a.counters + kCtrBlocks, 1u);
@@ -1230,19 +1336,18 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   if (ticket != gridDim.x - 1) return;
   __threadfence();
   // last block of this GPU: take the shard totals, leave the accumulators zero for the next launch
-  unsigned long long* tot = sacc;  // [3][Wpad]
-  __syncthreads();
-  for (int i = threadIdx.x; i < 3 * Wpad; i += blockDim.x) {
+  unsigned long long* tot = slab;  // [kAccRows][Wpad]; the Poisson scratch follows it
+  for (int i = threadIdx.x; i < kAccRows * Wpad; i += blockDim.x) {
     tot[i] = __ldcg(a.gacc + i);
     a.gacc[i] = 0ull;
   }
   if (threadIdx.x == 0) { a.counters[kCtrSegment] = 0u; a.counters[kCtrBlocks] = 0u; }
-  __syncthreads();
-  __shared__ int timed_out;
-  if (threadIdx.x == 0) timed_out = 0;
+  // Poisson term of every walker: the bins of all blocks, added in fixed order (identical on every rank)
+  poisson_finish<NW, k2_threads(NW)>(a.pois, reinterpret_cast<double*>(tot + kAccRows * Wpad),
+                                     a.out + (size_t)MB_OUT_POISSON * a.Wtot + a.w0, a.W);
   if (a.peer.world > 1) {
     const int par = (int)(a.peer.seq & 1u), me = a.peer.rank, world = a.peer.world;
-    for (int i = threadIdx.x; i < 3 * Wpad; i += blockDim.x) {
+    for (int i = threadIdx.x; i < kAccRows * Wpad; i += blockDim.x) {
       const unsigned long long v = tot[i];
       for (int p = 0; p < world; ++p)  // my totals into slot `me` of every rank (peer stores)
         *reinterpret_cast<volatile unsigned long long*>(a.peer.xbuf[p] + xbuf_data_off(par, me) + i) = v;
@@ -1253,17 +1358,22 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
       volatile unsigned int* theirs =
           reinterpret_cast<volatile unsigned int*>(a.peer.xbuf[threadIdx.x]) + xbuf_flag_off(par, me);
       *theirs = a.peer.seq;  // publish
-      volatile unsigned int* mine =
+      volatile unsigned int* mine_flag =
           reinterpret_cast<volatile unsigned int*>(a.peer.xbuf[me]) + xbuf_flag_off(par, threadIdx.x);
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
       unsigned int spins = 0;
-      while (*mine != a.peer.seq) {  // bounded wait (~2 s) for source threadIdx.x
-        __nanosleep(64);
-        if (++spins > (1u << 24)) { timed_out = 1; break; }
+      while (*mine_flag != a.peer.seq) {  // bounded wait for source threadIdx.x
+        if ((++spins & 0xffu) == 0u) {
+          asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+          if (t1 - t0 > a.peer.timeout_ns) { timed_out = 1; break; }
+          __nanosleep(64);
+        }
       }
     }
     __threadfence_system();
     __syncthreads();
-    for (int i = threadIdx.x; i < 3 * Wpad; i += blockDim.x) {
+    for (int i = threadIdx.x; i < kAccRows * Wpad; i += blockDim.x) {
       unsigned long long t = 0ull;
       for (int r = 0; r < world; ++r)
         t += *reinterpret_cast<volatile unsigned long long*>(a.peer.xbuf[me] + xbuf_data_off(par, r) + i);
@@ -1272,9 +1382,9 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     __syncthreads();
   }
   for (int w = threadIdx.x; w < a.W; w += blockDim.x) {
-    const long long f = (long long)tot[w];
-    const unsigned long long nbad = tot[Wpad + w], nnan = tot[2 * Wpad + w];
-    a.out[(size_t)MB_OUT_STARSUM * a.Wtot + a.w0 + w] = (nnan || timed_out) ? nan("") : (double)f / kFixScale;
+    const unsigned long long nbad = tot[2 * Wpad + w], nnan = tot[3 * Wpad + w];
+    a.out[(size_t)MB_OUT_STARSUM * a.Wtot + a.w0 + w] =
+        (nnan || timed_out) ? nan("") : from_fix2((long long)tot[w], (long long)tot[Wpad + w]);
     a.out[(size_t)MB_OUT_NONFINITE * a.Wtot + a.w0 + w] = timed_out ? -1.0 : (double)nbad;
   }
   if (a.done_flag) {
@@ -1300,7 +1410,7 @@ struct KPixArgs {
   const double* ea;           // entry weights
   const uint32_t* ec;         // entry codes (FACTOR layout)
   const int64_t* pix_seg;     // [P][kPixWarps + 1] entry offsets of the pixel's warp pieces
-  const double* F;            // [P][nA + nB][Wpad]
+  const double* F;            // [P][nA + nB + nA][Wpad] (K0's layout: outer = age rows, inner = dust rows, plain age rows)
   const int32_t* pix_nstars;  // [P] S of each pixel's Poisson term
   double* out;                // [P][MB_OUT_ROWS][W]
   unsigned int* counters;     // [kCtrWords]: next pixel, blocks done (zero between launches)
@@ -1377,7 +1487,7 @@ __global__ void __launch_bounds__(kPixThreads, (NW <= 2 ? 2 : 1)) mb_k2_pixels(K
   constexpr int Wpad = 32 * NW;  // == a.Wpad
   constexpr uint32_t rowbytes = (uint32_t)Wpad * 8u;
   const uint32_t lanebytes = (NW == 1 ? lane : 2 * lane) * 8u;
-  // smem: [front: entry stage / Poisson task scratch][tables][spois Wpad][sacc 3 x Wpad]
+  // smem: [front: entry stage / Poisson task scratch][tables][spois Wpad][sacc kAccRows x Wpad]
   const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
   const uint32_t st_a = smem0 + (uint32_t)warp * kStageBytes;
   const uint32_t st_c = st_a + kStages * kChunk * 8u;
@@ -1398,10 +1508,10 @@ __global__ void __launch_bounds__(kPixThreads, (NW <= 2 ? 2 : 1)) mb_k2_pixels(K
     if (pix >= a.P) break;
     {  // this pixel's factor tables
       const int n2 = (a.nA + a.nB) * Wpad / 2;
-      const double2* src = reinterpret_cast<const double2*>(a.F + (size_t)pix * (a.nA + a.nB) * Wpad);
+      const double2* src = reinterpret_cast<const double2*>(a.F + (size_t)pix * (a.nA + a.nB + a.nA) * Wpad);
       double2* dst = reinterpret_cast<double2*>(sF);
       for (int i = threadIdx.x; i < n2; i += kPixThreads) dst[i] = __ldg(src + i);
-      for (int i = threadIdx.x; i < 3 * Wpad; i += kPixThreads) sacc[i] = 0ull;
+      for (int i = threadIdx.x; i < kAccRows * Wpad; i += kPixThreads) sacc[i] = 0ull;
     }
     __syncthreads();
     const double n_stars = (double)a.pix_nstars[pix];
@@ -1422,16 +1532,18 @@ __global__ void __launch_bounds__(kPixThreads, (NW <= 2 ? 2 : 1)) mb_k2_pixels(K
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
       const int w = (NW == 1) ? lane : 64 * (i >> 1) + 2 * lane + (i & 1);
-      const long long fixv = __double2ll_rn(L.acc[i].take_value() * kFixScale);
-      if (fixv) atomicAdd(sacc + w, (unsigned long long)fixv);
-      if (L.acc[i].bad) atomicAdd(sacc + Wpad + w, (unsigned long long)L.acc[i].bad);
-      if (L.acc[i].isnan) atomicAdd(sacc + 2 * Wpad + w, 1ull);
+      const Fix2 f = to_fix2(L.acc[i].take_value());
+      if (f.hi) atomicAdd(sacc + w, (unsigned long long)f.hi);
+      if (f.lo) atomicAdd(sacc + Wpad + w, (unsigned long long)f.lo);
+      if (L.acc[i].bad) atomicAdd(sacc + 2 * Wpad + w, (unsigned long long)L.acc[i].bad);
+      if (L.acc[i].isnan) atomicAdd(sacc + 3 * Wpad + w, 1ull);
     }
     __syncthreads();
     double* out = a.out + (size_t)pix * MB_OUT_ROWS * a.W;
     for (int w = threadIdx.x; w < a.W; w += kPixThreads) {
-      out[(size_t)MB_OUT_STARSUM * a.W + w] = sacc[2 * Wpad + w] ? nan("") : (double)(long long)sacc[w] / kFixScale;
-      out[(size_t)MB_OUT_NONFINITE * a.W + w] = (double)sacc[Wpad + w];
+      out[(size_t)MB_OUT_STARSUM * a.W + w] =
+          sacc[3 * Wpad + w] ? nan("") : from_fix2((long long)sacc[w], (long long)sacc[Wpad + w]);
+      out[(size_t)MB_OUT_NONFINITE * a.W + w] = (double)sacc[2 * Wpad + w];
       out[(size_t)MB_OUT_POISSON * a.W + w] = spois[w];
     }
     __syncthreads();  // tables, sacc and the stage are reused by the next pixel

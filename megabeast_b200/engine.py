@@ -69,7 +69,11 @@ class ModelSpec:
 class LikelihoodEngine:
     def __init__(self, spec, star_lnpgriddata, beast_moddata, massmult=None, devices=None,
                  mode="auto", star_range=None, n_stars_total=None, keep_indices=False,
-                 merge_duplicates=True, segments_per_warp=0, pixel_offsets=None, table_precision="fp64"):
+                 merge_duplicates=True, segments_per_warp=0, pixel_offsets=None, table_precision="fp64",
+                 split_inner=None):
+        """``split_inner``: FACTOR mode only -- the dust parameters kept in the inner factor table
+        (e.g. ``("Av",)``; the others join the age classes in the outer table).  ``None`` lets
+        ``mb_create`` choose (all of them when the product table fits shared memory)."""
         self.lib = _cabi.load()
         self._mb_lnlike = self.lib.mb_lnlike
         self._bufs = {}
@@ -144,6 +148,7 @@ class LikelihoodEngine:
                 opt.segments_per_warp = int(os.environ.get("MB_SEGMENTS_PER_WARP", segments_per_warp))
                 opt.tail_percent = int(os.environ.get("MB_TAIL_PERCENT", 0))
                 opt.table_precision = {"fp64": 0, "fp32": 1}[table_precision]
+                opt.split_inner_mask = sum(1 << (_cabi.PARAMS.index(p) - 1) for p in (split_inner or ()))
                 h = ctypes.c_void_p()
                 if pixel_offsets is not None:
                     _cabi.check(
@@ -206,6 +211,18 @@ class LikelihoodEngine:
             )
         )
         return rows[: offs[-1]], offs
+
+    def device_entries(self, i=0):
+        """Parity hook (``mb_device_entries``): the class-coded entry stream as the DEVICE holds it.
+        Returns (cls[n, 4] class index per parameter, weight[n], offsets[S_local + 1])."""
+        info = self.info(i)
+        n = max(1, info["n_entries"])
+        cls = np.zeros((n, _cabi.MB_NPARAM), dtype=np.int32)
+        weight = np.zeros(n)
+        offs = np.zeros(info["n_stars_local"] + 1, dtype=np.int64)
+        _cabi.check(self.lib.mb_device_entries(self.handles[i], n, cls.ctypes.data_as(_cabi.c_int32_p),
+                                               _cabi.dptr(weight), offs.ctypes.data_as(_cabi.c_int64_p)))
+        return cls[: offs[-1]], weight[: offs[-1]], offs
 
     # -- cross-GPU reduction fused into the likelihood kernel (one process per GPU) -------------
     def peer_export(self, i=0):

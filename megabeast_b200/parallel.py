@@ -92,7 +92,8 @@ class ShardedLikelihood:
                                        devices=[self.device], mode=mode,
                                        star_range=self.star_range,
                                        n_stars_total=S if n_stars_total is None else int(n_stars_total),
-                                       table_precision=getattr(model, "table_precision", "fp64"))
+                                       table_precision=getattr(model, "table_precision", "fp64"),
+                                       split_inner=getattr(model, "split_inner", None))
         # how the shard partials are added: "p2p" = inside the likelihood kernel over NVLink peer
         # memory (mb_peer_connect), "nccl" = one all-reduce after it; "auto" tries p2p first
         self.reduce = "none" if self.world == 1 else self._setup_reduce(reduce)

@@ -48,7 +48,8 @@ class MB_Model:
     verbose : print the three setup lines the reference prints (:31-33)
     """
 
-    def __init__(self, params, devices=None, mode="auto", verbose=False, table_precision="fp64"):
+    def __init__(self, params, devices=None, mode="auto", verbose=False, table_precision="fp64",
+                 split_inner=None):
         self.star_model = params.stellar_model
         self.dust_model = params.fd_model
         age_cls, mass_cls, dust_cls, _, self.prior_source = resolve_prior_classes()
@@ -89,6 +90,7 @@ class MB_Model:
         self.devices = devices
         self.mode = mode
         self.table_precision = table_precision
+        self.split_inner = split_inner  # FACTOR mode: dust parameters of the inner table (None = automatic)
         self._engines = {}  # identity of the data dictionaries -> (engine, strong refs)
         # the model structure (which priors are free, their boxes) is fixed at construction
         self._layout_cache = None
@@ -197,7 +199,7 @@ class MB_Model:
         try:
             engine = LikelihoodEngine(spec, star_lnpgriddata, beast_moddata, massmult=mm,
                                       devices=self.devices, mode=self.mode,
-                                      table_precision=self.table_precision)
+                                      table_precision=self.table_precision, split_inner=self.split_inner)
         except _cabi.MegabeastB200Error as exc:
             msg = str(exc)
             if "outside of model x range" in msg:

@@ -45,6 +45,11 @@ CONFIGS = {
     # production-like dust axes (A(V) 0-10 in steps of 0.1, 9 R(V), 5 f_A: 4,500 dust classes, too many
     # for shared memory -> `table_unique`, the class table gathered from L2)
     "fine_dust": dict(axes=(41, 4, 10, 100, 9, 5), S=100_000, K=50, W=64),
+    # small-G versions of production dust axes (parity tests): 900 and 1,800 dust classes
+    "dust900_small": dict(axes=(9, 2, 3, 100, 9, 1), S=400, K=24, W=16),
+    "dust1800_small": dict(axes=(9, 2, 2, 200, 9, 1), S=400, K=24, W=16),
+    # config 4's table shape (200 dust classes x 128 walkers = one 512-thread pass) on a small grid
+    "cfg4_shape_small": dict(axes=(41, 4, 3, 20, 10, 1), S=2_000, K=50, W=128),
     # one GPU's share of the PHAT-scale config 4 on 8 GPUs
     "cfg4_eighth": dict(axes=(41, 4, 61, 20, 10, 1), S=125_000, K=50, W=128),
 }

@@ -1,0 +1,186 @@
+"""
+FACTOR mode with the factor tables SPLIT (outer = age classes x some dust parameters, inner = the
+other dust parameters): the path production BEAST grids take, whose dust classes (100-200 A(V)
+values x 9 R(V)) do not fit shared memory as one product table.  Also: what the device holds,
+decoded (``mb_device_entries``), the config-4 table shape, and totals near zero.
+
+Tolerance 1e-9 relative against the oracle everywhere; decoded class codes and folded weights
+bit-exact.  Reference: /root/reference/megabeast/singlepop_dust_model.py:131-148 (product over
+the parameters), :194-229 (per-star gather, sum, log, sum).
+"""
+import copy
+
+import numpy as np
+import pytest
+
+from golden_util import assert_close, golden_names, load_golden
+from megabeast_b200 import MB_Model, lnprob, synth
+from megabeast_b200.engine import LikelihoodEngine
+from oracle import c_oracle
+from oracle import lnprob_port as port
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def _free_dust(settings):
+    return [p for p in ("Av", "Rv", "fA") if settings.fd_model[p]["prior"]["name"] != "fixed"]
+
+
+def _eval_one_by_one(model, phis, stars, moddata):
+    out = np.full(len(phis), np.nan)
+    kind = np.zeros(len(phis), np.int32)
+    for i, phi in enumerate(phis):
+        try:
+            out[i] = lnprob(phi, model, stars, moddata)
+        except ValueError:
+            kind[i] = 1
+        except SystemExit:
+            kind[i] = 2
+    return out, kind
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_goldens_with_every_split(name, capsys):
+    """Every golden vector (frozen from the reference) under every possible table split."""
+    settings, moddata, stars, phis, expect, kind = load_golden(name)
+    free = _free_dust(settings)
+    if MB_Model(copy.deepcopy(settings))._spec()[0].tabulated:
+        free = [p for p in free]  # tabulated parameters split like any other (K0 path)
+    splits = [tuple(p for j, p in enumerate(free) if (m >> j) & 1) for m in range(1, 1 << len(free))]
+    assert splits or not free
+    for split in splits:
+        model = MB_Model(copy.deepcopy(settings), mode="factor", split_inner=split)
+        got, gkind = _eval_one_by_one(model, phis, stars, moddata)
+        assert np.array_equal(gkind, kind), split
+        ok = kind == 0
+        assert_close(got[ok], expect[ok], RTOL)
+        info = model.engine_info()
+        want_mask = sum(1 << ("Av", "Rv", "fA").index(p) for p in split)
+        assert info["split_inner_mask"] == want_mask
+        if not kind.any():  # the batch evaluates all walkers in one launch
+            assert_close(lnprob(phis, model, stars, moddata), expect, RTOL)
+
+
+@pytest.mark.parametrize("cfg,mode,W", [("small", "uniform", 7), ("cfg1", "clustered", 45),
+                                         ("cfg1", "uniform", 64), ("cfg1", "uniform", 130)])
+@pytest.mark.parametrize("split", [("Av",), ("Rv",)])
+def test_split_vs_c_oracle(cfg, mode, W, split):
+    settings, moddata, stars, _ = synth.make_problem(cfg, mode=mode, seeds=(61, 62, 63))
+    pm = port.PortModel(copy.deepcopy(settings))
+    phis = synth.make_walkers(pm, W, seed=63)
+    expect = c_oracle.lnprob_batch(pm, phis, stars, moddata)
+    model = MB_Model(copy.deepcopy(settings), mode="factor", split_inner=split)
+    assert_close(lnprob(phis, model, stars, moddata), expect, RTOL)
+    info = model.engine_info()
+    assert info["n_outer_rows"] > info["n_age_classes"]  # a dust parameter really sits outside
+    assert abs(lnprob(phis[3], model, stars, moddata) - expect[3]) <= RTOL * abs(expect[3])
+
+
+@pytest.mark.parametrize("cfg,ndust", [("dust900_small", 900), ("dust1800_small", 1800)])
+def test_production_dust_axes(cfg, ndust):
+    """900 / 1,800 dust classes: the product table does not fit shared memory, AUTO must keep the
+    tables separate (A(V) inside, age x R(V) outside) and still match the oracle on >= 8 walkers;
+    the `table_unique` fallback (class table in global memory) must match as well."""
+    settings, moddata, stars, c = synth.make_problem(cfg, mode="uniform", seeds=(71, 72, 73))
+    pm = port.PortModel(copy.deepcopy(settings))
+    phis = synth.make_walkers(pm, 24, seed=73)
+    expect = c_oracle.lnprob_batch(pm, phis, stars, moddata)
+    model = MB_Model(copy.deepcopy(settings))
+    got = lnprob(phis, model, stars, moddata)
+    info = model.engine_info()
+    assert info["mode"] == "factor" and info["n_dust_classes"] == ndust
+    assert info["split_inner_mask"] == 1 and info["n_inner_rows"] == ndust // 9
+    assert info["n_outer_rows"] == info["n_age_classes"] * 9
+    assert info["launches_last_eval"] == 1
+    assert_close(got, expect, RTOL)
+    for W in (1, 33, 70):  # 32-, 64- and 128-walker pass shapes
+        ph = synth.make_walkers(pm, W, seed=74 + W)
+        assert_close(lnprob(ph, model, stars, moddata), c_oracle.lnprob_batch(pm, ph, stars, moddata), RTOL)
+    tu = MB_Model(copy.deepcopy(settings), mode="table_unique")
+    assert_close(lnprob(phis, tu, stars, moddata), expect, RTOL)
+    assert tu.engine_info()["mode"] == "table_unique"
+    # clustered (BEAST-like) indices on the same grid
+    _, mod_c, stars_c, _ = synth.make_problem(cfg, mode="clustered", seeds=(71, 75, 73))
+    assert_close(lnprob(phis, MB_Model(copy.deepcopy(settings)), stars_c, mod_c),
+                 c_oracle.lnprob_batch(pm, phis, stars_c, mod_c), RTOL)
+
+
+def test_cfg4_table_shape_single_pass_of_128_walkers():
+    """Config 4's plan: 200 dust classes x 128 walkers = 210 KB of tables, ONE pass of the 512-thread
+    kernel (two-chunk entry ring, reduction slabs over the dead tables, N-stars scratch in what is
+    left).  All 128 walkers against the oracle."""
+    settings, moddata, stars, cfg = synth.make_problem("cfg4_shape_small", seeds=(81, 82, 83))
+    pm = port.PortModel(copy.deepcopy(settings))
+    phis = synth.make_walkers(pm, 128, seed=83)
+    expect = c_oracle.lnprob_batch(pm, phis, stars, moddata)
+    model = MB_Model(copy.deepcopy(settings))
+    got = lnprob(phis, model, stars, moddata)
+    info = model.engine_info()
+    assert info["mode"] == "factor" and info["n_dust_classes"] == 200 and info["split_inner_mask"] == 3
+    assert info["walkers_per_pass"] == 128
+    assert_close(got, expect, RTOL)
+    assert_close(lnprob(phis[:100], model, stars, moddata), expect[:100], RTOL)
+
+
+def _class_index(values, col, histo):
+    if histo:  # interval of a left-constant step function, last node -> last height
+        return np.minimum(np.searchsorted(values, col, side="right") - 1, len(values) - 1)
+    idx = np.searchsorted(values, col)
+    assert np.array_equal(values[idx], col)
+    return idx
+
+
+@pytest.mark.parametrize("mode,split", [("factor", None), ("factor", ("Av",)), ("factor", ("Rv",)),
+                                        ("table_unique", None)])
+def test_device_entries_decode_bit_exact(mode, split):
+    """What the DEVICE holds: the class codes of every entry, decoded, must be the classes of the
+    grid rows the reference gathers (indxs[:, s][isfinite(vals[:, s])], :196-198), and the folded
+    weights vals*prior_weight*grid_weight*completeness bit for bit."""
+    settings, moddata, stars, phis, expect, kind = load_golden("masked_and_zero_stars")
+    model = MB_Model(copy.deepcopy(settings))
+    spec, perm, ndim = model._spec()
+    eng = LikelihoodEngine(spec, stars, moddata, mode=mode, keep_indices=True, merge_duplicates=False,
+                           split_inner=split)
+    cls, weight, offs = eng.device_entries()
+    flat, eoffs = port.gathered_indices(stars)
+    assert np.array_equal(offs, eoffs)
+    want_cls = np.zeros((flat.size, 4), dtype=np.int64)
+    for j, p in enumerate(("logA", "Av", "Rv", "fA")):
+        if spec.kinds[p] == "fixed":
+            continue
+        want_cls[:, j] = _class_index(eng.class_values(p), moddata[p][flat], spec.kinds[p] == "bins_histo")
+    vals, indxs = stars["vals"], stars["indxs"]
+    S = indxs.shape[1]
+    for s in range(S):
+        fin = np.isfinite(vals[:, s])
+        r = indxs[:, s][fin]
+        w = vals[:, s][fin] * moddata["prior_weight"][r] * moddata["grid_weight"][r] * moddata["completeness"][r]
+        assert np.array_equal(r, flat[eoffs[s]:eoffs[s + 1]])
+        want = sorted(zip(map(tuple, want_cls[eoffs[s]:eoffs[s + 1]]), w))
+        got = sorted(zip(map(tuple, cls[offs[s]:offs[s + 1]].astype(np.int64)), weight[offs[s]:offs[s + 1]]))
+        assert got == want, s
+    eng.close()
+
+
+def test_totals_near_zero_keep_relative_accuracy():
+    """|sum ln L| << 1: a one-word 2^-32 fixed-point sum has an absolute floor of ~1e-10 per segment
+    and would miss 1e-9 RELATIVE here; the two-word sum (2^-24 + 2^-68) does not."""
+    settings, moddata, stars, _ = synth.make_problem("small", seeds=(91, 92, 93))
+    settings.stellar_model["logA"]["prior"]["name"] = "fixed"  # no N-stars term: lnlike = sum ln L only
+    pm = port.PortModel(copy.deepcopy(settings))
+    S = 7
+    sub = {"indxs": np.ascontiguousarray(stars["indxs"][:, :S]), "vals": np.ascontiguousarray(stars["vals"][:, :S])}
+    phis = synth.make_walkers(pm, 9, seed=93)
+    phis = phis[0] * (1.0 + 1e-4 * np.random.default_rng(1).standard_normal(phis.shape))
+    physmod, _ = pm.physmod(phis[0], moddata)
+    L = port.star_sums(sub["vals"], sub["indxs"], physmod, moddata["prior_weight"], moddata["grid_weight"],
+                       moddata["completeness"])
+    delta = 1e-3 * np.array([1, -1, 1, -1, 1, -1, 0.5])
+    sub["vals"] = sub["vals"] / L * np.exp(delta)      # every star's L close to 1 for walker 0
+    expect = np.array([port.lnprob(p, pm, sub, moddata, loop=False) for p in phis])
+    assert np.all(np.abs(expect) < 0.5) and np.all(expect != 0.0)
+    for mode in ("factor", "table_unique", "table_grid", "elementwise"):
+        model = MB_Model(copy.deepcopy(settings), mode=mode)
+        assert_close(lnprob(phis, model, sub, moddata), expect, RTOL)
+        assert abs(lnprob(phis[2], model, sub, moddata) - expect[2]) <= RTOL * abs(expect[2])
