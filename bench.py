@@ -314,7 +314,7 @@ def run_ours(args):
     info = sharded.engine.info()
     ndim = sharded.ndim
     d_phi = torch.from_numpy(np.ascontiguousarray(phis[:, sharded.perm])).to(dev)
-    d_rows = torch.empty((3, W), dtype=torch.float64, device=dev)
+    d_rows = torch.empty((4, W), dtype=torch.float64, device=dev)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     K = args.steps
 
@@ -402,17 +402,17 @@ def run_ours(args):
         shw = ShardedLikelihood(MB_Model(copy.deepcopy(settings), devices=[local], mode=args.mode), stars, moddata,
                                 device=local, mode=args.mode, reduce=args.reduce,
                                 star_range=(0, cfg["S"]), n_stars_total=world * cfg["S"])
-        d_rows_w = torch.empty((3, W), dtype=torch.float64, device=dev)
+        d_rows_w = torch.empty((4, W), dtype=torch.float64, device=dev)
         weak_ms, _ = time_device(shw, d_rows_w, K, max(3, args.warmup))
         # every rank holds the same stars: the job's star sum must be N x the single-copy one
-        ratio = (d_rows_w[0] / (world * d_rows[0])).cpu().numpy()
+        ratio = ((d_rows_w[0] + d_rows_w[1]) / (world * (d_rows[0] + d_rows[1]))).cpu().numpy()
         weak = {"stars_per_gpu": cfg["S"], "stars_total": world * cfg["S"],
                 "value": world * W * K / (weak_ms * 1e-3), "unit": "100k-star-equivalent evals/s",
                 "job_evals_per_s": W * K / (weak_ms * 1e-3), "ms_per_step": weak_ms / K,
                 "reduce": shw.reduce,
                 "check_starsum_vs_n_copies_max_rel_err": float(np.max(np.abs(ratio - 1.0))),
                 "note": "per-GPU work fixed (each rank a full config-3 star shard), one reduction of "
-                        f"{2 * W} partials per step; value counts an evaluation over N x 100k stars as N evaluations"}
+                        f"{3 * W} partials per step; value counts an evaluation over N x 100k stars as N evaluations"}
         shw.close()
 
     # ---- per-kernel times (CUDA events inside the library, same stream) ------------------------------
@@ -432,7 +432,7 @@ def run_ours(args):
             kms[k] = kms.get(k, 0.0) + v / nprof
         tl = eng.last_k2_timeline()
         if len(tl):
-            ph = np.array([tl[:, 1].max(), tl[:, 2].max(), tl[:, 3].max(), tl[:, 4].max(), tl[:, 5].max()])
+            ph = np.array([tl[:, k].max() for k in range(1, 8)])
             phases = ph / nprof if phases is None else phases + ph / nprof
     eng.set_profiling(False)
     if world > 1:
@@ -450,10 +450,10 @@ def run_ours(args):
         try:
             sh2 = ShardedLikelihood(MB_Model(copy.deepcopy(settings), devices=[local], mode=args.mode), stars, moddata,
                                     device=local, mode=args.mode, reduce=other)
-            rows2 = torch.empty((3, W), dtype=torch.float64, device=dev)
+            rows2 = torch.empty((4, W), dtype=torch.float64, device=dev)
             sh2.lnlike_device(d_phi, rows2)
             torch.cuda.synchronize()
-            bitwise = bool(torch.equal(rows2[:2], d_rows[:2]))
+            bitwise = bool(torch.equal(rows2[0] + rows2[1], d_rows[0] + d_rows[1]) and torch.equal(rows2[2:], d_rows[2:]))
             sh2.close()
         except Exception as exc:  # e.g. no peer access on this box: say so, do not fail the bench
             bitwise = f"unavailable: {exc!r}"
@@ -568,7 +568,7 @@ def run_ours(args):
         "engine": {
             "engine_mode": mode, "n_free_parameters": ndim,
             "sharding": f"stars split over {world} rank(s), grid replicated; shard reduction: "
-                        + {"none": "none (1 GPU)", "nccl": f"one NCCL all-reduce of {2 * W} doubles per step",
+                        + {"none": "none (1 GPU)", "nccl": f"one NCCL all-reduce of {3 * W} doubles per step",
                            "p2p": "fused into K2's tail over NVLink peer memory (no collective launch)"}[sharded.reduce],
             "l2": "kept warm" if args.no_flush else f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB memset, outside the timed events)",
             "rank_alignment": "none (1 GPU)" if world == 1 else
@@ -579,7 +579,7 @@ def run_ours(args):
         },
         "clocks": clocks,
         "e2e": {"value": W * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * W * ndim,
-                "d2h_bytes_per_step": 8 * 3 * W, "ms_per_step": 1e3 * e2e_s / K,
+                "d2h_bytes_per_step": 8 * 4 * W, "ms_per_step": 1e3 * e2e_s / K,
                 "api": "megabeast_b200.lnprob(phis[W,ndim], MB_Model, star_lnpgriddata, beast_moddata)"
                        if world == 1 else "megabeast_b200.parallel.ShardedLikelihood.lnprob(phis[W,ndim])"},
         "gpu_launches": launches,
@@ -590,7 +590,8 @@ def run_ours(args):
         "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,
     }
     if phases is not None:
-        line["k2_phases_us"] = dict(zip(("tables_built", "nstars_bins_done", "star_loop_done", "block_reduced", "end"),
+        line["k2_phases_us"] = dict(zip(("tables_built", "nstars_bins_done", "star_loop_done", "block_reduced",
+                                         "last_block_totals_poisson_sent", "peers_received", "end"),
                                         [round(float(x), 2) for x in phases]))
         line["k2_phases_us"]["note"] = ("%globaltimer stamps inside K2, microseconds since its first block started, "
                                         "max over blocks, mean over the profiled launches (rank 0)")
@@ -723,7 +724,7 @@ def run_secondary_cfg4(args, world, rank, local, dev, barrier, max_over_ranks, a
                            star_range=(0, hi - lo), n_stars_total=S)
     t_ingest = time.perf_counter() - t0
     d_phi = torch.from_numpy(np.ascontiguousarray(phis[:, sh.perm])).to(dev)
-    d_rows = torch.empty((3, W4), dtype=torch.float64, device=dev)
+    d_rows = torch.empty((4, W4), dtype=torch.float64, device=dev)
     nsteps, nwarm = max(10, min(args.steps, 50)), 5
     for _ in range(nwarm):
         flush_l2()
@@ -784,7 +785,7 @@ def run_secondary_cfg4(args, world, rank, local, dev, barrier, max_over_ranks, a
             "value": W4 * nsteps / (dev_ms * 1e-3), "unit": UNIT, "ms_per_step": dev_ms / nsteps, "steps": nsteps,
             "scaling": "strong",
             "e2e": {"value": W4 * nsteps / e2e, "unit": UNIT, "ms_per_step": 1e3 * e2e / nsteps,
-                    "h2d_bytes_per_step": 8 * W4 * sh.ndim, "d2h_bytes_per_step": 8 * 3 * W4},
+                    "h2d_bytes_per_step": 8 * W4 * sh.ndim, "d2h_bytes_per_step": 8 * 4 * W4},
             "engine": {"engine_mode": info["mode"], "reduce": sh.reduce, "entries_rank0": info["n_entries"],
                        "dust_classes": info["n_dust_classes"], "walkers_per_pass": info["walkers_per_pass"],
                        "launches_per_step": info["launches_last_eval"], "synth_s": round(t_synth, 1),

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MB_ABI_VERSION 1
+#define MB_ABI_VERSION 2
 
 /* Ensemble parameters that can carry a free prior model, in phi order.  This is
  * MB_Model.params (singlepop_dust_model.py:29) without M_ini: a free IMF is unreachable in
@@ -158,9 +158,14 @@ typedef struct {
   int64_t reserved[3];
 } mb_info;
 
-/* Device result layout of mb_lnlike_device: three rows of W doubles.  The two rows that add over
- * star shards come first so that one all-reduce of 2*W doubles covers them. */
-enum { MB_OUT_STARSUM = 0, MB_OUT_NONFINITE = 1, MB_OUT_POISSON = 2, MB_OUT_ROWS = 3 };
+/* Device result layout of mb_lnlike_device: four rows of W doubles.  The sum over stars of ln(star
+ * prob) comes as TWO doubles, STARSUM (an exact multiple of 2^-24) and STARSUM_LO (the remainder, an
+ * exact multiple of 2^-68): the kernel accumulates it as two 64-bit integers, and each word converts
+ * to a double without rounding.  Adding the words of several shards in floating point (NCCL, or the
+ * host for several handles) is therefore exact, and STARSUM + STARSUM_LO -- the only rounding -- gives
+ * the same bits however the shards were added.  The three rows that add over star shards come first
+ * so that one all-reduce of 3*W doubles covers them. */
+enum { MB_OUT_STARSUM = 0, MB_OUT_STARSUM_LO = 1, MB_OUT_NONFINITE = 2, MB_OUT_POISSON = 3, MB_OUT_ROWS = 4 };
 
 #define MB_STATUS_OK 0
 #define MB_STATUS_NONFINITE_STAR 1 /* ValueError("invidual integrated star prob is not finite"), :216-217 */
@@ -204,17 +209,17 @@ int mb_lnlike_tabulated(mb_handle* h, const double* phi, int32_t W, int32_t ndim
 /* Split form for driving several handles (GPUs) from one host thread: begin() enqueues the
  * host->device copy, the kernels and the device->host copy on the handle's stream and returns;
  * end() waits and hands back the raw [MB_OUT_ROWS][W] result rows.  mb_combine() turns rows
- * (summed over shards by the caller: rows STARSUM and NONFINITE add, POISSON is shared) into
- * lnlike/status exactly as mb_lnlike does. */
+ * (summed over shards by the caller: rows STARSUM, STARSUM_LO and NONFINITE add, POISSON is shared) into
+ * lnlike/status exactly as mb_lnlike does: lnlike = POISSON + (STARSUM + STARSUM_LO). */
 int mb_lnlike_begin(mb_handle* h, const double* phi, int32_t W, int32_t ndim,
                     const double* const tab[MB_NPARAM]);
 int mb_lnlike_end(mb_handle* h, double* rows);
 void mb_combine(const double* rows, int32_t W, double* lnlike, int32_t* status);
 
 /* Multi-GPU building block: device pointers, asynchronous on `stream`.  d_out is
- * [MB_OUT_ROWS][W] doubles: partial sum of ln(star prob) over this handle's stars, the count of
- * non-finite stars, and the Poisson term (identical on every shard).  The caller all-reduces
- * the first 2*W doubles (rows STARSUM, NONFINITE: one NCCL allreduce) and adds POISSON once. */
+ * [MB_OUT_ROWS][W] doubles: partial sum of ln(star prob) over this handle's stars (two words), the
+ * count of non-finite stars, and the Poisson term (identical on every shard).  The caller all-reduces
+ * the first 3*W doubles (rows STARSUM, STARSUM_LO, NONFINITE: one NCCL allreduce) and adds POISSON once. */
 int mb_lnlike_device(mb_handle* h, const double* d_phi, int32_t W, int32_t ndim, double* d_out,
                      void* stream);
 
@@ -245,9 +250,22 @@ int mb_create_pixels(const mb_grid_desc* grid, const mb_stars_desc* stars, const
                      const int64_t* star_offsets, mb_handle** out);
 int mb_lnlike_pixels(mb_handle* h, const double* phi, int32_t W, int32_t ndim, double* lnlike,
                      int32_t* status);
+/* Same with host-evaluated tables for MB_TABULATED parameters: tab[p] is [n_pixels * W][n_classes[p]]
+ * (pixel-major, then walker), NULL for analytic parameters. */
+int mb_lnlike_pixels_tabulated(mb_handle* h, const double* phi, int32_t W, int32_t ndim,
+                               const double* const tab[MB_NPARAM], double* lnlike, int32_t* status);
 int mb_lnlike_pixels_device(mb_handle* h, const double* d_phi, int32_t W, int32_t ndim, double* d_out,
                             void* stream);
 int64_t mb_pixel_count(const mb_handle* h);
+
+/* Guard against stale device data.  The data dictionaries arrive as arguments on every call of the
+ * reference's lnlike (singlepop_dust_model.py:110) while the device copy is made once; a caller that
+ * mutates an array IN PLACE would otherwise be evaluated on old data.  mb_watch_host registers a host
+ * array (up to 16 per handle; ptr = NULL clears the list): the library fingerprints 16 words spread over
+ * it now and again at the start of every mb_lnlike* / mb_lnprob_box call, and fails with a message
+ * starting "MB_STALE" when they differ (the host side then rebuilds the handle).  This is the one
+ * exception to "host pointers are not retained": the CALLER keeps watched arrays alive. */
+int mb_watch_host(mb_handle* h, const void* ptr, int64_t nbytes);
 
 /* Distinct values ("classes") of a free parameter's grid column, ascending; the x at which a
  * host callable must be tabulated.  Returns the count; fills at most `cap` values. */
@@ -274,10 +292,11 @@ int mb_device_entries(const mb_handle* h, int64_t cap, int32_t* cls, double* wei
 int mb_set_profiling(mb_handle* h, int32_t on);
 int mb_last_kernel_ms(const mb_handle* h, float ms[MB_NKERNELS]);
 /* With profiling on, the last K2 launch also leaves per-block phase stamps (%globaltimer, in
- * microseconds since the first block started): us[block][6] = start, tables staged, Poisson
- * prologue done, star loop done, block reduced, end (last block only; -1 elsewhere).  Returns the
- * number of blocks written (at most cap_blocks), 0 if there is no timeline, -1 on error. */
-#define MB_TIMELINE_POINTS 6
+ * microseconds since the first block started): us[block][8] = start, tables staged, N-stars bins
+ * done, star loop done, block reduced, and for the last block (-1 elsewhere): totals read + Poisson
+ * term + shard totals sent to the peers, peers' totals received, end.  Returns the number of blocks
+ * written (at most cap_blocks), 0 if there is no timeline, -1 on error. */
+#define MB_TIMELINE_POINTS 8
 int mb_last_k2_timeline(const mb_handle* h, double* us, int32_t cap_blocks);
 
 /* One-time ingest (helpers.py:33-41 get_likelihoods): vals[k,s] = exp(lnp[k,s]) /

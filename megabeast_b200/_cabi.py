@@ -9,11 +9,12 @@ import os
 
 from . import build as _build
 
-MB_ABI_VERSION = 1
+MB_ABI_VERSION = 2
 MB_NPARAM = 4
 MB_MAX_NODES = 64
 MB_NKERNELS = 3
-MB_OUT_ROWS = 3
+MB_OUT_ROWS = 4
+MB_OUT_ADDITIVE_ROWS = 3  # STARSUM, STARSUM_LO, NONFINITE add over star shards; POISSON is shared
 PARAMS = ("logA", "Av", "Rv", "fA")  # enum mb_param order
 
 KIND = {
@@ -189,7 +190,12 @@ SIGNATURES = {
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p],
     ),
+    "mb_lnlike_pixels_tabulated": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, TabArray, ctypes.c_void_p, ctypes.c_void_p],
+    ),
     "mb_pixel_count": (ctypes.c_int64, [ctypes.c_void_p]),
+    "mb_watch_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
     "mb_peer_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "mb_peer_connect": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]),
     "mb_peer_disconnect": (ctypes.c_int, [ctypes.c_void_p]),

@@ -71,7 +71,8 @@ struct mb_handle {
   int c16 = 0;
   int64_t* d_seg[2] = {nullptr, nullptr};  // segment tables: [0] 768-thread kernels, [1] 512-thread kernel
   uint32_t* d_rowcode = nullptr;
-  uint16_t* d_rowsrc = nullptr;   // [nO + nI][4] look-up rows multiplied into a table row (K0 and K2's own table build)
+  uint16_t* d_rowsrc = nullptr;   // [nO + nI][4] look-up rows multiplied into a table row (K0)
+  uint16_t* d_rowslot = nullptr;  // the same as slots of K2's own table build (0xfffe: evaluated in place)
   uint16_t* d_lutslot = nullptr;  // [ncls_total] where a look-up row lives during K2's table build
   double* d_Pb = nullptr;         // [nbins][2][128] per-bin N-stars results of the running launch
   // ELEMENTWISE mode: the physics columns themselves, bin-sorted row list for the N-stars sums
@@ -129,6 +130,9 @@ struct mb_handle {
   unsigned long long peer_timeout_ns = 20000000000ull;  // MB_PEER_TIMEOUT_MS (default 20 s)
   int occ_cache[3] = {0, 0, 0};
   size_t occ_smem[3] = {0, 0, 0};
+  // host arrays the caller asked us to watch for in-place changes (mb_watch_host)
+  struct Watch { const void* ptr; int64_t nbytes; uint64_t fp; };
+  std::vector<Watch> watches;
   // pixel batches
   int64_t P = 0;
   int64_t* d_pix_seg = nullptr;
@@ -148,6 +152,35 @@ template <typename T>
 static int dev_upload(mb_handle* h, T** p, const std::vector<T>& v) {
   if (dev_alloc(h, p, (int64_t)v.size())) return 1;
   if (!v.empty()) CK(cudaMemcpy(*p, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// fingerprint of a host array: 16 eight-byte words spread evenly over it, plus its size (FNV-1a)
+static uint64_t host_fingerprint(const void* ptr, int64_t nbytes) {
+  uint64_t hsh = 1469598103934665603ull ^ (uint64_t)nbytes;
+  const int64_t nw = nbytes / 8;
+  if (nw <= 0) return hsh;
+  const unsigned char* base = static_cast<const unsigned char*>(ptr);
+  for (int i = 0; i < 16; ++i) {
+    uint64_t w;
+    memcpy(&w, base + 8 * ((nw - 1) * i / 15), 8);
+    hsh = (hsh ^ w) * 1099511628211ull;
+  }
+  return hsh;
+}
+static int check_watches(const mb_handle* h) {
+  for (size_t i = 0; i < h->watches.size(); ++i)
+    if (host_fingerprint(h->watches[i].ptr, h->watches[i].nbytes) != h->watches[i].fp)
+      return fail("MB_STALE: watched host array %zu changed in place since the device copy was made", i);
+  return 0;
+}
+
+extern "C" int mb_watch_host(mb_handle* h, const void* ptr, int64_t nbytes) {
+  if (!h) return fail("mb_watch_host: null handle");
+  if (!ptr) { h->watches.clear(); return 0; }
+  if (nbytes < 0) return fail("mb_watch_host: negative size");
+  if (h->watches.size() >= 16) return fail("mb_watch_host: at most 16 arrays");
+  h->watches.push_back({ptr, nbytes, host_fingerprint(ptr, nbytes)});
   return 0;
 }
 
@@ -235,7 +268,7 @@ static K2Smem k2_smem_plan(int kmode, int nO, int nI, int nbins, int Wpad, int e
   const int NW = Wpad / 32, threads = k2_threads(NW), warps = threads / 32;
   const size_t stage = (size_t)warps * k2_stage_bytes(NW);
   const size_t slabs = (size_t)warps * kAccRows * Wpad * 8;  // block reduction: one slab per warp
-  const size_t pois_row = 2 * (size_t)Wpad * 8;              // one warp's partial (S, C) for all walkers
+  const size_t pois_row = kPoisBins * 2 * (size_t)Wpad * 8;  // one warp's partial (S, C) of the bins in flight, all walkers
   p.tables = kmode == kModeFactor ? (size_t)(nO + nI) * Wpad * elem_bytes : 0;
   const bool slabs_over_tables = p.tables >= slabs;
   size_t base = stage;
@@ -323,7 +356,7 @@ extern "C" void mb_destroy(mb_handle* h) {
                   h->d_bin_agecls, h->d_phi, h->d_tab[0], h->d_tab[1], h->d_tab[2], h->d_tab[3],
                   h->d_F, h->d_counter, h->d_gacc, h->d_T, h->d_out, h->d_pix_seg, h->d_pix_nstars, h->d_Fpix,
                   h->d_timeline, h->d_col[0], h->d_col[1], h->d_col[2], h->d_col[3], h->d_gw, h->d_compl,
-                  h->d_rowsrc, h->d_lutslot, h->d_Pb, h->d_binrows, h->d_tile_start, h->d_bin_tile, h->d_partial, h->d_bin_age, h->d_Fage, h->d_SC};
+                  h->d_rowsrc, h->d_rowslot, h->d_lutslot, h->d_Pb, h->d_binrows, h->d_tile_start, h->d_bin_tile, h->d_partial, h->d_bin_age, h->d_Fage, h->d_SC};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -557,7 +590,7 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
   // look-up rows behind every table row, and where a look-up row lives while K2 builds its tables:
   // a parameter that is alone in its table is evaluated in place, the others in a scratch table
   std::vector<uint16_t> rowsrc((size_t)(h->nO + h->nI) * 4, (uint16_t)0xffff);
-  std::vector<uint16_t> lutslot((size_t)std::max(1, clsoff), (uint16_t)0);
+  std::vector<uint16_t> lutslot((size_t)std::max(1, clsoff), (uint16_t)0), rowslot;
   if (!elementwise) {
     const bool age_free = model->kind[MB_P_LOGA] != MB_FIXED;
     int n_outer_params = age_free ? 1 : 0, n_inner_params = 0;
@@ -586,7 +619,18 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
             alone ? (uint16_t)(0x8000u | (unsigned)((inner ? h->nO : 0) + c)) : (uint16_t)nscratch++;
     }
     h->nscratch = nscratch;
-    if (h->nO + h->nI >= 0x8000) return fail("more than 32767 factor-table rows");
+    if (h->nO + h->nI >= 0x7ff0) return fail("more than 32751 factor-table rows");
+    // K2's own table build reads the sources of a product row as slots directly
+    rowslot.assign(rowsrc.size(), (uint16_t)0xffff);
+    for (int r = 0; r < h->nO + h->nI; ++r) {
+      const uint16_t* src = &rowsrc[(size_t)r * 4];
+      if (src[0] != 0xffff && src[1] == 0xffff && lutslot[src[0]] == (uint16_t)(0x8000u | (unsigned)r)) {
+        rowslot[(size_t)r * 4] = 0xfffe;
+        continue;
+      }
+      for (int k = 0; k < 4; ++k)
+        if (src[k] != 0xffff) rowslot[(size_t)r * 4 + k] = lutslot[src[k]];
+    }
   }
 
   // ---- N-stars sufficient statistics (helpers.py:133-162) ----------------------------------------
@@ -817,6 +861,7 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
   if (!elementwise) {
     if (dev_upload(h, &h->d_rowsrc, rowsrc)) return 1;
     if (dev_upload(h, &h->d_lutslot, lutslot)) return 1;
+    if (dev_upload(h, &h->d_rowslot, rowslot)) return 1;
   }
   if (h->poisson && dev_alloc(h, &h->d_Pb, (int64_t)h->nbins * 2 * 128)) return 1;
   if (elementwise) {
@@ -935,12 +980,14 @@ static size_t pix_smem_bytes(int nA, int nB, int nbins, int Wpad) {
   return pix_front_bytes(nbins, Wpad) + (size_t)(nA + nB) * Wpad * 8 + (size_t)Wpad * 8 + (size_t)kAccRows * Wpad * 8;
 }
 
-static int eval_pixels_device(mb_handle* h, const double* d_phi, int W, int ndim, double* d_out, cudaStream_t st) {
+static int eval_pixels_device(mb_handle* h, const double* d_phi, int W, int ndim, double* d_out, cudaStream_t st,
+                              const double* const d_tab[MB_NPARAM] = nullptr) {
   if (h->P <= 0) return fail("handle was not created with mb_create_pixels");
   if (ndim != h->ndim) return fail("phi has %d columns, the model has %d free variables", ndim, h->ndim);
   if (W < 1 || W > 128) return fail("pixel batches take 1..128 walkers per pixel (got %d)", W);
   for (int p = 0; p < MB_NPARAM; ++p)
-    if (h->model.kind[p] == MB_TABULATED) return fail("tabulated prior models are not supported for pixel batches");
+    if (h->model.kind[p] == MB_TABULATED && !(d_tab && d_tab[p]))
+      return fail("parameter %d is tabulated but no table was passed (mb_lnlike_pixels_tabulated)", p);
   CK(cudaSetDevice(h->device));
   int NW = W <= 32 ? 1 : W <= 64 ? 2 : 4;
   const int Wpad = 32 * NW;
@@ -958,6 +1005,7 @@ static int eval_pixels_device(mb_handle* h, const double* d_phi, int W, int ndim
   if (prof) CK(cudaEventRecord(h->ev[0], st));
   K0Args k0{};
   k0.model = h->mdev; k0.clsx = h->d_clsx; k0.phi = d_phi; k0.F = h->d_Fpix;
+  for (int p = 0; p < MB_NPARAM; ++p) k0.tab[p] = d_tab ? d_tab[p] : nullptr;
   k0.rowsrc = h->d_rowsrc; k0.nrows = h->nA + h->nB; k0.nAge = h->nA;
   k0.W = W; k0.Wpad = Wpad; k0.ndim = ndim; k0.ncls_total = h->ncls_total;
   mb_k0_factors<<<(unsigned)(h->P * Wpad), kK0Threads, sizeof(double) * std::max(1, h->ncls_total), st>>>(k0);
@@ -1167,8 +1215,9 @@ static cudaError_t launch_k2(int NW, int grid, size_t smem, cudaStream_t st, con
   cudaLaunchAttribute attr{};
   attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr.val.programmaticStreamSerializationAllowed = 1;
+  static const bool no_pdl = getenv("MB_NO_PDL") && atoi(getenv("MB_NO_PDL"));  // A/B switch (measurements)
   cfg.attrs = &attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = no_pdl ? 0 : 1;
   switch (NW) {
     case 1: return cudaLaunchKernelEx(&cfg, mb_k2_stars<1, MODE, TF, OB>, a);
     case 2: return cudaLaunchKernelEx(&cfg, mb_k2_stars<2, MODE, TF, OB>, a);
@@ -1308,6 +1357,7 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     k2.slab_off = (int32_t)plan.slab_off;
     k2.pois.Ht = h->d_H; k2.pois.bin_agecls = h->d_bin_agecls; k2.pois.coef = h->d_coef; k2.pois.Pb = h->d_Pb;
     k2.pois.n_stars = (double)h->S_total; k2.pois.nbins = h->poisson ? h->nbins : 0;
+    k2.pois.lgamma_n1 = std::lgamma((double)h->S_total + 1.0);
     k2.pois.nwarps = plan.pois_warps; k2.pois.scratch_off = (int32_t)plan.pois_off;
     k2.pois.SC = elementwise ? h->d_SC : nullptr;
     // plain age factors (the `ageprior` of helpers.py:135): K1e's per-bin rows, K0's rows in global
@@ -1322,7 +1372,7 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     k2.build_tables = fused ? 1 : 0;
     if (fused) {
       k2.model = h->mdev; k2.clsx = h->d_clsx; k2.ndim = ndim; k2.ncls_total = h->ncls_total;
-      k2.rowsrc = h->d_rowsrc; k2.lutslot = h->d_lutslot; k2.nscratch = h->nscratch;
+      k2.rowsrc = h->d_rowslot; k2.lutslot = h->d_lutslot; k2.nscratch = h->nscratch;
       k2.phi = d_phi + (size_t)w0 * ndim;
       if (inline_phi) {
         k2.phi_inline = 1;
@@ -1388,6 +1438,7 @@ extern "C" int mb_lnlike_begin(mb_handle* h, const double* phi, int32_t W, int32
   if (W <= 0) return fail("mb_lnlike_begin: W must be positive");
   if (ndim != h->ndim) return fail("phi has %d columns, the model has %d free variables", ndim, h->ndim);
   if (ndim > 0 && !phi) return fail("mb_lnlike: phi is NULL");
+  if (!h->watches.empty() && check_watches(h)) return 1;
   CK(cudaSetDevice(h->device));
   const int64_t nphi = (int64_t)W * std::max(1, ndim), nout = (int64_t)MB_OUT_ROWS * W;
   // phi (a few KB) and the result rows (3 W doubles) travel through MAPPED pinned host memory:
@@ -1457,7 +1508,7 @@ extern "C" int mb_lnlike_end(mb_handle* h, double* rows) {
 
 extern "C" void mb_combine(const double* rows, int32_t W, double* lnlike, int32_t* status) {
   for (int w = 0; w < W; ++w) {
-    double tot = rows[MB_OUT_POISSON * W + w] + rows[MB_OUT_STARSUM * W + w];
+    double tot = rows[MB_OUT_POISSON * W + w] + (rows[MB_OUT_STARSUM * W + w] + rows[MB_OUT_STARSUM_LO * W + w]);
     int st = MB_STATUS_OK;
     if (rows[MB_OUT_NONFINITE * W + w] > 0.0) st |= MB_STATUS_NONFINITE_STAR;
     if (rows[MB_OUT_NONFINITE * W + w] < 0.0) st |= MB_STATUS_PEER_TIMEOUT;
@@ -1528,11 +1579,17 @@ extern "C" int mb_lnprob_box(mb_handle* h, const double* phi, int32_t W, int32_t
 
 extern "C" int mb_lnlike_pixels(mb_handle* h, const double* phi, int32_t W, int32_t ndim, double* lnlike,
                                 int32_t* status) {
+  return mb_lnlike_pixels_tabulated(h, phi, W, ndim, nullptr, lnlike, status);
+}
+
+extern "C" int mb_lnlike_pixels_tabulated(mb_handle* h, const double* phi, int32_t W, int32_t ndim,
+                                          const double* const tab[MB_NPARAM], double* lnlike, int32_t* status) {
   if (!h || !lnlike || !status) return fail("mb_lnlike_pixels: null argument");
   if (h->P <= 0) return fail("handle was not created with mb_create_pixels");
   if (ndim != h->ndim) return fail("phi has %d columns, the model has %d free variables", ndim, h->ndim);
   if (ndim > 0 && !phi) return fail("mb_lnlike_pixels: phi is NULL");
   if (W < 1) return fail("mb_lnlike_pixels: W must be positive");
+  if (!h->watches.empty() && check_watches(h)) return 1;
   CK(cudaSetDevice(h->device));
   const int64_t ncol = h->P * W;
   const int64_t nphi = ncol * std::max(1, ndim), nout = (int64_t)MB_OUT_ROWS * ncol;
@@ -1552,7 +1609,19 @@ extern "C" int mb_lnlike_pixels(mb_handle* h, const double* phi, int32_t W, int3
   double* ho = h->h_pin + nphi;
   if (ndim > 0) memcpy(hp, phi, sizeof(double) * (size_t)ncol * ndim);
   CK(cudaMemcpyAsync(h->d_phi, hp, sizeof(double) * (size_t)nphi, cudaMemcpyHostToDevice, h->stream));
-  if (eval_pixels_device(h, h->d_phi, W, ndim, h->d_out, h->stream)) return 1;
+  // host-evaluated tables of MB_TABULATED parameters: [P * W][n_classes]
+  const double* dtab[MB_NPARAM] = {nullptr, nullptr, nullptr, nullptr};
+  bool any_tab = false;
+  for (int p = 0; p < MB_NPARAM; ++p) {
+    if (h->model.kind[p] != MB_TABULATED) continue;
+    if (!tab || !tab[p]) return fail("parameter %d is tabulated but no table was passed", p);
+    const int64_t n = ncol * h->mdev.ncls[p];
+    if (ensure(h, &h->d_tab[p], &h->cap_tab[p], n)) return 1;
+    CK(cudaMemcpyAsync(h->d_tab[p], tab[p], sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    dtab[p] = h->d_tab[p];
+    any_tab = true;
+  }
+  if (eval_pixels_device(h, h->d_phi, W, ndim, h->d_out, h->stream, any_tab ? dtab : nullptr)) return 1;
   CK(cudaMemcpyAsync(ho, h->d_out, sizeof(double) * (size_t)nout, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   for (int64_t p = 0; p < h->P; ++p)  // rows are [p][3][W]

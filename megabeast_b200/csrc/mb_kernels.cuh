@@ -206,12 +206,14 @@ struct PoissonArgs {
   const double* fage;         // plain age factors [..][Wpad] in global memory, or null: read them from the
                               // tables / look-up rows in shared memory (fage_smem_off)
   double n_stars;             // S of the fit (:183-185)
+  double lgamma_n1;           // lgamma(S + 1), a constant of the fit
   int32_t nbins;              // 0: no N-stars term
   int32_t nwarps;             // warps of the block that take part (their partial sums must fit the scratch)
-  int32_t scratch_off;        // byte offset of the reduction scratch [nwarps][2][Wpad] in dynamic shared memory
+  int32_t scratch_off;        // byte offset of the reduction scratch [kPoisBins][nwarps][2][Wpad] in dynamic shared memory
   int32_t fage_smem_off;      // byte offset of the plain age-factor rows in dynamic shared memory (fage == null)
   const double* SC;           // ELEMENTWISE: bin sums [nbins][Wpad][2] already formed by K1b (else null)
 };
+constexpr int kPoisBins = 2;  // bins a block works on at a time (loads of both in flight together)
 
 // F: outer rows then inner rows, element (row, w) at F[row * Wpad + w]; shared memory (FACTOR mode with
 // fp64 tables) or global.  All threads of the block must call.  Lane l of a warp owns walkers
@@ -222,116 +224,150 @@ __device__ void poisson_bins(const PoissonArgs& pa, const double* F, int nO, int
   constexpr int Wpad = 32 * NW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int pw = pa.nwarps;
-  double* red = reinterpret_cast<double*>(smem_raw + pa.scratch_off);  // [pw][2][Wpad]
+  double* red = reinterpret_cast<double*>(smem_raw + pa.scratch_off);  // [kPoisBins][pw][2][Wpad]
   const double* fage = pa.fage ? pa.fage : reinterpret_cast<const double*>(smem_raw + pa.fage_smem_off);
   const double2* Ht = reinterpret_cast<const double2*>(pa.Ht);
   const double* FI = F + (size_t)nO * Wpad + lane;
-  for (int b = blockIdx.x; b < pa.nbins; b += gridDim.x) {
-    const int acls = __ldg(pa.bin_agecls + b);
+  for (int b0 = blockIdx.x; b0 < pa.nbins; b0 += kPoisBins * gridDim.x) {
+    // this pass: bins b0 and b0 + gridDim.x (the second may not exist)
+    const int nb = (b0 + (int)gridDim.x < pa.nbins) ? 2 : 1;
+    // the combining threads fetch their bin's constants now: the latency hides behind the sums
+    const int cw = threadIdx.x % Wpad, cb = threadIdx.x / Wpad;
+    int c_acls = 0;
+    double c_coef = 0.0;
+    if (cb < nb) {
+      c_acls = __ldg(pa.bin_agecls + b0 + cb * (int)gridDim.x);
+      c_coef = __ldg(pa.coef + b0 + cb * (int)gridDim.x);
+    }
     if (warp < pw) {
-      double S[NW], C[NW];
+      double S[kPoisBins][NW], C[kPoisBins][NW];
 #pragma unroll
-      for (int j = 0; j < NW; ++j) { S[j] = 0.0; C[j] = 0.0; }
+      for (int k = 0; k < kPoisBins; ++k)
+#pragma unroll
+        for (int j = 0; j < NW; ++j) { S[k][j] = 0.0; C[k][j] = 0.0; }
       if (pa.SC) {
         // ELEMENTWISE: S and C were summed over the grid rows themselves (mb_k1b_binsums)
         if (warp == 0) {
 #pragma unroll
-          for (int j = 0; j < NW; ++j) {
-            const double2 v = __ldg(reinterpret_cast<const double2*>(pa.SC) + (size_t)b * Wpad + lane + 32 * j);
-            S[j] = v.x; C[j] = v.y;
-          }
-        }
-      } else {
-        for (int od = 0; od < nOd; ++od) {
-          double s[NW], c[NW];
-#pragma unroll
-          for (int j = 0; j < NW; ++j) { s[j] = 0.0; c[j] = 0.0; }
-          const double2* hrow = Ht + ((size_t)b * nOd + od) * nI;
-          int i = warp;
-          // four independent (warp-uniform) loads of the statistics in flight, then the multiply-adds
-          for (; i + 3 * pw < nI; i += 4 * pw) {
-            double2 h[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) h[u] = __ldg(hrow + i + u * pw);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const double* f = FI + (size_t)(i + u * pw) * Wpad;
+          for (int k = 0; k < kPoisBins; ++k)
+            if (k < nb) {
 #pragma unroll
               for (int j = 0; j < NW; ++j) {
-                const double fv = f[32 * j];
-                s[j] = fma(h[u].x, fv, s[j]); c[j] = fma(h[u].y, fv, c[j]);
+                const double2 v = __ldg(reinterpret_cast<const double2*>(pa.SC) +
+                                        (size_t)(b0 + k * (int)gridDim.x) * Wpad + lane + 32 * j);
+                S[k][j] = v.x; C[k][j] = v.y;
               }
+            }
+        }
+      } else {
+        int acls[kPoisBins];
+#pragma unroll
+        for (int k = 0; k < kPoisBins; ++k) acls[k] = k < nb ? __ldg(pa.bin_agecls + b0 + k * (int)gridDim.x) : 0;
+        for (int od = 0; od < nOd; ++od) {
+          double s[kPoisBins][NW], c[kPoisBins][NW];
+#pragma unroll
+          for (int k = 0; k < kPoisBins; ++k)
+#pragma unroll
+            for (int j = 0; j < NW; ++j) { s[k][j] = 0.0; c[k][j] = 0.0; }
+          const double2* hrow0 = Ht + ((size_t)b0 * nOd + od) * nI;
+          const double2* hrow1 = Ht + ((size_t)(nb > 1 ? b0 + (int)gridDim.x : b0) * nOd + od) * nI;
+          int i = warp;
+          // two classes x two bins: four independent (warp-uniform) loads of the statistics in flight
+          for (; i + pw < nI; i += 2 * pw) {
+            const double2 h00 = __ldg(hrow0 + i), h01 = __ldg(hrow0 + i + pw);
+            const double2 h10 = __ldg(hrow1 + i), h11 = __ldg(hrow1 + i + pw);
+            const double* f0 = FI + (size_t)i * Wpad;
+            const double* f1 = FI + (size_t)(i + pw) * Wpad;
+#pragma unroll
+            for (int j = 0; j < NW; ++j) {
+              const double fv0 = f0[32 * j], fv1 = f1[32 * j];
+              s[0][j] = fma(h00.x, fv0, s[0][j]); c[0][j] = fma(h00.y, fv0, c[0][j]);
+              s[1][j] = fma(h10.x, fv0, s[1][j]); c[1][j] = fma(h10.y, fv0, c[1][j]);
+              s[0][j] = fma(h01.x, fv1, s[0][j]); c[0][j] = fma(h01.y, fv1, c[0][j]);
+              s[1][j] = fma(h11.x, fv1, s[1][j]); c[1][j] = fma(h11.y, fv1, c[1][j]);
             }
           }
           for (; i < nI; i += pw) {
-            const double2 h0 = __ldg(hrow + i);
+            const double2 h0 = __ldg(hrow0 + i), h1 = __ldg(hrow1 + i);
             const double* f = FI + (size_t)i * Wpad;
 #pragma unroll
             for (int j = 0; j < NW; ++j) {
               const double fv = f[32 * j];
-              s[j] = fma(h0.x, fv, s[j]); c[j] = fma(h0.y, fv, c[j]);
+              s[0][j] = fma(h0.x, fv, s[0][j]); c[0][j] = fma(h0.y, fv, c[0][j]);
+              s[1][j] = fma(h1.x, fv, s[1][j]); c[1][j] = fma(h1.y, fv, c[1][j]);
             }
           }
-          const double* fo = F + (size_t)(acls * nOd + od) * Wpad + lane;
 #pragma unroll
-          for (int j = 0; j < NW; ++j) {
-            const double fv = fo[32 * j];
-            S[j] = fma(fv, s[j], S[j]); C[j] = fma(fv, c[j], C[j]);
+          for (int k = 0; k < kPoisBins; ++k) {
+            const double* fo = F + (size_t)(acls[k] * nOd + od) * Wpad + lane;
+#pragma unroll
+            for (int j = 0; j < NW; ++j) {
+              const double fv = fo[32 * j];
+              S[k][j] = fma(fv, s[k][j], S[k][j]); C[k][j] = fma(fv, c[k][j], C[k][j]);
+            }
           }
         }
       }
 #pragma unroll
-      for (int j = 0; j < NW; ++j) {
-        red[((size_t)warp * 2 + 0) * Wpad + lane + 32 * j] = S[j];
-        red[((size_t)warp * 2 + 1) * Wpad + lane + 32 * j] = C[j];
-      }
+      for (int k = 0; k < kPoisBins; ++k)
+#pragma unroll
+        for (int j = 0; j < NW; ++j) {
+          red[(((size_t)k * pw + warp) * 2 + 0) * Wpad + lane + 32 * j] = S[k][j];
+          red[(((size_t)k * pw + warp) * 2 + 1) * Wpad + lane + 32 * j] = C[k][j];
+        }
     }
     __syncthreads();
-    if (threadIdx.x < Wpad) {
-      const int w = threadIdx.x;
+    if (cb < nb) {   // thread (bin cb, walker cw)
       double Sb = 0.0, Cb = 0.0;
       for (int wp = 0; wp < pw; ++wp) {  // fixed warp order
-        Sb += red[((size_t)wp * 2 + 0) * Wpad + w];
-        Cb += red[((size_t)wp * 2 + 1) * Wpad + w];
+        Sb += red[(((size_t)cb * pw + wp) * 2 + 0) * Wpad + cw];
+        Cb += red[(((size_t)cb * pw + wp) * 2 + 1) * Wpad + cw];
       }
       // helpers.py:152-162: ageprior * metprior * massmult / avemass * C / S, bins with S <= 0 skipped
-      const double fa = fage[(size_t)acls * Wpad + w];
-      const double term = Sb > 0.0 ? (fa * __ldg(pa.coef + b)) * (Cb / Sb) : 0.0;
-      pa.Pb[((size_t)b * 2 + 0) * Wpad + w] = Sb;
-      pa.Pb[((size_t)b * 2 + 1) * Wpad + w] = term;
+      const double fa = fage[(size_t)c_acls * Wpad + cw];
+      const double term = Sb > 0.0 ? (fa * c_coef) * (Cb / Sb) : 0.0;
+      const int b = b0 + cb * (int)gridDim.x;
+      pa.Pb[((size_t)b * 2 + 0) * Wpad + cw] = Sb;
+      pa.Pb[((size_t)b * 2 + 1) * Wpad + cw] = term;
     }
-    __syncthreads();  // the scratch is reused by the block's next bin
+    __syncthreads();  // the scratch is reused by the block's next pass
   }
 }
 
 // Last block of the launch: add the bins in fixed order -> Poisson term of every walker of the pass.
-// psum: scratch [THREADS / Wpad][2][Wpad] doubles.  All threads of the block must call.
+// Two steps so that the loads of the first are in flight together with the caller's other loads.
+struct PoisPart { double nrm, pred; };
 template <int NW, int THREADS>
-__device__ void poisson_finish(const PoissonArgs& pa, double* psum, double* out_row, int W) {
+__device__ __forceinline__ PoisPart poisson_finish_load(const PoissonArgs& pa) {
   constexpr int Wpad = 32 * NW, kParts = THREADS / Wpad;
   const int w = threadIdx.x % Wpad, part = threadIdx.x / Wpad;
-  double nrm = 0.0, pred = 0.0;
-  if (part < kParts)
-    for (int b = part; b < pa.nbins; b += kParts) {
-      nrm += __ldcg(pa.Pb + ((size_t)b * 2 + 0) * Wpad + w);
-      pred += __ldcg(pa.Pb + ((size_t)b * 2 + 1) * Wpad + w);
-    }
-  if (part < kParts) {
-    psum[((size_t)part * 2 + 0) * Wpad + w] = nrm;
-    psum[((size_t)part * 2 + 1) * Wpad + w] = pred;
+  PoisPart p{0.0, 0.0};
+#pragma unroll 4
+  for (int b = part; b < pa.nbins; b += kParts) {
+    p.nrm += __ldcg(pa.Pb + ((size_t)b * 2 + 0) * Wpad + w);
+    p.pred += __ldcg(pa.Pb + ((size_t)b * 2 + 1) * Wpad + w);
   }
+  return p;
+}
+// psum: scratch [THREADS / Wpad][2][Wpad] doubles.  All threads of the block must call.
+template <int NW, int THREADS>
+__device__ void poisson_finish(const PoissonArgs& pa, PoisPart p, double* psum, double* out_row, int W) {
+  constexpr int Wpad = 32 * NW, kParts = THREADS / Wpad;
+  const int w = threadIdx.x % Wpad, part = threadIdx.x / Wpad;
+  psum[((size_t)part * 2 + 0) * Wpad + w] = p.nrm;
+  psum[((size_t)part * 2 + 1) * Wpad + w] = p.pred;
   __syncthreads();
   if (threadIdx.x < W) {
-    nrm = 0.0; pred = 0.0;
-    for (int p = 0; p < kParts; ++p) {  // fixed order
-      nrm += psum[((size_t)p * 2 + 0) * Wpad + threadIdx.x];
-      pred += psum[((size_t)p * 2 + 1) * Wpad + threadIdx.x];
+    double nrm = 0.0, pred = 0.0;
+    for (int q = 0; q < kParts; ++q) {  // fixed order
+      nrm += psum[((size_t)q * 2 + 0) * Wpad + threadIdx.x];
+      pred += psum[((size_t)q * 2 + 1) * Wpad + threadIdx.x];
     }
     // helpers.py:133-134 divides every weight by the grand total first: a total of 0 (0/0 = nan
     // weights), nan or inf leaves no bin with S/total > 0 -> every bin skipped, pred = 0
     if (!(nrm > 0.0) || !(nrm < INFINITY)) pred = 0.0;
     double pois = 0.0;
-    if (pa.nbins > 0) pois = pa.n_stars * log(pred) - pred - lgamma(pa.n_stars + 1.0);  // :182-186
+    if (pa.nbins > 0) pois = pa.n_stars * log(pred) - pred - pa.lgamma_n1;  // :182-186
     out_row[threadIdx.x] = pois;
   }
   __syncthreads();
@@ -715,10 +751,14 @@ __device__ __forceinline__ Fix2 to_fix2(double v) {
   f.lo = __double2ll_rn((vs - (double)f.hi) * kFixLoScale);  // the difference is exact
   return f;
 }
-__device__ __forceinline__ double from_fix2(long long hi, long long lo) {
-  hi += lo >> 44;                                   // carry the whole units of lo (floor)
-  lo &= (1ll << 44) - 1;
-  return (double)hi * (1.0 / kFixHiScale) + (double)lo * (1.0 / (kFixHiScale * kFixLoScale));
+// The two words as doubles, after carrying the whole units of lo into hi: lo is then in [0, 2^44) and
+// converts exactly, hi converts exactly while |total| < 2^29 = 5.4e8 -- so words of several shards can
+// be added in floating point without rounding, and hi + lo is the only rounding of the whole sum.
+__device__ __forceinline__ double fix_hi_to_double(long long hi, long long lo) {
+  return (double)(hi + (lo >> 44)) * (1.0 / kFixHiScale);
+}
+__device__ __forceinline__ double fix_lo_to_double(long long lo) {
+  return (double)(lo & ((1ll << 44) - 1)) * (1.0 / (kFixHiScale * kFixLoScale));
 }
 enum { kCtrSegment = 0, kCtrBlocks = 1, kCtrWords = 2 };
 
@@ -758,22 +798,22 @@ enum { kModeFactor = 1, kModeTable = 2, kModeTableGrid = 3 };
 
 // ---- star shards on several GPUs: reduction over NVLink peer memory, fused into K2's tail --------
 // Every GPU owns an exchange buffer (cudaMalloc, opened by the other ranks through CUDA IPC):
-//   data [2 parities][MB_MAX_PEERS sources][4 * 128] u64   fixed-point log-sum (hi, lo), non-finite, nan
-//   flags[2 parities][MB_MAX_PEERS sources]         u32   sequence number of the data in the slot
-// The last block of rank r's K2 stores its shard totals into slot r of EVERY rank's buffer (plain
-// stores to peer addresses, NVLink), fences system-wide, publishes the launch's sequence number in
-// each flag, then waits for the flags of all sources in its own buffer and adds the slots.
-// Integer sums: the order is irrelevant, every rank gets bitwise the same totals.  Two parities:
-// a rank can be at most one launch ahead of the slowest one (it needs everyone's flag of launch n
-// to leave launch n), so launch n + 2 never overwrites data of launch n that is still being read.
+//   words [2 parities][MB_MAX_PEERS sources][2 * kXWords] u64
+// The last block of rank r's K2 sends its shard totals -- (hi, lo) fixed-point log-sum, non-finite and
+// nan counts per walker, kXWords 64-bit values -- into slot r of EVERY other rank's buffer as
+// 8-byte words that carry their own flag: [63:32] = sequence number of the launch, [31:0] = one
+// half of a value.  An aligned 8-byte store is a single transaction, so a reader that sees the
+// sequence number of its launch in a word holds valid data: no fence, no separate flag, one NVLink
+// one-way trip (the protocol NCCL calls LL).  Every rank then polls the words of all other sources in
+// its own buffer and adds the values to its own.  Integer sums: the order is irrelevant, every rank
+// gets bitwise the same totals.  Two parities: a rank can be at most one launch ahead of the slowest
+// one (it needs everyone's words of launch n to leave launch n), so launch n + 2 never overwrites
+// words of launch n that are still being read.
 constexpr int kXWords = kAccRows * 128;
-__host__ __device__ constexpr size_t xbuf_data_off(int par, int src) {   // in u64 words
-  return ((size_t)par * MB_MAX_PEERS + src) * kXWords;
+__host__ __device__ constexpr size_t xbuf_word_off(int par, int src) {   // in u64 words
+  return ((size_t)par * MB_MAX_PEERS + src) * 2 * kXWords;
 }
-__host__ __device__ constexpr size_t xbuf_flag_off(int par, int src) {   // in u32 words
-  return 2 * (size_t)2 * MB_MAX_PEERS * kXWords + (size_t)par * MB_MAX_PEERS + src;
-}
-constexpr size_t kXBufBytes = 8 * (size_t)2 * MB_MAX_PEERS * kXWords + 4 * (size_t)2 * MB_MAX_PEERS + 64;
+constexpr size_t kXBufBytes = 8 * (size_t)2 * MB_MAX_PEERS * 2 * kXWords + 64;
 struct PeerArgs {
   int32_t world, rank;   // world <= 1: single shard, no exchange
   uint32_t seq;          // sequence number of this launch, identical on all ranks
@@ -781,7 +821,10 @@ struct PeerArgs {
   unsigned long long* xbuf[MB_MAX_PEERS];  // exchange buffer of every rank, as mapped on THIS GPU
 };
 
-constexpr int kPhiInline = 1152;  // doubles of phi carried in K2's kernel parameters (e.g. 128 walkers x 9)
+#ifndef MB_PHI_INLINE
+#define MB_PHI_INLINE 1152
+#endif
+constexpr int kPhiInline = MB_PHI_INLINE;  // doubles of phi carried in K2's kernel parameters (e.g. 128 walkers x 9)
 struct K2Args {
   const double* ea;     // entry weights  [n_entries]
   const void* ec;       // entry codes    [n_entries]: uint32, or uint16 for the C16 kernels (padded by one)
@@ -806,8 +849,8 @@ struct K2Args {
   unsigned long long done_seq;
   int32_t build_tables, phi_inline, ndim, ncls_total;
   const double* clsx;        // class values [ncls_total]
-  const uint16_t* rowsrc;    // [nA + nB][4] look-up rows (class offsets included) multiplied into a table
-                             // row; 0xffff = none
+  const uint16_t* rowsrc;    // [nA + nB][4] the look-up rows multiplied into a table row, as SLOTS (see lutslot);
+                             // 0xffff = none, first = 0xfffe: the row is a look-up row evaluated in place
   const uint16_t* lutslot;   // [ncls_total] where a look-up row lives while the tables are built: bit 15 set =
                              // row (& 0x7fff) of the tables themselves (a parameter alone in its table is
                              // evaluated in place), else row of the scratch look-up table
@@ -816,7 +859,8 @@ struct K2Args {
   ModelDev model;
   double phi_in[kPhiInline];
 };
-constexpr int kTimelinePoints = 6;  // start, tables staged, Poisson done, stars done, block reduced, end
+constexpr int kTimelinePoints = 8;  // start, tables staged, N-stars bins done, stars done, block reduced,
+                                    // (last block:) totals + Poisson term + sent to peers, peers received, end
 __device__ __forceinline__ void stamp(unsigned long long* timeline, int point) {
   if (timeline && threadIdx.x == 0) {
     unsigned long long t;
@@ -1236,16 +1280,15 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     }
     __syncthreads();
     const int ntab = nrows * Wpad;
-#pragma unroll 2
+#pragma unroll 3
     for (int idx = threadIdx.x; idx < ntab; idx += blockDim.x) {
       const int r = idx / Wpad, w = idx - r * Wpad;
       // look-up rows of the table row (precomputed: no integer divisions here), multiplied in the
       // reference's left-to-right order (`cur_physmod *=`, :146-148)
       const ushort4 sr = srow[r];
-      if (sr.y == 0xffff && sr.x != 0xffff && sslot[sr.x] == (0x8000u | (unsigned)r)) continue;  // evaluated in place
+      if (sr.x == 0xfffe) continue;  // evaluated in place
       double v = 1.0;
-      auto lrow = [&](unsigned row) -> const double* {
-        const unsigned slot = sslot[row];
+      auto lrow = [&](unsigned slot) -> const double* {
         return (slot & 0x8000u) ? tab + (size_t)(slot & 0x7fffu) * Wpad : lut + (size_t)slot * Wpad;
       };
       if (sr.x != 0xffff) v *= lrow(sr.x)[w];
@@ -1335,56 +1378,68 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   stamp(a.timeline, 4);
   if (ticket != gridDim.x - 1) return;
   __threadfence();
-  // last block of this GPU: take the shard totals, leave the accumulators zero for the next launch
+  // last block of this GPU: take the shard totals, leave the accumulators zero for the next launch.
+  // (the loads of the totals and of the per-bin N-stars results are issued together)
   unsigned long long* tot = slab;  // [kAccRows][Wpad]; the Poisson scratch follows it
-  for (int i = threadIdx.x; i < kAccRows * Wpad; i += blockDim.x) {
-    tot[i] = __ldcg(a.gacc + i);
-    a.gacc[i] = 0ull;
+  unsigned long long mytot = 0ull;
+  if (threadIdx.x < kAccRows * Wpad) mytot = __ldcg(a.gacc + threadIdx.x);
+  const PoisPart ppart = poisson_finish_load<NW, k2_threads(NW)>(a.pois);
+  if (threadIdx.x < kAccRows * Wpad) {
+    tot[threadIdx.x] = mytot;
+    a.gacc[threadIdx.x] = 0ull;
   }
   if (threadIdx.x == 0) { a.counters[kCtrSegment] = 0u; a.counters[kCtrBlocks] = 0u; }
-  // Poisson term of every walker: the bins of all blocks, added in fixed order (identical on every rank)
-  poisson_finish<NW, k2_threads(NW)>(a.pois, reinterpret_cast<double*>(tot + kAccRows * Wpad),
+  const bool peers = a.peer.world > 1;
+  const int par = (int)(a.peer.seq & 1u), me = a.peer.rank, world = a.peer.world;
+  __syncthreads();   // tot[] complete
+  if (peers) {
+    // my totals to every other rank, each 64-bit value as two self-flagged words (see above)
+    for (int j = threadIdx.x; j < 2 * kAccRows * Wpad; j += blockDim.x) {
+      const unsigned long long v = tot[j >> 1];
+      const unsigned long long word = ((unsigned long long)a.peer.seq << 32) | (unsigned long long)(uint32_t)(v >> (32 * (j & 1)));
+      for (int p = 0; p < world; ++p)
+        if (p != me)
+          asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(a.peer.xbuf[p] + xbuf_word_off(par, me) + j), "l"(word) : "memory");
+    }
+  }
+  // Poisson term of every walker: the bins of all blocks, added in fixed order (identical on every
+  // rank); with peers this hides behind the NVLink flight of the words just sent
+  poisson_finish<NW, k2_threads(NW)>(a.pois, ppart, reinterpret_cast<double*>(tot + kAccRows * Wpad),
                                      a.out + (size_t)MB_OUT_POISSON * a.Wtot + a.w0, a.W);
-  if (a.peer.world > 1) {
-    const int par = (int)(a.peer.seq & 1u), me = a.peer.rank, world = a.peer.world;
-    for (int i = threadIdx.x; i < kAccRows * Wpad; i += blockDim.x) {
-      const unsigned long long v = tot[i];
-      for (int p = 0; p < world; ++p)  // my totals into slot `me` of every rank (peer stores)
-        *reinterpret_cast<volatile unsigned long long*>(a.peer.xbuf[p] + xbuf_data_off(par, me) + i) = v;
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < world) {
-      volatile unsigned int* theirs =
-          reinterpret_cast<volatile unsigned int*>(a.peer.xbuf[threadIdx.x]) + xbuf_flag_off(par, me);
-      *theirs = a.peer.seq;  // publish
-      volatile unsigned int* mine_flag =
-          reinterpret_cast<volatile unsigned int*>(a.peer.xbuf[me]) + xbuf_flag_off(par, threadIdx.x);
-      unsigned long long t0, t1;
-      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
-      unsigned int spins = 0;
-      while (*mine_flag != a.peer.seq) {  // bounded wait for source threadIdx.x
-        if ((++spins & 0xffu) == 0u) {
-          asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-          if (t1 - t0 > a.peer.timeout_ns) { timed_out = 1; break; }
-          __nanosleep(64);
+  stamp(a.timeline, 5);
+  if (peers) {
+    // thread i adds value i of every other source as it arrives (bounded wait)
+    if (threadIdx.x < kAccRows * Wpad) {
+      unsigned long long sum = tot[threadIdx.x];
+      unsigned long long t0 = 0ull;
+      for (int r = 0; r < world; ++r) {
+        if (r == me) continue;
+        const unsigned long long* src = a.peer.xbuf[me] + xbuf_word_off(par, r) + 2 * threadIdx.x;
+        unsigned long long w0, w1;
+        unsigned int spins = 0;
+        while (true) {
+          asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+          if ((uint32_t)(w0 >> 32) == a.peer.seq && (uint32_t)(w1 >> 32) == a.peer.seq) break;
+          if ((++spins & 0x3ffu) == 0u) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+            if (t0 == 0ull) t0 = t1;
+            if (t1 - t0 > a.peer.timeout_ns) { timed_out = 1; break; }
+          }
         }
+        sum += (w0 & 0xffffffffull) | (w1 << 32);
       }
-    }
-    __threadfence_system();
-    __syncthreads();
-    for (int i = threadIdx.x; i < kAccRows * Wpad; i += blockDim.x) {
-      unsigned long long t = 0ull;
-      for (int r = 0; r < world; ++r)
-        t += *reinterpret_cast<volatile unsigned long long*>(a.peer.xbuf[me] + xbuf_data_off(par, r) + i);
-      tot[i] = t;
+      tot[threadIdx.x] = sum;
     }
     __syncthreads();
   }
+  stamp(a.timeline, 6);
   for (int w = threadIdx.x; w < a.W; w += blockDim.x) {
     const unsigned long long nbad = tot[2 * Wpad + w], nnan = tot[3 * Wpad + w];
-    a.out[(size_t)MB_OUT_STARSUM * a.Wtot + a.w0 + w] =
-        (nnan || timed_out) ? nan("") : from_fix2((long long)tot[w], (long long)tot[Wpad + w]);
+    // each word converts exactly (|word| < 2^53): the caller's STARSUM + STARSUM_LO is the only rounding
+    const bool bad_sum = nnan || timed_out;
+    a.out[(size_t)MB_OUT_STARSUM * a.Wtot + a.w0 + w] = bad_sum ? nan("") : fix_hi_to_double((long long)tot[w], (long long)tot[Wpad + w]);
+    a.out[(size_t)MB_OUT_STARSUM_LO * a.Wtot + a.w0 + w] = bad_sum ? 0.0 : fix_lo_to_double((long long)tot[Wpad + w]);
     a.out[(size_t)MB_OUT_NONFINITE * a.Wtot + a.w0 + w] = timed_out ? -1.0 : (double)nbad;
   }
   if (a.done_flag) {
@@ -1394,7 +1449,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     __syncthreads();
     if (threadIdx.x == 0) *a.done_flag = a.done_seq;
   }
-  stamp(a.timeline, 5);
+  stamp(a.timeline, 7);
 }
 
 // ---- pixel batches: many independent small ensembles over one shared grid -----------------------
@@ -1541,8 +1596,8 @@ __global__ void __launch_bounds__(kPixThreads, (NW <= 2 ? 2 : 1)) mb_k2_pixels(K
     __syncthreads();
     double* out = a.out + (size_t)pix * MB_OUT_ROWS * a.W;
     for (int w = threadIdx.x; w < a.W; w += kPixThreads) {
-      out[(size_t)MB_OUT_STARSUM * a.W + w] =
-          sacc[3 * Wpad + w] ? nan("") : from_fix2((long long)sacc[w], (long long)sacc[Wpad + w]);
+      out[(size_t)MB_OUT_STARSUM * a.W + w] = sacc[3 * Wpad + w] ? nan("") : fix_hi_to_double((long long)sacc[w], (long long)sacc[Wpad + w]);
+      out[(size_t)MB_OUT_STARSUM_LO * a.W + w] = sacc[3 * Wpad + w] ? 0.0 : fix_lo_to_double((long long)sacc[Wpad + w]);
       out[(size_t)MB_OUT_NONFINITE * a.W + w] = (double)sacc[2 * Wpad + w];
       out[(size_t)MB_OUT_POISSON * a.W + w] = spois[w];
     }

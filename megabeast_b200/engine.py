@@ -212,6 +212,16 @@ class LikelihoodEngine:
         )
         return rows[: offs[-1]], offs
 
+    def watch(self, arrays):
+        """Guard against in-place changes of the host arrays the device copy was made from
+        (``mb_watch_host``): every later evaluation first compares a fingerprint of each array and
+        fails with ``MB_STALE`` when one changed.  The engine keeps the arrays alive."""
+        self._watched = [a for a in arrays if isinstance(a, np.ndarray) and a.flags.c_contiguous][:16]
+        for h in self.handles:
+            _cabi.check(self.lib.mb_watch_host(h, None, 0))
+            for a in self._watched:
+                _cabi.check(self.lib.mb_watch_host(h, ctypes.c_void_p(a.ctypes.data), a.nbytes))
+
     def device_entries(self, i=0):
         """Parity hook (``mb_device_entries``): the class-coded entry stream as the DEVICE holds it.
         Returns (cls[n, 4] class index per parameter, weight[n], offsets[S_local + 1])."""
@@ -252,10 +262,11 @@ class LikelihoodEngine:
         return dict(zip(_cabi.KERNEL_NAMES, list(ms)))
 
     def last_k2_timeline(self, i=0):
-        """Per-block phase stamps of the last K2 launch (profiling on): array [blocks][6] in
-        microseconds -- start, tables staged, Poisson done, star loop done, block reduced, end."""
+        """Per-block phase stamps of the last K2 launch (profiling on): array [blocks][8] in
+        microseconds -- start, tables staged, N-stars bins done, star loop done, block reduced, and for
+        the last block: Poisson term done + shard totals sent, peers' totals received, end (-1 elsewhere)."""
         cap = 1024
-        us = np.empty((cap, 6))
+        us = np.empty((cap, 8))
         n = self.lib.mb_last_k2_timeline(self.handles[i], _cabi.dptr(us), cap)
         if n < 0:
             _cabi.check(1)
@@ -275,8 +286,8 @@ class LikelihoodEngine:
         return t, keep
 
     def lnlike_rows(self, phis, tabs=None):
-        """Raw result rows [3][W] (sum over this engine's stars of ln(star prob); count of
-        non-finite stars; Poisson term), summed over the engine's devices."""
+        """Raw result rows [4][W] (sum over this engine's stars of ln(star prob) in two exact words;
+        count of non-finite stars; Poisson term), summed over the engine's devices."""
         phis = np.ascontiguousarray(phis, dtype=np.float64)
         if phis.ndim != 2:
             raise ValueError("phis must be (W, ndim)")
@@ -291,7 +302,9 @@ class LikelihoodEngine:
             if total is None:
                 total = rows
             else:
-                total[:2] += rows[:2]  # STARSUM and NONFINITE add over shards, POISSON is shared
+                # STARSUM, STARSUM_LO and NONFINITE add over shards (the two STARSUM words are exact
+                # multiples of 2^-24 / 2^-68: no rounding here), POISSON is shared
+                total[:_cabi.MB_OUT_ADDITIVE_ROWS] += rows[:_cabi.MB_OUT_ADDITIVE_ROWS]
         return total
 
     def combine(self, rows):
@@ -319,20 +332,22 @@ class LikelihoodEngine:
             return out, status
         return self.combine(self.lnlike_rows(phis, tabs))
 
-    def lnlike_pixels(self, phis):
-        """Pixel batch: phis [P][W][ndim] -> (lnlike[P][W], status[P][W]), one launch."""
+    def lnlike_pixels(self, phis, tabs=None):
+        """Pixel batch: phis [P][W][ndim] -> (lnlike[P][W], status[P][W]), one launch.  ``tabs``:
+        host-evaluated tables {param: [P*W][n_classes]} for tabulated parameters."""
         phis = np.ascontiguousarray(phis, dtype=np.float64)
         if phis.ndim != 3 or phis.shape[0] != self.n_pixels:
             raise ValueError(f"phis must be ({self.n_pixels}, W, ndim)")
         P, W, ndim = phis.shape
         out = np.empty((P, W))
         status = np.empty((P, W), dtype=np.int32)
-        _cabi.check(self.lib.mb_lnlike_pixels(self.handles[0], phis.ctypes.data, W, ndim,
-                                              out.ctypes.data, status.ctypes.data))
+        t, keep = self._tabs(tabs or {}, P * W)
+        _cabi.check(self.lib.mb_lnlike_pixels_tabulated(self.handles[0], phis.ctypes.data, W, ndim, t,
+                                                        out.ctypes.data, status.ctypes.data))
         return out, status
 
     def lnlike_pixels_device(self, d_phi, W, ndim, d_out, stream=0):
-        """Device-pointer form: d_phi [P][W][ndim], d_out [P][3][W], asynchronous on ``stream``."""
+        """Device-pointer form: d_phi [P][W][ndim], d_out [P][4][W], asynchronous on ``stream``."""
         _cabi.check(self.lib.mb_lnlike_pixels_device(self.handles[0], ctypes.c_void_p(d_phi), W, ndim,
                                                      ctypes.c_void_p(d_out), ctypes.c_void_p(stream)))
 
@@ -358,7 +373,7 @@ class LikelihoodEngine:
 
     def lnlike_device(self, d_phi, W, ndim, d_out, stream=0, i=0):
         """Asynchronous device-pointer form (``mb_lnlike_device``): ``d_phi`` [W][ndim] and
-        ``d_out`` [3][W] are raw device addresses, ``stream`` a raw ``cudaStream_t``."""
+        ``d_out`` [4][W] are raw device addresses, ``stream`` a raw ``cudaStream_t``."""
         _cabi.check(
             self.lib.mb_lnlike_device(
                 self.handles[i], ctypes.c_void_p(d_phi), W, ndim, ctypes.c_void_p(d_out),

@@ -1,7 +1,7 @@
 """
 Star-sharded ensemble likelihood across processes: one process per GPU (``torchrun``), every
 rank owns a contiguous shard of stars plus a replicated grid, evaluates all W walkers on its
-shard, and ONE reduction of 2*W values (partial sums of ln(star prob) + non-finite counts) per
+shard, and ONE reduction of 3*W values (partial sums of ln(star prob) in two exact words + non-finite counts) per
 step completes the likelihood (BASELINE.json north_star item 4).  The
 reduction runs either as one NCCL all-reduce after the kernels ("nccl") or -- the default when
 the GPUs can map each other's memory -- INSIDE the likelihood kernel: the last block of every
@@ -16,7 +16,7 @@ import numpy as np
 from . import _cabi
 from .engine import LikelihoodEngine, shard_bounds
 
-__all__ = ["dist_info", "allreduce_rows", "combine_rows", "ShardedLikelihood"]
+__all__ = ["dist_info", "allreduce_rows", "reduce_host_rows", "combine_rows", "ShardedLikelihood"]
 
 
 def dist_info(group=None):
@@ -32,23 +32,39 @@ def dist_info(group=None):
 
 
 def allreduce_rows(rows, group=None):
-    """Sum the shard-additive rows (STARSUM, NONFINITE = the first 2*W values) of a [3][W]
-    tensor over all ranks, in place; the POISSON row is identical everywhere and is left alone.
-    Works for CUDA tensors (NCCL) and CPU tensors (gloo)."""
+    """Sum the shard-additive rows (STARSUM, STARSUM_LO, NONFINITE = the first 3*W values) of a
+    [4][W] tensor over all ranks, in place; the POISSON row is identical everywhere and is left
+    alone.  The two STARSUM words are exact multiples of 2^-24 and 2^-68, so this floating-point sum
+    is exact.  Works for CUDA tensors (NCCL) and CPU tensors (gloo)."""
     import torch.distributed as dist
 
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         W = rows.shape[1]
-        dist.all_reduce(rows.view(-1)[: 2 * W], op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(rows.view(-1)[: _cabi.MB_OUT_ADDITIVE_ROWS * W], op=dist.ReduceOp.SUM, group=group)
     return rows
+
+
+def reduce_host_rows(rows, group=None, device=None):
+    """Sum host rows [4][W] (numpy) over the ranks: STARSUM, STARSUM_LO and NONFINITE add, POISSON is shared.
+    gloo groups reduce the CPU tensor directly, NCCL groups go through ``device``."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return rows
+    t = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float64))
+    if dist.get_backend(group) == "nccl":
+        t = t.to(device)
+    allreduce_rows(t, group)
+    return t.cpu().numpy()
 
 
 def combine_rows(rows):
     """(lnlike[W], status[W]) from reduced rows -- the arithmetic of ``mb_combine``."""
     rows = np.asarray(rows, dtype=np.float64)
-    total = rows[2] + rows[0]
-    status = np.where(rows[1] > 0.0, _cabi.STATUS_NONFINITE_STAR, 0).astype(np.int32)
-    status |= np.where(rows[1] < 0.0, _cabi.STATUS_PEER_TIMEOUT, 0).astype(np.int32)
+    total = rows[3] + (rows[0] + rows[1])  # POISSON + (STARSUM + STARSUM_LO), as mb_combine
+    status = np.where(rows[2] > 0.0, _cabi.STATUS_NONFINITE_STAR, 0).astype(np.int32)
+    status |= np.where(rows[2] < 0.0, _cabi.STATUS_PEER_TIMEOUT, 0).astype(np.int32)
     status |= np.where(total == 0.0, _cabi.STATUS_TOTAL_ZERO, 0).astype(np.int32)
     return total, status
 
@@ -76,8 +92,6 @@ class ShardedLikelihood:
         self.rank, self.world = dist_info(group)
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.spec, self.perm, self.ndim = model._spec()
-        if self.spec.tabulated:
-            raise NotImplementedError("tabulated prior models are single-process only")
         mm = None
         if model.compute_N_stars:
             model.massmultipliers = precompute_mass_multipliers(
@@ -100,7 +114,8 @@ class ShardedLikelihood:
         self._cap = 0
         self._ensure(64)
         # device variable order == reference order (the usual case): lnprob can be one C call
-        self._fast_ok = self.perm.size == self.ndim and np.array_equal(self.perm, np.arange(self.ndim))
+        self._fast_ok = (not self.spec.tabulated and self.perm.size == self.ndim
+                         and np.array_equal(self.perm, np.arange(self.ndim)))
 
     def _setup_reduce(self, want):
         import torch.distributed as dist
@@ -143,19 +158,26 @@ class ShardedLikelihood:
         W = d_phi.shape[0]
         if d_rows is None:
             self._ensure(W)
-            d_rows = self.d_rows if W == self._cap else self.d_rows.view(-1)[: 3 * W].view(3, W)
+            d_rows = self.d_rows if W == self._cap else self.d_rows.view(-1)[: 4 * W].view(4, W)
         stream = t.cuda.current_stream(self.device).cuda_stream
         self.engine.lnlike_device(d_phi.data_ptr(), W, self.ndim, d_rows.data_ptr(), stream)
         if self.reduce == "nccl":
             allreduce_rows(d_rows, self.group)
         return d_rows  # "p2p": the kernel already summed the shards over NVLink
 
-    def lnlike_rows(self, phis):
-        """Host phi (W, ndim in device order) -> reduced host rows [3][W]."""
+    def lnlike_rows(self, phis, tabs=None):
+        """Host phi (W, ndim in device order) -> reduced host rows [4][W].  ``tabs``: host-evaluated
+        tables of tabulated prior models (every rank evaluates the same callable on the same class
+        values, so all ranks pass identical tables)."""
         if self.reduce in ("p2p", "none"):
             # one C call: phi and the rows go through mapped pinned memory, the kernels run on the
             # handle's own stream and (p2p) add the shards over NVLink themselves -- no torch ops
-            return self.engine.lnlike_rows(phis)
+            return self.engine.lnlike_rows(phis, tabs)
+        if tabs:
+            # tabulated models go through the host form of the library (it uploads the tables); the
+            # shard partials are then added by the process group
+            rows = self.engine.lnlike_rows(phis, tabs)
+            return reduce_host_rows(rows, self.group, self.torch.device("cuda", self.device))
         t = self.torch
         phis = np.ascontiguousarray(phis, dtype=np.float64)
         W = phis.shape[0]
@@ -164,9 +186,9 @@ class ShardedLikelihood:
         h_phi.numpy()[...] = phis.reshape(W, -1) if self.ndim else 0.0
         d_phi = self.d_phi[:W]
         d_phi.copy_(h_phi, non_blocking=True)
-        d_rows = self.d_rows.view(-1)[: 3 * W].view(3, W)
+        d_rows = self.d_rows.view(-1)[: 4 * W].view(4, W)
         self.lnlike_device(d_phi, d_rows)
-        h_rows = self.h_rows.view(-1)[: 3 * W].view(3, W)
+        h_rows = self.h_rows.view(-1)[: 4 * W].view(4, W)
         h_rows.copy_(d_rows, non_blocking=True)
         t.cuda.current_stream(self.device).synchronize()
         return h_rows.numpy()
@@ -188,7 +210,8 @@ class ShardedLikelihood:
             inside = np.isfinite(lp)
             status = np.zeros(1, dtype=np.int32)
             if inside.any():
-                rows = self.lnlike_rows(phis[inside][:, self.perm])
+                tabs = self.model._tables(self.engine, self.spec, phis[inside]) if self.spec.tabulated else None
+                rows = self.lnlike_rows(phis[inside][:, self.perm], tabs)
                 vals, status = combine_rows(rows)
                 out[inside] = lp[inside] + vals
         if status.any():

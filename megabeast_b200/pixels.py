@@ -25,11 +25,11 @@ __all__ = ["PixelEnsemble"]
 
 
 class PixelEnsemble:
-    def __init__(self, params, star_lnpgriddata, beast_moddata, star_offsets, device=0):
-        self.model = MB_Model(params, devices=[device])
+    def __init__(self, params, star_lnpgriddata, beast_moddata, star_offsets, device=0, model=None):
+        """``model``: an existing ``MB_Model`` to use instead of building one from ``params`` (e.g. one
+        whose prior callables were replaced)."""
+        self.model = model if model is not None else MB_Model(params, devices=[device])
         self.spec, perm, self.ndim = self.model._spec()
-        if self.spec.tabulated:
-            raise NotImplementedError("tabulated prior models are not supported for pixel batches")
         self.perm = None if self.model._identity_perm(perm, self.ndim) else perm
         self.star_offsets = np.ascontiguousarray(star_offsets, dtype=np.int64)
         self.n_pixels = self.star_offsets.size - 1
@@ -47,9 +47,23 @@ class PixelEnsemble:
         """(P, W, ndim) -> (P, W); raises like ``MB_Model.lnlike`` if any walker of any pixel hits a
         non-finite star or an exactly-zero total."""
         phis = np.asarray(phis, dtype=np.float64)
-        vals, status = self.engine.lnlike_pixels(phis if self.perm is None else phis[..., self.perm])
+        vals, status = self.engine.lnlike_pixels(self._device_phi(phis), self._tables(phis))
         self._raise(status)
         return vals
+
+    def _device_phi(self, phis):
+        if self.perm is None:
+            return phis if phis.shape[-1] == self.ndim else phis[..., :self.ndim]
+        return phis[..., self.perm]
+
+    def _tables(self, phis):
+        """Prior models the device does not know: the host callable evaluated on the parameter's
+        class values for every (pixel, walker) -> tables [P*W][n_classes] (singlepop_dust_model.py:
+        55-67,146-148: whatever callable the installed BEAST provides)."""
+        if not self.spec.tabulated:
+            return None
+        P, W, _ = phis.shape
+        return self.model._tables(self.engine, self.spec, phis.reshape(P * W, -1))
 
     @staticmethod
     def _raise(status):
@@ -72,7 +86,7 @@ class PixelEnsemble:
             safe = phis.copy()
             start = np.asarray(self.model.start_params()[1], dtype=np.float64)
             safe[~inside] = start
-        vals, status = self.engine.lnlike_pixels(safe if self.perm is None else safe[..., self.perm])
+        vals, status = self.engine.lnlike_pixels(self._device_phi(safe), self._tables(safe))
         self._raise(np.where(inside, status, 0))
         return np.where(inside, lp + vals, -np.inf)
 

@@ -179,8 +179,18 @@ class MB_Model:
     # -- device-resident data ------------------------------------------------------------------------
     @staticmethod
     def _data_key(star_lnpgriddata, beast_moddata):
-        return (id(star_lnpgriddata), id(beast_moddata), id(star_lnpgriddata["indxs"]),
-                id(star_lnpgriddata["vals"]), id(beast_moddata["prior_weight"]))
+        """Identity of the data a device copy was made from: the two dictionaries, and for every
+        array that went to the device its object id, data pointer and shape.
+        In-place changes of the VALUES are caught by the library's fingerprint check
+        (``mb_watch_host``, see ``_engine_for``)."""
+        key = [id(star_lnpgriddata), id(beast_moddata)]
+        for d, names in ((star_lnpgriddata, ("indxs", "vals")),
+                         (beast_moddata, ("prior_weight", "grid_weight", "completeness"))):
+            for name in names:
+                a = d[name]
+                ai = getattr(a, "__array_interface__", None)
+                key.append((id(a), ai["data"][0], ai["shape"]) if ai is not None else id(a))
+        return tuple(key)
 
     def _engine_for(self, star_lnpgriddata, beast_moddata):
         key = self._data_key(star_lnpgriddata, beast_moddata)
@@ -210,6 +220,11 @@ class MB_Model:
         for old in list(self._engines.values()):  # one resident data set at a time
             old[0].close()
         self._last_data = None
+        # let the library notice in-place changes of the arrays the device copy was made from
+        watch = [star_lnpgriddata["vals"], star_lnpgriddata["indxs"], beast_moddata["prior_weight"],
+                 beast_moddata["grid_weight"], beast_moddata["completeness"]]
+        watch += [beast_moddata[p] for p in _cabi.PARAMS if spec.kinds[p] != "fixed"]
+        engine.watch(watch)
         if self._identity_perm(perm, ndim):
             perm = None  # device order == reference order (the usual case): no column shuffle
         self._engines = {key: (engine, (spec, perm, ndim), (star_lnpgriddata, beast_moddata))}
@@ -246,7 +261,13 @@ class MB_Model:
         self._store_phi(phis[-1])
         if perm is None and phis.shape[1] != ndim:
             phis = phis[:, :ndim]
-        vals, status = engine.lnlike(phis if perm is None else phis[:, perm], tabs)
+        try:
+            vals, status = engine.lnlike(phis if perm is None else phis[:, perm], tabs)
+        except _cabi.MegabeastB200Error as exc:
+            if "MB_STALE" not in str(exc):
+                raise
+            self._drop_engines()  # the arrays were changed in place: new device copy, same call again
+            return self.lnlike(phi, star_lnpgriddata, beast_moddata)
         if status.any():
             if np.any(status & _cabi.STATUS_PEER_TIMEOUT):
                 raise RuntimeError("a peer GPU did not deliver its star shard (timeout)")
@@ -255,6 +276,12 @@ class MB_Model:
             print(0.0)
             raise SystemExit
         return vals[0] if single else vals.copy()
+
+    def _drop_engines(self):
+        for old in list(self._engines.values()):
+            old[0].close()
+        self._engines = {}
+        self._last_data = None
 
     @staticmethod
     def _identity_perm(perm, ndim):
@@ -302,7 +329,13 @@ class MB_Model:
         if perm is not None or spec.tabulated or len(engine.handles) != 1 or phis.shape[1] != ndim:
             return None
         lows, highs = self._box()
-        vals, status, last = engine.lnprob_box(phis, lows, highs)
+        try:
+            vals, status, last = engine.lnprob_box(phis, lows, highs)
+        except _cabi.MegabeastB200Error as exc:
+            if "MB_STALE" not in str(exc):
+                raise
+            self._drop_engines()
+            return None  # the general path rebuilds the device copy
         if last >= 0:
             self._store_phi(phis[last])
         if status.any():

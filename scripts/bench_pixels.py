@@ -65,7 +65,7 @@ def main():
     phis = np.clip(phis, *pe.model._box())
     dev = torch.device("cuda", local)
     d_phi = torch.from_numpy(np.ascontiguousarray(phis)).to(dev)
-    d_out = torch.empty((P, 3, W), dtype=torch.float64, device=dev)
+    d_out = torch.empty((P, 4, W), dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
     for _ in range(5):

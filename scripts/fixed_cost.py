@@ -22,7 +22,7 @@ def run(name, W, mask_all=False, mode="auto"):
     sh = ShardedLikelihood(model, stars, moddata, device=0, mode=mode)
     dev = torch.device("cuda", 0)
     d_phi = torch.from_numpy(np.ascontiguousarray(phis[:, sh.perm])).to(dev)
-    d_rows = torch.empty((3, W), dtype=torch.float64, device=dev)
+    d_rows = torch.empty((4, W), dtype=torch.float64, device=dev)
     for _ in range(5):
         sh.lnlike_device(d_phi, d_rows)
     torch.cuda.synchronize()

@@ -39,6 +39,15 @@ if has eighth; then
     summ $OUT/${TAG}_bench_${wl}_n1.json
   done
 fi
+if has launch; then
+  # where do the ~7 us between the CUDA events and the kernel's own first/last stamps go?
+  MB_NO_PDL=1 timeout 600 python bench.py --workload cfg3_eighth --steps 200 --warmup 10 --no-cpu-baseline --no-clustered --no-sustained > $OUT/${TAG}_bench_eighth_nopdl.json 2> $OUT/${TAG}_bench_eighth_nopdl.err; echo "eighth no-PDL rc=$?"
+  summ $OUT/${TAG}_bench_eighth_nopdl.json
+  mkdir -p build_variants
+  python -c "from megabeast_b200 import build; build.build(force=True, defines=['MB_PHI_INLINE=64'], out='build_variants/lib_phi64.so')" && \
+  MEGABEAST_B200_LIB=$PWD/build_variants/lib_phi64.so timeout 600 python bench.py --workload cfg3_eighth --steps 200 --warmup 10 --no-cpu-baseline --no-clustered --no-sustained > $OUT/${TAG}_bench_eighth_phi64.json 2> $OUT/${TAG}_bench_eighth_phi64.err; echo "eighth small-params rc=$?"
+  summ $OUT/${TAG}_bench_eighth_phi64.json
+fi
 if has finedust; then
   timeout 900 python bench.py --workload fine_dust --steps 50 --warmup 5 --cpu-sample 8 --no-clustered > $OUT/${TAG}_bench_fine_dust_n1.json 2> $OUT/${TAG}_bench_fine_dust_n1.err; echo "bench fine_dust rc=$?"; tail -3 $OUT/${TAG}_bench_fine_dust_n1.err
   summ $OUT/${TAG}_bench_fine_dust_n1.json

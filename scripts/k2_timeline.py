@@ -18,7 +18,7 @@ for name in sys.argv[1:] or ["cfg3", "cfg3_eighth"]:
     sh = ShardedLikelihood(model, stars, moddata, device=0)
     dev = torch.device("cuda", 0)
     d_phi = torch.from_numpy(np.ascontiguousarray(phis)).to(dev)
-    d_rows = torch.empty((3, len(phis)), dtype=torch.float64, device=dev)
+    d_rows = torch.empty((4, len(phis)), dtype=torch.float64, device=dev)
     for _ in range(5):
         sh.lnlike_device(d_phi, d_rows)
     torch.cuda.synchronize()
@@ -39,5 +39,5 @@ for name in sys.argv[1:] or ["cfg3", "cfg3_eighth"]:
         if len(grp):
             print(f"  {label:22s} " + "  ".join(f"{n}={np.mean(grp[:, k]):6.2f}" for k, n in enumerate(names[:5])))
     print(f"  max over blocks        " + "  ".join(f"{n}={np.max(t[:, k]):6.2f}" for k, n in enumerate(names[:5]))
-          + f"  end={np.max(t[:, 5]):6.2f}")
+          + f"  end={np.max(t[:, 7]):6.2f}")
     sh.close()

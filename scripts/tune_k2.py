@@ -50,7 +50,7 @@ def one(lib, workload, index_mode):
     sh = ShardedLikelihood(model, stars, moddata, device=0)
     dev = torch.device("cuda", 0)
     d_phi = torch.from_numpy(np.ascontiguousarray(phis[:, sh.perm])).to(dev)
-    d_rows = torch.empty((3, len(phis)), dtype=torch.float64, device=dev)
+    d_rows = torch.empty((4, len(phis)), dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     if os.environ.get("MB_NO_FLUSH"):
         flush = torch.empty(16, dtype=torch.uint8, device=dev)
@@ -79,7 +79,7 @@ def one(lib, workload, index_mode):
     print(json.dumps({"lib": os.path.basename(lib), "step_ms": tot / n,
                       "evals_per_s": cfg["W"] * n / (tot * 1e-3),
                       "kernel_ms": {k: round(v, 5) for k, v in kms.items()},
-                      "checksum": float(d_rows[0].sum().item())}), flush=True)
+                      "checksum": float((d_rows[0] + d_rows[1]).sum().item())}), flush=True)
 
 
 def run(workload="cfg3", index_mode="uniform"):

@@ -71,7 +71,8 @@ def test_struct_layouts_match_header_sizes():
 
 def test_combine_is_host_arithmetic():
     lib = _cabi.load()
-    rows = np.array([[-10.0, 0.0, 5.0], [0.0, 0.0, 2.0], [-1.5, 0.0, 1.0]])  # STARSUM, NONFINITE, POISSON
+    # STARSUM, STARSUM_LO, NONFINITE, POISSON
+    rows = np.array([[-10.0, 0.0, 5.0], [-0.25, 0.0, 0.125], [0.0, 0.0, 2.0], [-1.25, 0.0, 0.875]])
     out = np.empty(3)
     st = np.empty(3, np.int32)
     lib.mb_combine(_cabi.dptr(np.ascontiguousarray(rows)), 3, _cabi.dptr(out), st.ctypes.data_as(_cabi.c_int32_p))

@@ -54,8 +54,9 @@ def test_fullsize_shard_additivity_and_star_order(cfg3):
                                n_stars_total=S)
         rows.append(eng.lnlike_rows(phis).copy())
         eng.close()
-    total = rows[0][0] + rows[1][0] + rows[0][2]  # STARSUM parts + the (shared) Poisson row
-    assert np.array_equal(rows[0][2], rows[1][2])
+    # STARSUM words of the two shards (exact sums) + the (shared) Poisson row
+    total = ((rows[0][0] + rows[1][0]) + (rows[0][1] + rows[1][1])) + rows[0][3]
+    assert np.array_equal(rows[0][3], rows[1][3])
     assert np.allclose(total, vals, rtol=1e-13, atol=0)
     order = np.random.default_rng(0).permutation(S)
     shuffled = {"indxs": np.ascontiguousarray(stars["indxs"][:, order]),

@@ -1,8 +1,11 @@
 """
 Two real GPUs, one process each: star-sharded likelihood with the shard reduction (a) fused into
 the kernel over NVLink peer memory and (b) as one NCCL all-reduce.  Skipped with fewer than two
-devices.  Both must reproduce the oracle (1e-9 relative) and agree with each other bit for bit
-(the shard totals are added as integers).
+devices.  Both must reproduce the oracle (1e-9 relative) and agree with each other bit for bit:
+the kernel delivers the shard totals as two exact words (multiples of 2^-24 and 2^-68), so adding
+them as integers inside the kernel or as doubles in NCCL is the same sum, rounded once.
+Also: a prior model the device does not know (host callable, tabulated on the class values by every
+rank) through both reductions.
 """
 import copy
 import os
@@ -22,6 +25,15 @@ def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
+
+
+def _host_lognormal(x, mode, sigma):
+    x = np.asarray(x, dtype=float)
+    y = np.zeros_like(x)
+    g = x > 0
+    mu = np.log(mode) + sigma ** 2
+    y[g] = (1.0 / np.sqrt(2.0 * np.pi)) / (x[g] * sigma) * np.exp(-0.5 * ((np.log(x[g]) - mu) / sigma) ** 2)
+    return y
 
 
 def _worker(rank, world, port_no, q):
@@ -46,6 +58,15 @@ def _worker(rank, world, port_no, q):
             out[mode] = np.array(vals)
             out[mode + "_one"] = float(sh.lnprob(phis[0]))
             sh.close()
+            # the same model with the A(V) prior as an opaque host callable (-> MB_TABULATED)
+            mt = MB_Model(copy.deepcopy(settings))
+            av = mt.physics_model["Av"]
+            av["name"] = "some_future_beast_model"
+            av["model"] = lambda x, av=av: _host_lognormal(x, av["mean"], av["sigma"])
+            sht = ShardedLikelihood(mt, stars, moddata, device=rank, reduce=mode)
+            assert sht.spec.tabulated == ["Av"] and sht.reduce == mode
+            out[mode + "_tab"] = np.array(sht.lnprob(phis))
+            sht.close()
         q.put((rank, out))
     finally:
         dist.destroy_process_group()
@@ -81,5 +102,8 @@ def test_two_gpu_star_sharding_p2p_and_nccl():
             assert np.array_equal(got[~fin], want[~fin])
             assert np.max(np.abs(got[fin] - want[fin]) / np.abs(want[fin])) < 1e-9
             assert abs(res[rank][mode + "_one"] - want[0]) < 1e-9 * abs(want[0])
+            tab = res[rank][mode + "_tab"]
+            assert np.array_equal(tab[~fin], want[~fin])
+            assert np.max(np.abs(tab[fin] - want[fin]) / np.abs(want[fin])) < 1e-9
         assert np.array_equal(res[rank]["p2p"], res[0]["p2p"])  # every rank holds the same totals
     assert np.array_equal(res[0]["p2p"], res[0]["nccl"])

@@ -184,3 +184,56 @@ def test_totals_near_zero_keep_relative_accuracy():
         model = MB_Model(copy.deepcopy(settings), mode=mode)
         assert_close(lnprob(phis, model, sub, moddata), expect, RTOL)
         assert abs(lnprob(phis[2], model, sub, moddata) - expect[2]) <= RTOL * abs(expect[2])
+
+
+def _host_lognormal(x, mode, sigma):
+    x = np.asarray(x, dtype=float)
+    y = np.zeros_like(x)
+    g = x > 0
+    mu = np.log(mode) + sigma ** 2
+    y[g] = (1.0 / np.sqrt(2.0 * np.pi)) / (x[g] * sigma) * np.exp(-0.5 * ((np.log(x[g]) - mu) / sigma) ** 2)
+    return y
+
+
+def test_pixel_batch_with_a_host_tabulated_model():
+    """A prior model the device does not know (an opaque host callable, as an installed BEAST with a
+    new model name would provide: singlepop_dust_model.py:55-67,146-148) inside a pixel batch: every
+    (pixel, walker) table is evaluated on the class values and shipped; same numbers as the analytic
+    model."""
+    from megabeast_b200.pixels import PixelEnsemble
+
+    settings, moddata, stars, offs = synth.make_pixel_problem(n_pixels=9, mean_stars=25, seeds=(3, 4, 7))
+    pe = PixelEnsemble(copy.deepcopy(settings), stars, moddata, offs)
+    pm = port.PortModel(copy.deepcopy(settings))
+    phis = np.stack([synth.make_walkers(pm, 12, seed=300 + p) for p in range(len(offs) - 1)])
+    want = pe.lnprob(phis)
+    pe.close()
+    s2 = copy.deepcopy(settings)
+    model = MB_Model(s2, devices=[0])
+    av = model.physics_model["Av"]
+    av["name"] = "some_future_beast_model"
+    av["model"] = lambda x, av=av: _host_lognormal(x, av["mean"], av["sigma"])
+    pe2 = PixelEnsemble(None, stars, moddata, offs, model=model)
+    assert pe2.spec.tabulated == ["Av"]
+    got = pe2.lnprob(phis)
+    assert_close(got, want, 1e-12)
+    pe2.close()
+
+
+def test_in_place_change_of_the_data_is_noticed():
+    """The data dictionaries arrive on every call (singlepop_dust_model.py:110) but live on the device:
+    an array changed IN PLACE must not be evaluated from the stale copy."""
+    settings, moddata, stars, _ = synth.make_problem("small", seeds=(95, 96, 97))
+    stars = {"indxs": stars["indxs"].copy(), "vals": stars["vals"].copy()}
+    pm = port.PortModel(copy.deepcopy(settings))
+    phis = synth.make_walkers(pm, 5, seed=97)
+    model = MB_Model(copy.deepcopy(settings))
+    assert_close(lnprob(phis, model, stars, moddata), c_oracle.lnprob_batch(pm, phis, stars, moddata), RTOL)
+    stars["vals"] *= 3.0                                   # same objects, same pointers, new numbers
+    assert_close(lnprob(phis, model, stars, moddata), c_oracle.lnprob_batch(pm, phis, stars, moddata), RTOL)
+    moddata["completeness"] *= 0.5
+    assert_close(lnprob(phis[0], model, stars, moddata), c_oracle.lnprob_batch(pm, phis[:1], stars, moddata)[0], RTOL)
+    moddata["completeness"] *= 2.0
+    # a NEW array object under the same key is noticed as well (key: ids, data pointers, shapes)
+    stars["vals"] = stars["vals"] / 3.0
+    assert_close(lnprob(phis, model, stars, moddata), c_oracle.lnprob_batch(pm, phis, stars, moddata), RTOL)
