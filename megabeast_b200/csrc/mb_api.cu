@@ -252,8 +252,10 @@ static size_t k1e_smem_bytes(int Wpad, int ndim) {
 // size the front.
 struct K2Smem {
   size_t front = 0, tables = 0, total = 0, slab_off = 0;
+  size_t scratch_off = 0;   // table-build / N-stars scratch: 0 (shares the stage) or right after the stage
   size_t pois_off = 0;      // N-stars scratch: after the look-up rows when the tables are built in the kernel
   int pois_warps = 0;       // warps whose partial sums fit
+  bool separate = false;    // stage and scratch disjoint: the entry stage is primed before the table build
   bool fuse_fits = false;   // the scratch of the in-kernel table build fits as well
 };
 // scratch of the in-kernel table build: look-up rows | ln x, 1/x per class | per-walker constants |
@@ -262,38 +264,43 @@ static size_t k2_fuse_scratch(int nscratch, int ncls_total, int nrows, int Wpad,
   return 8 * ((size_t)nscratch * Wpad + 2 * (size_t)ncls_total + 6 * (size_t)MB_NPARAM * Wpad + (size_t)nrows +
               (size_t)((ncls_total + 3) / 4) + phi_doubles);
 }
+// Layouts are tried in order of preference: tables built in the kernel before a separate K0 launch,
+// a private scratch (stage primed early, one barrier less) before a shared one.
 static K2Smem k2_smem_plan(int kmode, int nO, int nI, int nbins, int Wpad, int elem_bytes, int max_smem,
                            size_t fuse_scratch = 0, int nscratch = 0) {
-  K2Smem p;
   const int NW = Wpad / 32, threads = k2_threads(NW), warps = threads / 32;
   const size_t stage = (size_t)warps * k2_stage_bytes(NW);
   const size_t slabs = (size_t)warps * kAccRows * Wpad * 8;  // block reduction: one slab per warp
   const size_t pois_row = kPoisBins * 2 * (size_t)Wpad * 8;  // one warp's partial (S, C) of the bins in flight, all walkers
-  p.tables = kmode == kModeFactor ? (size_t)(nO + nI) * Wpad * elem_bytes : 0;
-  const bool slabs_over_tables = p.tables >= slabs;
-  size_t base = stage;
-  if (!slabs_over_tables) base = std::max(base, slabs);
-  auto finish = [&](size_t front, size_t pois_off) {
-    int pw = 0;
+  const size_t tables = kmode == kModeFactor ? (size_t)(nO + nI) * Wpad * elem_bytes : 0;
+  const bool slabs_over_tables = tables >= slabs;
+  static const bool no_separate = getenv("MB_NO_PRIME") && atoi(getenv("MB_NO_PRIME"));  // A/B switch (measurements)
+  auto layout = [&](bool sep, bool fused, K2Smem& p) -> bool {
+    p = K2Smem();
+    p.tables = tables;
+    p.separate = sep;
+    p.fuse_fits = fused;
+    p.scratch_off = sep ? ((stage + 15) & ~(size_t)15) : 0;
+    p.pois_off = p.scratch_off + (fused ? (size_t)nscratch * Wpad * 8 : 0);
+    size_t front = std::max(stage, p.scratch_off + (fused ? fuse_scratch : 0));
+    if (!slabs_over_tables) front = std::max(front, slabs);
     if (nbins > 0) {
-      const size_t avail = (size_t)max_smem > p.tables + pois_off ? (size_t)max_smem - p.tables - pois_off : 0;
-      pw = (int)std::min<size_t>((size_t)warps, avail / pois_row);
-      front = std::max(front, pois_off + (size_t)std::max(pw, 1) * pois_row);
+      if (tables + p.pois_off + pois_row > (size_t)max_smem) return false;
+      const size_t avail = (size_t)max_smem - tables - p.pois_off;
+      p.pois_warps = (int)std::min<size_t>((size_t)warps, avail / pois_row);
+      if (sep && p.pois_warps < warps) return false;  // a private scratch is only worth it at full width
+      front = std::max(front, p.pois_off + (size_t)p.pois_warps * pois_row);
     }
-    p.pois_off = pois_off;
-    p.pois_warps = pw;
     p.front = (front + 15) & ~(size_t)15;
+    p.slab_off = slabs_over_tables ? p.front : 0;
+    p.total = p.front + p.tables;
+    return p.total <= (size_t)max_smem;
   };
-  finish(base, 0);
-  if (fuse_scratch > 0) {
-    const K2Smem plain = p;
-    finish(std::max(base, fuse_scratch), (size_t)nscratch * Wpad * 8);
-    if (p.front + p.tables <= (size_t)max_smem && (nbins == 0 || p.pois_warps >= 1)) p.fuse_fits = true;
-    else p = plain;
-  }
-  p.slab_off = slabs_over_tables ? p.front : 0;
-  p.total = p.front + p.tables;
-  if (nbins > 0 && p.pois_warps < 1) p.total = (size_t)max_smem + 1;  // no room for the N-stars scratch
+  K2Smem p;
+  for (int fused = fuse_scratch > 0 ? 1 : 0; fused >= 0; --fused)
+    for (int sep = no_separate ? 0 : 1; sep >= 0; --sep)
+      if (layout(sep != 0, fused != 0, p)) return p;
+  p.total = (size_t)max_smem + 1;  // nothing fits
   return p;
 }
 
@@ -1354,6 +1361,7 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     k2.gacc = h->d_gacc; k2.counters = h->d_counter; k2.out = d_out;
     k2.nA = h->nO; k2.nB = h->nI; k2.nOd = h->nOd; k2.Wpad = Wpad; k2.W = wp; k2.w0 = w0; k2.Wtot = W;
     k2.tab_off = (int32_t)plan.front;
+    k2.scratch_off = (int32_t)plan.scratch_off; k2.separate = plan.separate ? 1 : 0;
     k2.slab_off = (int32_t)plan.slab_off;
     k2.pois.Ht = h->d_H; k2.pois.bin_agecls = h->d_bin_agecls; k2.pois.coef = h->d_coef; k2.pois.Pb = h->d_Pb;
     k2.pois.n_stars = (double)h->S_total; k2.pois.nbins = h->poisson ? h->nbins : 0;
@@ -1366,7 +1374,8 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     else if (!fused) k2.pois.fage = Fage;
     else {
       k2.pois.fage = nullptr;
-      k2.pois.fage_smem_off = h->age_slot < 0 ? (int32_t)plan.front : (int32_t)((size_t)h->age_slot * Wpad * 8);
+      k2.pois.fage_smem_off = h->age_slot < 0 ? (int32_t)plan.front
+                                               : (int32_t)(plan.scratch_off + (size_t)h->age_slot * Wpad * 8);
     }
     if (d_flag && w0 + wp >= W) { k2.done_flag = d_flag; k2.done_seq = flag_seq; }  // the last pass publishes
     k2.build_tables = fused ? 1 : 0;

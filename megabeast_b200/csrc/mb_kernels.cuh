@@ -220,7 +220,7 @@ constexpr int kPoisBins = 2;  // bins a block works on at a time (loads of both 
 // l, l + 32, ... (8-byte loads, conflict free).
 template <int NW, int THREADS>
 __device__ void poisson_bins(const PoissonArgs& pa, const double* F, int nO, int nOd, int nI,
-                             unsigned char* smem_raw) {
+                             unsigned char* smem_raw, bool scratch_is_private) {
   constexpr int Wpad = 32 * NW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int pw = pa.nwarps;
@@ -228,7 +228,10 @@ __device__ void poisson_bins(const PoissonArgs& pa, const double* F, int nO, int
   const double* fage = pa.fage ? pa.fage : reinterpret_cast<const double*>(smem_raw + pa.fage_smem_off);
   const double2* Ht = reinterpret_cast<const double2*>(pa.Ht);
   const double* FI = F + (size_t)nO * Wpad + lane;
+  bool first_pass = true;
   for (int b0 = blockIdx.x; b0 < pa.nbins; b0 += kPoisBins * gridDim.x) {
+    if (!first_pass) __syncthreads();  // the scratch is reused by the block's next pass
+    first_pass = false;
     // this pass: bins b0 and b0 + gridDim.x (the second may not exist)
     const int nb = (b0 + (int)gridDim.x < pa.nbins) ? 2 : 1;
     // the combining threads fetch their bin's constants now: the latency hides behind the sums
@@ -330,8 +333,10 @@ __device__ void poisson_bins(const PoissonArgs& pa, const double* F, int nO, int
       pa.Pb[((size_t)b * 2 + 0) * Wpad + cw] = Sb;
       pa.Pb[((size_t)b * 2 + 1) * Wpad + cw] = term;
     }
-    __syncthreads();  // the scratch is reused by the block's next pass
   }
+  // the entry stage shares the scratch: the combining threads must be done before any warp streams.
+  // With a private scratch the other warps go straight on to their stars.
+  if (!scratch_is_private) __syncthreads();
 }
 
 // Last block of the launch: add the bins in fixed order -> Poisson term of every walker of the pass.
@@ -838,6 +843,9 @@ struct K2Args {
   int32_t nA, nB, Wpad, W, w0, Wtot;   // nA = rows of the OUTER table (age classes x nOd), nB = rows of the INNER table
   int32_t nOd;               // outer-dust combinations per age class (1: the classic age | dust split)
   int32_t tab_off;           // byte offset of the factor tables in dynamic shared memory
+  int32_t scratch_off;       // byte offset of the table-build scratch: 0 (it shares the entry stage) or right
+                             // after the stage (`separate` layout: the stage can be primed before the build)
+  int32_t separate;          // 1: stage and scratch are disjoint
   int32_t slab_off;          // byte offset of the block-reduction slabs (0, or tab_off: over the dead tables)
   PoissonArgs pois;          // N-stars term: every block computes some (age, Z) bins before the star loop
   PeerArgs peer;             // cross-GPU reduction of the shard totals
@@ -1077,6 +1085,33 @@ struct Lanes {
   }
 };
 
+// One chunk of kChunk entries into ring slot `slot` of this warp's stage (one commit group).
+template <bool C16>
+__device__ __forceinline__ void issue_chunk(const double* __restrict__ ga, const void* __restrict__ gcodes,
+                                            int64_t p, const int64_t end, int slot, uint32_t sa_lane,
+                                            uint32_t sc_lane, int lane) {
+  if (p + lane < end) {
+    cp_async8(sa_lane + slot * (kChunk * 8u), ga + p + lane);
+    if (!C16) cp_async4(sc_lane + slot * (kChunk * 4u), static_cast<const uint32_t*>(gcodes) + p + lane);
+  }
+  if (C16 && lane < kChunk / 2 && p + 2 * lane < end)  // two codes per lane (the array is padded by one)
+    cp_async4(sc_lane + slot * (kChunk * 2u), static_cast<const uint16_t*>(gcodes) + p + 2 * lane);
+  cp_async_commit();
+}
+// The first STAGES - 1 chunks of a range, issued ahead of time (K2 does this for every warp's first
+// segment before it builds the factor tables: the cold-HBM latency of the entry stream then hides
+// behind the table build).  stream_range(..., primed = true) must follow with the same arguments.
+template <int STAGES, int OB>
+__device__ __forceinline__ void stream_prime(const double* __restrict__ ga, const void* __restrict__ gcodes,
+                                             int64_t pos, const int64_t end, const uint32_t st_a,
+                                             const uint32_t st_c, const int lane) {
+  constexpr bool C16 = OB > 0;
+  pos -= C16 ? (pos & 1) : 0;
+#pragma unroll
+  for (int k = 0; k < STAGES - 1; ++k)
+    issue_chunk<C16>(ga, gcodes, pos + (int64_t)k * kChunk, end, k, st_a + lane * 8u, st_c + lane * 4u, lane);
+}
+
 // Stream entries [pos, end) through this warp's double-buffered stage (weights at st_a, codes at
 // st_c) and fold them into L.  Per group of four entries the warp issues three broadcast loads
 // (four codes; two weight pairs) = 1.5 shared-memory wavefronts per entry, then per entry one
@@ -1084,11 +1119,10 @@ struct Lanes {
 template <int NW, int MODE, typename TF, int STAGES = kStages, int OB = 0>
 __device__ __forceinline__ void stream_range(Lanes<NW, MODE, TF, OB>& L, const double* __restrict__ ga,
                                              const void* __restrict__ gcodes, int64_t pos, const int64_t end,
-                                             const uint32_t st_a, const uint32_t st_c, const int lane) {
+                                             const uint32_t st_a, const uint32_t st_c, const int lane,
+                                             const bool primed = false) {
   constexpr bool C16 = OB > 0;
   constexpr uint32_t kCodeBytes = C16 ? 2u : 4u;
-  const uint32_t* gc = static_cast<const uint32_t*>(gcodes);          // 32-bit codes
-  const uint16_t* gc16 = static_cast<const uint16_t*>(gcodes);        // 16-bit codes, fetched in 4-byte aligned pairs
   // 16-bit codes: chunks start on an even entry.  A range that starts on an odd one stages the
   // entry before it too and skips it: the first chunk handles entries 1..3 one by one, then groups
   int lead = C16 ? (int)(pos & 1) : 0;
@@ -1096,17 +1130,11 @@ __device__ __forceinline__ void stream_range(Lanes<NW, MODE, TF, OB>& L, const d
   const uint32_t sa = keep_in_register(st_a), sc = keep_in_register(st_c);
   const uint32_t sa_lane = keep_in_register(st_a + lane * 8u), sc_lane = keep_in_register(st_c + lane * 4u);
   // ring of STAGES chunk buffers: STAGES - 1 chunks are in flight while one is processed
-  auto issue = [&](int64_t p, int slot) {
-    if (p + lane < end) {
-      cp_async8(sa_lane + slot * (kChunk * 8u), ga + p + lane);
-      if (!C16) cp_async4(sc_lane + slot * (kChunk * 4u), gc + p + lane);
-    }
-    if (C16 && lane < kChunk / 2 && p + 2 * lane < end)  // two codes per lane (the array is padded by one)
-      cp_async4(sc_lane + slot * (kChunk * 2u), gc16 + p + 2 * lane);
-    cp_async_commit();
-  };
+  auto issue = [&](int64_t p, int slot) { issue_chunk<C16>(ga, gcodes, p, end, slot, sa_lane, sc_lane, lane); };
+  if (!primed) {
 #pragma unroll
-  for (int k = 0; k < STAGES - 1; ++k) issue(pos + (int64_t)k * kChunk, k);
+    for (int k = 0; k < STAGES - 1; ++k) issue(pos + (int64_t)k * kChunk, k);
+  }
   int slot = 0;
   while (pos < end) {
     int ahead = slot + STAGES - 1;
@@ -1186,6 +1214,15 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   stamp(a.timeline, 0);
   // launched with programmatic stream serialization: wait here for K0 (the tables) to complete
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  // every warp's first segment: its first chunks are requested now, so that the cold-HBM latency of
+  // the entry stream hides behind the table build (needs a stage that the build does not use as scratch)
+  const int nwarps_total = (int)gridDim.x * kK2Warps;
+  int s = (int)blockIdx.x * kK2Warps + warp;
+  bool primed = false;
+  if (a.separate && s < a.nseg) {
+    stream_prime<STAGES, OB>(a.ea, a.ec, a.seg[s], a.seg[s + 1], st_a, st_c, lane);
+    primed = true;
+  }
   // this block's slices of the N-stars statistics: pull them into L2 while the tables are built
   if (a.pois.nbins > 0 && !a.pois.SC) {
     const int per_bin = a.nOd * a.nB * 16;  // bytes
@@ -1205,7 +1242,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     // multiply-add chain and one branch-free exp per (class, walker) -- no divisions there.
     // (mb_k0_factors evaluates the textbook form; the two agree to an ulp or two.)
     const ModelDev& m = a.model;
-    double* lut = reinterpret_cast<double*>(smem_raw);              // [nscratch][Wpad]
+    double* lut = reinterpret_cast<double*>(smem_raw + a.scratch_off);  // [nscratch][Wpad]
     double* tab = reinterpret_cast<double*>(smem_raw + a.tab_off);  // [nA + nB][Wpad]
     const int ncls = a.ncls_total, nrows = a.nA + a.nB;
     double* lxs = lut + (size_t)a.nscratch * Wpad;                  // [ncls][2] ln x, 1/x of the class value
@@ -1318,7 +1355,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   // staged (always the fp64 ones: from shared memory when they are there, else from global memory)
   if (a.pois.nbins > 0) {
     const double* Ftab = (MODE == kModeFactor && !kF32) ? reinterpret_cast<const double*>(smem_raw + a.tab_off) : a.FA;
-    poisson_bins<NW, k2_threads(NW)>(a.pois, Ftab, a.nA, a.nOd, a.nB, smem_raw);
+    poisson_bins<NW, k2_threads(NW)>(a.pois, Ftab, a.nA, a.nOd, a.nB, smem_raw, a.separate != 0);
   }
 
   stamp(a.timeline, 2);
@@ -1332,11 +1369,11 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   long long fixhi[NW], fixlo[NW];
 #pragma unroll
   for (int i = 0; i < NW; ++i) { fixhi[i] = 0; fixlo[i] = 0; }
-  const int nwarps_total = (int)gridDim.x * kK2Warps;
-  int s = (int)blockIdx.x * kK2Warps + warp, s_next = 0;
+  int s_next = 0;
   while (s < a.nseg) {
     if (lane == 0) s_next = nwarps_total + (int)atomicAdd(a.counters + kCtrSegment, 1u);
-    stream_range<NW, MODE, TF, STAGES, OB>(L, a.ea, a.ec, a.seg[s], a.seg[s + 1], st_a, st_c, lane);
+    stream_range<NW, MODE, TF, STAGES, OB>(L, a.ea, a.ec, a.seg[s], a.seg[s + 1], st_a, st_c, lane, primed);
+    primed = false;
     L.close();
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
