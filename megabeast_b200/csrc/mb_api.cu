@@ -254,8 +254,11 @@ struct K2Smem {
   size_t front = 0, tables = 0, total = 0, slab_off = 0;
   size_t scratch_off = 0;   // table-build / N-stars scratch: 0 (shares the stage) or right after the stage
   size_t pois_off = 0;      // N-stars scratch: after the look-up rows when the tables are built in the kernel
-  int pois_warps = 0;       // warps whose partial sums fit
+  size_t hts_off = 0;       // one-warp-per-bin N-stars scheme: staged statistics
+  int hts_slices = 0;
+  int pois_warps = 0;       // block-wide N-stars scheme: warps whose partial sums fit
   bool separate = false;    // stage and scratch disjoint: the entry stage is primed before the table build
+  bool warp_private = false;// N-stars term: one warp per bin (few dust classes)
   bool fuse_fits = false;   // the scratch of the in-kernel table build fits as well
 };
 // scratch of the in-kernel table build: look-up rows | ln x, 1/x per class | per-walker constants |
@@ -264,27 +267,36 @@ static size_t k2_fuse_scratch(int nscratch, int ncls_total, int nrows, int Wpad,
   return 8 * ((size_t)nscratch * Wpad + 2 * (size_t)ncls_total + 6 * (size_t)MB_NPARAM * Wpad + (size_t)nrows +
               (size_t)((ncls_total + 3) / 4) + phi_doubles);
 }
+constexpr int kPoisPrivateMaxClasses = 512;  // one warp per bin up to this many dust classes
 // Layouts are tried in order of preference: tables built in the kernel before a separate K0 launch,
-// a private scratch (stage primed early, one barrier less) before a shared one.
+// a private scratch (stage primed early, no barrier around the N-stars bins) before a shared one.
+// nD = dust classes per bin, bins_per_block = most bins a block can get (0: no one-warp-per-bin scheme).
 static K2Smem k2_smem_plan(int kmode, int nO, int nI, int nbins, int Wpad, int elem_bytes, int max_smem,
-                           size_t fuse_scratch = 0, int nscratch = 0) {
+                           size_t fuse_scratch = 0, int nscratch = 0, int nD = 0, int bins_per_block = 0,
+                           bool have_sc = false) {
   const int NW = Wpad / 32, threads = k2_threads(NW), warps = threads / 32;
   const size_t stage = (size_t)warps * k2_stage_bytes(NW);
   const size_t slabs = (size_t)warps * kAccRows * Wpad * 8;  // block reduction: one slab per warp
   const size_t pois_row = kPoisBins * 2 * (size_t)Wpad * 8;  // one warp's partial (S, C) of the bins in flight, all walkers
   const size_t tables = kmode == kModeFactor ? (size_t)(nO + nI) * Wpad * elem_bytes : 0;
   const bool slabs_over_tables = tables >= slabs;
-  static const bool no_separate = getenv("MB_NO_PRIME") && atoi(getenv("MB_NO_PRIME"));  // A/B switch (measurements)
-  auto layout = [&](bool sep, bool fused, K2Smem& p) -> bool {
+  static const bool no_separate = getenv("MB_NO_PRIME") && atoi(getenv("MB_NO_PRIME"));        // A/B switches
+  static const bool no_private = getenv("MB_NO_WARP_BINS") && atoi(getenv("MB_NO_WARP_BINS"));  // (measurements)
+  auto layout = [&](bool sep, bool fused, bool priv, K2Smem& p) -> bool {
     p = K2Smem();
     p.tables = tables;
     p.separate = sep;
     p.fuse_fits = fused;
+    p.warp_private = priv;
     p.scratch_off = sep ? ((stage + 15) & ~(size_t)15) : 0;
     p.pois_off = p.scratch_off + (fused ? (size_t)nscratch * Wpad * 8 : 0);
     size_t front = std::max(stage, p.scratch_off + (fused ? fuse_scratch : 0));
     if (!slabs_over_tables) front = std::max(front, slabs);
-    if (nbins > 0) {
+    if (nbins > 0 && priv) {
+      p.hts_off = (p.scratch_off + (fused ? fuse_scratch : 0) + 15) & ~(size_t)15;
+      p.hts_slices = have_sc ? 0 : std::min(warps, std::max(1, bins_per_block));
+      front = std::max(front, p.hts_off + (size_t)p.hts_slices * nD * 16);
+    } else if (nbins > 0) {
       if (tables + p.pois_off + pois_row > (size_t)max_smem) return false;
       const size_t avail = (size_t)max_smem - tables - p.pois_off;
       p.pois_warps = (int)std::min<size_t>((size_t)warps, avail / pois_row);
@@ -296,10 +308,14 @@ static K2Smem k2_smem_plan(int kmode, int nO, int nI, int nbins, int Wpad, int e
     p.total = p.front + p.tables;
     return p.total <= (size_t)max_smem;
   };
+  const bool private_ok = !no_private && !no_separate && nbins > 0 && bins_per_block > 0 &&
+                          (have_sc || (nD > 0 && nD <= kPoisPrivateMaxClasses));
   K2Smem p;
-  for (int fused = fuse_scratch > 0 ? 1 : 0; fused >= 0; --fused)
+  for (int fused = fuse_scratch > 0 ? 1 : 0; fused >= 0; --fused) {
+    if (private_ok && layout(true, fused != 0, true, p)) return p;
     for (int sep = no_separate ? 0 : 1; sep >= 0; --sep)
-      if (layout(sep != 0, fused != 0, p)) return p;
+      if (layout(sep != 0, fused != 0, false, p)) return p;
+  }
   p.total = (size_t)max_smem + 1;  // nothing fits
   return p;
 }
@@ -395,6 +411,109 @@ static void build_segments(const mb_handle* h, int t, std::vector<int64_t>& seg)
     if (j < ends.size() && ends[j] > seg.back()) seg.push_back(ends[j]);
   }
   if (n > 0 && seg.back() != n) seg.push_back(n);
+}
+
+// Entry build on the device (mb_build_entries + mb_compact_entries): uploads this handle's columns of
+// the sparse arrays and the three static grid columns, leaves the packed entry stream in d_ea / d_ec
+// (or d_ec16) and the per-star bookkeeping the segment and pixel tables need on the host.
+static int build_entries_device(mb_handle* h, const mb_grid_desc* grid, const mb_stars_desc* stars, int64_t s0,
+                                int64_t s1, const uint32_t* rowcode, int mode, bool merge, int64_t n_pixels,
+                                const int64_t* pix_off, std::vector<int64_t>& star_end_pos,
+                                std::vector<int64_t>& pix_ent, std::vector<int64_t>& pix_se) {
+  const int64_t K = stars->K, S = stars->S, Sl = s1 - s0, G = grid->G;
+  h->n_entries = h->n_entries_raw = h->n_runs = 0;
+  struct Temps {
+    std::vector<void*> p;
+    ~Temps() { for (void* q : p) cudaFree(q); }
+    int get(void** out, size_t bytes) {
+      *out = nullptr;
+      cudaError_t e = cudaMalloc(out, std::max<size_t>(bytes, 16));
+      if (e != cudaSuccess) return fail("cudaMalloc of %zu bytes for the entry build failed: %s", bytes, cudaGetErrorString(e));
+      p.push_back(*out);
+      return 0;
+    }
+  } tmp;
+  std::vector<int32_t> cnt((size_t)Sl, 0), nraw((size_t)Sl, 0), nrun((size_t)Sl, 0);
+  int32_t* d_cnt = nullptr; double* d_ta = nullptr; uint32_t* d_tc = nullptr;
+  if (Sl > 0 && K > 0) {
+    int64_t* d_idx; double* d_val; uint32_t* d_rc = nullptr; double *d_pw, *d_gw, *d_cm;
+    int32_t *d_nraw, *d_nrun, *d_err;
+    if (tmp.get((void**)&d_idx, sizeof(int64_t) * (size_t)(K * Sl)) || tmp.get((void**)&d_val, sizeof(double) * (size_t)(K * Sl)) ||
+        tmp.get((void**)&d_pw, sizeof(double) * (size_t)G) || tmp.get((void**)&d_gw, sizeof(double) * (size_t)G) ||
+        tmp.get((void**)&d_cm, sizeof(double) * (size_t)G) || tmp.get((void**)&d_ta, sizeof(double) * (size_t)(K * Sl)) ||
+        tmp.get((void**)&d_tc, sizeof(uint32_t) * (size_t)(K * Sl)) || tmp.get((void**)&d_cnt, sizeof(int32_t) * (size_t)Sl) ||
+        tmp.get((void**)&d_nraw, sizeof(int32_t) * (size_t)Sl) || tmp.get((void**)&d_nrun, sizeof(int32_t) * (size_t)Sl) ||
+        tmp.get((void**)&d_err, sizeof(int32_t)))
+      return 1;
+    if (rowcode) {
+      if (tmp.get((void**)&d_rc, sizeof(uint32_t) * (size_t)G)) return 1;
+      CK(cudaMemcpy(d_rc, rowcode, sizeof(uint32_t) * (size_t)G, cudaMemcpyHostToDevice));
+    }
+    // this handle's columns [s0, s1) of the (K, S) arrays
+    CK(cudaMemcpy2D(d_idx, sizeof(int64_t) * (size_t)Sl, stars->indxs + s0, sizeof(int64_t) * (size_t)S,
+                    sizeof(int64_t) * (size_t)Sl, (size_t)K, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy2D(d_val, sizeof(double) * (size_t)Sl, stars->vals + s0, sizeof(double) * (size_t)S,
+                    sizeof(double) * (size_t)Sl, (size_t)K, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_pw, grid->prior_weight, sizeof(double) * (size_t)G, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_gw, grid->grid_weight, sizeof(double) * (size_t)G, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_cm, grid->completeness, sizeof(double) * (size_t)G, cudaMemcpyHostToDevice));
+    const int32_t no_err = 0x7fffffff;
+    CK(cudaMemcpy(d_err, &no_err, sizeof no_err, cudaMemcpyHostToDevice));
+    BuildArgs ba{};
+    ba.indxs = d_idx; ba.vals = d_val; ba.K = K; ba.S = Sl; ba.G = G; ba.rowcode = d_rc;
+    ba.pw = d_pw; ba.gw = d_gw; ba.cm = d_cm; ba.mode = mode; ba.nB = h->nB; ba.merge = merge ? 1 : 0;
+    ba.tmp_a = d_ta; ba.tmp_c = d_tc; ba.cnt = d_cnt; ba.nraw = d_nraw; ba.nrun = d_nrun; ba.err_star = d_err;
+    const int blocks = (int)std::min<int64_t>((Sl + kBuildWarps - 1) / kBuildWarps, (int64_t)h->sm_count * 32);
+    if (K <= 32) mb_build_entries<32><<<blocks, 32 * kBuildWarps, 0, h->stream>>>(ba);
+    else if (K <= 64) mb_build_entries<64><<<blocks, 32 * kBuildWarps, 0, h->stream>>>(ba);
+    else mb_build_entries<128><<<blocks, 32 * kBuildWarps, 0, h->stream>>>(ba);
+    CK(cudaGetLastError());
+    int32_t err = no_err;
+    CK(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(int32_t) * (size_t)Sl, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(nraw.data(), d_nraw, sizeof(int32_t) * (size_t)Sl, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(nrun.data(), d_nrun, sizeof(int32_t) * (size_t)Sl, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&err, d_err, sizeof err, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (err != no_err) {  // report as numpy would: the first offending point of the first offending star
+      const int64_t s = s0 + err;
+      for (int64_t kk = 0; kk < K; ++kk) {
+        if (!std::isfinite(stars->vals[kk * S + s])) continue;
+        const int64_t r = stars->indxs[kk * S + s];
+        if (r < -G || r >= G)
+          return fail("index %lld is out of bounds for axis 0 with size %lld (star %lld)", (long long)r, (long long)G, (long long)s);
+      }
+      return fail("index out of bounds for axis 0 with size %lld (star %lld)", (long long)G, (long long)s);
+    }
+  }
+  // prefix sums: entry offsets per star, ends of the non-empty stars, pixel bookkeeping
+  std::vector<int64_t> offs((size_t)Sl + 1, 0), nonempty_before((size_t)Sl + 1, 0);
+  for (int64_t s = 0; s < Sl; ++s) {
+    offs[(size_t)s + 1] = offs[(size_t)s] + cnt[(size_t)s];
+    nonempty_before[(size_t)s + 1] = nonempty_before[(size_t)s] + (cnt[(size_t)s] > 0 ? 1 : 0);
+    if (cnt[(size_t)s] > 0) star_end_pos.push_back(offs[(size_t)s + 1]);
+    h->n_entries_raw += nraw[(size_t)s];
+    h->n_runs += nrun[(size_t)s];
+  }
+  h->n_entries = offs[(size_t)Sl];
+  for (int64_t p = 0; p <= n_pixels && n_pixels > 0; ++p) {
+    pix_ent.push_back(offs[(size_t)(pix_off[p] - s0)]);
+    pix_se.push_back(nonempty_before[(size_t)(pix_off[p] - s0)]);
+  }
+  if (dev_alloc(h, &h->d_ea, h->n_entries)) return 1;
+  if (h->c16) {
+    if (dev_alloc(h, &h->d_ec16, h->n_entries + 2)) return 1;  // padded: codes are fetched in pairs
+    CK(cudaMemsetAsync(h->d_ec16, 0, sizeof(uint16_t) * (size_t)(h->n_entries + 2), h->stream));
+  } else if (dev_alloc(h, &h->d_ec, h->n_entries)) return 1;
+  if (h->n_entries > 0) {
+    int64_t* d_offs;
+    if (tmp.get((void**)&d_offs, sizeof(int64_t) * offs.size())) return 1;
+    CK(cudaMemcpyAsync(d_offs, offs.data(), sizeof(int64_t) * offs.size(), cudaMemcpyHostToDevice, h->stream));
+    const int blocks = (int)std::min<int64_t>((Sl * 32 + 255) / 256, (int64_t)h->sm_count * 16);
+    mb_compact_entries<<<blocks, 256, 0, h->stream>>>(d_ta, d_tc, d_cnt, d_offs, Sl, K, h->d_ea, h->d_ec, h->d_ec16, h->ob);
+    CK(cudaGetLastError());
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
 }
 
 static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
@@ -739,89 +858,6 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
   if (K > 0 && S > 0 && (!stars->indxs || !stars->vals)) return fail("indxs/vals are NULL");
   h->S_local = s1 - s0;
   h->S_total = stars->n_stars_total > 0 ? stars->n_stars_total : S;
-  std::vector<Entry> entries;
-  std::vector<uint32_t> codes;
-  entries.reserve((size_t)((s1 - s0) * K));
-  codes.reserve((size_t)((s1 - s0) * K));
-  std::vector<int64_t> star_end_pos;  // entry count after each non-empty star
-  std::vector<Entry> cur;
-  if (o.keep_indices) h->kept_offs.assign(1, 0);
-  const bool merge = o.merge_duplicates != 0;
-  // pixel batches: entry / star-end bookkeeping per pixel
-  std::vector<int64_t> pix_ent, pix_se;
-  int64_t next_pix = 0;
-  for (int64_t s = s0; s < s1; ++s) {
-    while (next_pix < n_pixels && pix_off[next_pix] == s) {
-      pix_ent.push_back((int64_t)entries.size());
-      pix_se.push_back((int64_t)star_end_pos.size());
-      ++next_pix;
-    }
-    cur.clear();
-    for (int64_t kk = 0; kk < K; ++kk) {
-      double v = stars->vals[kk * S + s];
-      if (!std::isfinite(v)) continue;  // :196 -- the index of a masked entry is never read
-      int64_t r = stars->indxs[kk * S + s];
-      if (r < 0) r += G;  // numpy negative indexing
-      if (r < 0 || r >= G)
-        return fail("index %lld is out of bounds for axis 0 with size %lld (star %lld)",
-                    (long long)stars->indxs[kk * S + s], (long long)G, (long long)s);
-      Entry e;
-      e.a = v * grid->prior_weight[r] * grid->grid_weight[r] * grid->completeness[r];
-      const uint32_t rc = elementwise ? 0u : rowcode[(size_t)r];
-      // (TABLE modes always use the classic split: outer class = age class, inner class = dust class)
-      const uint32_t cO = (rc >> kAgeShift) & kAgeMask, cI = rc & kDustMask;
-      e.meta = cO;
-      e.idx = mode == MB_MODE_FACTOR ? cI : mode == MB_MODE_TABLE_UNIQUE ? cO * (uint32_t)h->nB + cI : (uint32_t)r;
-      cur.push_back(e);
-      if (o.keep_indices) h->kept_rows.push_back(r);
-    }
-    if (o.keep_indices) h->kept_offs.push_back((int64_t)h->kept_rows.size());
-    h->n_entries_raw += (int64_t)cur.size();
-    if (cur.empty()) continue;  // sums to 0.0 -> skipped by the reference too (:218-221)
-    // runs of equal outer class (FACTOR reloads the outer factor once per run); ties by table row
-    std::stable_sort(cur.begin(), cur.end(), [](const Entry& x, const Entry& y) {
-      return x.meta != y.meta ? x.meta < y.meta : x.idx < y.idx;
-    });
-    size_t first = entries.size();
-    for (const Entry& e : cur) {
-      if (merge && entries.size() > first) {
-        Entry& last = entries.back();
-        if (last.idx == e.idx && last.meta == e.meta) { last.a += e.a; continue; }
-      }
-      entries.push_back(e);
-    }
-    // device code words: FACTOR [31] new run, [30] new star, [29:20] outer class, [19:0] inner class;
-    // TABLE modes read the full product from the table: [31] new star, [30:0] table row
-    uint32_t prevA = 0xffffffffu;
-    for (size_t i = first; i < entries.size(); ++i) {
-      const uint32_t cA = entries[i].meta;
-      uint32_t code;
-      if (mode == MB_MODE_FACTOR) {
-        code = (cA << kAgeShift) | entries[i].idx;
-        if (i == first) code |= kNewRun | kNewStar;
-        else if (cA != prevA) code |= kNewRun;
-        if (code & kNewRun) ++h->n_runs;
-      } else {
-        code = entries[i].idx;
-        if (i == first) code |= kNewRun;
-      }
-      codes.push_back(code);
-      prevA = cA;
-    }
-    star_end_pos.push_back((int64_t)entries.size());
-  }
-  h->n_entries = (int64_t)entries.size();
-  while (next_pix <= n_pixels && n_pixels > 0) {  // trailing empty pixels + the end sentinel
-    pix_ent.push_back((int64_t)entries.size());
-    pix_se.push_back((int64_t)star_end_pos.size());
-    ++next_pix;
-  }
-
-  // ---- segments: star aligned, one table per block shape ---------------------------------------------
-  // measured on B200 (config 3 and its 1/2, 1/8 shards): 1 segment per resident warp beats 2, 4, 8
-  // by 3-4 % -- per-segment costs (pipeline restart, one log) outweigh what dynamic balancing
-  // recovers -- so the segment count must match the warps the launch really has: one table for
-  // the 768-thread kernels (up to 64 walkers per pass) and one for the 512-thread kernel (128).
   // 16-bit code words where the class counts allow: 4 + 10 or 6 + 8 bits of (outer, inner) class
   h->ob = 0;
   if (mode == MB_MODE_FACTOR && h->table_bytes == 8 && n_pixels == 0 && !getenv("MB_CODES32")) {
@@ -829,6 +865,121 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
     else if (h->nO <= 64 && h->nI <= 256) h->ob = 6;
   }
   h->c16 = h->ob > 0;
+  const bool merge = o.merge_duplicates != 0;
+  std::vector<int64_t> star_end_pos;  // entry count after each non-empty star
+  std::vector<int64_t> pix_ent, pix_se;  // pixel batches: entry / star-end bookkeeping per pixel
+  if (o.keep_indices) {  // parity hook: the grid rows that are dereferenced, in the reference's order
+    h->kept_offs.assign(1, 0);
+    for (int64_t s = s0; s < s1; ++s) {
+      for (int64_t kk = 0; kk < K; ++kk) {
+        if (!std::isfinite(stars->vals[kk * S + s])) continue;
+        int64_t r = stars->indxs[kk * S + s];
+        h->kept_rows.push_back(r < 0 ? r + G : r);
+      }
+      h->kept_offs.push_back((int64_t)h->kept_rows.size());
+    }
+  }
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto& e : h->ev) CK(cudaEventCreate(&e));
+  // The build runs on the device (mb_build_entries); the host loop below is the same algorithm, kept
+  // for stars with more than 128 sparse points and as an A/B switch (MB_HOST_BUILD=1) -- the two
+  // produce bit-identical entry streams (tests/test_gpu_split_tables.py::test_device_build_equals_host_build)
+  const bool host_build = K > 128 || (getenv("MB_HOST_BUILD") && atoi(getenv("MB_HOST_BUILD")));
+  if (!host_build) {
+    if (build_entries_device(h, grid, stars, s0, s1, elementwise ? nullptr : rowcode.data(), mode, merge,
+                             n_pixels, pix_off, star_end_pos, pix_ent, pix_se)) return 1;
+  } else {
+    std::vector<Entry> entries;
+    std::vector<uint32_t> codes;
+    entries.reserve((size_t)((s1 - s0) * K));
+    codes.reserve((size_t)((s1 - s0) * K));
+    std::vector<Entry> cur;
+    int64_t next_pix = 0;
+    for (int64_t s = s0; s < s1; ++s) {
+      while (next_pix < n_pixels && pix_off[next_pix] == s) {
+        pix_ent.push_back((int64_t)entries.size());
+        pix_se.push_back((int64_t)star_end_pos.size());
+        ++next_pix;
+      }
+      cur.clear();
+      for (int64_t kk = 0; kk < K; ++kk) {
+        double v = stars->vals[kk * S + s];
+        if (!std::isfinite(v)) continue;  // :196 -- the index of a masked entry is never read
+        int64_t r = stars->indxs[kk * S + s];
+        if (r < 0) r += G;  // numpy negative indexing
+        if (r < 0 || r >= G)
+          return fail("index %lld is out of bounds for axis 0 with size %lld (star %lld)",
+                      (long long)stars->indxs[kk * S + s], (long long)G, (long long)s);
+        Entry e;
+        e.a = v * grid->prior_weight[r] * grid->grid_weight[r] * grid->completeness[r];
+        const uint32_t rc = elementwise ? 0u : rowcode[(size_t)r];
+        // (TABLE modes always use the classic split: outer class = age class, inner class = dust class)
+        const uint32_t cO = (rc >> kAgeShift) & kAgeMask, cI = rc & kDustMask;
+        e.meta = cO;
+        e.idx = mode == MB_MODE_FACTOR ? cI : mode == MB_MODE_TABLE_UNIQUE ? cO * (uint32_t)h->nB + cI : (uint32_t)r;
+        cur.push_back(e);
+      }
+      h->n_entries_raw += (int64_t)cur.size();
+      if (cur.empty()) continue;  // sums to 0.0 -> skipped by the reference too (:218-221)
+      // runs of equal outer class (FACTOR reloads the outer factor once per run); ties by table row
+      std::stable_sort(cur.begin(), cur.end(), [](const Entry& x, const Entry& y) {
+        return x.meta != y.meta ? x.meta < y.meta : x.idx < y.idx;
+      });
+      size_t first = entries.size();
+      for (const Entry& e : cur) {
+        if (merge && entries.size() > first) {
+          Entry& last = entries.back();
+          if (last.idx == e.idx && last.meta == e.meta) { last.a += e.a; continue; }
+        }
+        entries.push_back(e);
+      }
+      // device code words: FACTOR [31] new run, [30] new star, [29:20] outer class, [19:0] inner class;
+      // TABLE modes read the full product from the table: [31] new star, [30:0] table row
+      uint32_t prevA = 0xffffffffu;
+      for (size_t i = first; i < entries.size(); ++i) {
+        const uint32_t cA = entries[i].meta;
+        uint32_t code;
+        if (mode == MB_MODE_FACTOR) {
+          code = (cA << kAgeShift) | entries[i].idx;
+          if (i == first) code |= kNewRun | kNewStar;
+          else if (cA != prevA) code |= kNewRun;
+          if (code & kNewRun) ++h->n_runs;
+        } else {
+          code = entries[i].idx;
+          if (i == first) code |= kNewRun;
+        }
+        codes.push_back(code);
+        prevA = cA;
+      }
+      star_end_pos.push_back((int64_t)entries.size());
+    }
+    h->n_entries = (int64_t)entries.size();
+    while (next_pix <= n_pixels && n_pixels > 0) {  // trailing empty pixels + the end sentinel
+      pix_ent.push_back((int64_t)entries.size());
+      pix_se.push_back((int64_t)star_end_pos.size());
+      ++next_pix;
+    }
+
+    // upload
+    std::vector<double> wts(entries.size());
+    for (size_t i = 0; i < entries.size(); ++i) wts[i] = entries[i].a;
+    if (dev_upload(h, &h->d_ea, wts)) return 1;
+    if (h->c16) {
+      std::vector<uint16_t> c16(codes.size() + 2, (uint16_t)0);  // padded: codes are fetched in pairs
+      for (size_t i = 0; i < codes.size(); ++i) {
+        const uint32_t c = codes[i];
+        c16[i] = (uint16_t)(((c & kNewRun) ? 0x8000u : 0u) | ((c & kNewStar) ? 0x4000u : 0u) |
+                            (((c >> kAgeShift) & kAgeMask) << (14 - h->ob)) | (c & kDustMask));
+      }
+      if (dev_upload(h, &h->d_ec16, c16)) return 1;
+    } else if (dev_upload(h, &h->d_ec, codes)) return 1;
+  }
+
+  // ---- segments: star aligned, one table per block shape ---------------------------------------------
+  // measured on B200 (config 3 and its 1/2, 1/8 shards): 1 segment per resident warp beats 2, 4, 8
+  // by 3-4 % -- per-segment costs (pipeline restart, one log) outweigh what dynamic balancing
+  // recovers -- so the segment count must match the warps the launch really has: one table for
+  // the 768-thread kernels (up to 64 walkers per pass) and one for the 512-thread kernel (128).
   h->spw = o.segments_per_warp > 0 ? o.segments_per_warp : 1;
   // ... optionally plus a tail pool: the last tail_percent of the entries cut into small segments
   // that warps claim dynamically after their own big one.  Measured on B200 (4-16 %, config 3 and
@@ -845,23 +996,7 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
   // ---- upload ----------------------------------------------------------------------------------------
   std::vector<double> clsx_all;
   for (int p = 0; p < MB_NPARAM; ++p) clsx_all.insert(clsx_all.end(), h->clsx[p].begin(), h->clsx[p].end());
-  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  for (auto& e : h->ev) CK(cudaEventCreate(&e));
   if (dev_upload(h, &h->d_clsx, clsx_all)) return 1;
-  {
-    std::vector<double> wts(entries.size());
-    for (size_t i = 0; i < entries.size(); ++i) wts[i] = entries[i].a;
-    if (dev_upload(h, &h->d_ea, wts)) return 1;
-    if (h->c16) {
-      std::vector<uint16_t> c16(codes.size() + 2, (uint16_t)0);  // padded: codes are fetched in pairs
-      for (size_t i = 0; i < codes.size(); ++i) {
-        const uint32_t c = codes[i];
-        c16[i] = (uint16_t)(((c & kNewRun) ? 0x8000u : 0u) | ((c & kNewStar) ? 0x4000u : 0u) |
-                            (((c >> kAgeShift) & kAgeMask) << (14 - h->ob)) | (c & kDustMask));
-      }
-      if (dev_upload(h, &h->d_ec16, c16)) return 1;
-    } else if (dev_upload(h, &h->d_ec, codes)) return 1;
-  }
   if (dev_upload(h, &h->d_seg[0], seg[0])) return 1;
   if (dev_upload(h, &h->d_seg[1], seg[1])) return 1;
   if (mode == MB_MODE_TABLE_GRID && dev_upload(h, &h->d_rowcode, rowcode)) return 1;
@@ -1283,8 +1418,10 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     const size_t fuse_scratch = k2_fuse_scratch(h->nscratch, h->ncls_total, nrows, Wpad, inline_phi ? (size_t)wp * ndim : 0);
     const bool may_fuse = kmode == kModeFactor && h->table_bytes == 8 && !d_tab && !h->no_fuse &&
                           h->ncls_total < 0x7fff && (!h_phi || inline_phi);
+    // most (age, Z) bins a block can get: the launch has at least min(nbins, SMs) blocks
+    const int bins_per_block = h->nbins > 0 ? (h->nbins + std::min(h->nbins, h->sm_count) - 1) / std::min(h->nbins, h->sm_count) : 0;
     const K2Smem plan = k2_smem_plan(kmode, h->nO, h->nI, h->nbins, Wpad, h->table_bytes, h->max_smem,
-                                     may_fuse ? fuse_scratch : 0, h->nscratch);
+                                     may_fuse ? fuse_scratch : 0, h->nscratch, h->nOd * h->nI, bins_per_block, elementwise);
     const bool fused = may_fuse && plan.fuse_fits;
     if (prof) CK(cudaEventRecord(h->ev[0], st));
     if (!elementwise && !fused) {
@@ -1367,6 +1504,7 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     k2.pois.n_stars = (double)h->S_total; k2.pois.nbins = h->poisson ? h->nbins : 0;
     k2.pois.lgamma_n1 = std::lgamma((double)h->S_total + 1.0);
     k2.pois.nwarps = plan.pois_warps; k2.pois.scratch_off = (int32_t)plan.pois_off;
+    k2.pois.warp_private = plan.warp_private ? 1 : 0; k2.pois.hts_off = (int32_t)plan.hts_off; k2.pois.hts_slices = plan.hts_slices;
     k2.pois.SC = elementwise ? h->d_SC : nullptr;
     // plain age factors (the `ageprior` of helpers.py:135): K1e's per-bin rows, K0's rows in global
     // memory, or -- tables built inside K2 -- the outer table itself / the scratch look-up rows

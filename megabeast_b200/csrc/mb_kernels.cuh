@@ -212,6 +212,11 @@ struct PoissonArgs {
   int32_t scratch_off;        // byte offset of the reduction scratch [kPoisBins][nwarps][2][Wpad] in dynamic shared memory
   int32_t fage_smem_off;      // byte offset of the plain age-factor rows in dynamic shared memory (fage == null)
   const double* SC;           // ELEMENTWISE: bin sums [nbins][Wpad][2] already formed by K1b (else null)
+  // few dust classes: ONE WARP per bin (lanes = walkers, no cross-warp sums, no block barriers); the warp's
+  // first bin's statistics are staged into shared memory (cp.async at kernel start)
+  int32_t warp_private;       // 1: this scheme
+  int32_t hts_off;            // byte offset of the staged statistics [hts_slices][nOd * nI][2]
+  int32_t hts_slices;         // warps that have a slice
 };
 constexpr int kPoisBins = 2;  // bins a block works on at a time (loads of both in flight together)
 
@@ -337,6 +342,71 @@ __device__ void poisson_bins(const PoissonArgs& pa, const double* F, int nO, int
   // the entry stage shares the scratch: the combining threads must be done before any warp streams.
   // With a private scratch the other warps go straight on to their stars.
   if (!scratch_is_private) __syncthreads();
+}
+
+// One warp per bin: block b's warp k owns bins b + (k + m * warps) * gridDim.x.  Lanes are walkers, so a
+// lane ends with its walkers' complete (S, C): no scratch, no barrier; the other warps of the block are
+// already streaming stars.  For tables of a few hundred rows (a bin is ~nI broadcast loads + row reads).
+template <int NW, int THREADS>
+__device__ void poisson_bins_private(const PoissonArgs& pa, const double* F, int nO, int nOd, int nI,
+                                     unsigned char* smem_raw) {
+  constexpr int Wpad = 32 * NW, kWarps = THREADS / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double* fage = pa.fage ? pa.fage : reinterpret_cast<const double*>(smem_raw + pa.fage_smem_off);
+  const double2* Ht = reinterpret_cast<const double2*>(pa.Ht);
+  const double* FI = F + (size_t)nO * Wpad + lane;
+  const int nD = nOd * nI;
+  const double2* hts = reinterpret_cast<const double2*>(smem_raw + pa.hts_off) + (size_t)warp * nD;
+  for (int k = warp;; k += kWarps) {
+    const int b = (int)blockIdx.x + k * (int)gridDim.x;
+    if (b >= pa.nbins) break;
+    const int acls = __ldg(pa.bin_agecls + b);
+    const double coef = __ldg(pa.coef + b);
+    double S[NW], C[NW];
+#pragma unroll
+    for (int j = 0; j < NW; ++j) { S[j] = 0.0; C[j] = 0.0; }
+    if (pa.SC) {
+#pragma unroll
+      for (int j = 0; j < NW; ++j) {
+        const double2 v = __ldg(reinterpret_cast<const double2*>(pa.SC) + (size_t)b * Wpad + lane + 32 * j);
+        S[j] = v.x; C[j] = v.y;
+      }
+    } else {
+      const bool staged = k == warp && warp < pa.hts_slices;
+      if (staged) { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); __syncwarp(); }
+      const double2* hrow = staged ? hts : Ht + (size_t)b * nD;
+      for (int od = 0; od < nOd; ++od) {
+        double s[NW], c[NW];
+#pragma unroll
+        for (int j = 0; j < NW; ++j) { s[j] = 0.0; c[j] = 0.0; }
+#pragma unroll 4
+        for (int i = 0; i < nI; ++i) {
+          const double2 h = hrow[(size_t)od * nI + i];   // warp-uniform: a broadcast
+          const double* f = FI + (size_t)i * Wpad;
+#pragma unroll
+          for (int j = 0; j < NW; ++j) {
+            const double fv = f[32 * j];
+            s[j] = fma(h.x, fv, s[j]); c[j] = fma(h.y, fv, c[j]);
+          }
+        }
+        const double* fo = F + (size_t)(acls * nOd + od) * Wpad + lane;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) {
+          const double fv = fo[32 * j];
+          S[j] = fma(fv, s[j], S[j]); C[j] = fma(fv, c[j], C[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NW; ++j) {
+      const int w = lane + 32 * j;
+      // helpers.py:152-162: ageprior * metprior * massmult / avemass * C / S, bins with S <= 0 skipped
+      const double fa = fage[(size_t)acls * Wpad + w];
+      const double term = S[j] > 0.0 ? (fa * coef) * (C[j] / S[j]) : 0.0;
+      pa.Pb[((size_t)b * 2 + 0) * Wpad + w] = S[j];
+      pa.Pb[((size_t)b * 2 + 1) * Wpad + w] = term;
+    }
+  }
 }
 
 // Last block of the launch: add the bins in fixed order -> Poisson term of every walker of the pass.
@@ -1216,15 +1286,33 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   asm volatile("griddepcontrol.wait;" ::: "memory");
   // every warp's first segment: its first chunks are requested now, so that the cold-HBM latency of
   // the entry stream hides behind the table build (needs a stage that the build does not use as scratch)
+  // (the segment bounds are requested first; the chunks themselves once the table build has issued
+  // its own first loads, so that the two cold-memory latencies overlap instead of adding up)
   const int nwarps_total = (int)gridDim.x * kK2Warps;
   int s = (int)blockIdx.x * kK2Warps + warp;
   bool primed = false;
-  if (a.separate && s < a.nseg) {
-    stream_prime<STAGES, OB>(a.ea, a.ec, a.seg[s], a.seg[s + 1], st_a, st_c, lane);
-    primed = true;
+  int64_t seg_lo = 0, seg_hi = 0;
+  const bool want_prime = a.separate && s < a.nseg;
+  if (want_prime) { seg_lo = __ldg(a.seg + s); seg_hi = __ldg(a.seg + s + 1); }
+  auto prime_now = [&]() {
+    if (want_prime && !primed) {
+      stream_prime<STAGES, OB>(a.ea, a.ec, seg_lo, seg_hi, st_a, st_c, lane);
+      primed = true;
+    }
+  };
+  // N-stars term, one warp per bin: the statistics of this warp's first bin on their way to shared memory
+  if (a.pois.nbins > 0 && a.pois.warp_private && !a.pois.SC && warp < a.pois.hts_slices) {
+    const int b = (int)blockIdx.x + warp * (int)gridDim.x, nD = a.nOd * a.nB;
+    if (b < a.pois.nbins) {
+      const double2* src = reinterpret_cast<const double2*>(a.pois.Ht) + (size_t)b * nD;
+      const uint32_t dst = smem0 + (uint32_t)a.pois.hts_off + (uint32_t)warp * (uint32_t)nD * 16u;
+      for (int i = lane; i < nD; i += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + 16u * i), "l"(src + i));
+    }
+    cp_async_commit();
   }
   // this block's slices of the N-stars statistics: pull them into L2 while the tables are built
-  if (a.pois.nbins > 0 && !a.pois.SC) {
+  if (a.pois.nbins > 0 && !a.pois.SC && !a.pois.warp_private) {
     const int per_bin = a.nOd * a.nB * 16;  // bytes
     for (int b = blockIdx.x; b < a.pois.nbins; b += gridDim.x) {
       const char* base = reinterpret_cast<const char*>(a.pois.Ht) + (size_t)b * per_bin;
@@ -1285,6 +1373,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
         }
       }
     }
+    prime_now();
     __syncthreads();
     {
       ExpCoef ec;
@@ -1348,14 +1437,17 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
       double2* dst = reinterpret_cast<double2*>(smem_raw + a.tab_off);
       for (int i = threadIdx.x; i < n2; i += blockDim.x) dst[i] = __ldg(src + i);
     }
+    prime_now();
     __syncthreads();
   }
+  prime_now();
   stamp(a.timeline, 1);
   // N-stars prologue: this block's (age, Z) bins for all walkers of the pass, on the tables it just
   // staged (always the fp64 ones: from shared memory when they are there, else from global memory)
   if (a.pois.nbins > 0) {
     const double* Ftab = (MODE == kModeFactor && !kF32) ? reinterpret_cast<const double*>(smem_raw + a.tab_off) : a.FA;
-    poisson_bins<NW, k2_threads(NW)>(a.pois, Ftab, a.nA, a.nOd, a.nB, smem_raw, a.separate != 0);
+    if (a.pois.warp_private) poisson_bins_private<NW, k2_threads(NW)>(a.pois, Ftab, a.nA, a.nOd, a.nB, smem_raw);
+    else poisson_bins<NW, k2_threads(NW)>(a.pois, Ftab, a.nA, a.nOd, a.nB, smem_raw, a.separate != 0);
   }
 
   stamp(a.timeline, 2);
@@ -1645,6 +1737,140 @@ __global__ void __launch_bounds__(kPixThreads, (NW <= 2 ? 2 : 1)) mb_k2_pixels(K
   if (threadIdx.x == 0) ticket = atomicAdd(a.counters + kCtrBlocks, 1u);
   __syncthreads();
   if (ticket == gridDim.x - 1 && threadIdx.x == 0) { a.counters[kCtrSegment] = 0u; a.counters[kCtrBlocks] = 0u; }
+}
+
+// ---- one-time entry build on the device (SURVEY.md 8(f) "next #1") -------------------------------------
+// What mb_create does with a star's sparse points, for all stars at once: mask the non-finite values
+// (singlepop_dust_model.py:196 -- their indices are never dereferenced), fold the three static gathers into
+// one weight vals*prior_weight[r]*grid_weight[r]*completeness[r] (:207-213, same multiplication order),
+// look the class code of row r up, sort the star's entries by (outer class, table row) so that equal
+// outer classes form runs, pre-sum entries that share all class codes (in the order of their sparse
+// points: deterministic), flag run and star starts.  One warp per star; the star's points are sorted
+// by a bitonic network in shared memory (N = 32, 64 or 128 slots).  Entries land in a padded
+// per-star temporary; mb_compact_entries packs them once the host has prefix-summed the counts.
+struct BuildArgs {
+  const int64_t* indxs;      // [K][S] this handle's columns of the (n_lnps, n_stars) arrays
+  const double* vals;
+  int64_t K, S, G;
+  const uint32_t* rowcode;   // [G] outer class << 20 | inner class; null: no class codes (by-row modes on any grid)
+  const double* pw;          // prior_weight, grid_weight, completeness [G]
+  const double* gw;
+  const double* cm;
+  int32_t mode;              // MB_MODE_*: what the code word's low bits hold
+  int32_t nB;                // TABLE_UNIQUE: row = age class * nB + dust class
+  int32_t merge;
+  double* tmp_a;             // [S][K] weights
+  uint32_t* tmp_c;           // [S][K] 32-bit code words
+  int32_t* cnt;              // [S] entries kept, [S] finite points, [S] runs
+  int32_t* nraw;
+  int32_t* nrun;
+  int32_t* err_star;         // smallest star with an index out of bounds (INT_MAX: none)
+};
+constexpr int kBuildWarps = 4;
+
+template <int N>
+__global__ void __launch_bounds__(32 * kBuildWarps) mb_build_entries(const BuildArgs a) {
+  __shared__ unsigned long long skey[kBuildWarps][N];
+  __shared__ double sw[kBuildWarps][N];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long* key = skey[warp];
+  double* wt = sw[warp];
+  for (int64_t s = (int64_t)blockIdx.x * kBuildWarps + warp; s < a.S; s += (int64_t)gridDim.x * kBuildWarps) {
+    int nfin = 0;
+    for (int k = lane; k < N; k += 32) {
+      unsigned long long kv = ~0ull;  // padding and masked points sort last
+      double w = 0.0;
+      if (k < a.K) {
+        const double v = a.vals[(size_t)k * a.S + s];
+        if (isfinite(v)) {
+          int64_t r = a.indxs[(size_t)k * a.S + s];
+          if (r < 0) r += a.G;  // numpy negative indexing
+          if (r < 0 || r >= a.G) {
+            atomicMin(a.err_star, (int)s);
+          } else {
+            w = v * a.pw[r] * a.gw[r] * a.cm[r];
+            const uint32_t rc = a.rowcode ? a.rowcode[r] : 0u;
+            const uint32_t cO = (rc >> kAgeShift) & kAgeMask, cI = rc & kDustMask;
+            const uint32_t idx = a.mode == MB_MODE_FACTOR ? cI : a.mode == MB_MODE_TABLE_UNIQUE ? cO * (uint32_t)a.nB + cI : (uint32_t)r;
+            kv = ((unsigned long long)cO << 40) | ((unsigned long long)idx << 8) | (unsigned long long)k;
+            ++nfin;
+          }
+        }
+      }
+      key[k] = kv; wt[k] = w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nfin += __shfl_xor_sync(0xffffffffu, nfin, o);
+    __syncwarp();
+    // bitonic sort of (key, weight) pairs, ascending; keys are distinct (they end in the point number)
+    for (int k = 2; k <= N; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = lane; t < N / 2; t += 32) {
+          const int i = ((t / j) * 2 * j) + (t % j), l = i + j;
+          const bool up = (i & k) == 0;
+          const unsigned long long ki = key[i], kl = key[l];
+          if ((ki > kl) == up) {
+            key[i] = kl; key[l] = ki;
+            const double wi = wt[i]; wt[i] = wt[l]; wt[l] = wi;
+          }
+        }
+        __syncwarp();
+      }
+    // heads of groups of equal class codes (all entries are heads when duplicates are not merged)
+    int base = 0, runs = 0;
+    for (int i0 = 0; i0 < nfin; i0 += 32) {
+      const int i = i0 + lane;
+      bool head = false, newrun = false;
+      double wsum = 0.0;
+      unsigned long long c = 0ull;
+      if (i < nfin) {
+        c = key[i] >> 8;
+        const unsigned long long cp = i > 0 ? key[i - 1] >> 8 : ~0ull;
+        head = !a.merge || i == 0 || c != cp;
+        newrun = i == 0 || (c >> 32) != (cp >> 32);
+        if (head) {
+          wsum = wt[i];
+          if (a.merge)
+            for (int j = i + 1; j < nfin && (key[j] >> 8) == c; ++j) wsum += wt[j];  // in point order
+        }
+      }
+      const unsigned hm = __ballot_sync(0xffffffffu, head);
+      if (head) {
+        const int pos = base + __popc(hm & ((1u << lane) - 1u));
+        const uint32_t cO = (uint32_t)(c >> 32), idx = (uint32_t)c;
+        uint32_t code;
+        if (a.mode == MB_MODE_FACTOR) code = (cO << kAgeShift) | idx | (i == 0 ? (kNewRun | kNewStar) : newrun ? kNewRun : 0u);
+        else code = idx | (i == 0 ? kNewRun : 0u);
+        a.tmp_a[(size_t)s * a.K + pos] = wsum;
+        a.tmp_c[(size_t)s * a.K + pos] = code;
+      }
+      base += __popc(hm);
+      runs += __popc(__ballot_sync(0xffffffffu, head && newrun));
+    }
+    if (lane == 0) { a.cnt[s] = base; a.nraw[s] = nfin; a.nrun[s] = a.mode == MB_MODE_FACTOR ? runs : 0; }
+    __syncwarp();
+  }
+}
+
+// pack the per-star temporaries into the entry stream: offs[s] = entries before star s
+__global__ void __launch_bounds__(256) mb_compact_entries(const double* __restrict__ tmp_a, const uint32_t* __restrict__ tmp_c,
+                                                          const int32_t* __restrict__ cnt, const int64_t* __restrict__ offs,
+                                                          int64_t S, int64_t K, double* __restrict__ ea,
+                                                          uint32_t* __restrict__ ec, uint16_t* __restrict__ ec16, int ob) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t s = wid; s < S; s += nw) {
+    const int n = cnt[s];
+    const int64_t off = offs[s];
+    for (int i = lane; i < n; i += 32) {
+      ea[off + i] = tmp_a[(size_t)s * K + i];
+      const uint32_t c = tmp_c[(size_t)s * K + i];
+      if (ec16)
+        ec16[off + i] = (uint16_t)(((c & kNewRun) ? 0x8000u : 0u) | ((c & kNewStar) ? 0x4000u : 0u) |
+                                   (((c >> kAgeShift) & kAgeMask) << (14 - ob)) | (c & kDustMask));
+      else ec[off + i] = c;
+    }
+  }
 }
 
 // ---- one-time ingest: helpers.py:33-41 ---------------------------------------------------------

@@ -237,3 +237,52 @@ def test_in_place_change_of_the_data_is_noticed():
     # a NEW array object under the same key is noticed as well (key: ids, data pointers, shapes)
     stars["vals"] = stars["vals"] / 3.0
     assert_close(lnprob(phis, model, stars, moddata), c_oracle.lnprob_batch(pm, phis, stars, moddata), RTOL)
+
+
+@pytest.mark.parametrize("cfg,mode,split,merge", [
+    ("small", "factor", None, True), ("small", "factor", None, False), ("cfg1", "factor", ("Av",), True),
+    ("cfg1", "table_unique", None, True), ("cfg2", "factor", None, True), ("cfg1", "table_grid", None, True),
+    ("cfg1", "elementwise", None, False)])
+def test_device_build_equals_host_build(cfg, mode, split, merge, monkeypatch):
+    """The entry stream is built on the device (mask, fold, class look-up, per-star bitonic sort, merge,
+    flags: mb_build_entries); the host loop it replaces is kept behind MB_HOST_BUILD=1.  Both must leave
+    bit-identical data on the device, and the same likelihood."""
+    settings, moddata, stars, _ = synth.make_problem(cfg, mode="clustered", seeds=(101, 102, 103))
+    model = MB_Model(copy.deepcopy(settings))
+    spec, perm, ndim = model._spec()
+    mm = port.mass_multipliers(moddata, {"name": "kroupa"})
+    phis = synth.make_walkers(port.PortModel(copy.deepcopy(settings)), 9, seed=103)[:, perm]
+    out = {}
+    for which in ("device", "host"):
+        if which == "host":
+            monkeypatch.setenv("MB_HOST_BUILD", "1")
+        else:
+            monkeypatch.delenv("MB_HOST_BUILD", raising=False)
+        eng = LikelihoodEngine(spec, stars, moddata, massmult=mm, mode=mode, keep_indices=True,
+                               merge_duplicates=merge, split_inner=split)
+        info = eng.info()
+        if mode in ("factor", "table_unique"):
+            data = eng.device_entries()
+        else:
+            data = eng.gathered_indices()
+        out[which] = (data, {k: info[k] for k in ("n_entries", "n_entries_raw", "n_runs", "code_bytes")},
+                      eng.lnlike(phis)[0].copy())
+        eng.close()
+    assert out["device"][1] == out["host"][1]
+    for a, b in zip(out["device"][0], out["host"][0]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(out["device"][2], out["host"][2])
+
+
+def test_device_build_reports_bad_indices_like_numpy():
+    settings, moddata, stars, _ = synth.make_problem("small", seeds=(105, 106, 107))
+    stars = {"indxs": stars["indxs"].copy(), "vals": stars["vals"].copy()}
+    G = len(moddata["Av"])
+    stars["indxs"][3, 17] = G + 5           # a finite point with an index past the grid
+    model = MB_Model(copy.deepcopy(settings))
+    phis = synth.make_walkers(port.PortModel(copy.deepcopy(settings)), 3, seed=107)
+    with pytest.raises(IndexError, match=f"index {G + 5} is out of bounds for axis 0 with size {G}"):
+        lnprob(phis, model, stars, moddata)
+    stars["indxs"][3, 17] = -1              # numpy's negative indexing: the last row
+    want = c_oracle.lnprob_batch(port.PortModel(copy.deepcopy(settings)), phis, stars, moddata)
+    assert_close(lnprob(phis, MB_Model(copy.deepcopy(settings)), stars, moddata), want, RTOL)
