@@ -1415,7 +1415,7 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     // host phi travels in the kernel parameters and is staged in shared memory; a batch too large
     // for that keeps K0 (one read of the mapped host memory per walker instead of one per block)
     const bool inline_phi = h_phi && (int64_t)wp * ndim <= kPhiInline;
-    const size_t fuse_scratch = k2_fuse_scratch(h->nscratch, h->ncls_total, nrows, Wpad, inline_phi ? (size_t)wp * ndim : 0);
+    const size_t fuse_scratch = k2_fuse_scratch(h->nscratch, h->ncls_total, nrows, Wpad, (size_t)wp * ndim);
     const bool may_fuse = kmode == kModeFactor && h->table_bytes == 8 && !d_tab && !h->no_fuse &&
                           h->ncls_total < 0x7fff && (!h_phi || inline_phi);
     // most (age, Z) bins a block can get: the launch has at least min(nbins, SMs) blocks

@@ -344,22 +344,26 @@ __device__ void poisson_bins(const PoissonArgs& pa, const double* F, int nO, int
   if (!scratch_is_private) __syncthreads();
 }
 
-// One warp per bin: block b's warp k owns bins b + (k + m * warps) * gridDim.x.  Lanes are walkers, so a
-// lane ends with its walkers' complete (S, C): no scratch, no barrier; the other warps of the block are
-// already streaming stars.  For tables of a few hundred rows (a bin is ~nI broadcast loads + row reads).
+// One warp per bin: the block's bins b = blockIdx.x + k * gridDim.x are claimed one at a time (shared
+// counter) by warps that have finished their stars.  Lanes are walkers, so a lane ends with its
+// walkers' complete (S, C): no scratch, no barrier.  For tables of a few hundred rows (a bin is ~nI
+// broadcast loads + row reads).
 template <int NW, int THREADS>
 __device__ void poisson_bins_private(const PoissonArgs& pa, const double* F, int nO, int nOd, int nI,
-                                     unsigned char* smem_raw) {
-  constexpr int Wpad = 32 * NW, kWarps = THREADS / 32;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                                     unsigned char* smem_raw, int* bin_ctr) {
+  constexpr int Wpad = 32 * NW;
+  const int lane = threadIdx.x & 31;
   const double* fage = pa.fage ? pa.fage : reinterpret_cast<const double*>(smem_raw + pa.fage_smem_off);
   const double2* Ht = reinterpret_cast<const double2*>(pa.Ht);
   const double* FI = F + (size_t)nO * Wpad + lane;
   const int nD = nOd * nI;
-  const double2* hts = reinterpret_cast<const double2*>(smem_raw + pa.hts_off) + (size_t)warp * nD;
-  for (int k = warp;; k += kWarps) {
+  while (true) {
+    int k = 0;
+    if (lane == 0) k = atomicAdd(bin_ctr, 1);
+    k = __shfl_sync(0xffffffffu, k, 0);
     const int b = (int)blockIdx.x + k * (int)gridDim.x;
     if (b >= pa.nbins) break;
+    const double2* hts = reinterpret_cast<const double2*>(smem_raw + pa.hts_off) + (size_t)k * nD;
     const int acls = __ldg(pa.bin_agecls + b);
     const double coef = __ldg(pa.coef + b);
     double S[NW], C[NW];
@@ -372,9 +376,8 @@ __device__ void poisson_bins_private(const PoissonArgs& pa, const double* F, int
         S[j] = v.x; C[j] = v.y;
       }
     } else {
-      const bool staged = k == warp && warp < pa.hts_slices;
-      if (staged) { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); __syncwarp(); }
-      const double2* hrow = staged ? hts : Ht + (size_t)b * nD;
+      // (slice k was staged at kernel start by warp k and made visible by the table build's barrier)
+      const double2* hrow = k < pa.hts_slices ? hts : Ht + (size_t)b * nD;
       for (int od = 0; od < nOd; ++od) {
         double s[NW], c[NW];
 #pragma unroll
@@ -1281,6 +1284,10 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   const uint32_t st_c = st_a + STAGES * kChunk * 8u;
   const uint32_t tabA = smem0 + (uint32_t)a.tab_off + lanebytes;
   const uint32_t tabB = tabA + (uint32_t)a.nA * rowbytes;
+  __shared__ unsigned int ticket;
+  __shared__ int timed_out;
+  __shared__ int bin_ctr;       // next of the block's N-stars bins (claimed by warps after their stars)
+  if (threadIdx.x == 0) bin_ctr = 0;
   stamp(a.timeline, 0);
   // launched with programmatic stream serialization: wait here for K0 (the tables) to complete
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1300,7 +1307,8 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
       primed = true;
     }
   };
-  // N-stars term, one warp per bin: the statistics of this warp's first bin on their way to shared memory
+  // N-stars term, one warp per bin: the statistics of the block's first bins on their way to shared memory
+  bool hts_pending = false;
   if (a.pois.nbins > 0 && a.pois.warp_private && !a.pois.SC && warp < a.pois.hts_slices) {
     const int b = (int)blockIdx.x + warp * (int)gridDim.x, nD = a.nOd * a.nB;
     if (b < a.pois.nbins) {
@@ -1310,7 +1318,15 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + 16u * i), "l"(src + i));
     }
     cp_async_commit();
+    hts_pending = true;
   }
+  // (this copy group is the warp's oldest: waiting for it leaves the primed chunks in flight)
+  auto hts_wait = [&]() {
+    if (hts_pending) {
+      if (primed) cp_async_wait<STAGES - 1>(); else cp_async_wait<0>();
+      hts_pending = false;
+    }
+  };
   // this block's slices of the N-stars statistics: pull them into L2 while the tables are built
   if (a.pois.nbins > 0 && !a.pois.SC && !a.pois.warp_private) {
     const int per_bin = a.nOd * a.nB * 16;  // bytes
@@ -1339,13 +1355,19 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     unsigned short* sslot = reinterpret_cast<unsigned short*>(srow + nrows);  // [ncls] (padded to 8 bytes)
     // phi: carried in the kernel parameters (copied to shared memory with indexed constant loads --
     // reads of the parameter space through a generic pointer are slow) or in device memory
+    // The later phases read it from shared memory in both cases: a first touch of device memory there
+    // would be a cold miss queued behind the entry chunks requested in between.
     const double* ph = a.phi;
-    if (a.phi_inline) {
-      double* sphi = reinterpret_cast<double*>(sslot + ((ncls + 3) & ~3));
+    double* sphi = reinterpret_cast<double*>(sslot + ((ncls + 3) & ~3));
+    {
       const int n = a.W * a.ndim;
-      for (int i = threadIdx.x; i < n; i += blockDim.x) sphi[i] = a.phi_in[i];
-      __syncthreads();
-      ph = sphi;
+      if (a.phi_inline) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) sphi[i] = a.phi_in[i];
+        __syncthreads();
+        ph = sphi;
+      } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) sphi[i] = __ldg(a.phi + i);  // visible after the next barrier
+      }
     }
     const double inv_sqrt_2pi = 0.3989422804014326779399460599343819;
     // (the row lists ride along with the first phase: their L2 latency hides behind the logarithms)
@@ -1375,6 +1397,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     }
     prime_now();
     __syncthreads();
+    ph = sphi;
     {
       ExpCoef ec;
 #pragma unroll
@@ -1423,6 +1446,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
       if (sr.w != 0xffff) v *= lrow(sr.w)[w];
       tab[idx] = v;
     }
+    hts_wait();
     __syncthreads();
   } else if (MODE == kModeFactor) {
     const int n2 = (a.nA + a.nB) * Wpad / 2;
@@ -1438,17 +1462,18 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
       for (int i = threadIdx.x; i < n2; i += blockDim.x) dst[i] = __ldg(src + i);
     }
     prime_now();
+    hts_wait();
     __syncthreads();
+  } else {
+    prime_now();
+    if (a.pois.nbins > 0 && a.pois.warp_private) { hts_wait(); __syncthreads(); }  // (also publishes bin_ctr)
   }
-  prime_now();
   stamp(a.timeline, 1);
   // N-stars prologue: this block's (age, Z) bins for all walkers of the pass, on the tables it just
   // staged (always the fp64 ones: from shared memory when they are there, else from global memory)
-  if (a.pois.nbins > 0) {
-    const double* Ftab = (MODE == kModeFactor && !kF32) ? reinterpret_cast<const double*>(smem_raw + a.tab_off) : a.FA;
-    if (a.pois.warp_private) poisson_bins_private<NW, k2_threads(NW)>(a.pois, Ftab, a.nA, a.nOd, a.nB, smem_raw);
-    else poisson_bins<NW, k2_threads(NW)>(a.pois, Ftab, a.nA, a.nOd, a.nB, smem_raw, a.separate != 0);
-  }
+  const double* Ftab = (MODE == kModeFactor && !kF32) ? reinterpret_cast<const double*>(smem_raw + a.tab_off) : a.FA;
+  if (a.pois.nbins > 0 && !a.pois.warp_private)
+    poisson_bins<NW, k2_threads(NW)>(a.pois, Ftab, a.nA, a.nOd, a.nB, smem_raw, a.separate != 0);
 
   stamp(a.timeline, 2);
   Lanes<NW, MODE, TF, OB> L;
@@ -1474,11 +1499,15 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     }
     s = __shfl_sync(0xffffffffu, s_next, 0);
   }
+  // Few dust classes: the block's (age, Z) bins are taken by whichever warps finish their stars first --
+  // warps wait here for the block's slowest one anyway (segments end on star boundaries), so the
+  // N-stars term costs the critical path nothing.  The tables are still intact (the reduction slabs
+  // move over them only after the barrier below).
+  if (a.pois.nbins > 0 && a.pois.warp_private)
+    poisson_bins_private<NW, k2_threads(NW)>(a.pois, Ftab, a.nA, a.nOd, a.nB, smem_raw, &bin_ctr);
 
   // ---- K3 (fused): warp -> block (slabs) -> grid (global atomics) reduction over stars,
   // all in integers; the last block to finish converts and writes the result rows.
-  __shared__ unsigned int ticket;
-  __shared__ int timed_out;
   __syncthreads();
   stamp(a.timeline, 3);
   // every warp parks its per-walker integers in its own slab of the (now idle) stage, then
