@@ -217,6 +217,7 @@ struct PoissonArgs {
   int32_t warp_private;       // 1: this scheme
   int32_t hts_off;            // byte offset of the staged statistics [hts_slices][nOd * nI][2]
   int32_t hts_slices;         // warps that have a slice
+  int32_t bins_first;         // 1: the bins are taken before the star loop (A/B switch MB_BINS_FIRST; default: after)
 };
 constexpr int kPoisBins = 2;  // bins a block works on at a time (loads of both in flight together)
 
@@ -1349,8 +1350,8 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     double* lut = reinterpret_cast<double*>(smem_raw + a.scratch_off);  // [nscratch][Wpad]
     double* tab = reinterpret_cast<double*>(smem_raw + a.tab_off);  // [nA + nB][Wpad]
     const int ncls = a.ncls_total, nrows = a.nA + a.nB;
-    double* lxs = lut + (size_t)a.nscratch * Wpad;                  // [ncls][2] ln x, 1/x of the class value
-    double* cw = lxs + 2 * ncls;                                    // [NPARAM][Wpad][6] per-walker lognormal constants
+    double* lxs = lut + (size_t)a.nscratch * Wpad;                  // [ncls][3] ln x, 1/x, x of the class value
+    double* cw = lxs + 3 * ncls;                                    // [NPARAM][Wpad][6] per-walker lognormal constants
     ushort4* srow = reinterpret_cast<ushort4*>(cw + 6 * MB_NPARAM * Wpad);  // [nrows] look-up rows of a table row
     unsigned short* sslot = reinterpret_cast<unsigned short*>(srow + nrows);  // [ncls] (padded to 8 bytes)
     // phi: carried in the kernel parameters (copied to shared memory with indexed constant loads --
@@ -1378,8 +1379,9 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     for (int idx = threadIdx.x; idx < ncls + MB_NPARAM * Wpad; idx += blockDim.x) {
       if (idx < ncls) {
         const double x = __ldg(a.clsx + idx);
-        lxs[2 * idx] = x > 0.0 ? log(x) : 0.0;
-        lxs[2 * idx + 1] = x > 0.0 ? 1.0 / x : 0.0;  // x <= 0: the lognormal is exactly 0 there
+        lxs[3 * idx] = x > 0.0 ? log(x) : 0.0;
+        lxs[3 * idx + 1] = x > 0.0 ? 1.0 / x : 0.0;  // x <= 0: the lognormal is exactly 0 there
+        lxs[3 * idx + 2] = x;
       } else {
         const int j = idx - ncls, p = j / Wpad, w = j - p * Wpad;
         const double* th = ph + (size_t)(w < a.W ? w : a.W - 1) * a.ndim + m.voff[p];
@@ -1411,7 +1413,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
         for (int q = 1; q < MB_NPARAM; ++q)
           if (i >= m.clsoff[q]) p = q;
         const double* c = cw + 6 * (p * Wpad + w);
-        const double lx = lxs[2 * i], rx = lxs[2 * i + 1];
+        const double lx = lxs[3 * i], rx = lxs[3 * i + 1];
         double v = 1.0;
         if (m.kind[p] == MB_LOGNORMAL) {
           const double t = (lx - c[0]) * c[1];
@@ -1421,7 +1423,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
           v = (c[2] * rx) * exp_nonpos(-0.5 * (t1 * t1), ec) + (c[5] * rx) * exp_nonpos(-0.5 * (t2 * t2), ec);
         } else if (m.kind[p] != MB_FIXED) {
           // padding columns repeat the last walker
-          v = prior_eval(m, p, ph + (size_t)(w < a.W ? w : a.W - 1) * a.ndim + m.voff[p], __ldg(a.clsx + i));
+          v = prior_eval(m, p, ph + (size_t)(w < a.W ? w : a.W - 1) * a.ndim + m.voff[p], lxs[3 * i + 2]);
         }
         const unsigned slot = sslot[i];
         ((slot & 0x8000u) ? tab + (size_t)(slot & 0x7fffu) * Wpad : lut + (size_t)slot * Wpad)[w] = v;
@@ -1474,6 +1476,8 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   const double* Ftab = (MODE == kModeFactor && !kF32) ? reinterpret_cast<const double*>(smem_raw + a.tab_off) : a.FA;
   if (a.pois.nbins > 0 && !a.pois.warp_private)
     poisson_bins<NW, k2_threads(NW)>(a.pois, Ftab, a.nA, a.nOd, a.nB, smem_raw, a.separate != 0);
+  if (a.pois.nbins > 0 && a.pois.warp_private && a.pois.bins_first)
+    poisson_bins_private<NW, k2_threads(NW)>(a.pois, Ftab, a.nA, a.nOd, a.nB, smem_raw, &bin_ctr);
 
   stamp(a.timeline, 2);
   Lanes<NW, MODE, TF, OB> L;
@@ -1503,7 +1507,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   // warps wait here for the block's slowest one anyway (segments end on star boundaries), so the
   // N-stars term costs the critical path nothing.  The tables are still intact (the reduction slabs
   // move over them only after the barrier below).
-  if (a.pois.nbins > 0 && a.pois.warp_private)
+  if (a.pois.nbins > 0 && a.pois.warp_private && !a.pois.bins_first)
     poisson_bins_private<NW, k2_threads(NW)>(a.pois, Ftab, a.nA, a.nOd, a.nB, smem_raw, &bin_ctr);
 
   // ---- K3 (fused): warp -> block (slabs) -> grid (global atomics) reduction over stars,
