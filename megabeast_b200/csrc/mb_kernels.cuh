@@ -711,8 +711,15 @@ __global__ void __launch_bounds__(kK1eThreads, LN ? 2 : 3) mb_k1_elementwise(con
     }
     __syncthreads();
     double s0 = 0.0, s1 = 0.0, c0 = 0.0, c1 = 0.0;
-    for (int r = rlane; r < nrows; r += rows_per_pass) {
-      double v0 = 1.0, v1 = 1.0;
+    // physmod of one grid row for this thread's two walkers
+    auto eval_row = [&](int r, double& v0, double& v1) {
+      v0 = 1.0; v1 = 1.0;
+      // LN: the lognormal dust factors share ONE exp per walker -- the product of
+      // (c2 / x) exp(-t^2 / 2) over the parameters is (prod c2 / x) exp(-sum t^2 / 2); the fp64 exp is
+      // what bounds this kernel.  Where the summed exponent is below -700 (or not a number) the
+      // factors are evaluated and multiplied one by one as the reference does, so that underflow to
+      // subnormals / zero happens exactly where numpy's happens.
+      double e0 = 0.0, e1 = 0.0, pf0 = 1.0, pf1 = 1.0;
 #pragma unroll
       for (int p = 0; p < MB_NPARAM; ++p) {  // logA, Av, Rv, fA: the reference's `cur_physmod *=` order
         if (kinds[p] == MB_FIXED) continue;
@@ -727,8 +734,8 @@ __global__ void __launch_bounds__(kK1eThreads, LN ? 2 : 3) mb_k1_elementwise(con
           const double (&c)[2][3] = lc[LN ? p - MB_P_AV : 0];
           // x <= 0: the row part holds ln x = 0 and 1/x = 0, so the factor is exactly 0 as it must be
           const double t0 = (lx - c[0][0]) * c[0][1], t1 = (lx - c[1][0]) * c[1][1];
-          v0 *= (c[0][2] * rx) * exp_nonpos(-0.5 * (t0 * t0), ec);
-          v1 *= (c[1][2] * rx) * exp_nonpos(-0.5 * (t1 * t1), ec);
+          e0 = fma(-0.5 * t0, t0, e0); e1 = fma(-0.5 * t1, t1, e1);
+          pf0 *= c[0][2] * rx; pf1 *= c[1][2] * rx;
           continue;
         }
         const double* th0 = sphi + (size_t)(2 * pair) * ndim + m.voff[p];
@@ -738,11 +745,44 @@ __global__ void __launch_bounds__(kK1eThreads, LN ? 2 : 3) mb_k1_elementwise(con
         v0 *= k1e_eval(kinds[p], th0, cc, r0, r1, ri);
         v1 *= k1e_eval(kinds[p], th0 + ndim, cc + kK1eWalkerVals, r0, r1, ri);
       }
+      if (LN) {
+        if (e0 > -700.0 && e1 > -700.0) {
+          v0 *= pf0 * exp_nonpos(e0, ec);
+          v1 *= pf1 * exp_nonpos(e1, ec);
+        } else {  // rare: factor by factor, in the reference's order
+#pragma unroll
+          for (int p = MB_P_AV; p < MB_NPARAM; ++p) {
+            if (kinds[p] != MB_LOGNORMAL) continue;
+            const int i = p * kK1eRows + r;
+            const double lx = sr0[i], rx = sr1[i];
+            const double (&c)[2][3] = lc[LN ? p - MB_P_AV : 0];
+            const double t0 = (lx - c[0][0]) * c[0][1], t1 = (lx - c[1][0]) * c[1][1];
+            v0 *= (c[0][2] * rx) * exp_nonpos(-0.5 * (t0 * t0), ec);
+            v1 *= (c[1][2] * rx) * exp_nonpos(-0.5 * (t1 * t1), ec);
+          }
+        }
+      }
+    };
+    auto emit_row = [&](int r, double v0, double v1) {
       __stcs(reinterpret_cast<double2*>(a.T + (size_t)srow[r] * Wpad + 2 * pair), make_double2(v0, v1));
       if (a.partial) {
         s0 = fma(v0, sgw[r], s0); s1 = fma(v1, sgw[r], s1);
         c0 = fma(v0, sgc[r], c0); c1 = fma(v1, sgc[r], c1);
       }
+    };
+    // two rows per iteration: two independent exp chains in flight per thread
+    int r = rlane;
+    for (; r + rows_per_pass < nrows; r += 2 * rows_per_pass) {
+      double va0, va1, vb0, vb1;
+      eval_row(r, va0, va1);
+      eval_row(r + rows_per_pass, vb0, vb1);
+      emit_row(r, va0, va1);
+      emit_row(r + rows_per_pass, vb0, vb1);
+    }
+    if (r < nrows) {
+      double v0, v1;
+      eval_row(r, v0, v1);
+      emit_row(r, v0, v1);
     }
     if (a.partial) {  // combine the row lanes in fixed order -> this tile's partial bin sums
       double* mine = scomb + 4 * threadIdx.x;

@@ -77,6 +77,7 @@ class LikelihoodEngine:
         self.lib = _cabi.load()
         self._mb_lnlike = self.lib.mb_lnlike
         self._bufs = {}
+        self._zero_status = {}
         self.spec = spec
         self.handles = []
         self.devices = list(devices) if devices is not None else [0]
@@ -351,23 +352,30 @@ class LikelihoodEngine:
         _cabi.check(self.lib.mb_lnlike_pixels_device(self.handles[0], ctypes.c_void_p(d_phi), W, ndim,
                                                      ctypes.c_void_p(d_out), ctypes.c_void_p(stream)))
 
+    def zero_status(self, W):
+        """The bytes of W all-clear status words (for a fast "anything flagged?" test)."""
+        z = self._zero_status.get(W)
+        if z is None:
+            z = self._zero_status[W] = bytes(4 * W)
+        return z
+
     def lnprob_box(self, phis, lo, hi):
         """(lnprob[W], status[W], last_inside) for flat box priors, one C call (``mb_lnprob_box``):
         -inf outside the box without evaluating the likelihood.  Single device, analytic models.
         The returned arrays are reused by the next call with the same W."""
-        if not (phis.dtype == np.float64 and phis.flags.c_contiguous):
-            phis = np.ascontiguousarray(phis, dtype=np.float64)
         W, ndim = phis.shape
-        buf = self._bufs.get(-W)
+        buf = self._bufs.get((-W, ndim))
         if buf is None or buf[5] is not lo or buf[6] is not hi:
             out, status, last = np.empty(W), np.empty(W, dtype=np.int32), ctypes.c_int32(-1)
+            stage = np.empty((W, ndim))  # phi is copied here: fetching an array's address costs more than the copy
             # everything that does not change between calls is converted to ctypes once
-            buf = self._bufs[-W] = (out, status, last, self.lib.mb_lnprob_box,
-                                    (ctypes.c_void_p(lo.ctypes.data), ctypes.c_void_p(hi.ctypes.data),
-                                     ctypes.c_void_p(out.ctypes.data), ctypes.c_void_p(status.ctypes.data),
-                                     ctypes.byref(last)), lo, hi)
-        out, status, last, fn, (p_lo, p_hi, p_out, p_status, p_last) = buf[:5]
-        if fn(self.handles[0], phis.__array_interface__["data"][0], W, ndim, p_lo, p_hi, p_out, p_status, p_last):
+            buf = self._bufs[(-W, ndim)] = (out, status, last, self.lib.mb_lnprob_box,
+                                            (ctypes.c_void_p(lo.ctypes.data), ctypes.c_void_p(hi.ctypes.data),
+                                             ctypes.c_void_p(out.ctypes.data), ctypes.c_void_p(status.ctypes.data),
+                                             ctypes.byref(last), ctypes.c_void_p(stage.ctypes.data)), lo, hi, stage)
+        out, status, last, fn, (p_lo, p_hi, p_out, p_status, p_last, p_stage) = buf[:5]
+        np.copyto(buf[7], phis)
+        if fn(self.handles[0], p_stage, W, ndim, p_lo, p_hi, p_out, p_status, p_last):
             _cabi.check(1)
         return out, status, last.value
 

@@ -147,7 +147,7 @@ class MB_Model:
                 else:
                     targets.append((mod, vname))
             self._store_targets = targets
-        for (box, key), v in zip(targets, phi):
+        for (box, key), v in zip(targets, phi.tolist() if hasattr(phi, "tolist") else phi):
             box[key] = v
 
     def _spec(self):
@@ -338,7 +338,7 @@ class MB_Model:
             return None  # the general path rebuilds the device copy
         if last >= 0:
             self._store_phi(phis[last])
-        if status.any():
+        if status.tobytes() != engine.zero_status(len(status)):  # (cheaper than status.any() on 64 ints)
             if np.any(status & _cabi.STATUS_PEER_TIMEOUT):
                 raise RuntimeError("a peer GPU did not deliver its star shard (timeout)")
             if np.any(status & _cabi.STATUS_NONFINITE_STAR):

@@ -286,3 +286,26 @@ def test_device_build_reports_bad_indices_like_numpy():
     stars["indxs"][3, 17] = -1              # numpy's negative indexing: the last row
     want = c_oracle.lnprob_batch(port.PortModel(copy.deepcopy(settings)), phis, stars, moddata)
     assert_close(lnprob(phis, MB_Model(copy.deepcopy(settings)), stars, moddata), want, RTOL)
+
+
+def test_elementwise_one_exp_path_and_its_underflow_fallback():
+    """K1e evaluates the lognormal dust factors of a row with ONE exp (summed exponents) and falls back to
+    factor-by-factor evaluation where the sum is below -700.  Walkers with the narrowest allowed sigmas
+    drive most rows into that regime (factors underflow to exactly 0, stars whose points all vanish are
+    skipped like in the reference)."""
+    settings, moddata, stars, _ = synth.make_problem("cfg1", mode="clustered", seeds=(111, 112, 113))
+    rng = np.random.default_rng(9)
+    moddata = dict(moddata)
+    for key in ("Av", "Rv"):  # a non-Cartesian grid: ELEMENTWISE is the only mode that takes it
+        moddata[key] = moddata[key] * (1.0 + 1e-3 * rng.standard_normal(moddata[key].size))
+    pm = port.PortModel(copy.deepcopy(settings))
+    phis = synth.make_walkers(pm, 12, seed=113)
+    phis[:, 6] = np.linspace(0.05, 0.12, 12)      # Av sigma at the narrow end of its box
+    phis[:, 8] = np.linspace(0.05, 0.30, 12)[::-1]  # Rv sigma
+    phis[::3, 5] = 4.5                             # Av mean far from most of the grid
+    assert all(pm.lnprior(p) == 0.0 for p in phis)
+    expect = c_oracle.lnprob_batch(pm, phis, stars, moddata)
+    model = MB_Model(copy.deepcopy(settings))
+    got = lnprob(phis, model, stars, moddata)
+    assert model.engine_info()["mode"] == "elementwise"
+    assert_close(got, expect, RTOL)
