@@ -292,16 +292,23 @@ static K2Smem k2_smem_plan(int kmode, int nO, int nI, int nbins, int Wpad, int e
     p.pois_off = p.scratch_off + (fused ? (size_t)nscratch * Wpad * 8 : 0);
     size_t front = std::max(stage, p.scratch_off + (fused ? fuse_scratch : 0));
     if (!slabs_over_tables) front = std::max(front, slabs);
-    if (nbins > 0 && priv) {
-      p.hts_off = (p.scratch_off + (fused ? fuse_scratch : 0) + 15) & ~(size_t)15;
-      p.hts_slices = have_sc ? 0 : std::min(warps, std::max(1, bins_per_block));
-      front = std::max(front, p.hts_off + (size_t)p.hts_slices * nD * 16);
-    } else if (nbins > 0) {
+    if (nbins > 0 && !priv) {
       if (tables + p.pois_off + pois_row > (size_t)max_smem) return false;
       const size_t avail = (size_t)max_smem - tables - p.pois_off;
       p.pois_warps = (int)std::min<size_t>((size_t)warps, avail / pois_row);
       if (sep && p.pois_warps < warps) return false;  // a private scratch is only worth it at full width
       front = std::max(front, p.pois_off + (size_t)p.pois_warps * pois_row);
+    }
+    front = (front + 15) & ~(size_t)15;
+    if (nbins > 0 && !have_sc && nD > 0 && bins_per_block > 0) {
+      // the statistics of the block's bins staged in shared memory (cp.async at kernel start), after
+      // everything else: the one-warp-per-bin scheme needs all of them, the block-wide one takes what fits
+      const size_t slice = (size_t)nD * 16;
+      const size_t room = tables + front < (size_t)max_smem ? (size_t)max_smem - tables - front : 0;
+      p.hts_off = front;
+      p.hts_slices = (int)std::min<size_t>((size_t)std::min(bins_per_block, 64), room / slice);
+      if (priv && p.hts_slices < std::min(bins_per_block, warps)) return false;
+      front += (size_t)p.hts_slices * slice;
     }
     p.front = (front + 15) & ~(size_t)15;
     p.slab_off = slabs_over_tables ? p.front : 0;

@@ -234,10 +234,10 @@ __device__ void poisson_bins(const PoissonArgs& pa, const double* F, int nO, int
   const double* fage = pa.fage ? pa.fage : reinterpret_cast<const double*>(smem_raw + pa.fage_smem_off);
   const double2* Ht = reinterpret_cast<const double2*>(pa.Ht);
   const double* FI = F + (size_t)nO * Wpad + lane;
-  bool first_pass = true;
+  const double2* hts = reinterpret_cast<const double2*>(smem_raw + pa.hts_off);
+  int pass = -1;
   for (int b0 = blockIdx.x; b0 < pa.nbins; b0 += kPoisBins * gridDim.x) {
-    if (!first_pass) __syncthreads();  // the scratch is reused by the block's next pass
-    first_pass = false;
+    if (++pass > 0) __syncthreads();  // the scratch is reused by the block's next pass
     // this pass: bins b0 and b0 + gridDim.x (the second may not exist)
     const int nb = (b0 + (int)gridDim.x < pa.nbins) ? 2 : 1;
     // the combining threads fetch their bin's constants now: the latency hides behind the sums
@@ -278,13 +278,17 @@ __device__ void poisson_bins(const PoissonArgs& pa, const double* F, int nO, int
           for (int k = 0; k < kPoisBins; ++k)
 #pragma unroll
             for (int j = 0; j < NW; ++j) { s[k][j] = 0.0; c[k][j] = 0.0; }
-          const double2* hrow0 = Ht + ((size_t)b0 * nOd + od) * nI;
-          const double2* hrow1 = Ht + ((size_t)(nb > 1 ? b0 + (int)gridDim.x : b0) * nOd + od) * nI;
+          // (slices 2 pass, 2 pass + 1 of the statistics staged in shared memory at kernel start, if they fit)
+          const double2* hrow0 = (2 * pass < pa.hts_slices ? hts + (size_t)(2 * pass) * nOd * nI
+                                                           : Ht + (size_t)b0 * nOd * nI) + (size_t)od * nI;
+          const double2* hrow1 = nb > 1 ? (2 * pass + 1 < pa.hts_slices ? hts + (size_t)(2 * pass + 1) * nOd * nI
+                                                                        : Ht + (size_t)(b0 + (int)gridDim.x) * nOd * nI) + (size_t)od * nI
+                                        : hrow0;
           int i = warp;
           // two classes x two bins: four independent (warp-uniform) loads of the statistics in flight
           for (; i + pw < nI; i += 2 * pw) {
-            const double2 h00 = __ldg(hrow0 + i), h01 = __ldg(hrow0 + i + pw);
-            const double2 h10 = __ldg(hrow1 + i), h11 = __ldg(hrow1 + i + pw);
+            const double2 h00 = hrow0[i], h01 = hrow0[i + pw];
+            const double2 h10 = hrow1[i], h11 = hrow1[i + pw];
             const double* f0 = FI + (size_t)i * Wpad;
             const double* f1 = FI + (size_t)(i + pw) * Wpad;
 #pragma unroll
@@ -297,7 +301,7 @@ __device__ void poisson_bins(const PoissonArgs& pa, const double* F, int nO, int
             }
           }
           for (; i < nI; i += pw) {
-            const double2 h0 = __ldg(hrow0 + i), h1 = __ldg(hrow1 + i);
+            const double2 h0 = hrow0[i], h1 = hrow1[i];
             const double* f = FI + (size_t)i * Wpad;
 #pragma unroll
             for (int j = 0; j < NW; ++j) {
@@ -1348,14 +1352,17 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
       primed = true;
     }
   };
-  // N-stars term, one warp per bin: the statistics of the block's first bins on their way to shared memory
+  // N-stars term: the statistics of the block's first bins (b = blockIdx.x + k gridDim.x, slice k) on
+  // their way to shared memory, so that the sums over the dust classes later run without global latency
   bool hts_pending = false;
-  if (a.pois.nbins > 0 && a.pois.warp_private && !a.pois.SC && warp < a.pois.hts_slices) {
-    const int b = (int)blockIdx.x + warp * (int)gridDim.x, nD = a.nOd * a.nB;
-    if (b < a.pois.nbins) {
+  if (a.pois.nbins > 0 && !a.pois.SC && a.pois.hts_slices > 0) {
+    const int nD = a.nOd * a.nB;
+    for (int k = 0; k < a.pois.hts_slices; ++k) {
+      const int b = (int)blockIdx.x + k * (int)gridDim.x;
+      if (b >= a.pois.nbins) break;
       const double2* src = reinterpret_cast<const double2*>(a.pois.Ht) + (size_t)b * nD;
-      const uint32_t dst = smem0 + (uint32_t)a.pois.hts_off + (uint32_t)warp * (uint32_t)nD * 16u;
-      for (int i = lane; i < nD; i += 32)
+      const uint32_t dst = smem0 + (uint32_t)a.pois.hts_off + (uint32_t)k * (uint32_t)nD * 16u;
+      for (int i = threadIdx.x; i < nD; i += blockDim.x)
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + 16u * i), "l"(src + i));
     }
     cp_async_commit();
@@ -1369,7 +1376,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     }
   };
   // this block's slices of the N-stars statistics: pull them into L2 while the tables are built
-  if (a.pois.nbins > 0 && !a.pois.SC && !a.pois.warp_private) {
+  if (a.pois.nbins > 0 && !a.pois.SC && a.pois.hts_slices == 0) {
     const int per_bin = a.nOd * a.nB * 16;  // bytes
     for (int b = blockIdx.x; b < a.pois.nbins; b += gridDim.x) {
       const char* base = reinterpret_cast<const char*>(a.pois.Ht) + (size_t)b * per_bin;
@@ -1508,7 +1515,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     __syncthreads();
   } else {
     prime_now();
-    if (a.pois.nbins > 0 && a.pois.warp_private) { hts_wait(); __syncthreads(); }  // (also publishes bin_ctr)
+    if (a.pois.nbins > 0 && (a.pois.warp_private || a.pois.hts_slices > 0)) { hts_wait(); __syncthreads(); }  // (also publishes bin_ctr)
   }
   stamp(a.timeline, 1);
   // N-stars prologue: this block's (age, Z) bins for all walkers of the pass, on the tables it just
