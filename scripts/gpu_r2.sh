@@ -71,6 +71,14 @@ if has n8 && [ "$NG" -ge 8 ]; then
   timeout 1500 $TR --nproc-per-node 8 --master-port 29548 bench.py --gpus 8 --steps 100 --warmup 10 > $OUT/${TAG}_bench_cfg3_n8.json 2> $OUT/${TAG}_bench_cfg3_n8.err; echo "bench cfg3 n8 rc=$?"; tail -3 $OUT/${TAG}_bench_cfg3_n8.err
   summ $OUT/${TAG}_bench_cfg3_n8.json
 fi
+if has pixels; then
+  if [ "$NG" -ge 2 ]; then
+    timeout 900 $TR --nproc-per-node $NG --master-port 29551 scripts/bench_pixels.py --steps 30 --check 16 > $OUT/${TAG}_bench_cfg5_n$NG.json 2> $OUT/${TAG}_bench_cfg5_n$NG.err; echo "cfg5 pixels n$NG rc=$?"; tail -2 $OUT/${TAG}_bench_cfg5_n$NG.err
+  else
+    timeout 900 python scripts/bench_pixels.py --steps 30 --check 16 > $OUT/${TAG}_bench_cfg5_n1.json 2> $OUT/${TAG}_bench_cfg5_n1.err; echo "cfg5 pixels n1 rc=$?"; tail -2 $OUT/${TAG}_bench_cfg5_n1.err
+  fi
+  tail -c 1500 $OUT/${TAG}_bench_cfg5_n*.json
+fi
 if has ncu; then
   SHORT="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-clustered --no-sustained"
   timeout 600 $SHORT > $OUT/${TAG}_plain.log 2>&1 &&

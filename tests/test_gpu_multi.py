@@ -72,13 +72,14 @@ def _worker(rank, world, port_no, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_two_gpu_star_sharding_p2p_and_nccl():
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_star_sharding_p2p_and_nccl(world):
     from megabeast_b200 import synth
     from oracle import c_oracle
     from oracle import lnprob_port as port
 
-    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port_no = _free_port()
