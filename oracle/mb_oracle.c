@@ -110,7 +110,8 @@ int mbo_lnlike_batch(int64_t G, const double* const* cols, const double* prior_w
   int off[MBO_NPARAM], k = 0;
   for (int p = 0; p < MBO_NPARAM; ++p) { off[p] = k; k += nvars_of(model, p); }
   if (k != ndim) return -2;
-  const int poisson = model->kind[0] != MBO_FIXED;   /* :71-74 */
+  /* :71-74; nbins == 0: the caller wants the sum over stars alone (bench.py adds shard sums of several ranks) */
+  const int poisson = model->kind[0] != MBO_FIXED && nbins > 0;
   int fail = 0;
 #ifdef _OPENMP
   if (nthreads > 0) omp_set_num_threads(nthreads);
