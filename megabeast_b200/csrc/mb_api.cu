@@ -506,11 +506,16 @@ static int build_entries_device(mb_handle* h, const mb_grid_desc* grid, const mb
     pix_ent.push_back(offs[(size_t)(pix_off[p] - s0)]);
     pix_se.push_back(nonempty_before[(size_t)(pix_off[p] - s0)]);
   }
-  if (dev_alloc(h, &h->d_ea, h->n_entries)) return 1;
+  // (padded: the ring copies whole chunks, so it reads up to a chunk past the last entry)
+  if (dev_alloc(h, &h->d_ea, h->n_entries + kEntryPad)) return 1;
+  CK(cudaMemsetAsync(h->d_ea + h->n_entries, 0, sizeof(double) * kEntryPad, h->stream));
   if (h->c16) {
-    if (dev_alloc(h, &h->d_ec16, h->n_entries + 2)) return 1;  // padded: codes are fetched in pairs
-    CK(cudaMemsetAsync(h->d_ec16, 0, sizeof(uint16_t) * (size_t)(h->n_entries + 2), h->stream));
-  } else if (dev_alloc(h, &h->d_ec, h->n_entries)) return 1;
+    if (dev_alloc(h, &h->d_ec16, h->n_entries + kEntryPad)) return 1;
+    CK(cudaMemsetAsync(h->d_ec16 + h->n_entries, 0, sizeof(uint16_t) * kEntryPad, h->stream));
+  } else {
+    if (dev_alloc(h, &h->d_ec, h->n_entries + kEntryPad)) return 1;
+    CK(cudaMemsetAsync(h->d_ec + h->n_entries, 0, sizeof(uint32_t) * kEntryPad, h->stream));
+  }
   if (h->n_entries > 0) {
     int64_t* d_offs;
     if (tmp.get((void**)&d_offs, sizeof(int64_t) * offs.size())) return 1;
@@ -968,11 +973,13 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
     }
 
     // upload
-    std::vector<double> wts(entries.size());
+    // (padded: the ring copies whole chunks, so it reads up to a chunk past the last entry)
+    std::vector<double> wts(entries.size() + kEntryPad, 0.0);
     for (size_t i = 0; i < entries.size(); ++i) wts[i] = entries[i].a;
     if (dev_upload(h, &h->d_ea, wts)) return 1;
+    codes.resize(codes.size() + kEntryPad, 0u);
     if (h->c16) {
-      std::vector<uint16_t> c16(codes.size() + 2, (uint16_t)0);  // padded: codes are fetched in pairs
+      std::vector<uint16_t> c16(codes.size(), (uint16_t)0);
       for (size_t i = 0; i < codes.size(); ++i) {
         const uint32_t c = codes[i];
         c16[i] = (uint16_t)(((c & kNewRun) ? 0x8000u : 0u) | ((c & kNewStar) ? 0x4000u : 0u) |
@@ -1506,6 +1513,8 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     k2.nA = h->nO; k2.nB = h->nI; k2.nOd = h->nOd; k2.Wpad = Wpad; k2.W = wp; k2.w0 = w0; k2.Wtot = W;
     k2.tab_off = (int32_t)plan.front;
     k2.scratch_off = (int32_t)plan.scratch_off; k2.separate = plan.separate ? 1 : 0;
+    static const bool no_tma = getenv("MB_NO_TMA") && atoi(getenv("MB_NO_TMA"));  // A/B switch: per-lane cp.async ring
+    k2.use_tma = no_tma ? 0 : 1;
     k2.slab_off = (int32_t)plan.slab_off;
     k2.pois.Ht = h->d_H; k2.pois.bin_agecls = h->d_bin_agecls; k2.pois.coef = h->d_coef; k2.pois.Pb = h->d_Pb;
     k2.pois.n_stars = (double)h->S_total; k2.pois.nbins = h->poisson ? h->nbins : 0;

@@ -964,6 +964,7 @@ struct K2Args {
   int32_t scratch_off;       // byte offset of the table-build scratch: 0 (it shares the entry stage) or right
                              // after the stage (`separate` layout: the stage can be primed before the build)
   int32_t separate;          // 1: stage and scratch are disjoint
+  int32_t use_tma;           // 1: the entry ring is filled by bulk copies (TMA) completing on mbarriers
   int32_t slab_off;          // byte offset of the block-reduction slabs (0, or tab_off: over the dead tables)
   PoissonArgs pois;          // N-stars term: every block computes some (age, Z) bins before the star loop
   PeerArgs peer;             // cross-GPU reduction of the shard totals
@@ -1203,52 +1204,93 @@ struct Lanes {
   }
 };
 
-// One chunk of kChunk entries into ring slot `slot` of this warp's stage (one commit group).
-template <bool C16>
-__device__ __forceinline__ void issue_chunk(const double* __restrict__ ga, const void* __restrict__ gcodes,
-                                            int64_t p, const int64_t end, int slot, uint32_t sa_lane,
-                                            uint32_t sc_lane, int lane) {
-  if (p + lane < end) {
-    cp_async8(sa_lane + slot * (kChunk * 8u), ga + p + lane);
-    if (!C16) cp_async4(sc_lane + slot * (kChunk * 4u), static_cast<const uint32_t*>(gcodes) + p + lane);
-  }
-  if (C16 && lane < kChunk / 2 && p + 2 * lane < end)  // two codes per lane (the array is padded by one)
-    cp_async4(sc_lane + slot * (kChunk * 2u), static_cast<const uint16_t*>(gcodes) + p + 2 * lane);
-  cp_async_commit();
+// ---- the entry ring: chunks of kChunk entries, STAGES slots per warp ---------------------------------
+// Two ways to fill a slot.  TMA = true (default): ONE lane issues two bulk copies (cp.async.bulk, the
+// TMA engine: 256 B of weights, 64 or 128 B of codes) that complete on the slot's mbarrier -- no LSU
+// instructions per lane, the staging writes do not go through the load/store pipe that the factor
+// reads saturate.  Bulk copies need 16-byte aligned addresses and sizes, so chunks start on a multiple
+// of 8 (16-bit codes) or 4 (32-bit codes) entries and are always copied whole: a range that starts
+// in between skips up to 7 leading entries of its first chunk, and the entry arrays are padded at
+// the end (kEntryPad).  TMA = false: per-lane cp.async (LDGSTS) with commit groups, as on Ampere.
+constexpr int kEntryPad = 64;   // entries allocated past the end of the entry arrays
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 28)) __trap();  // a copy that never lands must not hang the GPU
+  } while (!ok);
+}
+
+// One chunk of kChunk entries into ring slot `slot` of this warp's stage.
+template <bool C16, bool TMA>
+__device__ __forceinline__ void issue_chunk(const double* __restrict__ ga, const void* __restrict__ gcodes,
+                                            int64_t p, const int64_t end, int slot, uint32_t st_a,
+                                            uint32_t st_c, uint32_t bar0, int lane) {
+  constexpr uint32_t kCodeBytes = C16 ? 2u : 4u;
+  if (TMA) {
+    if (lane == 0 && p < end) {
+      const uint32_t bar = bar0 + 8u * slot;
+      mbar_expect_tx(bar, kChunk * (8u + kCodeBytes));
+      bulk_g2s(st_a + slot * (kChunk * 8u), ga + p, kChunk * 8u, bar);
+      bulk_g2s(st_c + slot * (kChunk * kCodeBytes), static_cast<const char*>(gcodes) + p * kCodeBytes, kChunk * kCodeBytes, bar);
+    }
+  } else {
+    const uint32_t sa_lane = st_a + lane * 8u, sc_lane = st_c + lane * 4u;
+    if (p + lane < end) {
+      cp_async8(sa_lane + slot * (kChunk * 8u), ga + p + lane);
+      if (!C16) cp_async4(sc_lane + slot * (kChunk * 4u), static_cast<const uint32_t*>(gcodes) + p + lane);
+    }
+    if (C16 && lane < kChunk / 2 && p + 2 * lane < end)  // two codes per lane (the array is padded)
+      cp_async4(sc_lane + slot * (kChunk * 2u), static_cast<const uint16_t*>(gcodes) + p + 2 * lane);
+    cp_async_commit();
+  }
+}
+template <bool C16, bool TMA>
+__host__ __device__ constexpr int chunk_align() { return TMA ? (C16 ? 8 : 4) : (C16 ? 2 : 1); }
+
 // The first STAGES - 1 chunks of a range, issued ahead of time (K2 does this for every warp's first
 // segment before it builds the factor tables: the cold-HBM latency of the entry stream then hides
 // behind the table build).  stream_range(..., primed = true) must follow with the same arguments.
-template <int STAGES, int OB>
+template <int STAGES, int OB, bool TMA>
 __device__ __forceinline__ void stream_prime(const double* __restrict__ ga, const void* __restrict__ gcodes,
                                              int64_t pos, const int64_t end, const uint32_t st_a,
-                                             const uint32_t st_c, const int lane) {
+                                             const uint32_t st_c, const uint32_t bar0, const int lane) {
   constexpr bool C16 = OB > 0;
-  pos -= C16 ? (pos & 1) : 0;
+  pos -= pos & (chunk_align<C16, TMA>() - 1);
 #pragma unroll
   for (int k = 0; k < STAGES - 1; ++k)
-    issue_chunk<C16>(ga, gcodes, pos + (int64_t)k * kChunk, end, k, st_a + lane * 8u, st_c + lane * 4u, lane);
+    issue_chunk<C16, TMA>(ga, gcodes, pos + (int64_t)k * kChunk, end, k, st_a, st_c, bar0, lane);
 }
 
-// Stream entries [pos, end) through this warp's double-buffered stage (weights at st_a, codes at
-// st_c) and fold them into L.  Per group of four entries the warp issues three broadcast loads
-// (four codes; two weight pairs) = 1.5 shared-memory wavefronts per entry, then per entry one
-// IMAD (table row address), NW/2 x LDS.128 (factors), NW x DFMA and one sign test.
-template <int NW, int MODE, typename TF, int STAGES = kStages, int OB = 0>
+// Stream entries [pos, end) through this warp's ring (weights at st_a, codes at st_c) and fold them
+// into L.  Per group of four entries the warp issues three broadcast loads (four codes; two weight
+// pairs) = 1.25-1.5 shared-memory wavefronts per entry, then per entry one IMAD (table row address),
+// NW/2 x LDS.128 (factors), NW x DFMA and one sign test.  `par`: the ring's mbarrier phase bits (TMA).
+template <int NW, int MODE, typename TF, int STAGES = kStages, int OB = 0, bool TMA = false>
 __device__ __forceinline__ void stream_range(Lanes<NW, MODE, TF, OB>& L, const double* __restrict__ ga,
                                              const void* __restrict__ gcodes, int64_t pos, const int64_t end,
                                              const uint32_t st_a, const uint32_t st_c, const int lane,
-                                             const bool primed = false) {
+                                             const bool primed = false, const uint32_t bar0 = 0, uint32_t* par = nullptr) {
   constexpr bool C16 = OB > 0;
   constexpr uint32_t kCodeBytes = C16 ? 2u : 4u;
-  // 16-bit codes: chunks start on an even entry.  A range that starts on an odd one stages the
-  // entry before it too and skips it: the first chunk handles entries 1..3 one by one, then groups
-  int lead = C16 ? (int)(pos & 1) : 0;
+  // chunks start on an aligned entry; a range that starts in between stages the entries before it too
+  // and skips them: its first chunk handles entries one by one up to the next multiple of four
+  int lead = (int)(pos & (chunk_align<C16, TMA>() - 1));
   pos -= lead;
   const uint32_t sa = keep_in_register(st_a), sc = keep_in_register(st_c);
-  const uint32_t sa_lane = keep_in_register(st_a + lane * 8u), sc_lane = keep_in_register(st_c + lane * 4u);
   // ring of STAGES chunk buffers: STAGES - 1 chunks are in flight while one is processed
-  auto issue = [&](int64_t p, int slot) { issue_chunk<C16>(ga, gcodes, p, end, slot, sa_lane, sc_lane, lane); };
+  auto issue = [&](int64_t p, int slot) { issue_chunk<C16, TMA>(ga, gcodes, p, end, slot, sa, sc, bar0, lane); };
   if (!primed) {
 #pragma unroll
     for (int k = 0; k < STAGES - 1; ++k) issue(pos + (int64_t)k * kChunk, k);
@@ -1258,33 +1300,37 @@ __device__ __forceinline__ void stream_range(Lanes<NW, MODE, TF, OB>& L, const d
     int ahead = slot + STAGES - 1;
     if (ahead >= STAGES) ahead -= STAGES;
     issue(pos + (int64_t)(STAGES - 1) * kChunk, ahead);
-    cp_async_wait<STAGES - 1>();
-    __syncwarp();
-    uint32_t pa = sa + slot * (kChunk * 8u), pc = sc + slot * (kChunk * kCodeBytes);
-    int n = (int)min((int64_t)kChunk, end - pos);
-    if (C16 && lead) {
-      for (int i = 1; i < 4 && i < n; ++i) {
-        const uint32_t c = lds_stage_u16(pc + 2u * i);
-        const double a = lds_stage_d(pa + 8u * i);
-        double f[NW];
-        L.load_factors(c, f);
-        L.step(a, c, f);
-      }
-      n = n > 4 ? n - 4 : 0; pa += 32u; pc += 8u;
-      lead = 0;
+    if (TMA) {
+      mbar_wait(bar0 + 8u * slot, (*par >> slot) & 1u);
+      *par ^= 1u << slot;
+    } else {
+      cp_async_wait<STAGES - 1>();
+      __syncwarp();
     }
-    for (; n >= 4; n -= 4, pa += 32u, pc += 4u * kCodeBytes) {
+    const uint32_t pa = sa + slot * (kChunk * 8u), pc = sc + slot * (kChunk * kCodeBytes);
+    const int n = (int)min((int64_t)kChunk, end - pos);
+    int i = lead;
+    lead = 0;
+    auto single = [&](int j) {
+      const uint32_t c = C16 ? lds_stage_u16(pc + 2u * j) : lds_stage_u(pc + 4u * j);
+      const double a = lds_stage_d(pa + 8u * j);
+      double f[NW];
+      L.load_factors(c, f);
+      L.step(a, c, f);
+    };
+    for (; i < n && (i & 3); ++i) single(i);
+    for (; i + 4 <= n; i += 4) {
       uint4 c;
       bool any_boundary;
       if (C16) {  // four codes in one 8-byte broadcast
-        const uint2 cc = lds_stage_u2(pc);
+        const uint2 cc = lds_stage_u2(pc + 2u * i);
         c = make_uint4(cc.x, cc.x >> 16, cc.y, cc.y >> 16);
         any_boundary = ((cc.x | cc.y) & 0x80008000u) != 0;
       } else {
-        c = lds_stage_u4(pc);
+        c = lds_stage_u4(pc + 4u * i);
         any_boundary = (int32_t)(c.x | c.y | c.z | c.w) < 0;
       }
-      const double2 a01 = lds_stage_d2(pa), a23 = lds_stage_d2(pa + 16u);
+      const double2 a01 = lds_stage_d2(pa + 8u * i), a23 = lds_stage_d2(pa + 8u * i + 16u);
       double f0[NW], f1[NW], f2[NW], f3[NW];
       L.load_factors(c.x, f0); L.load_factors(c.y, f1); L.load_factors(c.z, f2); L.load_factors(c.w, f3);
       // (the vote makes the uniformity of the branch visible to the compiler: no BSSY/BSYNC pair)
@@ -1294,18 +1340,12 @@ __device__ __forceinline__ void stream_range(Lanes<NW, MODE, TF, OB>& L, const d
         L.mac(a01.x, f0); L.mac2(a01.y, f1); L.mac(a23.x, f2); L.mac2(a23.y, f3);
       }
     }
-    for (; n > 0; --n, pa += 8u, pc += kCodeBytes) {
-      const uint32_t c = C16 ? lds_stage_u16(pc) : lds_stage_u(pc);
-      const double a = lds_stage_d(pa);
-      double f[NW];
-      L.load_factors(c, f);
-      L.step(a, c, f);
-    }
-    __syncwarp();
+    for (; i < n; ++i) single(i);
+    __syncwarp();   // every lane is done with the slot before it is refilled
     if (++slot == STAGES) slot = 0;
     pos += kChunk;
   }
-  cp_async_wait<0>();
+  if (!TMA) cp_async_wait<0>();
 }
 
 // Prologue: factor tables (built in place or copied), then this block's (age, Z) bins of the N-stars
@@ -1346,9 +1386,24 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   int64_t seg_lo = 0, seg_hi = 0;
   const bool want_prime = a.separate && s < a.nseg;
   if (want_prime) { seg_lo = __ldg(a.seg + s); seg_hi = __ldg(a.seg + s + 1); }
+  // the ring's mbarriers (bulk-copy mode): one per slot, armed and waited on by this warp alone
+  __shared__ __align__(8) unsigned long long ring_bar[kK2Warps * kStages];
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&ring_bar[warp * kStages]);
+  uint32_t ring_par = 0;
+  const bool tma = a.use_tma != 0;
+  if (tma) {
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < STAGES; ++k) mbar_init(bar0 + 8u * k, 1u);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    __syncwarp();
+  }
   auto prime_now = [&]() {
     if (want_prime && !primed) {
-      stream_prime<STAGES, OB>(a.ea, a.ec, seg_lo, seg_hi, st_a, st_c, lane);
+      if (tma) stream_prime<STAGES, OB, true>(a.ea, a.ec, seg_lo, seg_hi, st_a, st_c, bar0, lane);
+      else stream_prime<STAGES, OB, false>(a.ea, a.ec, seg_lo, seg_hi, st_a, st_c, bar0, lane);
       primed = true;
     }
   };
@@ -1371,7 +1426,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   // (this copy group is the warp's oldest: waiting for it leaves the primed chunks in flight)
   auto hts_wait = [&]() {
     if (hts_pending) {
-      if (primed) cp_async_wait<STAGES - 1>(); else cp_async_wait<0>();
+      if (primed && !tma) cp_async_wait<STAGES - 1>(); else cp_async_wait<0>();
       hts_pending = false;
     }
   };
@@ -1540,7 +1595,8 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   int s_next = 0;
   while (s < a.nseg) {
     if (lane == 0) s_next = nwarps_total + (int)atomicAdd(a.counters + kCtrSegment, 1u);
-    stream_range<NW, MODE, TF, STAGES, OB>(L, a.ea, a.ec, a.seg[s], a.seg[s + 1], st_a, st_c, lane, primed);
+    if (tma) stream_range<NW, MODE, TF, STAGES, OB, true>(L, a.ea, a.ec, a.seg[s], a.seg[s + 1], st_a, st_c, lane, primed, bar0, &ring_par);
+    else stream_range<NW, MODE, TF, STAGES, OB, false>(L, a.ea, a.ec, a.seg[s], a.seg[s + 1], st_a, st_c, lane, primed);
     primed = false;
     L.close();
 #pragma unroll

@@ -15,11 +15,12 @@ print("%-14s %-12s %8.2f us/step  k2=%.2f  e2e=%.2f us  tables=%.2f bins=%.2f lo
     p.get("tables_built", 0), p.get("nstars_bins_done", 0), p.get("star_loop_done", 0), p.get("block_reduced", 0), p.get("end", 0)))
 PY
 }
+VARIANTS=${2:-"default:MB_X=0 notma:MB_NO_TMA=1"}
+timeout 900 python -m pytest tests -q -m gpu -x > $OUT/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $OUT/${TAG}_pytest.log
 for rep in 1 2; do
 for wl in cfg3_eighth cfg3; do
-  run default $wl MB_X=0
-  run binsfirst $wl MB_BINS_FIRST=1
-  run nowarpbins $wl MB_NO_WARP_BINS=1
-  run noprime $wl MB_NO_PRIME=1
+  for v in $VARIANTS; do
+    run ${v%%:*} $wl ${v#*:}
+  done
 done
 done
