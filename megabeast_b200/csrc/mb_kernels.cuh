@@ -1390,7 +1390,11 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   __shared__ __align__(8) unsigned long long ring_bar[kK2Warps * kStages];
   const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&ring_bar[warp * kStages]);
   uint32_t ring_par = 0;
-  const bool tma = a.use_tma != 0;
+  // MB_RING: 0 = only the cp.async ring is compiled, 1 = only the bulk-copy ring, 2 = both (run-time switch)
+#ifndef MB_RING
+#define MB_RING 2
+#endif
+  const bool tma = MB_RING == 1 || (MB_RING == 2 && a.use_tma != 0);
   if (tma) {
     if (lane == 0) {
 #pragma unroll
