@@ -1521,8 +1521,8 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     k2.pois.lgamma_n1 = std::lgamma((double)h->S_total + 1.0);
     k2.pois.nwarps = plan.pois_warps; k2.pois.scratch_off = (int32_t)plan.pois_off;
     k2.pois.warp_private = plan.warp_private ? 1 : 0; k2.pois.hts_off = (int32_t)plan.hts_off; k2.pois.hts_slices = plan.hts_slices;
-    static const bool bins_first = getenv("MB_BINS_FIRST") && atoi(getenv("MB_BINS_FIRST"));  // A/B switch (measurements)
-    k2.pois.bins_first = bins_first ? 1 : 0;
+    static const bool bins_last = getenv("MB_BINS_LAST") && atoi(getenv("MB_BINS_LAST"));  // A/B switch (measurements)
+    k2.pois.bins_first = bins_last ? 0 : 1;
     k2.pois.SC = elementwise ? h->d_SC : nullptr;
     // plain age factors (the `ageprior` of helpers.py:135): K1e's per-bin rows, K0's rows in global
     // memory, or -- tables built inside K2 -- the outer table itself / the scratch look-up rows

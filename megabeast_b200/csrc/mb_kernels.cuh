@@ -217,7 +217,8 @@ struct PoissonArgs {
   int32_t warp_private;       // 1: this scheme
   int32_t hts_off;            // byte offset of the staged statistics [hts_slices][nOd * nI][2]
   int32_t hts_slices;         // warps that have a slice
-  int32_t bins_first;         // 1: the bins are taken before the star loop (A/B switch MB_BINS_FIRST; default: after)
+  int32_t bins_first;         // 1 (default): the bins are claimed right after the table build by the first warps
+                              // to get there; 0 (MB_BINS_LAST=1): after the star loop by the first warps to finish
 };
 constexpr int kPoisBins = 2;  // bins a block works on at a time (loads of both in flight together)
 
@@ -1390,9 +1391,13 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   __shared__ __align__(8) unsigned long long ring_bar[kK2Warps * kStages];
   const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&ring_bar[warp * kStages]);
   uint32_t ring_par = 0;
-  // MB_RING: 0 = only the cp.async ring is compiled, 1 = only the bulk-copy ring, 2 = both (run-time switch)
+  // MB_RING: 0 = only the cp.async ring is compiled (default), 1 = only the bulk-copy (TMA) ring, 2 = both
+  // (run-time switch MB_NO_TMA).  Measured on B200, same box, config 3 / its 1/8 shard (us per step):
+  // 127.45 / 37.88 with 0, 128.3 / 38.0 with 1, 128.0-129.2 / 37.95-38.5 with 2 (profiles/r2_ab_ring.txt):
+  // the bulk copies take ~1.5 % of the shared-memory wavefronts off the load/store pipe, but the
+  // mbarrier try_wait per chunk costs more than cp.async.wait_group does once the data has landed.
 #ifndef MB_RING
-#define MB_RING 2
+#define MB_RING 0
 #endif
   const bool tma = MB_RING == 1 || (MB_RING == 2 && a.use_tma != 0);
   if (tma) {

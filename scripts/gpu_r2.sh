@@ -55,6 +55,8 @@ if has finedust; then
   summ $OUT/${TAG}_bench_fine_dust_clustered_n1.json
   timeout 900 python bench.py --workload fine_dust --mode table_unique --steps 50 --warmup 5 --no-cpu-baseline --no-clustered > $OUT/${TAG}_bench_fine_dust_tu_n1.json 2> $OUT/${TAG}_bench_fine_dust_tu_n1.err; echo "bench fine_dust table_unique rc=$?"
   summ $OUT/${TAG}_bench_fine_dust_tu_n1.json
+  timeout 900 python bench.py --workload fine_dust --index-mode clustered --mode table_unique --steps 50 --warmup 5 --no-cpu-baseline > $OUT/${TAG}_bench_fine_dust_tu_clustered_n1.json 2> $OUT/${TAG}_bench_fine_dust_tu_clustered_n1.err; echo "bench fine_dust table_unique clustered rc=$?"
+  summ $OUT/${TAG}_bench_fine_dust_tu_clustered_n1.json
 fi
 if has cfg4n1; then
   timeout 1200 python bench.py --workload cfg4 --steps 30 --warmup 5 --cpu-sample 8 --no-clustered > $OUT/${TAG}_bench_cfg4_n1.json 2> $OUT/${TAG}_bench_cfg4_n1.err; echo "bench cfg4 n1 rc=$?"; tail -3 $OUT/${TAG}_bench_cfg4_n1.err
@@ -91,5 +93,11 @@ if has ncu; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:mb_k2_stars -s 4 -c 2 \
       -f -o $OUT/${TAG}_k2_eighth $SHORT --workload cfg3_eighth > $OUT/${TAG}_ncu_k2_eighth.log 2>&1
   echo "ncu k2 eighth rc=$?"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:mb_k2_stars -s 4 -c 2 \
+      -f -o $OUT/${TAG}_k2_fine_dust $SHORT --workload fine_dust > $OUT/${TAG}_ncu_k2_fine_dust.log 2>&1
+  echo "ncu k2 fine_dust rc=$?"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"mb_k1_elementwise|mb_k2_stars" -s 8 -c 4 \
+      -f -o $OUT/${TAG}_elementwise $SHORT --mode elementwise > $OUT/${TAG}_ncu_elementwise.log 2>&1
+  echo "ncu elementwise rc=$?"
 fi
 ls -la $OUT | tail -25
