@@ -325,14 +325,14 @@ def run_ours(args):
     def time_device(sh, rows, nsteps, nwarm):
         for _ in range(nwarm):
             flush_l2()
-            align_ranks()
+            sh.rendezvous()
             sh.lnlike_device(d_phi, rows)
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
         barrier()
         t_w = time.perf_counter()
         for i in range(nsteps):
             flush_l2()
-            align_ranks()
+            sh.rendezvous()
             evs[i][0].record()
             sh.lnlike_device(d_phi, rows)
             evs[i][1].record()
@@ -426,6 +426,7 @@ def run_ours(args):
     for _ in range(nprof):
         flush_l2()
         barrier()
+        sharded.rendezvous()
         sharded.lnlike_device(d_phi, d_rows)
         torch.cuda.synchronize()
         for k, v in eng.last_kernel_ms().items():
@@ -572,7 +573,8 @@ def run_ours(args):
                            "p2p": "fused into K2's tail over NVLink peer memory (no collective launch)"}[sharded.reduce],
             "l2": "kept warm" if args.no_flush else f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB memset, outside the timed events)",
             "rank_alignment": "none (1 GPU)" if world == 1 else
-                              "device-side rendezvous (4-byte NCCL all-reduce) enqueued after the flush, before the start event",
+                              "device-side rendezvous (mb_peer_rendezvous: flags over NVLink peer memory; a 4-byte NCCL all-reduce "
+                              "when the shards are reduced by NCCL) enqueued after the flush, before the start event",
             "entries": n_ent, "entries_raw": raw, "runs": info["n_runs"], "age_classes": nA, "dust_classes": nB,
             "outer_rows": nO, "inner_rows": nI, "split_inner_mask": info["split_inner_mask"],
             "code_bytes": info["code_bytes"], "bins": info["n_bins"], "ingest_s": round(t_ingest, 3),
@@ -728,13 +730,13 @@ def run_secondary_cfg4(args, world, rank, local, dev, barrier, max_over_ranks, a
     nsteps, nwarm = max(10, min(args.steps, 50)), 5
     for _ in range(nwarm):
         flush_l2()
-        align_ranks()
+        sh.rendezvous()
         sh.lnlike_device(d_phi, d_rows)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
     barrier()
     for i in range(nsteps):
         flush_l2()
-        align_ranks()
+        sh.rendezvous()
         evs[i][0].record()
         sh.lnlike_device(d_phi, d_rows)
         evs[i][1].record()

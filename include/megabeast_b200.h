@@ -237,6 +237,11 @@ int mb_lnlike_device(mb_handle* h, const double* d_phi, int32_t W, int32_t ndim,
 int mb_peer_export(mb_handle* h, void* token);
 int mb_peer_connect(mb_handle* h, int32_t rank, int32_t world, const void* tokens);
 int mb_peer_disconnect(mb_handle* h);
+/* Device-side rendezvous of the connected ranks on `stream` (a one-warp kernel: every rank raises a flag
+ * in all peers over NVLink and waits for theirs): all ranks' next kernels start within one NVLink
+ * latency of each other.  A measurement aid (bench.py aligns the ranks ahead of every timed launch);
+ * the likelihood never needs it.  No-op without peers.  All ranks must call it the same number of times. */
+int mb_peer_rendezvous(mb_handle* h, void* stream);
 
 /* Pixel batches (origin old/megabeast_fit.py:97-182, a serial loop of one
  * fit per sky pixel): n_pixels independent ensembles over ONE shared grid.  Pixel p owns the stars

@@ -199,6 +199,7 @@ SIGNATURES = {
     "mb_peer_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "mb_peer_connect": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]),
     "mb_peer_disconnect": (ctypes.c_int, [ctypes.c_void_p]),
+    "mb_peer_rendezvous": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "mb_class_values": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, c_double_p, ctypes.c_int32]),
     "mb_gathered_indices": (ctypes.c_int, [ctypes.c_void_p, c_int64_p, ctypes.c_int64, c_int64_p]),
     "mb_device_entries": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, c_int32_p, c_double_p, c_int64_p]),

@@ -102,7 +102,7 @@ struct mb_handle {
   unsigned long long* d_xbuf = nullptr;        // this GPU's exchange buffer (cudaMalloc: IPC-exportable)
   unsigned long long* peer_xbuf[MB_MAX_PEERS] = {};
   int peer_world = 1, peer_rank = 0;
-  unsigned int peer_seq = 0;
+  unsigned int peer_seq = 0, rdv_seq = 0;
   double* d_T = nullptr;  int64_t cap_T = 0;
   int max_blocks = 0;
   double* d_out = nullptr;  int64_t cap_out = 0;
@@ -374,6 +374,19 @@ extern "C" int mb_peer_connect(mb_handle* h, int32_t rank, int32_t world, const 
   h->peer_world = world;
   h->peer_rank = rank;
   h->peer_seq = 0;
+  h->rdv_seq = 0;
+  return 0;
+}
+
+extern "C" int mb_peer_rendezvous(mb_handle* h, void* stream) {
+  if (!h) return fail("null handle");
+  if (h->peer_world <= 1) return 0;
+  CK(cudaSetDevice(h->device));
+  PeerArgs pa{};
+  pa.world = h->peer_world; pa.rank = h->peer_rank; pa.seq = ++h->rdv_seq; pa.timeout_ns = h->peer_timeout_ns;
+  for (int p = 0; p < h->peer_world; ++p) pa.xbuf[p] = h->peer_xbuf[p];
+  mb_rendezvous<<<1, 32, 0, (cudaStream_t)stream>>>(pa);
+  CK(cudaGetLastError());
   return 0;
 }
 

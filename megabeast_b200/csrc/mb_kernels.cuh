@@ -937,7 +937,11 @@ constexpr int kXWords = kAccRows * 128;
 __host__ __device__ constexpr size_t xbuf_word_off(int par, int src) {   // in u64 words
   return ((size_t)par * MB_MAX_PEERS + src) * 2 * kXWords;
 }
-constexpr size_t kXBufBytes = 8 * (size_t)2 * MB_MAX_PEERS * 2 * kXWords + 64;
+// rendezvous flags (mb_peer_rendezvous): [2 parities][MB_MAX_PEERS sources] u32 after the words
+__host__ __device__ constexpr size_t xbuf_rdv_off(int par, int src) {   // in u32 words
+  return 2 * (size_t)2 * MB_MAX_PEERS * 2 * kXWords + (size_t)par * MB_MAX_PEERS + src;
+}
+constexpr size_t kXBufBytes = 8 * (size_t)2 * MB_MAX_PEERS * 2 * kXWords + 4 * (size_t)2 * MB_MAX_PEERS + 64;
 struct PeerArgs {
   int32_t world, rank;   // world <= 1: single shard, no exchange
   uint32_t seq;          // sequence number of this launch, identical on all ranks
@@ -948,6 +952,26 @@ struct PeerArgs {
 #ifndef MB_PHI_INLINE
 #define MB_PHI_INLINE 1152
 #endif
+// Device-side rendezvous of the ranks of a peer group: every rank raises its flag in all peers and
+// waits for theirs, so all ranks leave within one NVLink latency of the last arrival.  Used to align
+// the ranks ahead of a timed launch (bench.py) -- the likelihood itself never needs it.
+__global__ void mb_rendezvous(PeerArgs peer) {
+  const int t = threadIdx.x, par = (int)(peer.seq & 1u);
+  if (t >= peer.world || t == peer.rank) return;
+  *(reinterpret_cast<volatile unsigned int*>(peer.xbuf[t]) + xbuf_rdv_off(par, peer.rank)) = peer.seq;
+  volatile unsigned int* mine = reinterpret_cast<volatile unsigned int*>(peer.xbuf[peer.rank]) + xbuf_rdv_off(par, t);
+  unsigned long long t0 = 0ull;
+  unsigned int spins = 0;
+  while (*mine != peer.seq) {
+    if ((++spins & 0x3ffu) == 0u) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+      if (t0 == 0ull) t0 = t1;
+      if (t1 - t0 > peer.timeout_ns) break;  // give up quietly: this is only an alignment aid
+    }
+  }
+}
+
 constexpr int kPhiInline = MB_PHI_INLINE;  // doubles of phi carried in K2's kernel parameters (e.g. 128 walkers x 9)
 struct K2Args {
   const double* ea;     // entry weights  [n_entries]

@@ -250,6 +250,10 @@ class LikelihoodEngine:
             raise ValueError("need one token per rank")
         _cabi.check(self.lib.mb_peer_connect(self.handles[i], rank, world, blob))
 
+    def peer_rendezvous(self, stream=0, i=0):
+        """Device-side rendezvous of the connected ranks on ``stream`` (measurement aid)."""
+        _cabi.check(self.lib.mb_peer_rendezvous(self.handles[i], ctypes.c_void_p(stream)))
+
     def peer_disconnect(self, i=0):
         _cabi.check(self.lib.mb_peer_disconnect(self.handles[i]))
 

@@ -165,6 +165,21 @@ class ShardedLikelihood:
             allreduce_rows(d_rows, self.group)
         return d_rows  # "p2p": the kernel already summed the shards over NVLink
 
+    def rendezvous(self):
+        """Align the ranks on the current stream ahead of a timed launch: over the NVLink exchange
+        buffers when the shards are reduced there, else with a tiny NCCL all-reduce."""
+        if self.world == 1:
+            return
+        t = self.torch
+        if self.reduce == "p2p":
+            self.engine.peer_rendezvous(t.cuda.current_stream(self.device).cuda_stream)
+        else:
+            import torch.distributed as dist
+
+            if not hasattr(self, "_tick"):
+                self._tick = t.zeros(1, dtype=t.float32, device=t.device("cuda", self.device))
+            dist.all_reduce(self._tick, group=self.group)
+
     def lnlike_rows(self, phis, tabs=None):
         """Host phi (W, ndim in device order) -> reduced host rows [4][W].  ``tabs``: host-evaluated
         tables of tabulated prior models (every rank evaluates the same callable on the same class
