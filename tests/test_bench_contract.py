@@ -1,7 +1,7 @@
 """
 bench.py's driver contract, checked without a GPU on the reference arm: exactly ONE line on
 stdout, valid JSON, the keys the driver reads.  (The GPU arm prints the same keys plus the
-device-side ones; profiles/r1_bench_cfg3_n1.json is such a line.)
+device-side ones; profiles/r2_bench_cfg3_n1.json and profiles/r2_bench_cfg3_n8.json are such lines.)
 """
 import json
 import os
@@ -29,7 +29,7 @@ def test_reference_arm_prints_one_json_line():
 
 
 def test_committed_gpu_bench_line_has_the_contract_keys():
-    with open(os.path.join(ROOT, "profiles", "r1_bench_cfg3_n1.json")) as f:
+    with open(os.path.join(ROOT, "profiles", "r2_bench_cfg3_n1.json")) as f:
         line = json.loads(f.read().strip().splitlines()[-1])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
                 "scaling", "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches",
@@ -39,4 +39,31 @@ def test_committed_gpu_bench_line_has_the_contract_keys():
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(line["cpu_baseline"])
     assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(line["e2e"])
     assert line["gpu_launches"] == line["steps"]          # one launch per step
-    assert "workload" in line["config"]
+    assert set(line["config"]) == {"workload", "index_mode"}   # byte-identical in both arms
+    assert line["parity"]["walkers_checked"] >= 8 and line["parity"]["max_rel_err_e2e_path"] < 1e-9
+    assert line["sustained"]["seconds"] >= 2.0
+
+
+def test_both_arms_print_the_same_config():
+    """The driver compares the `config` objects of the two arms: they come from one function."""
+    import argparse
+    import bench
+
+    a = argparse.Namespace(workload="cfg3", index_mode="uniform")
+    cfg = {"S": 100000, "K": 50}
+    assert bench.workload_config(a, cfg, 1000400, 64) == bench.workload_config(a, cfg, 1000400, 64)
+    with open(os.path.join(ROOT, "profiles", "r2_bench_cfg3_n1.json")) as f:
+        ours = json.loads(f.read().strip().splitlines()[-1])["config"]
+    assert ours == bench.workload_config(a, cfg, 1000400, 64)
+
+
+def test_committed_eight_gpu_line_carries_parity_and_config4():
+    with open(os.path.join(ROOT, "profiles", "r2_bench_cfg3_n8.json")) as f:
+        line = json.loads(f.read().strip().splitlines()[-1])
+    assert line["n_gpus"] == 8 and line["scaling"] == "strong"
+    p = line["parity"]
+    assert p["walkers_checked"] >= 8 and p["max_rel_err_device_path"] < 1e-9 and p["p2p_equals_nccl_bitwise"] is True
+    s = line["secondary"]
+    assert s["workload"].startswith("cfg4") and s["parity"]["max_rel_err_device_path"] < 1e-9
+    assert s["parity"]["walkers_checked"] >= 4
+    assert line["kernel_ms"]["k2_stars"] <= line["ms_per_step"] * 1.15   # per-kernel time consistent with the step
