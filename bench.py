@@ -340,7 +340,7 @@ def run_ours(args):
         t_w = time.perf_counter() - t_w
         return max_over_ranks(sum(a.elapsed_time(b) for a, b in evs)), t_w
 
-    def time_e2e(call, nsteps, nwarm):
+    def time_e2e(call, nsteps, nwarm, sh=None):
         for _ in range(nwarm):
             flush_l2()
             out = call()
@@ -348,7 +348,11 @@ def run_ours(args):
         tot = 0.0
         for i in range(nsteps):
             flush_l2()
-            barrier()  # N > 1: a sampler's ranks leave step n together; the flush must not de-align them
+            # N > 1: a sampler's ranks leave step n together (the in-kernel exchange releases them within a
+            # microsecond); the flush must not de-align them, so they meet on the device before the clock starts
+            if sh is not None and world > 1:
+                sh.rendezvous()
+            torch.cuda.synchronize()
             t0 = time.perf_counter()
             out = call()
             tot += time.perf_counter() - t0
@@ -371,7 +375,7 @@ def run_ours(args):
     else:
         def e2e_call():
             return sharded.lnprob(phis)
-    e2e_s, e2e_vals = time_e2e(e2e_call, K, max(3, args.warmup))
+    e2e_s, e2e_vals = time_e2e(e2e_call, K, max(3, args.warmup), sharded)
     sampler.phase = None
 
     # ---- sustained: back-to-back launches for >= 2 s, clocks and power sampled under load ---------------
@@ -749,7 +753,8 @@ def run_secondary_cfg4(args, world, rank, local, dev, barrier, max_over_ranks, a
     e2e = 0.0
     for _ in range(nsteps):
         flush_l2()
-        barrier()
+        sh.rendezvous()
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         vals_e2e = sh.lnprob(phis)
         e2e += time.perf_counter() - t0
