@@ -58,7 +58,7 @@ def parse_args():
     ap.add_argument("--split-inner", default="", help="FACTOR mode: dust parameters of the inner table, e.g. Av or Av,Rv")
     ap.add_argument("--walkers", type=int, default=0, help="override the config's walker count")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample", type=int, default=8, help="walkers the CPU baseline / parity check evaluates")
+    ap.add_argument("--cpu-sample", type=int, default=24, help="walkers the CPU baseline / parity check evaluates")
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps (not the headline)")
     ap.add_argument("--all-modes", action="store_true", help="also time the other engine modes")
     ap.add_argument("--no-clustered", action="store_true",
@@ -581,7 +581,8 @@ def run_ours(args):
                               "when the shards are reduced by NCCL) enqueued after the flush, before the start event",
             "entries": n_ent, "entries_raw": raw, "runs": info["n_runs"], "age_classes": nA, "dust_classes": nB,
             "outer_rows": nO, "inner_rows": nI, "split_inner_mask": info["split_inner_mask"],
-            "code_bytes": info["code_bytes"], "bins": info["n_bins"], "ingest_s": round(t_ingest, 3),
+            "code_bytes": info["code_bytes"], "bins": info["n_bins"], "ingest_s": round(sharded.t_create, 3),
+            "peer_connect_s": round(sharded.t_connect, 3), "setup_s": round(t_ingest, 3),
         },
         "clocks": clocks,
         "e2e": {"value": W * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * W * ndim,
@@ -796,7 +797,7 @@ def run_secondary_cfg4(args, world, rank, local, dev, barrier, max_over_ranks, a
             "engine": {"engine_mode": info["mode"], "reduce": sh.reduce, "entries_rank0": info["n_entries"],
                        "dust_classes": info["n_dust_classes"], "walkers_per_pass": info["walkers_per_pass"],
                        "launches_per_step": info["launches_last_eval"], "synth_s": round(t_synth, 1),
-                       "ingest_s": round(t_ingest, 2)},
+                       "ingest_s": round(sh.t_create, 3), "peer_connect_s": round(sh.t_connect, 3)},
             "parity": {"walkers_checked": n, "max_rel_err_device_path": float(rel.max()),
                        "max_rel_err_e2e_path": float(rel2.max()), "tolerance": 1e-9,
                        "status_flags": int(status_dev.max()),

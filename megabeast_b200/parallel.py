@@ -102,6 +102,9 @@ class ShardedLikelihood:
         # default: the arrays hold the whole job and this rank takes its contiguous share; a rank
         # whose arrays hold only its own stars passes star_range=(0, S_local) and the job's total
         self.star_range = shard_bounds(S, self.world, self.rank) if star_range is None else tuple(star_range)
+        import time as _time
+
+        t0 = _time.perf_counter()
         self.engine = LikelihoodEngine(self.spec, star_lnpgriddata, beast_moddata, massmult=mm,
                                        devices=[self.device], mode=mode,
                                        star_range=self.star_range,
@@ -110,7 +113,10 @@ class ShardedLikelihood:
                                        split_inner=getattr(model, "split_inner", None))
         # how the shard partials are added: "p2p" = inside the likelihood kernel over NVLink peer
         # memory (mb_peer_connect), "nccl" = one all-reduce after it; "auto" tries p2p first
+        self.t_create = _time.perf_counter() - t0   # ingest: class coding + entry build + uploads
+        t0 = _time.perf_counter()
         self.reduce = "none" if self.world == 1 else self._setup_reduce(reduce)
+        self.t_connect = _time.perf_counter() - t0  # peer mapping (CUDA IPC + peer access), once per process group
         self._cap = 0
         self._ensure(64)
         # device variable order == reference order (the usual case): lnprob can be one C call
