@@ -18,21 +18,25 @@
 // (production BEAST grids: 100-200 A(V) values x 9 R(V)) keep the parameters separate: inner = A(V),
 // outer = age x R(V) (x f_A), and a star's entries are sorted into runs of equal outer class.
 //
-// K0  mb_k0_factors      one block per walker: prior models on the classes -> factor tables FA, FB
+// K0  mb_k0_factors      one block per walker: prior models on the classes -> factor tables FO, FI
 //                        (TABLE modes, tabulated models, pixel batches; in FACTOR mode K2 builds
 //                        the tables itself in its prologue and K0 is not launched)
 // K1  mb_k1_expand       TABLE modes: physmod table T[u][w] = FA*FB          (HBM write bound)
 // K1e mb_k1_elementwise  ELEMENTWISE mode: physmod[g][w] from the grid's physics columns, row by
 //                        row (any grid, no class coding); K1b mb_k1b_binsums adds its per-tile
 //                        N-stars partial sums per (age, Z) bin
-// K2  mb_k2_stars<..>    prologue: (FACTOR) the factor tables, built in shared memory; (first W
-//                        blocks) N-stars sufficient statistics x FB -> per-bin sums -> expected N ->
-//                        Poisson term.  Then the hot loop:
+// K2  mb_k2_stars<..>    prologue: (FACTOR) the factor tables, built in shared memory while the first
+//                        entry chunks are already on their way; every block takes some (age, Z) bins of
+//                        the N-stars statistics x FI x FO -> per-bin sums (one warp per bin when the
+//                        tables are small).  Then the hot loop:
 //                        stream (weight, code) entries once for all walkers, look the factors up
 //                        (smem) or gather T rows (L2/HBM), per-star fp64 sum, log via
 //                        mantissa/exponent product.  K3 is fused into its tail: warp -> block ->
-//                        grid (-> GPUs over NVLink peer memory) reduction in 64-bit fixed point
+//                        grid (-> GPUs over NVLink peer memory) reduction in two-word fixed point;
+//                        the last block also adds the bins -> expected N -> Poisson term
 // KPX mb_k2_pixels<..>   pixel batches: one block per pixel at a time, same inner loop
+// KB  mb_build_entries   once per mb_create: (star, sparse point) pairs -> the sorted, merged, flagged
+//                        entry stream (one warp per star, bitonic sort); mb_compact_entries packs it
 //
 // Lanes of a warp are WALKERS, a warp walks one star's entries at a time, so every control
 // decision in K2 (run boundary, end of star) is warp-uniform.
