@@ -103,7 +103,6 @@ struct mb_handle {
   unsigned long long* peer_xbuf[MB_MAX_PEERS] = {};
   int peer_world = 1, peer_rank = 0;
   unsigned int peer_seq = 0, rdv_seq = 0;
-  size_t last_smem = 0; int last_threads = 0;   // shape of the last K2 launch
   double* d_T = nullptr;  int64_t cap_T = 0;
   int max_blocks = 0;
   double* d_out = nullptr;  int64_t cap_out = 0;
@@ -381,14 +380,8 @@ extern "C" int mb_peer_connect(mb_handle* h, int32_t rank, int32_t world, const 
 
 extern "C" int mb_peer_rendezvous(mb_handle* h, void* stream) {
   if (!h) return fail("null handle");
-  CK(cudaSetDevice(h->device));
-  static const bool warm = getenv("MB_SHAPE_WARMUP") && atoi(getenv("MB_SHAPE_WARMUP"));
-  if (warm && h->last_smem > 0) {
-    static bool attr_set = false;
-    if (!attr_set) { CK(cudaFuncSetAttribute(mb_shape_warmup, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem)); attr_set = true; }
-    mb_shape_warmup<<<h->sm_count, h->last_threads, h->last_smem, (cudaStream_t)stream>>>();
-  }
   if (h->peer_world <= 1) return 0;
+  CK(cudaSetDevice(h->device));
   PeerArgs pa{};
   pa.world = h->peer_world; pa.rank = h->peer_rank; pa.seq = ++h->rdv_seq; pa.timeout_ns = h->peer_timeout_ns;
   for (int p = 0; p < h->peer_world; ++p) pa.xbuf[p] = h->peer_xbuf[p];
@@ -1513,7 +1506,6 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     }
     if (prof) CK(cudaEventRecord(h->ev[2], st));
     size_t smem = plan.total;
-    h->last_smem = smem; h->last_threads = k2_threads(NW);
     // occupancy query cached per pass shape (it costs microseconds of host time per call)
     int& cached = h->occ_cache[NW == 1 ? 0 : NW == 2 ? 1 : 2];
     if (cached <= 0 || h->occ_smem[NW == 1 ? 0 : NW == 2 ? 1 : 2] != smem) {

@@ -976,14 +976,6 @@ __global__ void mb_rendezvous(PeerArgs peer) {
   }
 }
 
-// An empty launch with K2's block shape and shared-memory size (measurement aid, see mb_peer_rendezvous
-// in the header): after a kernel with another shared-memory carve-out (bench.py's L2 flush) the SMs
-// are re-partitioned by this launch, not by the timed one -- as between two steps of a real sampler.
-__global__ void mb_shape_warmup() {
-  extern __shared__ __align__(16) unsigned char warm_smem[];
-  if (threadIdx.x == 0xffffffffu) warm_smem[0] = 0;
-}
-
 constexpr int kPhiInline = MB_PHI_INLINE;  // doubles of phi carried in K2's kernel parameters (e.g. 128 walkers x 9)
 struct K2Args {
   const double* ea;     // entry weights  [n_entries]

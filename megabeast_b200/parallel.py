@@ -11,8 +11,6 @@ rank's K2 stores its shard totals into all peers over NVLink and adds what the p
 torch is used for what it is good at here -- device buffers, the current stream and
 ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests); the likelihood itself is the C ABI.
 """
-import os
-
 import numpy as np
 
 from . import _cabi
@@ -176,11 +174,9 @@ class ShardedLikelihood:
     def rendezvous(self):
         """Align the ranks on the current stream ahead of a timed launch: over the NVLink exchange
         buffers when the shards are reduced there, else with a tiny NCCL all-reduce."""
-        t = self.torch
         if self.world == 1:
-            if os.environ.get("MB_SHAPE_WARMUP"):
-                self.engine.peer_rendezvous(t.cuda.current_stream(self.device).cuda_stream)
             return
+        t = self.torch
         if self.reduce == "p2p":
             self.engine.peer_rendezvous(t.cuda.current_stream(self.device).cuda_stream)
         else:
