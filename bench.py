@@ -293,14 +293,6 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    tick = torch.zeros(1, dtype=torch.float32, device=dev)
-
-    def align_ranks():
-        """Device-side rendezvous on the current stream (asynchronous for the host): every rank's
-        next kernel starts when the slowest rank arrives.  Outside the timed events."""
-        if world > 1:
-            dist.all_reduce(tick)
-
     def max_over_ranks(x):
         if world == 1:
             return x
@@ -483,7 +475,7 @@ def run_ours(args):
     secondary = None
     want_secondary = args.secondary == "cfg4" or (args.secondary == "auto" and world == 8 and args.workload == "cfg3")
     if world > 1 and want_secondary:
-        secondary = run_secondary_cfg4(args, world, rank, local, dev, barrier, max_over_ranks, align_ranks, flush_l2)
+        secondary = run_secondary_cfg4(args, world, rank, local, dev, barrier, max_over_ranks, flush_l2)
 
     if rank != 0:
         sampler.stop_flag = True
@@ -699,7 +691,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_secondary_cfg4(args, world, rank, local, dev, barrier, max_over_ranks, align_ranks, flush_l2):
+def run_secondary_cfg4(args, world, rank, local, dev, barrier, max_over_ranks, flush_l2):
     """BASELINE config 4 (PHAT scale: 1,000,000 stars x 50 points, 2,000,800-row grid, 128 walkers), star-sharded
     over the ranks.  Every rank synthesises only ITS shard of stars (seed = 2 + 1000 * rank; the grid, seed 1,
     is replicated), so the job is the concatenation of the shards.  Parity: every rank runs the C oracle on its

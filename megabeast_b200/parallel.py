@@ -81,7 +81,12 @@ class ShardedLikelihood:
     """
 
     def __init__(self, model, star_lnpgriddata, beast_moddata, device=None, mode="auto", group=None,
-                 reduce="auto", star_range=None, n_stars_total=None):
+                 reduce="auto", star_range=None, n_stars_total=None, check_sync=False):
+        """``check_sync``: every ``lnprob`` call first verifies (one small all-reduce) that all ranks
+        were handed the same phi.  The fused NVLink reduction needs every rank to issue the same
+        sequence of launches -- identical phi, hence identical in-box compaction -- and a rank that
+        diverges would leave the others waiting for its shard until the peer timeout.  Off by default
+        (it costs a collective per call); switch it on while wiring up a new driver."""
         import torch
 
         from .helpers import precompute_mass_multipliers
@@ -117,6 +122,7 @@ class ShardedLikelihood:
         t0 = _time.perf_counter()
         self.reduce = "none" if self.world == 1 else self._setup_reduce(reduce)
         self.t_connect = _time.perf_counter() - t0  # peer mapping (CUDA IPC + peer access), once per process group
+        self.check_sync = bool(check_sync)
         self._cap = 0
         self._ensure(64)
         # device variable order == reference order (the usual case): lnprob can be one C call
@@ -214,10 +220,27 @@ class ShardedLikelihood:
         t.cuda.current_stream(self.device).synchronize()
         return h_rows.numpy()
 
+    def _assert_same_phi(self, phis):
+        import torch.distributed as dist
+
+        t = self.torch
+        # (sum, sum of squares, count) of phi: min and max over the ranks must agree
+        a = np.ascontiguousarray(phis, dtype=np.float64)
+        sig = t.tensor([float(a.sum()), float((a * a).sum()), float(a.size)], dtype=t.float64)
+        if dist.get_backend(self.group) == "nccl":
+            sig = sig.to(t.device("cuda", self.device))
+        lo, hi = sig.clone(), sig.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
+        if not t.equal(lo, hi):
+            raise RuntimeError("ShardedLikelihood.lnprob: the ranks were called with different phi")
+
     def lnprob(self, phi):
         phi = np.asarray(phi, dtype=np.float64)
         single = phi.ndim == 1
         phis = phi[None, :] if single else phi
+        if self.check_sync and self.world > 1:
+            self._assert_same_phi(phis)
         if self.reduce in ("p2p", "none") and self._fast_ok and phis.shape[1] == self.ndim:
             # one C call per rank (mb_lnprob_box): prior box, likelihood of the in-box walkers on
             # this rank's shard, shard totals added inside the kernel over NVLink, combine.  Every

@@ -51,8 +51,15 @@ def _worker(rank, world, port_no, q):
         phis[3, 5] = 99.0  # one walker outside the box: -inf, likelihood not evaluated
         out = {}
         for mode in ("p2p", "nccl"):
-            sh = ShardedLikelihood(MB_Model(copy.deepcopy(settings)), stars, moddata, device=rank, reduce=mode)
+            sh = ShardedLikelihood(MB_Model(copy.deepcopy(settings)), stars, moddata, device=rank, reduce=mode,
+                                   check_sync=True)
             assert sh.reduce == mode
+            # ranks that were handed different phi are caught before anything is launched
+            try:
+                sh.lnprob(phis * (1.0 + 1e-6 * rank))
+                out[mode + "_desync_caught"] = world == 1
+            except RuntimeError as exc:
+                out[mode + "_desync_caught"] = "different phi" in str(exc)
             for _ in range(3):  # several launches: sequence numbers / parities advance
                 vals = sh.lnprob(phis)
             out[mode] = np.array(vals)
@@ -103,6 +110,7 @@ def test_multi_gpu_star_sharding_p2p_and_nccl(world):
             assert np.array_equal(got[~fin], want[~fin])
             assert np.max(np.abs(got[fin] - want[fin]) / np.abs(want[fin])) < 1e-9
             assert abs(res[rank][mode + "_one"] - want[0]) < 1e-9 * abs(want[0])
+            assert res[rank][mode + "_desync_caught"] is True
             tab = res[rank][mode + "_tab"]
             assert np.array_equal(tab[~fin], want[~fin])
             assert np.max(np.abs(tab[fin] - want[fin]) / np.abs(want[fin])) < 1e-9
