@@ -351,6 +351,11 @@ def run_ours(args):
         barrier()
         return max_over_ranks(tot), out
 
+    # ---- device-timed value ------------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:   # (one NVML poller per job: the ranks share the host's cores)
+        sampler.start()
+    sampler.phase = "timed"
     if world > 1:
         # every rank's MAIN thread on its own host core where there are enough of them (the helper threads of
         # CUDA / NCCL exist by now and keep their masks): the end-to-end path is a chain of microsecond-scale
@@ -361,12 +366,6 @@ def run_ours(args):
                 os.sched_setaffinity(0, {cores[local * (len(cores) // world)]})
         except (AttributeError, OSError):
             pass
-
-    # ---- device-timed value ------------------------------------------------------------------------
-    sampler = ClockSampler(local)
-    if rank == 0:   # (one NVML poller per job: the ranks share the host's cores)
-        sampler.start()
-    sampler.phase = "timed"
     total_ms, t_wall = time_device(sharded, d_rows, K, max(3, args.warmup))
     launches = sharded.engine.info()["launches_last_eval"] * K
     rows_dev = d_rows.cpu().numpy()
