@@ -1234,13 +1234,15 @@ struct Lanes {
 };
 
 // ---- the entry ring: chunks of kChunk entries, STAGES slots per warp ---------------------------------
-// Two ways to fill a slot.  TMA = true (default): ONE lane issues two bulk copies (cp.async.bulk, the
+// Two ways to fill a slot.  TMA = false (the default build, -DMB_RING=0): per-lane cp.async (LDGSTS)
+// with commit groups.  TMA = true (-DMB_RING=1): ONE lane issues two bulk copies (cp.async.bulk, the
 // TMA engine: 256 B of weights, 64 or 128 B of codes) that complete on the slot's mbarrier -- no LSU
 // instructions per lane, the staging writes do not go through the load/store pipe that the factor
 // reads saturate.  Bulk copies need 16-byte aligned addresses and sizes, so chunks start on a multiple
 // of 8 (16-bit codes) or 4 (32-bit codes) entries and are always copied whole: a range that starts
 // in between skips up to 7 leading entries of its first chunk, and the entry arrays are padded at
-// the end (kEntryPad).  TMA = false: per-lane cp.async (LDGSTS) with commit groups, as on Ampere.
+// the end (kEntryPad).  Both are correct (the GPU tests pass with either); the bulk-copy ring measured
+// 0.7 % slower on B200 (profiles/r2_ab_ring.txt), so it is not the default.
 constexpr int kEntryPad = 64;   // entries allocated past the end of the entry arrays
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
