@@ -278,7 +278,8 @@ def run_ours(args):
     # CPU baseline first: its worker processes are forked before this process holds a CUDA context
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        n_cpu = max(1, min(args.cpu_sample, W))
+        # (a whole number of rounds of one walker per host core)
+        n_cpu = max(1, min(W, -(-args.cpu_sample // host_cores()) * host_cores()))
         cpu = cpu_baseline_and_values(settings, moddata, stars, phis, n_cpu)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; megabeast_b200 has no CPU fallback")
