@@ -1443,11 +1443,10 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     // for that keeps K0 (one read of the mapped host memory per walker instead of one per block)
     const bool inline_phi = h_phi && (int64_t)wp * ndim <= kPhiInline;
     const size_t fuse_scratch = k2_fuse_scratch(h->nscratch, h->ncls_total, nrows, Wpad, (size_t)wp * ndim);
-    // (MB_PHI_MAPPED=1: a host phi that does not ride in the parameters is read by K2 from the mapped pinned
-    // buffer instead of falling back to K0 -- with -DMB_PHI_INLINE=8 this is the small-parameter-block variant)
-    static const bool phi_mapped = getenv("MB_PHI_MAPPED") && atoi(getenv("MB_PHI_MAPPED"));
+    // (measured: letting every block read a host phi from the mapped pinned buffer instead costs 24 us per
+    // call -- 148 blocks x 4.6 KB over PCIe -- against the 11.7 KB parameter block's < 1 us)
     const bool may_fuse = kmode == kModeFactor && h->table_bytes == 8 && !d_tab && !h->no_fuse &&
-                          h->ncls_total < 0x7fff && (!h_phi || inline_phi || phi_mapped);
+                          h->ncls_total < 0x7fff && (!h_phi || inline_phi);
     // most (age, Z) bins a block can get: the launch has at least min(nbins, SMs) blocks
     const int bins_per_block = h->nbins > 0 ? (h->nbins + std::min(h->nbins, h->sm_count) - 1) / std::min(h->nbins, h->sm_count) : 0;
     const K2Smem plan = k2_smem_plan(kmode, h->nO, h->nI, h->nbins, Wpad, h->table_bytes, h->max_smem,

@@ -16,12 +16,13 @@ print("%-14s %-12s %8.2f us/step  k2=%.2f  e2e=%.2f us  tables=%.2f bins=%.2f lo
 PY
 }
 mkdir -p build_variants
-python -c "from megabeast_b200 import build; build.build(force=True, defines=['MB_PHI_INLINE=8'], out='build_variants/lib_phi8.so')"
-VARIANTS=${2:-"default:MB_X=0 smallparams_mapped:MEGABEAST_B200_LIB=$PWD/build_variants/lib_phi8.so,MB_PHI_MAPPED=1"}
+python -c "from megabeast_b200 import build; build.build(force=True, defines=['MB_RING=0'], out='build_variants/lib_ring0.so')"
+python -c "from megabeast_b200 import build; build.build(force=True, defines=['MB_RING=1'], out='build_variants/lib_ring1.so')"
+VARIANTS=${2:-"both_tma:MB_X=0 both_cpasync:MB_NO_TMA=1 only_cpasync:MEGABEAST_B200_LIB=$PWD/build_variants/lib_ring0.so only_tma:MEGABEAST_B200_LIB=$PWD/build_variants/lib_ring1.so"}
 for rep in 1 2; do
 for wl in cfg3_eighth cfg3; do
   for v in $VARIANTS; do
-    run ${v%%:*} $wl $(echo ${v#*:} | tr "," " ")
+    run ${v%%:*} $wl ${v#*:}
   done
 done
 done
