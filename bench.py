@@ -64,8 +64,9 @@ def parse_args():
     ap.add_argument("--no-clustered", action="store_true",
                     help="skip the extra measurement with clustered (BEAST-like) sparse indices")
     ap.add_argument("--no-sustained", action="store_true", help="skip the 2 s back-to-back block")
-    ap.add_argument("--secondary", default="auto", choices=["auto", "cfg4", "none"],
-                    help="N > 1: also measure BASELINE config 4 sharded over the ranks (auto: at N = 8)")
+    ap.add_argument("--secondary", default="auto", choices=["auto", "cfg4", "cfg5", "both", "none"],
+                    help="N > 1: also measure BASELINE config 4 (stars sharded over the ranks) and config 5 (pixel "
+                         "batches, pixels split over the ranks); auto: both at N = 8")
     ap.add_argument("--table-precision", default="fp64", choices=["fp64", "fp32"],
                     help="fp32: 32-bit factor tables on chip, stated tolerance 1e-7 (not the headline)")
     ap.add_argument("--reduce", default="auto", choices=["auto", "p2p", "nccl"],
@@ -484,10 +485,12 @@ def run_ours(args):
         barrier()
 
     # ---- secondary (N = 8): BASELINE config 4, sharded over the same ranks ---------------------------------
-    secondary = None
-    want_secondary = args.secondary == "cfg4" or (args.secondary == "auto" and world == 8 and args.workload == "cfg3")
-    if world > 1 and want_secondary:
+    secondary = secondary5 = None
+    auto_secondary = args.secondary == "auto" and world == 8 and args.workload == "cfg3"
+    if world > 1 and (args.secondary in ("cfg4", "both") or auto_secondary):
         secondary = run_secondary_cfg4(args, world, rank, local, dev, barrier, max_over_ranks, flush_l2)
+    if world > 1 and (args.secondary in ("cfg5", "both") or auto_secondary):
+        secondary5 = run_secondary_cfg5(args, world, rank, local, dev, barrier, max_over_ranks, flush_l2)
 
     if rank != 0:
         sampler.stop_flag = True
@@ -614,6 +617,8 @@ def run_ours(args):
         line["parity"] = parity
     if secondary is not None:
         line["secondary"] = secondary
+    if secondary5 is not None:
+        line["secondary_cfg5"] = secondary5
 
     # ---- CPU baseline + full-size parity ----------------------------------------------------------------
     if cpu is not None:
@@ -812,6 +817,95 @@ def run_secondary_cfg4(args, world, rank, local, dev, barrier, max_over_ranks, f
     sh.close()
     barrier()
     return out
+
+
+def run_secondary_cfg5(args, world, rank, local, dev, barrier, max_over_ranks, flush_l2):
+    """BASELINE config 5 (batched independent spatial-pixel fits: 4,096 pixels x ~500 stars each over a shared
+    1M-row grid, all walkers of all pixels in one launch across the GPUs): every rank owns 4,096 / N pixels
+    (its own seeds; the grid, seed 1, is shared), no collective on the data path -- pixels are independent.
+    Device-timed (CUDA events per launch, max over ranks), end to end through PixelEnsemble.lnprob with
+    host arrays, parity of 8 pixels per rank against the per-pixel oracle."""
+    import copy
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from megabeast_b200 import synth
+    from megabeast_b200.pixels import PixelEnsemble
+    from oracle import c_oracle
+    from oracle import lnprob_port as port
+
+    P = 4096 // world
+    axes = synth.CONFIGS["cfg3"]["axes"]
+    t0 = time.perf_counter()
+    settings, moddata, stars, offs = synth.make_pixel_problem(
+        n_pixels=P, mean_stars=500, axes=axes, K=50, mode=args.index_mode, seeds=(1, 2 + 10 * rank, 4 + 10 * rank))
+    t_synth = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    pe = PixelEnsemble(copy.deepcopy(settings), stars, moddata, offs, device=local)
+    t_ingest = time.perf_counter() - t0
+    W, ndim = 45, pe.ndim
+    rng = np.random.default_rng(3)
+    start = np.asarray(pe.model.start_params()[1], dtype=float)
+    phis = np.clip(start * (1.0 + 0.05 * rng.standard_normal((P, W, ndim))), *pe.model._box())
+    d_phi = torch.from_numpy(np.ascontiguousarray(phis)).to(dev)
+    d_out = torch.empty((P, 4, W), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    nsteps = max(10, min(args.steps, 30))
+    for _ in range(5):
+        flush_l2()
+        pe.engine.lnlike_pixels_device(d_phi.data_ptr(), W, ndim, d_out.data_ptr(), stream)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
+    barrier()
+    for i in range(nsteps):
+        flush_l2()
+        evs[i][0].record()
+        pe.engine.lnlike_pixels_device(d_phi.data_ptr(), W, ndim, d_out.data_ptr(), stream)
+        evs[i][1].record()
+    barrier()
+    dev_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
+    vals = pe.lnprob(phis)
+    barrier()
+    e2e = 0.0
+    for _ in range(5):
+        flush_l2()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        vals = pe.lnprob(phis)
+        e2e += time.perf_counter() - t0
+    barrier()
+    e2e = max_over_ranks(e2e) / 5
+    err = 0.0
+    ncheck = 8
+    for p in range(ncheck):
+        sub = {"indxs": np.ascontiguousarray(stars["indxs"][:, offs[p]:offs[p + 1]]),
+               "vals": np.ascontiguousarray(stars["vals"][:, offs[p]:offs[p + 1]])}
+        want = c_oracle.lnprob_batch(port.PortModel(copy.deepcopy(settings)), phis[p], sub, moddata)
+        err = max(err, float(np.max(np.abs(vals[p] - want) / np.abs(want))))
+    err = max_over_ranks(err)
+    info = pe.engine.info()
+    pe.close()
+    barrier()
+    if rank != 0:
+        return None
+    step_ms = dev_ms / nsteps
+    return {
+        "workload": f"cfg5: {P * world} pixels x ~500 stars x 50 sparse points, shared {info['G']}-row grid, {W} walkers per "
+                    f"pixel, docs-example model; {P} pixels per rank, all walkers of all pixels in one launch per rank",
+        "index_mode": args.index_mode,
+        "metric": "pixel-ensemble lnprob evals/sec (one eval = one walker of one pixel over the pixel's stars)",
+        "value": P * world * W / (step_ms * 1e-3), "unit": UNIT, "ms_per_step": step_ms, "steps": nsteps,
+        "scaling": "weak", "pixel_walkers_per_step": P * world * W,
+        "e2e": {"value": P * world * W / e2e, "unit": UNIT, "ms_per_step": 1e3 * e2e,
+                "h2d_bytes_per_step": 8 * P * W * ndim, "d2h_bytes_per_step": 8 * 4 * P * W,
+                "api": "megabeast_b200.pixels.PixelEnsemble.lnprob(phis[P,W,ndim]) with host arrays, per rank"},
+        "engine": {"entries_rank0": info["n_entries"], "stars_rank0": int(offs[-1]), "synth_s": round(t_synth, 1),
+                   "ingest_s": round(t_ingest, 2)},
+        "parity": {"pixels_checked_per_rank": ncheck, "walkers_per_pixel": W, "max_rel_err": err, "tolerance": 1e-9,
+                   "against": "oracle/mb_oracle.c on each checked pixel's stars alone (its own star count in the Poisson term); "
+                              "max over the ranks"},
+    }
 
 
 def main():
