@@ -261,6 +261,13 @@ int mb_lnlike_pixels_tabulated(mb_handle* h, const double* phi, int32_t W, int32
                                const double* const tab[MB_NPARAM], double* lnlike, int32_t* status);
 int mb_lnlike_pixels_device(mb_handle* h, const double* d_phi, int32_t W, int32_t ndim, double* d_out,
                             void* stream);
+/* replaces: lnprob(phi, ...) (singlepop_dust_model.py:277-304) for every walker of every pixel when every
+ * prior is a flat box (mb_lnprob_box for pixel batches): lnprob[p][w] = -inf, status 0 for a walker with any
+ * phi outside [lo, hi] -- it still occupies a column of the launch, evaluated at `park` ([ndim], inside the
+ * box, e.g. the start parameters) and discarded, as the reference never evaluates it (:302-303) -- else
+ * 0 + lnlike.  Analytic models only. */
+int mb_lnprob_pixels_box(mb_handle* h, const double* phi, int32_t W, int32_t ndim, const double* lo,
+                         const double* hi, const double* park, double* lnprob, int32_t* status);
 int64_t mb_pixel_count(const mb_handle* h);
 
 /* Guard against stale device data.  The data dictionaries arrive as arguments on every call of the

@@ -194,6 +194,11 @@ SIGNATURES = {
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, TabArray, ctypes.c_void_p, ctypes.c_void_p],
     ),
+    "mb_lnprob_pixels_box": (
+        ctypes.c_int,
+        [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p],
+    ),
     "mb_pixel_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "mb_watch_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
     "mb_peer_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),

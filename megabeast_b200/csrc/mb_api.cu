@@ -1762,8 +1762,26 @@ extern "C" int mb_lnlike_pixels(mb_handle* h, const double* phi, int32_t W, int3
   return mb_lnlike_pixels_tabulated(h, phi, W, ndim, nullptr, lnlike, status);
 }
 
+// Pixel batch from host arrays.  lo/hi/park (all or none): the flat prior box of mb_lnprob_pixels_box -- a
+// walker outside [lo, hi] is evaluated at `park` (it occupies a column either way) and reported as -inf.
+static int pixels_host_eval(mb_handle* h, const double* phi, int32_t W, int32_t ndim, const double* const tab[MB_NPARAM],
+                            double* lnlike, int32_t* status, const double* lo, const double* hi, const double* park);
+
 extern "C" int mb_lnlike_pixels_tabulated(mb_handle* h, const double* phi, int32_t W, int32_t ndim,
                                           const double* const tab[MB_NPARAM], double* lnlike, int32_t* status) {
+  return pixels_host_eval(h, phi, W, ndim, tab, lnlike, status, nullptr, nullptr, nullptr);
+}
+
+extern "C" int mb_lnprob_pixels_box(mb_handle* h, const double* phi, int32_t W, int32_t ndim, const double* lo,
+                                    const double* hi, const double* park, double* lnprob, int32_t* status) {
+  if (ndim > 0 && (!lo || !hi || !park)) return fail("mb_lnprob_pixels_box: null box array");
+  for (int k = 0; k < ndim; ++k)
+    if (!(park[k] >= lo[k] && park[k] <= hi[k])) return fail("mb_lnprob_pixels_box: park[%d] is outside the box", k);
+  return pixels_host_eval(h, phi, W, ndim, nullptr, lnprob, status, lo, hi, park);
+}
+
+static int pixels_host_eval(mb_handle* h, const double* phi, int32_t W, int32_t ndim, const double* const tab[MB_NPARAM],
+                            double* lnlike, int32_t* status, const double* lo, const double* hi, const double* park) {
   if (!h || !lnlike || !status) return fail("mb_lnlike_pixels: null argument");
   if (h->P <= 0) return fail("handle was not created with mb_create_pixels");
   if (ndim != h->ndim) return fail("phi has %d columns, the model has %d free variables", ndim, h->ndim);
@@ -1788,6 +1806,19 @@ extern "C" int mb_lnlike_pixels_tabulated(mb_handle* h, const double* phi, int32
   double* hp = h->h_pin;
   double* ho = h->h_pin + nphi;
   if (ndim > 0) memcpy(hp, phi, sizeof(double) * (size_t)ncol * ndim);
+  std::vector<int32_t>& outside = h->scratch_idx;  // columns outside the prior box
+  outside.clear();
+  if (lo && ndim > 0) {
+    for (int64_t c = 0; c < ncol; ++c) {
+      double* p = hp + (size_t)c * ndim;
+      bool inside = true;
+      for (int k = 0; k < ndim; ++k) inside &= !(p[k] < lo[k] || p[k] > hi[k]);  // same compare as mb_lnprob_box
+      if (!inside) {
+        memcpy(p, park, sizeof(double) * ndim);
+        outside.push_back((int32_t)c);
+      }
+    }
+  }
   CK(cudaMemcpyAsync(h->d_phi, hp, sizeof(double) * (size_t)nphi, cudaMemcpyHostToDevice, h->stream));
   // host-evaluated tables of MB_TABULATED parameters: [P * W][n_classes]
   const double* dtab[MB_NPARAM] = {nullptr, nullptr, nullptr, nullptr};
@@ -1806,6 +1837,10 @@ extern "C" int mb_lnlike_pixels_tabulated(mb_handle* h, const double* phi, int32
   CK(cudaStreamSynchronize(h->stream));
   for (int64_t p = 0; p < h->P; ++p)  // rows are [p][3][W]
     mb_combine(ho + (size_t)p * MB_OUT_ROWS * W, W, lnlike + (size_t)p * W, status + (size_t)p * W);
+  for (int32_t c : outside) {  // singlepop_dust_model.py:302-303: never evaluated in the reference
+    lnlike[c] = -INFINITY;
+    status[c] = MB_STATUS_OK;
+  }
   return 0;
 }
 

@@ -351,6 +351,24 @@ class LikelihoodEngine:
                                                         out.ctypes.data, status.ctypes.data))
         return out, status
 
+    def lnprob_pixels_box(self, phis, lo, hi, park):
+        """Pixel batch with the flat prior box applied in the C call (``mb_lnprob_pixels_box``): phis
+        [P][W][ndim] -> (lnprob[P][W] with -inf outside [lo, hi], status[P][W]).  ``park``: an in-box
+        position evaluated in place of the out-of-box walkers.  Analytic models."""
+        phis = np.ascontiguousarray(phis, dtype=np.float64)
+        if phis.ndim != 3 or phis.shape[0] != self.n_pixels:
+            raise ValueError(f"phis must be ({self.n_pixels}, W, ndim)")
+        P, W, ndim = phis.shape
+        lo, hi, park = (np.ascontiguousarray(a, dtype=np.float64) for a in (lo, hi, park))
+        if not (lo.size == hi.size == park.size == ndim):
+            raise ValueError("lo, hi and park must have ndim entries")
+        out = np.empty((P, W))
+        status = np.empty((P, W), dtype=np.int32)
+        _cabi.check(self.lib.mb_lnprob_pixels_box(self.handles[0], phis.ctypes.data, W, ndim, lo.ctypes.data,
+                                                  hi.ctypes.data, park.ctypes.data, out.ctypes.data,
+                                                  status.ctypes.data))
+        return out, status
+
     def lnlike_pixels_device(self, d_phi, W, ndim, d_out, stream=0):
         """Device-pointer form: d_phi [P][W][ndim], d_out [P][4][W], asynchronous on ``stream``."""
         _cabi.check(self.lib.mb_lnlike_pixels_device(self.handles[0], ctypes.c_void_p(d_phi), W, ndim,

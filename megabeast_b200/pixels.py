@@ -33,6 +33,7 @@ class PixelEnsemble:
         self.perm = None if self.model._identity_perm(perm, self.ndim) else perm
         self.star_offsets = np.ascontiguousarray(star_offsets, dtype=np.int64)
         self.n_pixels = self.star_offsets.size - 1
+        self._park = None
         mm = None
         if self.model.compute_N_stars:
             mm = precompute_mass_multipliers(beast_moddata, self.model.physics_model["M_ini"]["model"])
@@ -78,6 +79,16 @@ class PixelEnsemble:
         values and status flags are discarded, as the reference never evaluates them)."""
         phis = np.asarray(phis, dtype=np.float64)
         P, W, _ = phis.shape
+        lows, highs = self.model._box()
+        if self.perm is None and not self.spec.tabulated and phis.shape[-1] == self.ndim == lows.size:
+            # the box test, the parking of out-of-box walkers and the -inf all happen inside one C call
+            if self._park is None:
+                park = np.asarray(self.model.start_params()[1], dtype=np.float64)
+                inbox = park.size == lows.size and np.all((park >= lows) & (park <= highs))
+                self._park = park if inbox else 0.5 * (lows + highs)
+            vals, status = self.engine.lnprob_pixels_box(phis, lows, highs, self._park)
+            self._raise(status)
+            return vals
         lp = self.model.lnprior(phis.reshape(P * W, -1)).reshape(P, W)
         inside = np.isfinite(lp)
         # out-of-box walkers still occupy a column: park them on an in-box position of their pixel

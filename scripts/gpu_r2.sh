@@ -18,7 +18,7 @@ except Exception as e:
 e = d.get("engine", {})
 print("  N=%s %s value=%.0f ms/step=%.4f e2e=%.0f kernel_ms=%s" % (d["n_gpus"], e.get("engine_mode"), d["value"], d["ms_per_step"], d["e2e"]["value"], {k: round(v, 4) for k, v in d["kernel_ms"].items()}))
 print("  split=%s outer=%s inner=%s entries=%s runs=%s code_bytes=%s ingest_s=%s" % (e.get("split_inner_mask"), e.get("outer_rows"), e.get("inner_rows"), e.get("entries"), e.get("runs"), e.get("code_bytes"), e.get("ingest_s")))
-for k in ("k2_phases_us", "parity", "sustained", "cpu_baseline", "clustered_indices", "weak_scaling", "secondary", "onchip"):
+for k in ("k2_phases_us", "parity", "sustained", "cpu_baseline", "clustered_indices", "weak_scaling", "secondary", "secondary_cfg5", "onchip"):
     if k in d and d[k] is not None:
         print("  %s: %s" % (k, json.dumps(d[k])[:700]))
 EOF
@@ -68,6 +68,11 @@ if has n2 && [ "$NG" -ge 2 ]; then
     timeout 900 $TR --nproc-per-node $n --master-port $((29540 + n)) bench.py --gpus $n --steps 100 --warmup 10 > $OUT/${TAG}_bench_cfg3_n$n.json 2> $OUT/${TAG}_bench_cfg3_n$n.err; echo "bench cfg3 n$n rc=$?"; tail -3 $OUT/${TAG}_bench_cfg3_n$n.err
     summ $OUT/${TAG}_bench_cfg3_n$n.json
   done
+fi
+if has n2both && [ "$NG" -ge 2 ]; then
+  # the two secondary blocks of the 8-GPU line (configs 4 and 5), exercised on 2 GPUs
+  timeout 1500 $TR --nproc-per-node 2 --master-port 29546 bench.py --gpus 2 --steps 50 --warmup 10 --secondary both --no-sustained > $OUT/${TAG}_bench_cfg3_n2_both.json 2> $OUT/${TAG}_bench_cfg3_n2_both.err; echo "bench cfg3 n2 + cfg4 + cfg5 rc=$?"; tail -3 $OUT/${TAG}_bench_cfg3_n2_both.err
+  summ $OUT/${TAG}_bench_cfg3_n2_both.json
 fi
 if has n8 && [ "$NG" -ge 8 ]; then
   timeout 1500 $TR --nproc-per-node 8 --master-port 29548 bench.py --gpus 8 --steps 100 --warmup 10 > $OUT/${TAG}_bench_cfg3_n8.json 2> $OUT/${TAG}_bench_cfg3_n8.err; echo "bench cfg3 n8 rc=$?"; tail -3 $OUT/${TAG}_bench_cfg3_n8.err

@@ -67,3 +67,7 @@ def test_committed_eight_gpu_line_carries_parity_and_config4():
     assert s["workload"].startswith("cfg4") and s["parity"]["max_rel_err_device_path"] < 1e-9
     assert s["parity"]["walkers_checked"] >= 4
     assert line["kernel_ms"]["k2_stars"] <= line["ms_per_step"] * 1.15   # per-kernel time consistent with the step
+    if "secondary_cfg5" in line:   # lines written after the pixel block was added to bench.py
+        s5 = line["secondary_cfg5"]
+        assert s5["workload"].startswith("cfg5") and s5["parity"]["max_rel_err"] < 1e-9
+        assert s5["pixel_walkers_per_step"] == 4096 * 45 and s5["e2e"]["h2d_bytes_per_step"] > 0

@@ -220,6 +220,39 @@ def test_pixel_batch_with_a_host_tabulated_model():
     pe2.close()
 
 
+def test_pixel_batch_prior_box_in_the_c_call():
+    """``PixelEnsemble.lnprob`` applies the flat prior box inside one C call (``mb_lnprob_pixels_box``):
+    same values, bit for bit, as lnprior + lnlike composed on the host (singlepop_dust_model.py:277-304);
+    walkers outside the box are -inf and whatever their parked column computes is discarded -- also when
+    a whole pixel is outside, and at the box edges (<= and >= are inside, :255-271)."""
+    from megabeast_b200.pixels import PixelEnsemble
+
+    settings, moddata, stars, offs = synth.make_pixel_problem(n_pixels=11, mean_stars=30, seeds=(3, 4, 8))
+    pe = PixelEnsemble(copy.deepcopy(settings), stars, moddata, offs)
+    pm = port.PortModel(copy.deepcopy(settings))
+    P, W = len(offs) - 1, 20
+    phis = np.stack([synth.make_walkers(pm, W, seed=400 + p) for p in range(P)])
+    lows, highs = pe.model._box()
+    phis[1, 3, 0] = lows[0] - 1e-9
+    phis[1, 4, 2] = highs[2] + 1.0
+    phis[4, :, 7] = -50.0                      # every walker of pixel 4
+    phis[8, 0, 6] = highs[6]                   # on the edge: inside
+    phis[8, 1, 6] = lows[6]
+    got = pe.lnprob(phis)
+    outside = np.zeros((P, W), bool)
+    outside[1, 3] = outside[1, 4] = True
+    outside[4, :] = True
+    assert np.all(got[outside] == -np.inf) and np.all(np.isfinite(got[~outside]))
+    # the host composition of the same calls
+    lp = pe.model.lnprior(phis.reshape(P * W, -1)).reshape(P, W)
+    assert np.array_equal(np.isfinite(lp), ~outside)
+    safe = phis.copy()
+    safe[outside] = np.asarray(pe.model.start_params()[1], float)
+    vals, status = pe.engine.lnlike_pixels(safe)
+    assert np.array_equal(got, np.where(outside, -np.inf, lp + vals))
+    pe.close()
+
+
 def test_in_place_change_of_the_data_is_noticed():
     """The data dictionaries arrive on every call (singlepop_dust_model.py:110) but live on the device:
     an array changed IN PLACE must not be evaluated from the stale copy."""
