@@ -1150,7 +1150,7 @@ static size_t pix_smem_bytes(int nA, int nB, int nbins, int Wpad) {
 }
 
 static int eval_pixels_device(mb_handle* h, const double* d_phi, int W, int ndim, double* d_out, cudaStream_t st,
-                              const double* const d_tab[MB_NPARAM] = nullptr) {
+                              const double* const d_tab[MB_NPARAM] = nullptr, const double* d_box = nullptr) {
   if (h->P <= 0) return fail("handle was not created with mb_create_pixels");
   if (ndim != h->ndim) return fail("phi has %d columns, the model has %d free variables", ndim, h->ndim);
   if (W < 1 || W > 128) return fail("pixel batches take 1..128 walkers per pixel (got %d)", W);
@@ -1173,7 +1173,7 @@ static int eval_pixels_device(mb_handle* h, const double* d_phi, int W, int ndim
   const bool prof = h->profiling != 0;
   if (prof) CK(cudaEventRecord(h->ev[0], st));
   K0Args k0{};
-  k0.model = h->mdev; k0.clsx = h->d_clsx; k0.phi = d_phi; k0.F = h->d_Fpix;
+  k0.model = h->mdev; k0.clsx = h->d_clsx; k0.phi = d_phi; k0.F = h->d_Fpix; k0.box = d_box;
   for (int p = 0; p < MB_NPARAM; ++p) k0.tab[p] = d_tab ? d_tab[p] : nullptr;
   k0.rowsrc = h->d_rowsrc; k0.nrows = h->nA + h->nB; k0.nAge = h->nA;
   k0.W = W; k0.Wpad = Wpad; k0.ndim = ndim; k0.ncls_total = h->ncls_total;
@@ -1790,7 +1790,8 @@ static int pixels_host_eval(mb_handle* h, const double* phi, int32_t W, int32_t 
   if (!h->watches.empty() && check_watches(h)) return 1;
   CK(cudaSetDevice(h->device));
   const int64_t ncol = h->P * W;
-  const int64_t nphi = ncol * std::max(1, ndim), nout = (int64_t)MB_OUT_ROWS * ncol;
+  const int64_t nbox = lo ? 3 * (int64_t)ndim : 0;  // lo, hi, park travel behind phi in the same copy
+  const int64_t nphi = ncol * std::max(1, ndim) + nbox, nout = (int64_t)MB_OUT_ROWS * ncol;
   if (ensure(h, &h->d_phi, &h->cap_phi, nphi)) return 1;
   if (ensure(h, &h->d_out, &h->cap_out, nout)) return 1;
   if (nphi + nout > h->cap_pin) {
@@ -1806,18 +1807,13 @@ static int pixels_host_eval(mb_handle* h, const double* phi, int32_t W, int32_t 
   double* hp = h->h_pin;
   double* ho = h->h_pin + nphi;
   if (ndim > 0) memcpy(hp, phi, sizeof(double) * (size_t)ncol * ndim);
-  std::vector<int32_t>& outside = h->scratch_idx;  // columns outside the prior box
-  outside.clear();
-  if (lo && ndim > 0) {
-    for (int64_t c = 0; c < ncol; ++c) {
-      double* p = hp + (size_t)c * ndim;
-      bool inside = true;
-      for (int k = 0; k < ndim; ++k) inside &= !(p[k] < lo[k] || p[k] > hi[k]);  // same compare as mb_lnprob_box
-      if (!inside) {
-        memcpy(p, park, sizeof(double) * ndim);
-        outside.push_back((int32_t)c);
-      }
-    }
+  const double* d_box = nullptr;
+  if (nbox > 0) {
+    double* hb = hp + nphi - nbox;
+    memcpy(hb, lo, sizeof(double) * ndim);
+    memcpy(hb + ndim, hi, sizeof(double) * ndim);
+    memcpy(hb + 2 * ndim, park, sizeof(double) * ndim);
+    d_box = h->d_phi + (nphi - nbox);
   }
   CK(cudaMemcpyAsync(h->d_phi, hp, sizeof(double) * (size_t)nphi, cudaMemcpyHostToDevice, h->stream));
   // host-evaluated tables of MB_TABULATED parameters: [P * W][n_classes]
@@ -1832,8 +1828,20 @@ static int pixels_host_eval(mb_handle* h, const double* phi, int32_t W, int32_t 
     dtab[p] = h->d_tab[p];
     any_tab = true;
   }
-  if (eval_pixels_device(h, h->d_phi, W, ndim, h->d_out, h->stream, any_tab ? dtab : nullptr)) return 1;
+  if (eval_pixels_device(h, h->d_phi, W, ndim, h->d_out, h->stream, any_tab ? dtab : nullptr, d_box)) return 1;
   CK(cudaMemcpyAsync(ho, h->d_out, sizeof(double) * (size_t)nout, cudaMemcpyDeviceToHost, h->stream));
+  // While the device works: which columns are outside the box?  K0 makes the same IEEE compares on the same
+  // values and builds those columns from `park`; here they are only listed, to be reported as -inf.
+  std::vector<int32_t>& outside = h->scratch_idx;
+  outside.clear();
+  if (nbox > 0) {
+    for (int64_t c = 0; c < ncol; ++c) {
+      const double* p = phi + (size_t)c * ndim;
+      bool inside = true;
+      for (int k = 0; k < ndim; ++k) inside &= !(p[k] < lo[k] || p[k] > hi[k]);  // same compare as mb_lnprob_box
+      if (!inside) outside.push_back((int32_t)c);
+    }
+  }
   CK(cudaStreamSynchronize(h->stream));
   for (int64_t p = 0; p < h->P; ++p)  // rows are [p][3][W]
     mb_combine(ho + (size_t)p * MB_OUT_ROWS * W, W, lnlike + (size_t)p * W, status + (size_t)p * W);

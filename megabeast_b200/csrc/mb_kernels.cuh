@@ -148,6 +148,8 @@ struct K0Args {
   double* F;                  // [P][nrows + nAge][Wpad]: outer rows, inner rows, plain age rows
   const uint16_t* rowsrc;     // [nrows][4] look-up rows (class offsets included) multiplied into a table row; 0xffff = none
   int32_t nrows, nAge, W, Wpad, ndim, ncls_total;
+  const double* box;          // null, or [3][ndim] = lo, hi, park: a column with any phi outside [lo, hi] is built
+                              // from `park` instead (mb_lnprob_pixels_box; the host reports it as -inf)
 };
 constexpr int kK0Threads = 128;
 
@@ -161,6 +163,14 @@ __global__ void __launch_bounds__(kK0Threads) mb_k0_factors(const __grid_constan
   const int wr = w < a.W ? w : a.W - 1;
   const size_t col = (size_t)pix * a.W + wr;
   const double* ph = a.phi + col * a.ndim;
+  if (a.box) {  // block-uniform: every thread tests the same ndim values
+    bool outside = false;
+    for (int k = 0; k < a.ndim; ++k) {
+      const double v = ph[k];
+      outside |= v < a.box[k] || v > a.box[a.ndim + k];  // a NaN is inside, as in singlepop_dust_model.py:255-271
+    }
+    if (outside) ph = a.box + 2 * a.ndim;
+  }
   for (int i = threadIdx.x; i < a.ncls_total; i += kK0Threads) {
     int p = 0;
 #pragma unroll
