@@ -1025,7 +1025,16 @@ struct K2Args {
   ModelDev model;
   double phi_in[kPhiInline];
 };
-constexpr int kTimelinePoints = 8;  // start, tables staged, N-stars bins done, stars done, block reduced,
+// -DMB_WARP_STAMPS (measurement builds only, scripts/k2_warp_stamps.py): per warp, after the 8 block stamps --
+// table build left, star loop entered (after its N-stars bin, if it took one), star loop left, entries of its
+// first segment (as block start + 1000 ns per entry)
+#ifdef MB_WARP_STAMPS
+constexpr int kWarpStampWarps = 24, kWarpStampPoints = 4;
+#else
+constexpr int kWarpStampWarps = 0, kWarpStampPoints = 0;
+#endif
+constexpr int kTimelinePoints = 8 + kWarpStampWarps * kWarpStampPoints;
+                                    // start, tables staged, N-stars bins done, stars done, block reduced,
                                     // (last block:) totals + Poisson term + sent to peers, peers received, end
 __device__ __forceinline__ void stamp(unsigned long long* timeline, int point) {
   if (timeline && threadIdx.x == 0) {
@@ -1622,6 +1631,17 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     if (a.pois.nbins > 0 && (a.pois.warp_private || a.pois.hts_slices > 0)) { hts_wait(); __syncthreads(); }  // (also publishes bin_ctr)
   }
   stamp(a.timeline, 1);
+#ifdef MB_WARP_STAMPS
+  unsigned long long* wst = a.timeline ? a.timeline + (size_t)blockIdx.x * kTimelinePoints + 8 + warp * kWarpStampPoints : nullptr;
+  auto wstamp = [&](int k) {
+    if (wst && lane == 0 && warp < kWarpStampWarps) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      wst[k] = t;
+    }
+  };
+  wstamp(0);
+#endif
   // N-stars prologue: this block's (age, Z) bins for all walkers of the pass, on the tables it just
   // staged (always the fp64 ones: from shared memory when they are there, else from global memory)
   const double* Ftab = (MODE == kModeFactor && !kF32) ? reinterpret_cast<const double*>(smem_raw + a.tab_off) : a.FA;
@@ -1631,6 +1651,11 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     poisson_bins_private<NW, k2_threads(NW)>(a.pois, Ftab, a.nA, a.nOd, a.nB, smem_raw, &bin_ctr);
 
   stamp(a.timeline, 2);
+#ifdef MB_WARP_STAMPS
+  wstamp(1);
+  if (wst && lane == 0 && warp < kWarpStampWarps)
+    wst[3] = a.timeline[(size_t)blockIdx.x * kTimelinePoints] + 1000ull * (s < a.nseg ? (unsigned long long)(a.seg[s + 1] - a.seg[s]) : 0ull);
+#endif
   Lanes<NW, MODE, TF, OB> L;
   L.init(tabA, tabB, reinterpret_cast<const char*>(a.T) + lanebytes);
 
@@ -1659,6 +1684,9 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   // warps wait here for the block's slowest one anyway (segments end on star boundaries), so the
   // N-stars term costs the critical path nothing.  The tables are still intact (the reduction slabs
   // move over them only after the barrier below).
+#ifdef MB_WARP_STAMPS
+  wstamp(2);
+#endif
   if (a.pois.nbins > 0 && a.pois.warp_private && !a.pois.bins_first)
     poisson_bins_private<NW, k2_threads(NW)>(a.pois, Ftab, a.nA, a.nOd, a.nB, smem_raw, &bin_ctr);
 
