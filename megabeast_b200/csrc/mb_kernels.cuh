@@ -235,6 +235,12 @@ struct PoissonArgs {
                               // to get there; 0 (MB_BINS_LAST=1): after the star loop by the first warps to finish
 };
 constexpr int kPoisBins = 2;  // bins a block works on at a time (loads of both in flight together)
+// classes of a bin whose loads are in flight together in the one-warp-per-bin sum: the warp shares the load/store
+// pipe with 23 warps streaming stars, every dependent round trip costs ~200 cycles there
+#ifndef MB_BIN_UNROLL
+#define MB_BIN_UNROLL 4
+#endif
+constexpr int kBinUnroll = MB_BIN_UNROLL;
 
 // F: outer rows then inner rows, element (row, w) at F[row * Wpad + w]; shared memory (FACTOR mode with
 // fp64 tables) or global.  All threads of the block must call.  Lane l of a warp owns walkers
@@ -402,7 +408,7 @@ __device__ void poisson_bins_private(const PoissonArgs& pa, const double* F, int
         double s[NW], c[NW];
 #pragma unroll
         for (int j = 0; j < NW; ++j) { s[j] = 0.0; c[j] = 0.0; }
-#pragma unroll 4
+#pragma unroll kBinUnroll
         for (int i = 0; i < nI; ++i) {
           const double2 h = hrow[(size_t)od * nI + i];   // warp-uniform: a broadcast
           const double* f = FI + (size_t)i * Wpad;
