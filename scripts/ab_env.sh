@@ -8,7 +8,7 @@ B="python bench.py --steps 200 --warmup 10 --no-cpu-baseline --no-clustered --no
 for round in 1 2 3; do
   for v in unset 1; do
     if [ $v = unset ]; then unset $VAR; else export $VAR=1; fi
-    for wl in cfg3_eighth cfg3; do
+    for wl in ${WLS:-cfg3_eighth cfg3}; do
       timeout 300 $B --workload $wl > $OUT/ab.json 2> $OUT/ab.err || tail -3 $OUT/ab.err
       python - $OUT/ab.json "$VAR=$v" $wl $round <<'PY'
 import json, sys
