@@ -70,8 +70,6 @@ struct mb_handle {
   uint16_t* d_ec16 = nullptr;   // ... 16-bit codes: FACTOR mode, fp64 tables, <= 16 age classes (see Lanes)
   int c16 = 0;
   int64_t* d_seg[2] = {nullptr, nullptr};  // segment tables: [0] 768-thread kernels, [1] 512-thread kernel
-  int64_t* d_cut[2] = {nullptr, nullptr};  // equal pieces that may cut a star (build_cut_pieces), or null
-  int ncut[2] = {0, 0};                    // pieces in d_cut (= warps of a full launch)
   uint32_t* d_rowcode = nullptr;
   uint16_t* d_rowsrc = nullptr;   // [nO + nI][4] look-up rows multiplied into a table row (K0)
   uint16_t* d_rowslot = nullptr;  // the same as slots of K2's own table build (0xfffe: evaluated in place)
@@ -397,7 +395,7 @@ extern "C" void mb_destroy(mb_handle* h) {
   cudaSetDevice(h->device);
   if (h->peer_world > 1) mb_peer_disconnect(h);
   if (h->d_xbuf) cudaFree(h->d_xbuf);
-  void* ptrs[] = {h->d_clsx, h->d_ea, h->d_ec, h->d_ec16, h->d_seg[0], h->d_seg[1], h->d_cut[0], h->d_cut[1], h->d_rowcode, h->d_H, h->d_coef,
+  void* ptrs[] = {h->d_clsx, h->d_ea, h->d_ec, h->d_ec16, h->d_seg[0], h->d_seg[1], h->d_rowcode, h->d_H, h->d_coef,
                   h->d_bin_agecls, h->d_phi, h->d_tab[0], h->d_tab[1], h->d_tab[2], h->d_tab[3],
                   h->d_F, h->d_counter, h->d_gacc, h->d_T, h->d_out, h->d_pix_seg, h->d_pix_nstars, h->d_Fpix,
                   h->d_timeline, h->d_col[0], h->d_col[1], h->d_col[2], h->d_col[3], h->d_gw, h->d_compl,
@@ -433,37 +431,6 @@ static void build_segments(const mb_handle* h, int t, std::vector<int64_t>& seg)
     if (j < ends.size() && ends[j] > seg.back()) seg.push_back(ends[j]);
   }
   if (n > 0 && seg.back() != n) seg.push_back(n);
-}
-
-// Equal pieces for the warps of a full launch of block shape t (FACTOR mode, one block per SM).  Star-aligned
-// segments quantise a warp's share to whole stars -- at 1/8 of config 3 a warp gets 3 or 4 stars, 140 or 190
-// entries -- and a block ends with its longest segment (measured: scripts/k2_warp_stamps.py).  Here only the
-// BLOCK ranges are star aligned; inside a block every warp gets the same number of entries, cut anywhere:
-// boundaries [blocks * warps + 1].  K2 joins the two parts of a cut star through shared memory.  Every piece
-// must hold at least one star start, i.e. be at least as long as the longest star.  Empty = not applicable.
-static void build_cut_pieces(const mb_handle* h, int t, std::vector<int64_t>& cut) {
-  cut.clear();
-  const std::vector<int64_t>& ends = h->star_end_pos;
-  const int kw = k2_threads(t == 0 ? 2 : 4) / 32, nblocks = h->sm_count;
-  const int64_t n = h->n_entries;
-  if (ends.empty() || n <= 0 || h->spw != 1 || h->tail_frac > 0.0 || getenv("MB_NO_CUT")) return;
-  int64_t maxstar = 0, prev = 0;
-  for (int64_t e : ends) { maxstar = std::max(maxstar, e - prev); prev = e; }
-  if (n / ((int64_t)nblocks * kw) < maxstar + 1) return;
-  cut.reserve((size_t)nblocks * kw + 1);
-  cut.push_back(0);
-  int64_t b0 = 0;
-  for (int b = 0; b < nblocks; ++b) {
-    int64_t b1 = n;
-    if (b + 1 < nblocks) b1 = *std::lower_bound(ends.begin(), ends.end(), (n * (b + 1) + nblocks - 1) / nblocks);
-    const int64_t len = b1 - b0;
-    for (int w = 1; w <= kw; ++w) {
-      const int64_t hi = b0 + (len * w) / kw;
-      if (hi - cut.back() < maxstar) { cut.clear(); return; }
-      cut.push_back(hi);
-    }
-    b0 = b1;
-  }
 }
 
 // Entry build on the device (mb_build_entries + mb_compact_entries): uploads this handle's columns of
@@ -1059,14 +1026,6 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
   if (dev_upload(h, &h->d_clsx, clsx_all)) return 1;
   if (dev_upload(h, &h->d_seg[0], seg[0])) return 1;
   if (dev_upload(h, &h->d_seg[1], seg[1])) return 1;
-  if (mode == MB_MODE_FACTOR && n_pixels == 0) {
-    for (int t = 0; t < 1; ++t) {   // (the 768-thread kernels only, see eval_device)
-      std::vector<int64_t> cut;
-      build_cut_pieces(h, t, cut);
-      h->ncut[t] = cut.empty() ? 0 : (int)cut.size() - 1;
-      if (!cut.empty() && dev_upload(h, &h->d_cut[t], cut)) return 1;
-    }
-  }
   if (mode == MB_MODE_TABLE_GRID && dev_upload(h, &h->d_rowcode, rowcode)) return 1;
   if (!elementwise) {
     if (dev_upload(h, &h->d_rowsrc, rowsrc)) return 1;
@@ -1579,18 +1538,6 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     k2.pois.warp_private = plan.warp_private ? 1 : 0; k2.pois.hts_off = (int32_t)plan.hts_off; k2.pois.hts_slices = plan.hts_slices;
     static const bool bins_last = getenv("MB_BINS_LAST") && atoi(getenv("MB_BINS_LAST"));  // A/B switch (measurements)
     k2.pois.bins_first = bins_last ? 0 : 1;
-    // cut pieces (build_cut_pieces): one equal piece per warp of a full launch.  Needs the tables built in the
-    // kernel with a private scratch (the per-walker constants' 6 * NPARAM * Wpad doubles are dead after the
-    // build and hold the [warps][Wpad] exchange) and one block per SM
-    const int tcut = NW == 4 ? 1 : 0;
-    // (up to 64 walkers per pass: a warp's idle entry ring, 1.5 KB, then holds its last partial sums)
-    if (kmode == kModeFactor && fused && plan.separate && h->table_bytes == 8 && NW <= 2 && h->d_cut[tcut] &&
-        grid * kK2Warps == h->ncut[tcut]) {
-      k2.seg = h->d_cut[tcut];
-      k2.nseg = h->ncut[tcut];
-      k2.cut_mode = 1;
-      k2.cut_off = (int32_t)(plan.scratch_off + 8 * ((size_t)h->nscratch * Wpad + 3 * (size_t)h->ncls_total));
-    }
     k2.pois.SC = elementwise ? h->d_SC : nullptr;
     // plain age factors (the `ageprior` of helpers.py:135): K1e's per-bin rows, K0's rows in global
     // memory, or -- tables built inside K2 -- the outer table itself / the scratch look-up rows

@@ -996,12 +996,8 @@ constexpr int kPhiInline = MB_PHI_INLINE;  // doubles of phi carried in K2's ker
 struct K2Args {
   const double* ea;     // entry weights  [n_entries]
   const void* ec;       // entry codes    [n_entries]: uint32, or uint16 for the C16 kernels (padded by one)
-  const int64_t* seg;   // [nseg+1] entry offsets, star aligned -- or, with cut_mode, equal pieces that may cut a star
+  const int64_t* seg;   // [nseg+1] entry offsets, star aligned
   int32_t nseg;
-  int32_t cut_mode;     // 1: seg = one piece per warp of the launch (nseg = gridDim.x * warps), star aligned only at
-                        // the block boundaries (build_cut_pieces in mb_api.cu); the star cut between warps w-1 and w
-                        // of a block = last partial sum of w-1 (shared memory, cut_off) + head of w
-  int32_t cut_off;      // byte offset of the [warps][Wpad] exchange (dead table-build scratch)
   const double* FA;     // FACTOR: outer rows [nA][Wpad] then inner rows [nB][Wpad], contiguous (staged to smem)
   const double* T;      // TABLE*: [U][Wpad]
   unsigned long long* gacc;  // [kAccRows][Wpad] fixed-point log-sum (hi, lo), non-finite stars, nan flags (zero between launches)
@@ -1126,15 +1122,6 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
   asm("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr));
   return v;
 }
-// ordered forms (cut pieces: partial star sums handed from warp to warp behind a flag)
-__device__ __forceinline__ double lds_f64_ordered(uint32_t addr) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
-  asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(addr), "d"(v) : "memory");
-}
 __device__ __forceinline__ uint2 lds_u32x2(uint32_t addr) {
   uint2 v;
   asm("ld.shared.v2.u32 {%0,%1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(addr));
@@ -1192,11 +1179,6 @@ struct Lanes {
   static constexpr uint32_t rowbytes = 32u * NW * (MODE == 1 ? (uint32_t)sizeof(TF) : 8u);
   double run[NW], run2[NW];       // two partial sums of the current run (halves the DFMA chain)
   double star[NW], fa[NW];
-  // cut pieces (FACTOR mode): a piece may start inside a star.  With head_addr set (a shared-memory address,
-  // lane offset included), the first star boundary parks the sum so far there (element i at + 256 i) instead of
-  // folding it into acc -- it is only PART of that star; the warp joins it with the previous piece's last
-  // partial sum after its range (mb_k2_stars).  One register; nothing else is carried through the loop.
-  uint32_t head_addr;
   LogAcc acc[NW];
   uint32_t tabA, tabB;            // FACTOR: shared-memory byte addresses (lane offset included)
   const char* Tlane;              // TABLE*: global table base + lane offset
@@ -1205,7 +1187,6 @@ struct Lanes {
     tabA = keep_in_register(tabA_); tabB = keep_in_register(tabB_); Tlane = Tlane_;
 #pragma unroll
     for (int i = 0; i < NW; ++i) { run[i] = 0.0; run2[i] = 0.0; star[i] = 0.0; fa[i] = 1.0; acc[i].init(); }
-    head_addr = 0;
   }
   // factors of one entry for this lane's walkers
   // FACTOR: one table row element pair / element of this lane (byte address given)
@@ -1250,14 +1231,8 @@ struct Lanes {
 #pragma unroll
     for (int i = 0; i < NW; ++i) { star[i] = fma(fa[i], run[i] + run2[i], star[i]); run[i] = 0.0; run2[i] = 0.0; }
     if (MODE != kModeFactor || is_star(code)) {
-      if (MODE == kModeFactor && head_addr != 0) {   // (warp-uniform; at most once per piece)
 #pragma unroll
-        for (int i = 0; i < NW; ++i) { sts_f64(head_addr + 256u * i, star[i]); star[i] = 0.0; }
-        head_addr = 0;
-      } else {
-#pragma unroll
-        for (int i = 0; i < NW; ++i) { star_done(acc[i], star[i]); star[i] = 0.0; }
-      }
+      for (int i = 0; i < NW; ++i) { star_done(acc[i], star[i]); star[i] = 0.0; }
     }
     if (MODE == kModeFactor) lds_row(age(code) * rowbytes + tabA, fa);
   }
@@ -1272,14 +1247,6 @@ struct Lanes {
   __device__ __forceinline__ void step(double a, uint32_t code, const double* f) {
     if (is_run(code)) boundary(code);  // the new-run flag, warp-uniform
     mac(a, f);
-  }
-  // cut pieces: the range ended inside a star (or on its end): its sum so far, not folded into acc
-  __device__ __forceinline__ void close_partial(double* out) {
-#pragma unroll
-    for (int i = 0; i < NW; ++i) {
-      out[i] = fma(fa[i], run[i] + run2[i], star[i]);
-      star[i] = 0.0; run[i] = 0.0; run2[i] = 0.0;
-    }
   }
   // a streamed range ends on a star boundary: close the last star
   __device__ __forceinline__ void close() {
@@ -1461,10 +1428,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   __shared__ unsigned int ticket;
   __shared__ int timed_out;
   __shared__ int bin_ctr;       // next of the block's N-stars bins (claimed by warps after their stars)
-  __shared__ int cut_flag[kK2Warps];  // cut pieces: warp w has published its last partial star sum
   if (threadIdx.x == 0) bin_ctr = 0;
-  if (threadIdx.x < kK2Warps) cut_flag[threadIdx.x] = 0;  // (visible after the table build's barriers)
-  const bool cutm = MODE == kModeFactor && a.cut_mode != 0;
   stamp(a.timeline, 0);
   // launched with programmatic stream serialization: wait here for K0 (the tables) to complete
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1500,10 +1464,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     }
     __syncwarp();
   }
-  uint32_t code0 = 0;  // cut pieces: the piece's first code (it may start inside a run: its outer factor is fetched up front)
   auto prime_now = [&]() {
-    if (cutm && warp > 0 && s < a.nseg && !primed)
-      code0 = OB > 0 ? (uint32_t)__ldg(static_cast<const uint16_t*>(a.ec) + seg_lo) : __ldg(static_cast<const uint32_t*>(a.ec) + seg_lo);
     if (want_prime && !primed) {
       if (tma) stream_prime<STAGES, OB, true>(a.ea, a.ec, seg_lo, seg_hi, st_a, st_c, bar0, lane);
       else stream_prime<STAGES, OB, false>(a.ea, a.ec, seg_lo, seg_hi, st_a, st_c, bar0, lane);
@@ -1704,12 +1665,6 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   Lanes<NW, MODE, TF, OB> L;
   L.init(tabA, tabB, reinterpret_cast<const char*>(a.T) + lanebytes);
 
-  // (where a piece parks the head of the star it shares with the previous warp: [warps][Wpad] in the dead scratch)
-  const uint32_t head0 = smem0 + (uint32_t)a.cut_off + (uint32_t)warp * (Wpad * 8u) + 8u * lane;
-  if (cutm && warp > 0 && s < a.nseg) {
-    L.head_addr = head0;
-    L.lds_row(L.age(code0) * rowbytes + tabA, L.fa);
-  }
   // Segments: every warp starts with its own index (no atomic storm at kernel start); further
   // ones are claimed from a shared counter, one atomic per segment issued a segment ahead.  The
   // result does not depend on who processed what: a segment's value depends only on its own
@@ -1723,36 +1678,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
     if (tma) stream_range<NW, MODE, TF, STAGES, OB, true>(L, a.ea, a.ec, a.seg[s], a.seg[s + 1], st_a, st_c, lane, primed, bar0, &ring_par);
     else stream_range<NW, MODE, TF, STAGES, OB, false>(L, a.ea, a.ec, a.seg[s], a.seg[s + 1], st_a, st_c, lane, primed);
     primed = false;
-    if (cutm) {
-      // this piece's last star may continue in the next warp's piece: publish its sum so far (data, fence, flag)
-      // in this warp's own, now idle, entry ring; the block's last piece ends on a star end
-      if (warp + 1 < kK2Warps) {
-        double part[NW];
-        L.close_partial(part);
-#pragma unroll
-        for (int i = 0; i < NW; ++i) sts_f64(st_a + 8u * lane + 256u * i, part[i]);
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) *reinterpret_cast<volatile int*>(&cut_flag[warp]) = 1;
-      } else {
-        L.close();
-      }
-      // the star cut between the previous warp's piece and this one = its last partial sum + this head
-      if (warp > 0) {
-        if (lane == 0) {  // (published long ago unless the two warps finish together; never a hang: trap instead)
-          unsigned spins = 0;
-          while (*reinterpret_cast<volatile int*>(&cut_flag[warp - 1]) == 0)
-            if (++spins > (1u << 28)) __trap();
-        }
-        __syncwarp();
-        __threadfence_block();
-#pragma unroll
-        for (int i = 0; i < NW; ++i)
-          star_done(L.acc[i], lds_f64_ordered(st_a - k2_stage_bytes(NW) + 8u * lane + 256u * i) + lds_f64_ordered(head0 + 256u * i));
-      }
-    } else {
-      L.close();
-    }
+    L.close();
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
       const Fix2 f = to_fix2(L.acc[i].take_value());
