@@ -829,7 +829,6 @@ def run_secondary_cfg5(args, world, rank, local, dev, barrier, max_over_ranks, f
 
     import numpy as np
     import torch
-    import torch.distributed as dist
 
     from megabeast_b200 import synth
     from megabeast_b200.pixels import PixelEnsemble
