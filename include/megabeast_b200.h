@@ -280,7 +280,10 @@ int64_t mb_pixel_count(const mb_handle* h);
 int mb_watch_host(mb_handle* h, const void* ptr, int64_t nbytes);
 
 /* Distinct values ("classes") of a free parameter's grid column, ascending; the x at which a
- * host callable must be tabulated.  Returns the count; fills at most `cap` values. */
+ * host callable must be tabulated.  Returns the count; fills at most `cap` values.
+ * ELEMENTWISE mode (a column that cannot be class-coded) with an MB_TABULATED dust parameter: every
+ * grid row is its own class -- the G column values in row order, tab[p] is [W][G] (the cost the
+ * reference itself pays, singlepop_dust_model.py:146-148). */
 int mb_class_values(const mb_handle* h, int32_t param, double* out, int32_t cap);
 
 /* Parity hook: the grid rows this handle dereferences, star-major (needs keep_indices).

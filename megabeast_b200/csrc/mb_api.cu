@@ -633,8 +633,17 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
     for (int p = 0; p < MB_NPARAM; ++p) {
       md.ncls[p] = 1; md.clsoff[p] = 0; md.radix[p] = 0; h->clsx[p].clear(); code[p].clear();
       if (model->kind[p] == MB_FIXED) continue;
-      if (model->kind[p] == MB_TABULATED)
-        return fail("tabulated prior models need class-codable columns (not available in ELEMENTWISE mode)");
+      if (model->kind[p] == MB_TABULATED) {
+        // a host-evaluated model on a column that cannot be class-coded: every grid row is its own class --
+        // mb_class_values returns the column in row order, the table is [W][G] (the reference's own cost,
+        // singlepop_dust_model.py:146-148).  Dust parameters only: the age factor of an (age, Z) bin is
+        // needed apart from the rows (helpers.py:135)
+        if (p == MB_P_LOGA) return fail("a tabulated age model needs a class-codable logA column (not available in ELEMENTWISE mode)");
+        if (G > 0x7fffffffLL) return fail("grid too large for a per-row table");
+        md.ncls[p] = (int32_t)G;
+        h->clsx[p].assign(grid->col[p], grid->col[p] + G);
+        continue;
+      }
       const double* col = grid->col[p];
       const int n = model->nnodes[p];
       for (int64_t g = 0; g < G; ++g) {
@@ -1477,7 +1486,10 @@ static int eval_device(mb_handle* h, const double* d_phi, int W, int ndim, const
     if (elementwise) {
       K1eArgs k1{};
       k1.model = h->mdev;
-      for (int p = 0; p < MB_NPARAM; ++p) k1.col[p] = h->d_col[p];
+      for (int p = 0; p < MB_NPARAM; ++p) {
+        k1.col[p] = h->d_col[p];
+        k1.tab[p] = (d_tab && d_tab[p]) ? d_tab[p] + (size_t)w0 * (size_t)h->G : nullptr;
+      }
       k1.phi = d_phi + (size_t)w0 * ndim; k1.T = h->d_T; k1.G = h->G;
       k1.W = wp; k1.Wpad = Wpad; k1.ndim = ndim;
       if (h->poisson) {

@@ -526,6 +526,8 @@ constexpr int kK1eWalkerVals = 6;   // per (parameter, walker) derived constants
 struct K1eArgs {
   ModelDev model;
   const double* col[MB_NPARAM];  // device columns of the free parameters [G]
+  const double* tab[MB_NPARAM];  // MB_TABULATED dust parameters: the host callable's values on the whole column,
+                                 // [W][G] (every grid row is its own class here); null otherwise
   const double* phi;             // [W][ndim]
   double* T;                     // [G][Wpad]
   // N-stars term (helpers.py:133-162), optional: rows are visited in (age, Z)-bin order through
@@ -728,7 +730,7 @@ __global__ void __launch_bounds__(kK1eThreads, LN ? 2 : 3) mb_k1_elementwise(con
     __syncthreads();
     for (int i = threadIdx.x; i < MB_NPARAM * kK1eRows; i += kK1eThreads) {
       const int p = i / kK1eRows, r = i - p * kK1eRows;
-      if (m.kind[p] != MB_FIXED && r < nrows) {
+      if (m.kind[p] != MB_FIXED && m.kind[p] != MB_TABULATED && r < nrows) {
         double r0, r1; int ri;
         k1e_row_part(m, p, __ldg(a.col[p] + srow[r]), &r0, &r1, &ri);
         sr0[i] = r0; sr1[i] = r1; sri[i] = ri;
@@ -761,6 +763,12 @@ __global__ void __launch_bounds__(kK1eThreads, LN ? 2 : 3) mb_k1_elementwise(con
           const double t0 = (lx - c[0][0]) * c[0][1], t1 = (lx - c[1][0]) * c[1][1];
           e0 = fma(-0.5 * t0, t0, e0); e1 = fma(-0.5 * t1, t1, e1);
           pf0 *= c[0][2] * rx; pf1 *= c[1][2] * rx;
+          continue;
+        }
+        if (kinds[p] == MB_TABULATED) {  // (padding columns repeat the last walker)
+          const size_t g = (size_t)srow[r];
+          v0 *= __ldg(a.tab[p] + (size_t)min(2 * pair, a.W - 1) * a.G + g);
+          v1 *= __ldg(a.tab[p] + (size_t)min(2 * pair + 1, a.W - 1) * a.G + g);
           continue;
         }
         const double* th0 = sphi + (size_t)(2 * pair) * ndim + m.voff[p];

@@ -220,6 +220,30 @@ def test_pixel_batch_with_a_host_tabulated_model():
     pe2.close()
 
 
+def test_host_tabulated_model_on_a_non_cartesian_grid():
+    """The last combination that used to be refused: a prior model the device does not know (host callable)
+    on a grid whose dust columns cannot be class-coded (ELEMENTWISE mode).  Every grid row is then its own
+    class: the callable is evaluated on the whole column per walker, as the reference does
+    (singlepop_dust_model.py:146-148), and the [W][G] table rides along."""
+    settings, moddata, stars, _ = synth.make_problem("small", seeds=(21, 22, 23))
+    rng = np.random.default_rng(5)
+    moddata = dict(moddata)
+    for key in ("Av", "Rv"):
+        moddata[key] = moddata[key] * (1.0 + 1e-3 * rng.standard_normal(moddata[key].size))
+    pm = port.PortModel(copy.deepcopy(settings))
+    for W in (1, 9, 70, 140):     # one-walker, one pass, 128-wide pass, two passes
+        phis = synth.make_walkers(pm, W, seed=24 + W)
+        want = c_oracle.lnprob_batch(pm, phis, stars, moddata)
+        model = MB_Model(copy.deepcopy(settings))
+        av = model.physics_model["Av"]
+        av["name"] = "some_future_beast_model"
+        av["model"] = lambda x, av=av: _host_lognormal(x, av["mean"], av["sigma"])
+        got = lnprob(phis, model, stars, moddata)
+        info = model.engine_info()
+        assert info["mode"] == "elementwise" and info["n_classes"][1] == moddata["Av"].size   # (logA, Av, Rv, fA)
+        assert_close(got, want, RTOL)
+
+
 def test_pixel_batch_prior_box_in_the_c_call():
     """``PixelEnsemble.lnprob`` applies the flat prior box inside one C call (``mb_lnprob_pixels_box``):
     same values, bit for bit, as lnprior + lnlike composed on the host (singlepop_dust_model.py:277-304);
