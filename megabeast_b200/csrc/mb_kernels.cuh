@@ -1680,9 +1680,15 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
   long long fixhi[NW], fixlo[NW];
 #pragma unroll
   for (int i = 0; i < NW; ++i) { fixhi[i] = 0; fixlo[i] = 0; }
+  // (ptxas turns the claim -- written as atomicAdd() or as a PTX atom -- into its warp-aggregated form, leader
+  // atomic + SHFL of the result, so the warp WAITS for the atomic's round trip where it is issued: ~1.3 us per
+  // warp at the head of the loop with 3,552 warps hitting one address (ncu source page,
+  // profiles/r2_k2_source_hotspots.txt).  With one segment per warp -- the default -- there is nothing to
+  // claim, and the atomic is skipped.)
+  const bool more_segments = a.nseg > nwarps_total;
   int s_next = 0;
   while (s < a.nseg) {
-    if (lane == 0) s_next = nwarps_total + (int)atomicAdd(a.counters + kCtrSegment, 1u);
+    if (more_segments && lane == 0) s_next = nwarps_total + (int)atomicAdd(a.counters + kCtrSegment, 1u);
     if (tma) stream_range<NW, MODE, TF, STAGES, OB, true>(L, a.ea, a.ec, a.seg[s], a.seg[s + 1], st_a, st_c, lane, primed, bar0, &ring_par);
     else stream_range<NW, MODE, TF, STAGES, OB, false>(L, a.ea, a.ec, a.seg[s], a.seg[s + 1], st_a, st_c, lane, primed);
     primed = false;
@@ -1692,7 +1698,7 @@ __global__ void __launch_bounds__(k2_threads(NW), k2_min_blocks(NW)) mb_k2_stars
       const Fix2 f = to_fix2(L.acc[i].take_value());
       fixhi[i] += f.hi; fixlo[i] += f.lo;
     }
-    s = __shfl_sync(0xffffffffu, s_next, 0);
+    s = more_segments ? __shfl_sync(0xffffffffu, s_next, 0) : a.nseg;
   }
   // Few dust classes: the block's (age, Z) bins are taken by whichever warps finish their stars first --
   // warps wait here for the block's slowest one anyway (segments end on star boundaries), so the
