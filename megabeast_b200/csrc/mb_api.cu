@@ -541,6 +541,9 @@ static int build_entries_device(mb_handle* h, const mb_grid_desc* grid, const mb
   return 0;
 }
 
+// returned by create_impl when the class-coded plan turned out impossible late and mode AUTO may still take
+// the elementwise evaluation: mb_create then tries again with that mode
+constexpr int kRetryElementwise = 3;
 static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
                        const mb_model_desc* model, const mb_massmult_desc* mm,
                        const mb_options* opts, int64_t n_pixels, const int64_t* pix_off, mb_handle** out) {
@@ -779,7 +782,12 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
             alone ? (uint16_t)(0x8000u | (unsigned)((inner ? h->nO : 0) + c)) : (uint16_t)nscratch++;
     }
     h->nscratch = nscratch;
-    if (h->nO + h->nI >= 0x7ff0) return fail("more than 32751 factor-table rows");
+    if (h->nO + h->nI >= 0x7ff0) {
+      // (e.g. a small grid whose every row has its own A(V) and R(V): few enough classes per column to be
+      // coded, but their product is as large as the grid squared)
+      fail("more than 32751 factor-table rows");
+      return (o.mode == MB_MODE_AUTO && n_pixels == 0) ? kRetryElementwise : 1;
+    }
     // K2's own table build reads the sources of a product row as slots directly
     rowslot.assign(rowsrc.size(), (uint16_t)0xffff);
     for (int r = 0; r < h->nO + h->nI; ++r) {
@@ -1137,7 +1145,14 @@ static int create_impl(const mb_grid_desc* grid, const mb_stars_desc* stars,
 extern "C" int mb_create(const mb_grid_desc* grid, const mb_stars_desc* stars,
                          const mb_model_desc* model, const mb_massmult_desc* mm,
                          const mb_options* opts, mb_handle** out) {
-  return create_impl(grid, stars, model, mm, opts, 0, nullptr, out);
+  int rc = create_impl(grid, stars, model, mm, opts, 0, nullptr, out);
+  if (rc == kRetryElementwise) {
+    mb_options o2{};
+    if (opts) o2 = *opts;
+    o2.mode = MB_MODE_ELEMENTWISE;
+    rc = create_impl(grid, stars, model, mm, &o2, 0, nullptr, out);
+  }
+  return rc ? 1 : 0;
 }
 
 extern "C" int mb_create_pixels(const mb_grid_desc* grid, const mb_stars_desc* stars,

@@ -80,8 +80,7 @@ def walkers(settings, W, seed, extra=()):
     return np.array(phis)
 
 
-def main():
-    spdm, _ = load_reference()
+def round1_cases(spdm):
 
     # 1. docs-example model, uniform and clustered sparse indices
     for mode in ("uniform", "clustered"):
@@ -191,6 +190,49 @@ def main():
     np.savez_compressed(path, phis=phis, expect=e, kind=k,
                         note="inputs regenerate from synth.make_problem('cfg1') seeds (1,2,3)")
     print(f"{'cfg1_expect':28s} W={len(phis):3d} (inputs are re-generated, only phis+expect stored)")
+
+
+def round2_cases(spdm, only=None):
+    """Cases added in round 2 (the files of the earlier cases are not rewritten by `--only`)."""
+    def want(name):
+        return only is None or name in only
+
+    # 11. production dust axes in miniature: 100 A(V) x 9 R(V) = 900 free dust classes (what a real BEAST
+    #     grid has; the device splits its factor tables for these), uniform-random indices
+    if want("production_dust_axes"):
+        axes = (4, 1, 2, 100, 9, 1)
+        settings = synth.docs_example_settings()
+        mod = synth.make_grid(axes, seed=41)
+        stars = synth.make_star_data(mod, axes, 60, 12, seed=42)
+        phis = walkers(settings, 8, seed=11)
+        e, k = run_reference(spdm, settings, mod, stars, phis)
+        save("production_dust_axes", settings, mod, stars, phis, e, k,
+             "100 A(V) x 9 R(V) = 900 free dust classes on a 7,200-row grid")
+
+    # 12. a grid that is NOT Cartesian: every row has its own A(V) and R(V) value (nothing to class-code);
+    #     the reference does not care (singlepop_dust_model.py:146-148 evaluates the models on the columns)
+    if want("non_cartesian_grid"):
+        axes = (5, 2, 3, 6, 3, 1)
+        settings = synth.docs_example_settings()
+        mod = synth.make_grid(axes, seed=51)
+        rng = np.random.default_rng(53)
+        for key in ("Av", "Rv"):
+            mod[key] = mod[key] * (1.0 + 1e-3 * rng.standard_normal(mod[key].size))
+        stars = synth.make_star_data(mod, axes, 70, 10, seed=52, mode="clustered")
+        phis = walkers(settings, 8, seed=12)
+        e, k = run_reference(spdm, settings, mod, stars, phis)
+        save("non_cartesian_grid", settings, mod, stars, phis, e, k,
+             "every grid row its own A(V), R(V) value: no class coding possible")
+
+
+def main():
+    """`python tests/golden/make_golden.py` rewrites everything; `--only a,b` writes just those round-2 cases."""
+    spdm, _ = load_reference()
+    if "--only" in sys.argv:
+        round2_cases(spdm, sys.argv[sys.argv.index("--only") + 1].split(","))
+        return
+    round1_cases(spdm)
+    round2_cases(spdm)
 
 
 if __name__ == "__main__":

@@ -20,6 +20,12 @@ def golden_names():
     )
 
 
+def class_codable(name):
+    """False for the golden whose grid gives every row its own A(V) / R(V) value: only the elementwise
+    evaluation can take it; the class-coded modes must refuse it."""
+    return name != "non_cartesian_grid"
+
+
 def load_golden(name):
     with np.load(os.path.join(GOLDEN_DIR, name + ".npz")) as f:
         sj = json.loads(str(f["settings_json"]))

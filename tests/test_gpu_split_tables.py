@@ -13,7 +13,7 @@ import copy
 import numpy as np
 import pytest
 
-from golden_util import assert_close, golden_names, load_golden
+from golden_util import assert_close, class_codable, golden_names, load_golden
 from megabeast_b200 import MB_Model, lnprob, synth
 from megabeast_b200.engine import LikelihoodEngine
 from oracle import c_oracle
@@ -40,7 +40,7 @@ def _eval_one_by_one(model, phis, stars, moddata):
     return out, kind
 
 
-@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("name", [n for n in golden_names() if class_codable(n)])
 def test_goldens_with_every_split(name, capsys):
     """Every golden vector (frozen from the reference) under every possible table split."""
     settings, moddata, stars, phis, expect, kind = load_golden(name)
@@ -49,8 +49,15 @@ def test_goldens_with_every_split(name, capsys):
         free = [p for p in free]  # tabulated parameters split like any other (K0 path)
     splits = [tuple(p for j, p in enumerate(free) if (m >> j) & 1) for m in range(1, 1 << len(free))]
     assert splits or not free
+    ran = 0
     for split in splits:
         model = MB_Model(copy.deepcopy(settings), mode="factor", split_inner=split)
+        try:
+            got, gkind = _eval_one_by_one(model, phis[:1], stars, moddata)
+        except Exception as exc:   # a forced split whose tables are too large for shared memory is refused
+            assert "do not fit shared memory" in str(exc) and name == "production_dust_axes", (split, exc)
+            continue
+        ran += 1
         got, gkind = _eval_one_by_one(model, phis, stars, moddata)
         assert np.array_equal(gkind, kind), split
         ok = kind == 0
@@ -60,6 +67,7 @@ def test_goldens_with_every_split(name, capsys):
         assert info["split_inner_mask"] == want_mask
         if not kind.any():  # the batch evaluates all walkers in one launch
             assert_close(lnprob(phis, model, stars, moddata), expect, RTOL)
+    assert ran >= 1 or not splits
 
 
 @pytest.mark.parametrize("cfg,mode,W", [("small", "uniform", 7), ("cfg1", "clustered", 45),
