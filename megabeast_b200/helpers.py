@@ -57,7 +57,9 @@ def get_likelihoods(ppdf_file, beast_model_data, device=0):
 
 
 def _trapz(y, x):
-    return float(np.sum(np.diff(x) * (y[1:] + y[:-1]) / 2.0))
+    # a numpy scalar like np.trapz's: on a grid with a single M_ini value the reference gets 0/0 = nan
+    # (helpers.py:72-73,92), not a ZeroDivisionError
+    return np.float64(np.sum(np.diff(x) * (y[1:] + y[:-1]) / 2.0))
 
 
 def precompute_mass_multipliers(bphysparams, physmodmass):
@@ -73,7 +75,8 @@ def precompute_mass_multipliers(bphysparams, physmodmass):
     masspts = np.logspace(np.log10(mini.min()), np.log10(mini.max()), 100)
     massprior = np.asarray(physmodmass(masspts), dtype=float)
     totmass = _trapz(massprior, masspts)
-    avemass = _trapz(masspts * massprior, masspts) / totmass
+    with np.errstate(divide="ignore", invalid="ignore"):
+        avemass = _trapz(masspts * massprior, masspts) / totmass
 
     ages, ia = np.unique(loga, return_inverse=True)
     mets, iz = np.unique(zmet, return_inverse=True)
@@ -91,7 +94,8 @@ def precompute_mass_multipliers(bphysparams, physmodmass):
             if not np.isfinite(lo[k]):
                 raise ValueError("min() arg is an empty sequence")  # what the reference hits
             sel = (masspts >= lo[k]) & (masspts <= hi[k])
-            massmult[i, j] = widths[i] * _trapz(massprior[sel], masspts[sel]) / totmass
+            with np.errstate(divide="ignore", invalid="ignore"):
+                massmult[i, j] = widths[i] * _trapz(massprior[sel], masspts[sel]) / totmass
     return {"massmult": massmult, "ages": ages, "Zs": mets, "avemass": avemass}
 
 

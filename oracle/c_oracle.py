@@ -42,7 +42,9 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.isfile(_LIB):
+        src = os.path.join(_HERE, "mb_oracle.c")
+        # (the source is absent where only the built library travels; rebuild when it is there and newer)
+        if not os.path.isfile(_LIB) or (os.path.isfile(src) and os.path.getmtime(_LIB) < os.path.getmtime(src)):
             build()
         _lib = ctypes.CDLL(_LIB)
         _lib.mbo_lnlike_batch.restype = ctypes.c_int

@@ -234,8 +234,9 @@ def lnprob(phi, model, stars, moddata, loop=True):
 
 def _trapezoid(y, x):
     # same arithmetic as np.trapz (helpers.py:72,73,92): sum(dx * (y[1:] + y[:-1]) / 2)
+    # (a numpy scalar, as np.trapz returns: 0/0 on a grid with a single M_ini value is nan there, not an exception)
     y, x = np.asarray(y, float), np.asarray(x, float)
-    return float(np.sum(np.diff(x) * (y[1:] + y[:-1]) / 2.0))
+    return np.float64(np.sum(np.diff(x) * (y[1:] + y[:-1]) / 2.0))
 
 
 def mass_multipliers(moddata, mass_model):
@@ -245,7 +246,8 @@ def mass_multipliers(moddata, mass_model):
     mpts = np.logspace(np.log10(lo), np.log10(hi), 100)
     imf = priors.evaluate_prior_model(mass_model, mpts)
     tot = _trapezoid(imf, mpts)
-    avemass = _trapezoid(mpts * imf, mpts) / tot
+    with np.errstate(divide="ignore", invalid="ignore"):
+        avemass = _trapezoid(mpts * imf, mpts) / tot
     ages = np.unique(loga)
     widths = np.diff(10 ** priors.bin_boundaries(ages))
     mets = np.unique(zmet)
@@ -255,7 +257,8 @@ def mass_multipliers(moddata, mass_model):
             sel = (loga == a) & (zmet == z)
             mlo, mhi = min(mini[sel]), max(mini[sel])
             inr = (mpts >= mlo) & (mpts <= mhi)
-            mult[i, j] = widths[i] * _trapezoid(imf[inr], mpts[inr]) / tot
+            with np.errstate(divide="ignore", invalid="ignore"):
+                mult[i, j] = widths[i] * _trapezoid(imf[inr], mpts[inr]) / tot
     return {"massmult": mult, "ages": ages, "Zs": mets, "avemass": avemass}
 
 

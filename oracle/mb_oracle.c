@@ -160,6 +160,7 @@ int mbo_lnlike_batch(int64_t G, const double* const* cols, const double* prior_w
             double v = vals[kk * S + s];
             if (!isfinite(v)) continue;                          /* :196-198 */
             int64_t r = indxs[kk * S + s];
+            if (r < 0) r += G;                                    /* numpy indexing counts negative indices from the end */
             acc += v * physmod[r] * prior_weight[r] * grid_weight[r] * completeness[r];
           }
           if (!isfinite(acc)) { st |= 1; continue; }

@@ -224,6 +224,45 @@ def round2_cases(spdm, only=None):
         save("non_cartesian_grid", settings, mod, stars, phis, e, k,
              "every grid row its own A(V), R(V) value: no class coding possible")
 
+    # 13. what numpy indexing accepts and a BEAST file would not contain: the same grid row twice within a
+    #     star (the reference simply adds both, :207-213) and negative indices (counted from the end)
+    if want("duplicate_and_negative_indices"):
+        settings, mod, stars, cfg = synth.make_problem("tiny")
+        G = mod["Av"].size
+        stars["indxs"][1, :] = stars["indxs"][0, :]
+        stars["indxs"][2, ::2] -= G
+        phis = walkers(settings, 4, seed=13)
+        e, k = run_reference(spdm, settings, mod, stars, phis)
+        save("duplicate_and_negative_indices", settings, mod, stars, phis, e, k,
+             "every star holds one grid row twice; half the stars index one point from the end")
+
+    # 14. no stars at all: only the N-stars term is left, 0 ln(pred) - pred - lgamma(1) (:182-186)
+    if want("no_stars"):
+        settings, mod, stars, cfg = synth.make_problem("tiny")
+        stars = {"indxs": stars["indxs"][:, :0].copy(), "vals": stars["vals"][:, :0].copy()}
+        phis = walkers(settings, 3, seed=15)
+        e, k = run_reference(spdm, settings, mod, stars, phis)
+        save("no_stars", settings, mod, stars, phis, e, k, "star arrays of shape (K, 0)")
+
+    # 15. completeness 0 everywhere: every star sums to 0 (skipped) and the predicted number is 0 -> -inf
+    if want("zero_completeness"):
+        settings, mod, stars, cfg = synth.make_problem("tiny")
+        mod["completeness"] = np.zeros_like(mod["completeness"])
+        phis = walkers(settings, 3, seed=16)
+        e, k = run_reference(spdm, settings, mod, stars, phis)
+        save("zero_completeness", settings, mod, stars, phis, e, k, "completeness column all zero: ln(0) in the N-stars term")
+
+    # 16. a grid with ONE initial mass: the 100-point mass grid collapses, every IMF integral is 0 and the
+    #     mass multipliers are 0/0 -- the reference returns nan for every walker (helpers.py:72-73,92)
+    if want("single_mass_grid"):
+        axes = (5, 2, 1, 6, 3, 1)
+        settings = synth.docs_example_settings()
+        mod = synth.make_grid(axes, seed=61)
+        stars = synth.make_star_data(mod, axes, 40, 8, seed=62)
+        phis = walkers(settings, 3, seed=14)
+        e, k = run_reference(spdm, settings, mod, stars, phis)
+        save("single_mass_grid", settings, mod, stars, phis, e, k, "one M_ini value in the whole grid: nan")
+
 
 def main():
     """`python tests/golden/make_golden.py` rewrites everything; `--only a,b` writes just those round-2 cases."""

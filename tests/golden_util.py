@@ -43,7 +43,7 @@ def load_cfg1_expect():
 def assert_close(got, expect, rtol=1e-9):
     got, expect = np.asarray(got, float), np.asarray(expect, float)
     fin = np.isfinite(expect)
-    assert np.array_equal(got[~fin], expect[~fin]), (got, expect)
+    assert np.array_equal(got[~fin], expect[~fin], equal_nan=True), (got, expect)
     if fin.any():
         err = np.max(np.abs(got[fin] - expect[fin]) / np.abs(expect[fin]))
         assert err <= rtol, f"relative error {err:.3e} > {rtol}"
