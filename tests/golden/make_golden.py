@@ -263,6 +263,26 @@ def round2_cases(spdm, only=None):
         e, k = run_reference(spdm, settings, mod, stars, phis)
         save("single_mass_grid", settings, mod, stars, phis, e, k, "one M_ini value in the whole grid: nan")
 
+    # 17. (age, Z) bins without grid weight (helpers.py:156 skips them) -- one bin, and a whole age
+    if want("weightless_bins"):
+        settings, mod, stars, cfg = synth.make_problem("tiny")
+        mod["grid_weight"] = mod["grid_weight"].copy()
+        ages, mets = np.unique(mod["logA"]), np.unique(mod["Z"])
+        mod["grid_weight"][(mod["logA"] == ages[1]) & (mod["Z"] == mets[0])] = 0.0
+        mod["grid_weight"][mod["logA"] == ages[3]] = 0.0
+        phis = walkers(settings, 4, seed=17)
+        e, k = run_reference(spdm, settings, mod, stars, phis)
+        save("weightless_bins", settings, mod, stars, phis, e, k, "grid_weight 0 in one (age, Z) bin and in a whole age")
+
+    # 18. a star whose sum is negative: np.log gives nan (a warning, no exception) and the total is nan (:218-223)
+    if want("negative_star"):
+        settings, mod, stars, cfg = synth.make_problem("tiny")
+        fin = np.isfinite(stars["vals"][:, 4])
+        stars["vals"][fin, 4] = -np.abs(stars["vals"][fin, 4])
+        phis = walkers(settings, 3, seed=18)
+        e, k = run_reference(spdm, settings, mod, stars, phis)
+        save("negative_star", settings, mod, stars, phis, e, k, "one star with negative likelihood values: nan, not an exception")
+
 
 def main():
     """`python tests/golden/make_golden.py` rewrites everything; `--only a,b` writes just those round-2 cases."""
