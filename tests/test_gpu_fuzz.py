@@ -1,0 +1,59 @@
+"""
+The CUDA path against the C oracle on random small problems: grid shapes down to one class per axis, model
+variants (SFH fixed, R(V) fixed, A(V) fixed, f_A free, two_lognormal A(V)), 0-30 % masking, zeroed completeness
+rows, all-zero stars, out-of-box walkers, one star, one sparse point -- every engine mode.  Values to 1e-9
+relative, exceptions alike (singlepop_dust_model.py:216-217,225-227).
+"""
+import contextlib
+import copy
+import io
+
+import numpy as np
+import pytest
+
+from fuzz_util import random_problem
+from golden_util import assert_close
+from megabeast_b200 import MB_Model, lnprob
+from oracle import c_oracle
+from oracle import lnprob_port as port
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("mode", ["auto", "factor", "table_unique", "table_grid", "elementwise"])
+def test_random_small_problems_match_the_oracle(mode):
+    rng = np.random.default_rng(4242)
+    compared = 0
+    for _ in range(40):
+        try:
+            settings, moddata, stars, phis = random_problem(rng)
+        except ValueError:   # (fewer distinct grid rows than sparse points asked for)
+            continue
+        pm = port.PortModel(copy.deepcopy(settings))
+        want, wkind = np.full(len(phis), np.nan), np.zeros(len(phis), int)
+        for i, phi in enumerate(phis):   # the port one walker at a time: values and exceptions
+            try:
+                with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+                    want[i] = port.lnprob(phi, pm, stars, moddata, loop=False)
+            except ValueError:
+                wkind[i] = 1
+            except SystemExit:
+                wkind[i] = 2
+        model = MB_Model(copy.deepcopy(settings), mode=mode)
+        got, gkind = np.full(len(phis), np.nan), np.zeros(len(phis), int)
+        for i, phi in enumerate(phis):
+            try:
+                with contextlib.redirect_stdout(io.StringIO()):
+                    got[i] = lnprob(phi, model, stars, moddata)
+            except ValueError:
+                gkind[i] = 1
+            except SystemExit:
+                gkind[i] = 2
+        assert np.array_equal(gkind, wkind), (settings.fd_model, settings.stellar_model["logA"]["prior"], gkind, wkind)
+        ok = wkind == 0
+        assert_close(got[ok], want[ok], 1e-9)
+        if ok.all():   # and as one batch, against the C oracle
+            batch = lnprob(phis, model, stars, moddata)
+            assert_close(batch, c_oracle.lnprob_batch(port.PortModel(copy.deepcopy(settings)), phis, stars, moddata), 1e-9)
+        compared += 1
+    assert compared >= 30
