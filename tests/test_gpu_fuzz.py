@@ -13,7 +13,7 @@ import pytest
 
 from fuzz_util import random_problem
 from golden_util import assert_close
-from megabeast_b200 import MB_Model, lnprob
+from megabeast_b200 import MB_Model, lnprob, synth
 from oracle import c_oracle
 from oracle import lnprob_port as port
 
@@ -52,8 +52,11 @@ def test_random_small_problems_match_the_oracle(mode):
         assert np.array_equal(gkind, wkind), (settings.fd_model, settings.stellar_model["logA"]["prior"], gkind, wkind)
         ok = wkind == 0
         assert_close(got[ok], want[ok], 1e-9)
-        if ok.all():   # and as one batch, against the C oracle
-            batch = lnprob(phis, model, stars, moddata)
-            assert_close(batch, c_oracle.lnprob_batch(port.PortModel(copy.deepcopy(settings)), phis, stars, moddata), 1e-9)
+        if ok.all():   # and as one batch, against the C oracle -- also wide batches (64- and 128-walker kernels, two passes)
+            W = int(rng.choice([3, 3, 40, 70, 130]))
+            wide = phis if W == 3 else np.concatenate([phis, synth.make_walkers(pm, W - 3, seed=int(rng.integers(1 << 20)))])
+            expect = c_oracle.lnprob_batch(port.PortModel(copy.deepcopy(settings)), wide, stars, moddata)
+            if np.all(np.isfinite(expect)):   # (a batch raises as soon as any of its walkers would)
+                assert_close(lnprob(wide, model, stars, moddata), expect, 1e-9)
         compared += 1
     assert compared >= 30
