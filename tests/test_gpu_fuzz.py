@@ -60,3 +60,43 @@ def test_random_small_problems_match_the_oracle(mode):
                 assert_close(lnprob(wide, model, stars, moddata), expect, 1e-9)
         compared += 1
     assert compared >= 30
+
+
+def test_random_pixel_batches_match_the_per_pixel_oracle():
+    """Pixel batches on the same random problems: the stars cut into random pixels (empty ones included),
+    every model variant, 3 to 70 walkers per pixel; each pixel against the oracle run on its stars alone."""
+    from megabeast_b200.pixels import PixelEnsemble
+
+    rng = np.random.default_rng(777)
+    compared = 0
+    for _ in range(30):
+        try:
+            settings, moddata, stars, phis = random_problem(rng)
+        except ValueError:
+            continue
+        S = stars["indxs"].shape[1]
+        P = int(rng.integers(1, 6))
+        offs = np.sort(np.concatenate([[0, S], rng.integers(0, S + 1, size=P - 1)])).astype(np.int64)
+        pm = port.PortModel(copy.deepcopy(settings))
+        W = int(rng.choice([3, 9, 45, 70]))
+        walkers = np.stack([synth.make_walkers(pm, W, seed=int(rng.integers(1 << 20))) for _ in range(P)])
+        want = np.empty((P, W))
+        raises = False
+        for p in range(P):
+            sub = {"indxs": np.ascontiguousarray(stars["indxs"][:, offs[p]:offs[p + 1]]),
+                   "vals": np.ascontiguousarray(stars["vals"][:, offs[p]:offs[p + 1]])}
+            for w in range(W):
+                try:
+                    with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+                        want[p, w] = port.lnprob(walkers[p, w], port.PortModel(copy.deepcopy(settings)), sub, moddata, loop=False)
+                except (ValueError, SystemExit):
+                    raises = True
+        pe = PixelEnsemble(copy.deepcopy(settings), stars, moddata, offs)
+        if raises:   # the batch raises as soon as any walker of any pixel would
+            with pytest.raises((ValueError, SystemExit)), contextlib.redirect_stdout(io.StringIO()):
+                pe.lnprob(walkers)
+        else:
+            assert_close(pe.lnprob(walkers), want, 1e-9)
+            compared += 1
+        pe.close()
+    assert compared >= 15
