@@ -12,7 +12,7 @@ def random_problem(rng):
     them possibly outside the prior box), sometimes zeroed completeness rows or an all-zero star."""
     axes = tuple(int(rng.integers(lo, hi)) for lo, hi in ((2, 7), (1, 4), (2, 5), (2, 8), (1, 5), (1, 4)))
     settings = synth.docs_example_settings()
-    variant = int(rng.integers(0, 6))
+    variant = int(rng.integers(0, 8))
     if variant == 1:
         settings.stellar_model["logA"]["prior"]["name"] = "fixed"
     elif variant == 2:
@@ -27,6 +27,14 @@ def random_problem(rng):
             "prior": {"name": "flat", "minmax": [[0.005, 5.0], [0.005, 5.0], [0.05, 1.0], [0.05, 1.0], [0.1, 10.0]]}}
     elif variant == 5:
         settings.fd_model["Av"]["prior"]["name"] = "fixed"
+    elif variant == 6:   # SFH interpolated between 3 to 7 nodes instead of a step function
+        n = int(rng.integers(3, 8))
+        settings.stellar_model["x"] = list(np.linspace(6.0, 10.0, n))
+        settings.stellar_model["logA"] = {
+            "name": "bins_interp", "varnames": ["values"], "varinit": [list(rng.uniform(0.5e-8, 3e-8, n))],
+            "prior": {"name": "flat", "minmax": [[0.0] * n, [1e-3] * n]}}
+    elif variant == 7:   # a Salpeter IMF behind the mass multipliers (fixed, as upstream requires)
+        settings.stellar_model["M_ini"]["name"] = "salpeter"
     moddata = synth.make_grid(axes, seed=int(rng.integers(1 << 20)))
     S, K = int(rng.integers(1, 30)), int(rng.integers(1, 9))
     stars = synth.make_star_data(moddata, axes, S, K, seed=int(rng.integers(1 << 20)),
